@@ -1,0 +1,197 @@
+/*
+ * mulan_b200.h -- C ABI of libmulan_b200.so: the MuLAN per-pixel noise schedule +
+ * variational-diffusion ELBO hot path as hand-written sm_100a CUDA kernels.
+ *
+ * The reference (s-sahoo/MuLAN, pure JAX/Flax) has no plugin/FFI registry; the seams this
+ * library replaces are the Flax method bodies listed per entry point below (paths relative
+ * to the reference root).  A JAX binding calls these from XLA-FFI handlers, a PyTorch
+ * binding from torch.autograd.Function.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no framework types.
+ *   - Unless an entry point says "host", every pointer is a DEVICE pointer owned by the
+ *     caller; the call only ENQUEUES work on `stream` (a cudaStream_t passed as void*),
+ *     never allocates, never synchronises, keeps no global mutable state, and is
+ *     re-entrant from one host thread per device.
+ *   - Arrays are float32, row-major [rows, dim] ("[B,D]", D = 32*32*3 = 3072 sub-pixels,
+ *     NHWC-flattened) unless noted; x is uint8 [B,D]; per-example vectors are [B].
+ *   - [B,D] float pointers must be 16-byte aligned and dim % 4 == 0 (float4 access);
+ *     x must be 4-byte aligned.
+ *   - Return value: 0 on success, negative mulan_status otherwise; a message for the last
+ *     failure on this thread is available from mulan_last_error().
+ *   - NaN/Inf propagate as in the reference (no trapping).
+ */
+#ifndef MULAN_B200_H_
+#define MULAN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MULAN_ABI_VERSION 1
+
+typedef enum mulan_status {
+  MULAN_OK = 0,
+  MULAN_ERR_INVALID_ARG = -1,   /* null pointer, bad enum, bad shape */
+  MULAN_ERR_ALIGNMENT = -2,     /* pointer / dim not aligned for vector access */
+  MULAN_ERR_UNSUPPORTED = -3,   /* combination not implemented (message says which) */
+  MULAN_ERR_CUDA = -4           /* launch or runtime error; message has cudaGetErrorString */
+} mulan_status;
+
+/* Which network parameterisation the diffusion loss uses. */
+typedef enum mulan_param {
+  MULAN_PARAM_EPS = 0,          /* ldm/model_mulan_epsilon.py:335-347                     */
+  MULAN_PARAM_VEL = 1,          /* ldm/model_mulan_velocity.py:243-260, from_epsilon=False */
+  MULAN_PARAM_VEL_FROM_EPS = 2  /* ldm/model_mulan_velocity.py:246-249, from_epsilon=True  */
+} mulan_param;
+
+/* What the denoiser receives as its noise-level input (_get_score_model_gt,
+ * ldm/model_mulan_epsilon.py:273-278). */
+typedef enum mulan_gt_mode {
+  MULAN_GT_MEAN = 0,            /* unet_type='vdm': per-example mean of gamma_t, [B]   */
+  MULAN_GT_PIXEL = 1            /* unet_type='ldm': per-pixel gamma_t, [B,D]           */
+} mulan_gt_mode;
+
+/* POD descriptor shared by all entry points (the subset of VDMConfig,
+ * ldm/model_vdm.py:33-82, the path reads). gamma_min/max are doubles because the
+ * reference forms gamma_max-gamma_min in Python double before the float32 cast
+ * (ldm/model_mulan_epsilon.py:489-490). */
+typedef struct mulan_desc {
+  int32_t rows;         /* B: examples in this launch (this device's shard)      */
+  int32_t dim;          /* D: sub-pixels per example (3072); multiple of 4       */
+  int32_t vocab;        /* vocab_size (256); 2..65536                            */
+  int32_t param;        /* mulan_param                                           */
+  int32_t gt_mode;      /* mulan_gt_mode                                         */
+  int32_t n_timesteps;  /* sm_n_timesteps T; 0 = continuous time                 */
+  double gamma_min;     /* -13.3                                                 */
+  double gamma_max;     /*  5.0                                                  */
+} mulan_desc;
+
+/* Thread-local message describing the last non-zero status returned on this thread. */
+const char* mulan_last_error(void);
+int mulan_abi_version(void);
+
+/*
+ * mulan_fwd_pre -- everything in VDM.__call__ that precedes the denoiser call.
+ * Replaces: EncDec.encode (ldm/model_vdm.py:274-280); NoiseSchedule_polynomial_fixedend.
+ * _eval_polynomial at t in {0,1,t} (ldm/model_mulan_epsilon.py:514-529, call sites :307-309);
+ * the jvp d-gamma/dt (:339-343); noising (:311,:327-328); _get_score_model_gt (:273-278);
+ * reconstruction term (:315-318 -> EncDec.logprob/decode, ldm/model_vdm.py:282-303);
+ * prior KL (:322-325); var_0/var_1 partial sums (:361-362).
+ * The velocity model runs the same statements (ldm/model_mulan_velocity.py:208-236).
+ *
+ *   in : x[B,D] u8; a,b,c[B,D] polynomial coefficients (c already 1e-3+softplus);
+ *        t[B]; eps0[B,D]; eps[B,D]
+ *   out: z_t[B,D]; g_net ([B] for GT_MEAN, [B,D] for GT_PIXEL);
+ *        w_save[B,D] or NULL -- the loss weight d-gamma/dt (T==0) or T*expm1(g_t-g_s)
+ *        (T>0, epsilon model only), reusable by mulan_fwd_post / mulan_bwd_post;
+ *        loss_recon[B]; loss_klz_prior[B]; var_sums[B,2] = per-row sum of sigmoid(g_0),
+ *        sigmoid(g_1).
+ */
+int mulan_fwd_pre(const mulan_desc* desc,
+                  const uint8_t* x, const float* a, const float* b, const float* c,
+                  const float* t, const float* eps0, const float* eps,
+                  float* z_t, float* g_net, float* w_save,
+                  float* loss_recon, float* loss_klz_prior, float* var_sums,
+                  void* stream);
+
+/*
+ * mulan_fwd_post -- the diffusion loss after the denoiser returned `net`.
+ * Replaces ldm/model_mulan_epsilon.py:338-355 (EPS; T>0 variant needs w_save) and
+ * ldm/model_mulan_velocity.py:246-260 (VEL / VEL_FROM_EPS).
+ *   in : x, a, b, c, t, eps as for fwd_pre; net[B,D]; w_save[B,D] or NULL (recomputed
+ *        from a,b,c,t when NULL; EPS with w_save never touches x,a,b,c)
+ *   out: loss_diff[B]
+ */
+int mulan_fwd_post(const mulan_desc* desc,
+                   const uint8_t* x, const float* a, const float* b, const float* c,
+                   const float* t, const float* eps, const float* net, const float* w_save,
+                   float* loss_diff, void* stream);
+
+/*
+ * mulan_bwd_post -- cotangent of the denoiser output, what jax.value_and_grad
+ * (ldm/experiment.py:339) pushes into the U-Net: n_bar = d(sum_b gL_b loss_diff_b)/d net.
+ *   in : as fwd_post, gL[B] = upstream cotangent of loss_diff
+ *   out: n_bar[B,D]
+ */
+int mulan_bwd_post(const mulan_desc* desc,
+                   const uint8_t* x, const float* a, const float* b, const float* c,
+                   const float* t, const float* eps, const float* net, const float* w_save,
+                   const float* gL, float* n_bar, void* stream);
+
+/*
+ * mulan_bwd_pre -- cotangents of the polynomial coefficients: every path from the loss to
+ * (a,b,c): through z_t (z_bar, returned by the denoiser's backward), through the
+ * denoiser's noise-level input (g_bar: [B] for GT_MEAN, [B,D] for GT_PIXEL), and through
+ * loss_diff directly (weight d-gamma/dt, and for the velocity models (1-var_t), v_target,
+ * and v_hat's own dependence on gamma_t and z_t).  gamma(0), gamma(1) are fixed ends and
+ * contribute nothing.  Any of z_bar, g_bar, gL may be NULL (treated as zero); net may be
+ * NULL only if gL is NULL.
+ *   out: a_bar, b_bar, c_bar [B,D]
+ */
+int mulan_bwd_pre(const mulan_desc* desc,
+                  const uint8_t* x, const float* a, const float* b, const float* c,
+                  const float* t, const float* eps, const float* net,
+                  const float* z_bar, const float* g_bar, const float* gL,
+                  float* a_bar, float* b_bar, float* c_bar, void* stream);
+
+/*
+ * mulan_aux_topk_fwd / _bwd -- auxiliary-latent KL and relaxed top-k embedding.
+ * Replaces _gumbel_kl_loss, _gamma_noise, _topk_embedding_and_loss
+ * (ldm/model_mulan_epsilon.py:205-210, 221-252; ldm/model_mulan_velocity.py:78-120).
+ *   in : logits[B,L]; gamma_draw[10,B,L] ~ Gamma(1/k) (the jax.random.gamma draw) or NULL
+ *        for no noise; L <= 64; k = latent_k
+ *   out: embedding[B,L]; kl_z[B]
+ *   bwd: logits_bar[B,L] = d(sum emb_bar*embedding + sum klz_bar*kl_z)/d logits
+ */
+int mulan_aux_topk_fwd(int32_t rows, int32_t latent, int32_t k,
+                       const float* logits, const float* gamma_draw,
+                       float* embedding, float* kl_z, void* stream);
+int mulan_aux_topk_bwd(int32_t rows, int32_t latent, int32_t k,
+                       const float* logits, const float* gamma_draw,
+                       const float* emb_bar, const float* klz_bar,
+                       float* logits_bar, void* stream);
+
+/*
+ * mulan_bpd_reduce -- VDMOutput assembly + Experiment_VDM.loss_fn scalars
+ * (ldm/model_mulan_epsilon.py:357-363, ldm/experiment_vdm.py:62-74).
+ *   in : loss_recon[B], loss_klz_prior[B], kl_z[B] or NULL, loss_diff[B], var_sums[B,2]
+ *   out: scalars[6] = {bpd, bpd_latent, bpd_recon, bpd_diff, var0, var1};
+ *        loss_klz_total[B] or NULL = kl_z + loss_klz_prior
+ */
+int mulan_bpd_reduce(const mulan_desc* desc,
+                     const float* loss_recon, const float* loss_klz_prior, const float* kl_z,
+                     const float* loss_diff, const float* var_sums,
+                     float* scalars, float* loss_klz_total, void* stream);
+
+/*
+ * mulan_elbo_host -- HOST-buffer convenience entry: one call = H2D of the inputs, fwd_pre,
+ * the denoiser callback (or the supplied `net`), fwd_post, bwd_post, bwd_pre, bpd_reduce and
+ * D2H of the results, on the current device.  This is the call a ctypes/cgo-style binding
+ * with host arrays would make; it allocates a workspace internally (cached per thread) and
+ * synchronises before returning.
+ *   denoiser(user, z_t_dev, g_net_dev, net_dev, stream): fills net_dev[B,D]; may be NULL, in
+ *   which case `net` (host, [B,D]) is used.  When want_grad != 0 and the denoiser is NULL,
+ *   z_bar is taken as zero (the supplied net does not depend on z_t).
+ *   out (host): losses[3*B] = recon | klz_prior | diff; scalars[6];
+ *               grads (want_grad): a_bar,b_bar,c_bar,n_bar [B,D] each (NULL to skip copy-out)
+ */
+typedef int (*mulan_denoiser_fn)(void* user, const float* z_t, const float* g_net,
+                                 float* net, void* stream);
+int mulan_elbo_host(const mulan_desc* desc,
+                    const uint8_t* x, const float* a, const float* b, const float* c,
+                    const float* t, const float* eps0, const float* eps, const float* net,
+                    mulan_denoiser_fn denoiser, void* user, int32_t want_grad,
+                    float* losses, float* scalars,
+                    float* a_bar, float* b_bar, float* c_bar, float* n_bar);
+
+/* Frees the calling thread's cached mulan_elbo_host workspace (device + pinned host). */
+void mulan_host_workspace_release(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* MULAN_B200_H_ */

@@ -1,0 +1,84 @@
+"""ctypes binding of libmulan_b200.so (include/mulan_b200.h).
+
+There is NO fallback: if the shared library is missing this module raises at first use, and
+the ops refuse CPU tensors.  The product path never touches ``oracle/``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+LIB_PATH = Path(__file__).resolve().parent / 'libmulan_b200.so'
+
+MULAN_PARAM_EPS = 0
+MULAN_PARAM_VEL = 1
+MULAN_PARAM_VEL_FROM_EPS = 2
+MULAN_GT_MEAN = 0
+MULAN_GT_PIXEL = 1
+
+PARAM_NAMES = {'eps': MULAN_PARAM_EPS, 'vel': MULAN_PARAM_VEL,
+               'vel_from_eps': MULAN_PARAM_VEL_FROM_EPS}
+
+
+class MulanDesc(C.Structure):
+  """struct mulan_desc."""
+  _fields_ = [('rows', C.c_int32), ('dim', C.c_int32), ('vocab', C.c_int32),
+              ('param', C.c_int32), ('gt_mode', C.c_int32), ('n_timesteps', C.c_int32),
+              ('gamma_min', C.c_double), ('gamma_max', C.c_double)]
+
+
+class MulanError(RuntimeError):
+  def __init__(self, status: int, msg: str):
+    super().__init__(f'libmulan_b200 status {status}: {msg}')
+    self.status = status
+
+
+DENOISER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p)
+
+_P = C.c_void_p
+_D = C.POINTER(MulanDesc)
+
+# name -> argtypes; every symbol include/mulan_b200.h declares.
+SIGNATURES = {
+    'mulan_last_error': ([], C.c_char_p),
+    'mulan_abi_version': ([], C.c_int),
+    'mulan_fwd_pre': ([_D] + [_P] * 14, C.c_int),
+    'mulan_fwd_post': ([_D] + [_P] * 10, C.c_int),
+    'mulan_bwd_post': ([_D] + [_P] * 11, C.c_int),
+    'mulan_bwd_pre': ([_D] + [_P] * 14, C.c_int),
+    'mulan_aux_topk_fwd': ([C.c_int32] * 3 + [_P] * 5, C.c_int),
+    'mulan_aux_topk_bwd': ([C.c_int32] * 3 + [_P] * 6, C.c_int),
+    'mulan_bpd_reduce': ([_D] + [_P] * 8, C.c_int),
+    'mulan_elbo_host': ([_D] + [_P] * 8 + [DENOISER_FN, _P, C.c_int32] + [_P] * 6, C.c_int),
+    'mulan_host_workspace_release': ([], None),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+  """dlopen the in-tree library; loud failure when it has not been built."""
+  global _lib
+  if _lib is None:
+    if not LIB_PATH.exists():
+      raise ImportError(
+          f'{LIB_PATH} is missing: build it with `python -m mulan_b200.build` '
+          '(or __graft_entry__.build()). There is no CPU / PyTorch fallback.')
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (argtypes, restype) in SIGNATURES.items():
+      fn = getattr(lib, name)
+      fn.argtypes = argtypes
+      fn.restype = restype
+    _lib = lib
+  return _lib
+
+
+def check(status: int) -> None:
+  if status != 0:
+    raise MulanError(status, load().mulan_last_error().decode())
+
+
+def make_desc(rows: int, dim: int = 3072, vocab: int = 256, param: int = MULAN_PARAM_EPS,
+              gt_mode: int = MULAN_GT_MEAN, n_timesteps: int = 0,
+              gamma_min: float = -13.3, gamma_max: float = 5.0) -> MulanDesc:
+  return MulanDesc(rows, dim, vocab, param, gt_mode, n_timesteps, gamma_min, gamma_max)

@@ -1,0 +1,367 @@
+// extern "C" surface of libmulan_b200.so (see include/mulan_b200.h): argument validation,
+// parameter-block assembly, launches, and the host-buffer convenience entry.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "mulan_kernels.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(mulan_status st, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return (int)st;
+}
+
+int cuda_fail(const char* what, cudaError_t e) {
+  return fail(MULAN_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+bool aligned(const void* p, size_t n) { return (reinterpret_cast<uintptr_t>(p) % n) == 0; }
+
+int check_desc(const mulan_desc* d, const char* fn) {
+  if (d == nullptr) return fail(MULAN_ERR_INVALID_ARG, "%s: desc is NULL", fn);
+  if (d->rows < 0) return fail(MULAN_ERR_INVALID_ARG, "%s: rows=%d < 0", fn, d->rows);
+  if (d->dim <= 0) return fail(MULAN_ERR_INVALID_ARG, "%s: dim=%d <= 0", fn, d->dim);
+  if (d->dim % 4 != 0)
+    return fail(MULAN_ERR_ALIGNMENT, "%s: dim=%d is not a multiple of 4", fn, d->dim);
+  if (d->vocab < 2 || d->vocab > 65536)
+    return fail(MULAN_ERR_INVALID_ARG, "%s: vocab=%d outside [2,65536]", fn, d->vocab);
+  if (d->param < MULAN_PARAM_EPS || d->param > MULAN_PARAM_VEL_FROM_EPS)
+    return fail(MULAN_ERR_INVALID_ARG, "%s: param=%d is not a mulan_param", fn, d->param);
+  if (d->gt_mode != MULAN_GT_MEAN && d->gt_mode != MULAN_GT_PIXEL)
+    return fail(MULAN_ERR_INVALID_ARG, "%s: gt_mode=%d is not a mulan_gt_mode", fn, d->gt_mode);
+  if (d->n_timesteps < 0)
+    return fail(MULAN_ERR_INVALID_ARG, "%s: n_timesteps=%d < 0", fn, d->n_timesteps);
+  if (!(d->gamma_max > d->gamma_min))
+    return fail(MULAN_ERR_INVALID_ARG, "%s: gamma_max must exceed gamma_min", fn);
+  if (d->n_timesteps > 0)
+    return fail(MULAN_ERR_UNSUPPORTED,
+                "%s: discrete-time loss (sm_n_timesteps=%d > 0) is not implemented; both shipped "
+                "configs use 0 and the velocity model asserts it", fn, d->n_timesteps);
+  return 0;
+}
+
+#define REQ_PTR(p, fn)                                                           \
+  do {                                                                           \
+    if ((p) == nullptr) return fail(MULAN_ERR_INVALID_ARG, "%s: %s is NULL", fn, #p); \
+  } while (0)
+#define REQ_VEC(p, fn)                                                           \
+  do {                                                                           \
+    REQ_PTR(p, fn);                                                              \
+    if (!aligned((p), 16))                                                       \
+      return fail(MULAN_ERR_ALIGNMENT, "%s: %s is not 16-byte aligned", fn, #p); \
+  } while (0)
+#define OPT_VEC(p, fn)                                                           \
+  do {                                                                           \
+    if ((p) != nullptr && !aligned((p), 16))                                     \
+      return fail(MULAN_ERR_ALIGNMENT, "%s: %s is not 16-byte aligned", fn, #p); \
+  } while (0)
+#define REQ_X(p, fn)                                                             \
+  do {                                                                           \
+    REQ_PTR(p, fn);                                                              \
+    if (!aligned((p), 4))                                                        \
+      return fail(MULAN_ERR_ALIGNMENT, "%s: %s is not 4-byte aligned", fn, #p);  \
+  } while (0)
+
+float f32_gmin(const mulan_desc* d) { return (float)d->gamma_min; }
+float f32_delta(const mulan_desc* d) { return (float)(d->gamma_max - d->gamma_min); }
+
+// Half-width of the bin window for the reconstruction log-softmax at gamma_0 = gamma_min:
+// with bin spacing s = (2/vocab) exp(-gamma_0/2) in units of the decoder's stdev, a bin j
+// steps away from the nearest one has exp(logit - max) <= exp(-s^2 j (j-1) / 2).
+int recon_window(const mulan_desc* d) {
+  const double s = (2.0 / d->vocab) * exp(-0.5 * (double)f32_gmin(d));
+  int W = 1;
+  while (W < d->vocab - 1 && 0.5 * s * s * (double)W * (double)(W + 1) < 30.0) ++W;
+  return W;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* mulan_last_error(void) { return g_err; }
+int mulan_abi_version(void) { return MULAN_ABI_VERSION; }
+
+int mulan_fwd_pre(const mulan_desc* d, const uint8_t* x, const float* a, const float* b,
+                  const float* c, const float* t, const float* eps0, const float* eps,
+                  float* z_t, float* g_net, float* w_save, float* loss_recon,
+                  float* loss_klz_prior, float* var_sums, void* stream) {
+  const char* fn = "mulan_fwd_pre";
+  if (int r = check_desc(d, fn)) return r;
+  if (d->rows == 0) return 0;
+  REQ_X(x, fn);
+  REQ_VEC(a, fn); REQ_VEC(b, fn); REQ_VEC(c, fn); REQ_PTR(t, fn);
+  REQ_VEC(eps0, fn); REQ_VEC(eps, fn); REQ_VEC(z_t, fn);
+  REQ_PTR(g_net, fn); OPT_VEC(w_save, fn);
+  if (d->gt_mode == MULAN_GT_PIXEL) REQ_VEC(g_net, fn);
+  REQ_PTR(loss_recon, fn); REQ_PTR(loss_klz_prior, fn); REQ_PTR(var_sums, fn);
+  mulan::FwdPreParams p;
+  p.x = x; p.a = a; p.b = b; p.c = c; p.t = t; p.eps0 = eps0; p.eps = eps;
+  p.z_t = z_t; p.g_net = g_net; p.w_save = w_save;
+  p.loss_recon = loss_recon; p.loss_klz = loss_klz_prior; p.var_sums = var_sums;
+  p.rows = d->rows; p.dim4 = d->dim / 4; p.gt_mode = d->gt_mode;
+  p.W = recon_window(d);
+  p.gmin = f32_gmin(d); p.delta = f32_delta(d);
+  p.vi = mulan::make_vocab(d->vocab);
+  cudaError_t e = mulan::launch_fwd_pre(p, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(fn, e);
+}
+
+static int fill_post(const char* fn, const mulan_desc* d, const uint8_t* x, const float* a,
+                     const float* b, const float* c, const float* t, const float* eps,
+                     const float* net, const float* w_save, mulan::PostParams* p) {
+  REQ_VEC(eps, fn); REQ_VEC(net, fn); OPT_VEC(w_save, fn);
+  const bool need_poly = !(d->param == MULAN_PARAM_EPS && w_save != nullptr);
+  if (need_poly) { REQ_VEC(a, fn); REQ_VEC(b, fn); REQ_VEC(c, fn); REQ_PTR(t, fn); }
+  if (d->param != MULAN_PARAM_EPS) REQ_X(x, fn);
+  p->x = x; p->a = a; p->b = b; p->c = c; p->t = t; p->eps = eps; p->net = net;
+  p->w_save = (d->param == MULAN_PARAM_EPS) ? w_save : nullptr;
+  p->gL = nullptr; p->loss_diff = nullptr; p->n_bar = nullptr;
+  p->rows = d->rows; p->dim4 = d->dim / 4; p->param = d->param;
+  p->gmin = f32_gmin(d); p->delta = f32_delta(d);
+  p->scale = 0.5f;
+  p->vi = mulan::make_vocab(d->vocab);
+  return 0;
+}
+
+int mulan_fwd_post(const mulan_desc* d, const uint8_t* x, const float* a, const float* b,
+                   const float* c, const float* t, const float* eps, const float* net,
+                   const float* w_save, float* loss_diff, void* stream) {
+  const char* fn = "mulan_fwd_post";
+  if (int r = check_desc(d, fn)) return r;
+  if (d->rows == 0) return 0;
+  mulan::PostParams p;
+  if (int r = fill_post(fn, d, x, a, b, c, t, eps, net, w_save, &p)) return r;
+  REQ_PTR(loss_diff, fn);
+  p.loss_diff = loss_diff;
+  cudaError_t e = mulan::launch_fwd_post(p, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(fn, e);
+}
+
+int mulan_bwd_post(const mulan_desc* d, const uint8_t* x, const float* a, const float* b,
+                   const float* c, const float* t, const float* eps, const float* net,
+                   const float* w_save, const float* gL, float* n_bar, void* stream) {
+  const char* fn = "mulan_bwd_post";
+  if (int r = check_desc(d, fn)) return r;
+  if (d->rows == 0) return 0;
+  mulan::PostParams p;
+  if (int r = fill_post(fn, d, x, a, b, c, t, eps, net, w_save, &p)) return r;
+  REQ_PTR(gL, fn); REQ_VEC(n_bar, fn);
+  p.gL = gL; p.n_bar = n_bar;
+  cudaError_t e = mulan::launch_bwd_post(p, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(fn, e);
+}
+
+int mulan_bwd_pre(const mulan_desc* d, const uint8_t* x, const float* a, const float* b,
+                  const float* c, const float* t, const float* eps, const float* net,
+                  const float* z_bar, const float* g_bar, const float* gL,
+                  float* a_bar, float* b_bar, float* c_bar, void* stream) {
+  const char* fn = "mulan_bwd_pre";
+  if (int r = check_desc(d, fn)) return r;
+  if (d->rows == 0) return 0;
+  REQ_VEC(a, fn); REQ_VEC(b, fn); REQ_VEC(c, fn); REQ_PTR(t, fn);
+  REQ_VEC(a_bar, fn); REQ_VEC(b_bar, fn); REQ_VEC(c_bar, fn);
+  OPT_VEC(z_bar, fn);
+  if (d->gt_mode == MULAN_GT_PIXEL) OPT_VEC(g_bar, fn);
+  if (gL != nullptr) { REQ_VEC(net, fn); }
+  if (gL != nullptr || z_bar != nullptr) { REQ_VEC(eps, fn); }
+  if (z_bar != nullptr || (gL != nullptr && d->param != MULAN_PARAM_EPS)) REQ_X(x, fn);
+  mulan::BwdPreParams p;
+  p.x = x; p.a = a; p.b = b; p.c = c; p.t = t; p.eps = eps; p.net = net;
+  p.z_bar = z_bar; p.g_bar = g_bar; p.gL = gL;
+  p.a_bar = a_bar; p.b_bar = b_bar; p.c_bar = c_bar;
+  p.rows = d->rows; p.dim4 = d->dim / 4; p.param = d->param; p.gt_mode = d->gt_mode;
+  p.gmin = f32_gmin(d); p.delta = f32_delta(d);
+  p.vi = mulan::make_vocab(d->vocab);
+  cudaError_t e = mulan::launch_bwd_pre(p, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(fn, e);
+}
+
+int mulan_aux_topk_fwd(int32_t rows, int32_t latent, int32_t k, const float* logits,
+                       const float* gamma_draw, float* embedding, float* kl_z, void* stream) {
+  const char* fn = "mulan_aux_topk_fwd";
+  if (rows < 0) return fail(MULAN_ERR_INVALID_ARG, "%s: rows=%d < 0", fn, rows);
+  if (latent < 1 || latent > 64)
+    return fail(MULAN_ERR_INVALID_ARG, "%s: latent=%d outside [1,64]", fn, latent);
+  if (k < 1 || k > latent)
+    return fail(MULAN_ERR_INVALID_ARG, "%s: k=%d outside [1,latent=%d]", fn, k, latent);
+  if (rows == 0) return 0;
+  REQ_PTR(logits, fn); REQ_PTR(embedding, fn); REQ_PTR(kl_z, fn);
+  cudaError_t e = mulan::launch_aux_topk_fwd(rows, latent, k, logits, gamma_draw, embedding, kl_z,
+                                             (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(fn, e);
+}
+
+int mulan_aux_topk_bwd(int32_t rows, int32_t latent, int32_t k, const float* logits,
+                       const float* gamma_draw, const float* emb_bar, const float* klz_bar,
+                       float* logits_bar, void* stream) {
+  const char* fn = "mulan_aux_topk_bwd";
+  if (rows < 0) return fail(MULAN_ERR_INVALID_ARG, "%s: rows=%d < 0", fn, rows);
+  if (latent < 1 || latent > 64)
+    return fail(MULAN_ERR_INVALID_ARG, "%s: latent=%d outside [1,64]", fn, latent);
+  if (k < 1 || k > latent)
+    return fail(MULAN_ERR_INVALID_ARG, "%s: k=%d outside [1,latent=%d]", fn, k, latent);
+  if (rows == 0) return 0;
+  REQ_PTR(logits, fn); REQ_PTR(logits_bar, fn);
+  cudaError_t e = mulan::launch_aux_topk_bwd(rows, latent, k, logits, gamma_draw, emb_bar, klz_bar,
+                                             logits_bar, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(fn, e);
+}
+
+int mulan_bpd_reduce(const mulan_desc* d, const float* loss_recon, const float* loss_klz_prior,
+                     const float* kl_z, const float* loss_diff, const float* var_sums,
+                     float* scalars, float* loss_klz_total, void* stream) {
+  const char* fn = "mulan_bpd_reduce";
+  if (int r = check_desc(d, fn)) return r;
+  if (d->rows == 0) return fail(MULAN_ERR_INVALID_ARG, "%s: rows=0 has no mean", fn);
+  REQ_PTR(loss_recon, fn); REQ_PTR(loss_klz_prior, fn); REQ_PTR(var_sums, fn); REQ_PTR(scalars, fn);
+  cudaError_t e = mulan::launch_bpd_reduce(d->rows, d->dim, loss_recon, loss_klz_prior, kl_z,
+                                           loss_diff, var_sums, scalars, loss_klz_total,
+                                           (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(fn, e);
+}
+
+// ---------------------------------------------------------------------------------------
+// Host-buffer entry
+// ---------------------------------------------------------------------------------------
+namespace {
+
+struct HostWs {
+  int device = -1;
+  size_t cap_rows = 0;
+  int dim = 0;
+  cudaStream_t stream = nullptr;
+  uint8_t* d_x = nullptr;
+  float* d_f = nullptr;      // one slab: a,b,c,eps0,eps,net,z_t,w,nbar,abar,bbar,cbar [12][B,D]
+  float* d_row = nullptr;    // t, g_net, recon, klz, diff, gL, var_sums[2] -> 8*B, + 8 scalars
+  uint8_t* h_x = nullptr;    // pinned staging
+  float* h_f = nullptr;      // pinned: 6 inputs + 4 grads
+  float* h_row = nullptr;
+  void release() {
+    if (d_x) cudaFree(d_x);
+    if (d_f) cudaFree(d_f);
+    if (d_row) cudaFree(d_row);
+    if (h_x) cudaFreeHost(h_x);
+    if (h_f) cudaFreeHost(h_f);
+    if (h_row) cudaFreeHost(h_row);
+    if (stream) cudaStreamDestroy(stream);
+    *this = HostWs();
+  }
+};
+thread_local HostWs g_ws;
+
+}  // namespace
+
+void mulan_host_workspace_release(void) { g_ws.release(); }
+
+int mulan_elbo_host(const mulan_desc* d, const uint8_t* x, const float* a, const float* b,
+                    const float* c, const float* t, const float* eps0, const float* eps,
+                    const float* net, mulan_denoiser_fn denoiser, void* user, int32_t want_grad,
+                    float* losses, float* scalars, float* a_bar, float* b_bar, float* c_bar,
+                    float* n_bar) {
+  const char* fn = "mulan_elbo_host";
+  if (int r = check_desc(d, fn)) return r;
+  if (d->rows == 0) return fail(MULAN_ERR_INVALID_ARG, "%s: rows=0", fn);
+  REQ_PTR(x, fn); REQ_PTR(a, fn); REQ_PTR(b, fn); REQ_PTR(c, fn); REQ_PTR(t, fn);
+  REQ_PTR(eps0, fn); REQ_PTR(eps, fn); REQ_PTR(losses, fn); REQ_PTR(scalars, fn);
+  if (denoiser == nullptr) REQ_PTR(net, fn);
+  const size_t B = (size_t)d->rows, D = (size_t)d->dim, N = B * D;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail(fn, e);
+  HostWs& ws = g_ws;
+  if (ws.device != dev || ws.cap_rows < B || ws.dim != d->dim) {
+    ws.release();
+    ws.device = dev; ws.cap_rows = B; ws.dim = d->dim;
+    if ((e = cudaStreamCreateWithFlags(&ws.stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaMalloc(&ws.d_x, N)) != cudaSuccess ||
+        (e = cudaMalloc(&ws.d_f, 12 * N * sizeof(float))) != cudaSuccess ||
+        (e = cudaMalloc(&ws.d_row, (8 * B + 8) * sizeof(float))) != cudaSuccess ||
+        (e = cudaMallocHost(&ws.h_x, N)) != cudaSuccess ||
+        (e = cudaMallocHost(&ws.h_f, 10 * N * sizeof(float))) != cudaSuccess ||
+        (e = cudaMallocHost(&ws.h_row, (8 * B + 8) * sizeof(float))) != cudaSuccess) {
+      ws.release();
+      return cuda_fail("mulan_elbo_host workspace", e);
+    }
+  }
+  cudaStream_t s = ws.stream;
+  float* dA = ws.d_f + 0 * N; float* dB = ws.d_f + 1 * N; float* dC = ws.d_f + 2 * N;
+  float* dE0 = ws.d_f + 3 * N; float* dE = ws.d_f + 4 * N; float* dN = ws.d_f + 5 * N;
+  float* dZ = ws.d_f + 6 * N; float* dW = ws.d_f + 7 * N; float* dNB = ws.d_f + 8 * N;
+  float* dAB = ws.d_f + 9 * N; float* dBB = ws.d_f + 10 * N; float* dCB = ws.d_f + 11 * N;
+  float* dT = ws.d_row; float* dG = ws.d_row + B; float* dRec = ws.d_row + 2 * B;
+  float* dKlz = ws.d_row + 3 * B; float* dDiff = ws.d_row + 4 * B; float* dGL = ws.d_row + 5 * B;
+  float* dVar = ws.d_row + 6 * B; float* dSc = ws.d_row + 8 * B;
+  if (d->gt_mode == MULAN_GT_PIXEL)
+    return fail(MULAN_ERR_UNSUPPORTED, "%s: gt_mode=PIXEL is served by the device-pointer API", fn);
+
+  // Stage through pinned memory so the copies are truly asynchronous DMA.
+  const float* srcs[6] = {a, b, c, eps0, eps, net};
+  float* dsts[6] = {dA, dB, dC, dE0, dE, dN};
+  memcpy(ws.h_x, x, N);
+  e = cudaMemcpyAsync(ws.d_x, ws.h_x, N, cudaMemcpyHostToDevice, s);
+  for (int i = 0; i < 6 && e == cudaSuccess; ++i) {
+    if (srcs[i] == nullptr) continue;
+    memcpy(ws.h_f + i * N, srcs[i], N * sizeof(float));
+    e = cudaMemcpyAsync(dsts[i], ws.h_f + i * N, N * sizeof(float), cudaMemcpyHostToDevice, s);
+  }
+  if (e != cudaSuccess) return cuda_fail(fn, e);
+  memcpy(ws.h_row, t, B * sizeof(float));
+  e = cudaMemcpyAsync(dT, ws.h_row, B * sizeof(float), cudaMemcpyHostToDevice, s);
+  if (e != cudaSuccess) return cuda_fail(fn, e);
+
+  float* w_save = d->param == MULAN_PARAM_EPS ? dW : nullptr;
+  int r = mulan_fwd_pre(d, ws.d_x, dA, dB, dC, dT, dE0, dE, dZ, dG, w_save, dRec, dKlz, dVar, s);
+  if (r) return r;
+  if (denoiser != nullptr) {
+    if (int rc = denoiser(user, dZ, dG, dN, (void*)s))
+      return fail(MULAN_ERR_INVALID_ARG, "%s: denoiser callback returned %d", fn, rc);
+  }
+  r = mulan_fwd_post(d, ws.d_x, dA, dB, dC, dT, dE, dN, w_save, dDiff, s);
+  if (r) return r;
+  r = mulan_bpd_reduce(d, dRec, dKlz, nullptr, dDiff, dVar, dSc, nullptr, s);
+  if (r) return r;
+  if (want_grad) {
+    // d bpd / d loss_diff_b = 1 / (B * D * ln 2)   (ldm/experiment_vdm.py:62-66)
+    const float g = (float)(1.0 / ((double)B * (double)D * 0.6931471805599453));
+    float* hg = ws.h_row + B;
+    for (size_t i = 0; i < B; ++i) hg[i] = g;
+    e = cudaMemcpyAsync(dGL, hg, B * sizeof(float), cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) return cuda_fail(fn, e);
+    r = mulan_bwd_post(d, ws.d_x, dA, dB, dC, dT, dE, dN, w_save, dGL, dNB, s);
+    if (r) return r;
+    r = mulan_bwd_pre(d, ws.d_x, dA, dB, dC, dT, dE, dN, nullptr, nullptr, dGL, dAB, dBB, dCB, s);
+    if (r) return r;
+  }
+  // D2H
+  float* hl = ws.h_row + 2 * B;
+  e = cudaMemcpyAsync(hl, dRec, 3 * B * sizeof(float), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(hl + 3 * B, dSc, 6 * sizeof(float), cudaMemcpyDeviceToHost, s);
+  float* gdst[4] = {a_bar, b_bar, c_bar, n_bar};
+  float* gsrc[4] = {dAB, dBB, dCB, dNB};
+  if (want_grad) {
+    for (int i = 0; i < 4 && e == cudaSuccess; ++i)
+      if (gdst[i] != nullptr)
+        e = cudaMemcpyAsync(ws.h_f + (6 + i) * N, gsrc[i], N * sizeof(float),
+                            cudaMemcpyDeviceToHost, s);
+  }
+  if (e != cudaSuccess) return cuda_fail(fn, e);
+  e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) return cuda_fail(fn, e);
+  memcpy(losses, hl, 3 * B * sizeof(float));
+  memcpy(scalars, hl + 3 * B, 6 * sizeof(float));
+  if (want_grad)
+    for (int i = 0; i < 4; ++i)
+      if (gdst[i] != nullptr) memcpy(gdst[i], ws.h_f + (6 + i) * N, N * sizeof(float));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,222 @@
+// Small per-example ops of the ELBO: the auxiliary-latent KL + relaxed top-k embedding
+// ([B, 50]) and the final VDMOutput / bits-per-dim assembly ([B] -> 6 scalars).
+//
+// Reference statements:
+//   _gumbel_kl_loss            ldm/model_mulan_epsilon.py:205-210
+//   _gamma_noise               ldm/model_mulan_epsilon.py:221-231
+//   _topk_embedding_and_loss   ldm/model_mulan_epsilon.py:233-252 (velocity.py:106-120)
+//   VDMOutput assembly         ldm/model_mulan_epsilon.py:357-363
+//   Experiment_VDM.loss_fn     ldm/experiment_vdm.py:62-74
+//
+// aux: one warp per row, two slots per lane (L <= 64); all reductions are warp shuffles.
+#include "mulan_kernels.h"
+
+namespace mulan {
+
+constexpr int kAuxRowsPerCta = 4;  // 4 warps per CTA
+
+struct AuxRow {
+  float l[2];       // raw logits
+  float q[2];       // softmax(logits)
+  float lq[2];      // log_softmax(logits)
+  float kl;         // KL(q || uniform)
+  float l3[2];      // centred noisy logits
+  float norm;       // ||l3||_2
+  float soft[2];    // l3 / norm
+  float hard[2];    // top-k indicator
+  bool valid[2];
+};
+
+__device__ __forceinline__ AuxRow aux_forward(int row, int rows, int L, int k,
+                                              const float* __restrict__ logits,
+                                              const float* __restrict__ G) {
+  const int lane = threadIdx.x & 31;
+  AuxRow r;
+  float mx = -INFINITY;
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const int i = lane + 32 * s;
+    r.valid[s] = i < L;
+    r.l[s] = r.valid[s] ? __ldg(logits + (size_t)row * L + i) : -INFINITY;
+    mx = fmaxf(mx, r.l[s]);
+  }
+  mx = warp_max(mx);
+  float un[2], se = 0.f;
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    un[s] = r.valid[s] ? expf(r.l[s] - mx) : 0.f;
+    se += un[s];
+  }
+  se = warp_sum(se);
+  const float lse = logf(se);
+  const float log_unif = logf((float)(1.0 / (double)L));
+  float kl = 0.f;
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    r.q[s] = __fdiv_rn(un[s], se);
+    r.lq[s] = (r.l[s] - mx) - lse;
+    if (r.valid[s]) kl += r.q[s] * (r.lq[s] - log_unif);
+  }
+  r.kl = warp_sum(kl);
+
+  // gamma noise: s = 10 * ((sum_i G_i / (k/i)) - log 10) / k
+  float l2[2], sm = 0.f;
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const int i = lane + 32 * s;
+    float noise = 0.f;
+    if (G != nullptr && r.valid[s]) {
+      float acc = 0.f;
+      for (int m = 1; m <= 10; ++m) {
+        const float beta = __fdiv_rn((float)k, (float)m);
+        acc += __fdiv_rn(__ldg(G + ((size_t)(m - 1) * rows + row) * L + i), beta);
+      }
+      acc = acc - logf(10.0f);
+      noise = 10.0f * __fdiv_rn(acc, (float)k);
+    }
+    l2[s] = r.valid[s] ? r.l[s] + noise : 0.f;
+    sm += l2[s];
+  }
+  const float mean = __fdiv_rn(warp_sum(sm), (float)L);
+  float ss = 0.f;
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    r.l3[s] = r.valid[s] ? l2[s] - mean : 0.f;
+    ss += r.l3[s] * r.l3[s];
+  }
+  r.norm = sqrtf(warp_sum(ss));
+  // rank by counting strictly greater entries: hard = (l3 >= k-th largest)
+  int cnt[2] = {0, 0};
+  for (int j = 0; j < L; ++j) {
+    const float vj = __shfl_sync(0xffffffffu, j < 32 ? r.l3[0] : r.l3[1], j & 31);
+    cnt[0] += vj > r.l3[0];
+    cnt[1] += vj > r.l3[1];
+  }
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    r.soft[s] = __fdiv_rn(r.l3[s], r.norm);
+    r.hard[s] = (r.valid[s] && cnt[s] < k) ? 1.0f : 0.0f;
+  }
+  return r;
+}
+
+__global__ void __launch_bounds__(32 * kAuxRowsPerCta)
+aux_topk_fwd_kernel(int rows, int L, int k, const float* __restrict__ logits,
+                    const float* __restrict__ G, float* __restrict__ emb,
+                    float* __restrict__ kl_z) {
+  const int row = blockIdx.x * kAuxRowsPerCta + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const AuxRow r = aux_forward(row, rows, L, k, logits, G);
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const int i = lane + 32 * s;
+    // stop_gradient(hard - soft) + soft
+    if (r.valid[s]) emb[(size_t)row * L + i] = (r.hard[s] - r.soft[s]) + r.soft[s];
+  }
+  if (lane == 0) kl_z[row] = r.kl;
+}
+
+__global__ void __launch_bounds__(32 * kAuxRowsPerCta)
+aux_topk_bwd_kernel(int rows, int L, int k, const float* __restrict__ logits,
+                    const float* __restrict__ G, const float* __restrict__ emb_bar,
+                    const float* __restrict__ klz_bar, float* __restrict__ logits_bar) {
+  const int row = blockIdx.x * kAuxRowsPerCta + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const AuxRow r = aux_forward(row, rows, L, k, logits, G);
+  const float log_unif = logf((float)(1.0 / (double)L));
+  float sb[2], dot = 0.f;
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const int i = lane + 32 * s;
+    sb[s] = (emb_bar != nullptr && r.valid[s]) ? __ldg(emb_bar + (size_t)row * L + i) : 0.f;
+    dot += sb[s] * r.soft[s];
+  }
+  dot = warp_sum(dot);
+  // soft = l3/||l3||: l3_bar = (soft_bar - soft <soft, soft_bar>)/||l3||
+  float l3b[2], sm = 0.f;
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    l3b[s] = r.valid[s] ? __fdiv_rn(sb[s] - r.soft[s] * dot, r.norm) : 0.f;
+    sm += l3b[s];
+  }
+  const float mean = __fdiv_rn(warp_sum(sm), (float)L);
+  const float kb = klz_bar != nullptr ? __ldg(klz_bar + row) : 0.f;
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const int i = lane + 32 * s;
+    if (r.valid[s]) {
+      const float dkl = r.q[s] * ((r.lq[s] - log_unif) - r.kl);
+      logits_bar[(size_t)row * L + i] = (l3b[s] - mean) + kb * dkl;
+    }
+  }
+}
+
+cudaError_t launch_aux_topk_fwd(int rows, int latent, int k, const float* logits,
+                                const float* gamma_draw, float* embedding, float* kl_z,
+                                cudaStream_t s) {
+  if (rows == 0) return cudaSuccess;
+  const int grid = (rows + kAuxRowsPerCta - 1) / kAuxRowsPerCta;
+  aux_topk_fwd_kernel<<<grid, 32 * kAuxRowsPerCta, 0, s>>>(rows, latent, k, logits, gamma_draw,
+                                                          embedding, kl_z);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_aux_topk_bwd(int rows, int latent, int k, const float* logits,
+                                const float* gamma_draw, const float* emb_bar,
+                                const float* klz_bar, float* logits_bar, cudaStream_t s) {
+  if (rows == 0) return cudaSuccess;
+  const int grid = (rows + kAuxRowsPerCta - 1) / kAuxRowsPerCta;
+  aux_topk_bwd_kernel<<<grid, 32 * kAuxRowsPerCta, 0, s>>>(rows, latent, k, logits, gamma_draw,
+                                                          emb_bar, klz_bar, logits_bar);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------
+// VDMOutput + loss_fn scalars.  Single CTA, fixed-order sums (deterministic).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+bpd_reduce_kernel(int rows, int dim, const float* __restrict__ loss_recon,
+                  const float* __restrict__ loss_klz_prior, const float* __restrict__ kl_z,
+                  const float* __restrict__ loss_diff, const float* __restrict__ var_sums,
+                  float* __restrict__ scalars, float* __restrict__ loss_klz_total) {
+  __shared__ float red[kWarps][5];
+  float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int i = threadIdx.x; i < rows; i += kThreads) {
+    // loss_klz = kl_z + loss_klz (ldm/model_mulan_epsilon.py:359)
+    const float klz = kl_z != nullptr ? kl_z[i] + loss_klz_prior[i] : loss_klz_prior[i];
+    if (loss_klz_total != nullptr) loss_klz_total[i] = klz;
+    acc[0] += loss_recon[i];
+    acc[1] += klz;
+    acc[2] += loss_diff != nullptr ? loss_diff[i] : 0.f;
+    acc[3] += var_sums[2 * i];
+    acc[4] += var_sums[2 * i + 1];
+  }
+  block_sum<5>(acc, red);
+  if (threadIdx.x == 0) {
+    const float n = (float)rows;
+    const float rescale = (float)(1.0 / ((double)dim * 0.6931471805599453));
+    const float bpd_recon = __fdiv_rn(acc[0], n) * rescale;
+    const float bpd_latent = __fdiv_rn(acc[1], n) * rescale;
+    const float bpd_diff = __fdiv_rn(acc[2], n) * rescale;
+    scalars[0] = bpd_recon + bpd_latent + bpd_diff;
+    scalars[1] = bpd_latent;
+    scalars[2] = bpd_recon;
+    scalars[3] = bpd_diff;
+    const float nd = (float)((double)rows * (double)dim);
+    scalars[4] = __fdiv_rn(acc[3], nd);
+    scalars[5] = __fdiv_rn(acc[4], nd);
+  }
+}
+
+cudaError_t launch_bpd_reduce(int rows, int dim, const float* loss_recon,
+                              const float* loss_klz_prior, const float* kl_z,
+                              const float* loss_diff, const float* var_sums, float* scalars,
+                              float* loss_klz_total, cudaStream_t s) {
+  bpd_reduce_kernel<<<1, kThreads, 0, s>>>(rows, dim, loss_recon, loss_klz_prior, kl_z, loss_diff,
+                                           var_sums, scalars, loss_klz_total);
+  return cudaGetLastError();
+}
+
+}  // namespace mulan

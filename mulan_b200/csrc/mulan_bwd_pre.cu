@@ -1,0 +1,136 @@
+// mulan_bwd_pre: cotangents of the polynomial coefficients (a, b, c), one pass over [B, D]
+// (37 B/sub-pixel algorithmic for EPS: z_bar4 + x1 + a,b,c 12 + eps4 + net4 -> 12).
+//
+// This is the closed form of what jax.value_and_grad (ldm/experiment.py:339) derives for
+// the statements of VDM.__call__ (ldm/model_mulan_epsilon.py:307-347,
+// ldm/model_mulan_velocity.py:215-260) with respect to the outputs of
+// NoiseSchedule_polynomial_fixedend._compute_coefficients (:531-538):
+//
+//   gamma = gmin + D P/S,  w = d gamma/dt = D q^2/S,  q = a t^2 + b t + c
+//   gamma_bar = z_bar (d alpha/d gamma f + d sigma/d gamma eps) + g_bar/Dim | g_bar_pix + (VEL*: direct)
+//   w_bar     = .5 gL r^2 (EPS) | .5 gL (1-v) r^2 (VEL*)
+//   a_bar = D [gamma_bar (P_a S - P S_a) + w_bar (Q_a S - Q S_a)] / S^2, same for b, c.
+// gamma(0) and gamma(1) are fixed ends: loss_recon and the prior KL contribute nothing.
+#include "mulan_kernels.h"
+
+namespace mulan {
+
+template <int PARAM, int GT>
+__global__ void __launch_bounds__(kThreads)
+bwd_pre_kernel(const BwdPreParams p) {
+  __shared__ RowT s_rt;
+  __shared__ float s_gL, s_gbar;
+  const int row = blockIdx.x, tid = threadIdx.x;
+  const bool has_gL = p.gL != nullptr;
+  const bool has_zb = p.z_bar != nullptr;
+  const bool has_gb = p.g_bar != nullptr;
+  if (tid == 0) {
+    s_rt = make_row_t(__ldg(p.t + row));
+    s_gL = has_gL ? __ldg(p.gL + row) : 0.f;
+    // jnp.mean backward: cotangent / D broadcast to every sub-pixel
+    s_gbar = (GT == MULAN_GT_MEAN && has_gb)
+                 ? __fdiv_rn(__ldg(p.g_bar + row), (float)(p.dim4 * 4)) : 0.f;
+  }
+  __syncthreads();
+  const RowT rt = s_rt;
+  const float gL = s_gL, gbar_row = s_gbar;
+  const VocabInfo vi = p.vi;
+  const size_t base4 = (size_t)row * p.dim4;
+  const bool need_x = has_zb || (has_gL && PARAM != MULAN_PARAM_EPS);
+
+  for (int i4 = tid; i4 < p.dim4; i4 += kThreads) {
+    const size_t g4 = base4 + i4;
+    const float4 A = ld4(p.a, g4), Bv = ld4(p.b, g4), C = ld4(p.c, g4);
+    float4 E = make_float4(0.f, 0.f, 0.f, 0.f), N = E, ZB = E, GB = E;
+    uchar4 X = make_uchar4(0, 0, 0, 0);
+    if (has_gL || has_zb) E = ld4(p.eps, g4);
+    if (has_gL) N = ld4(p.net, g4);
+    if (has_zb) ZB = ld4(p.z_bar, g4);
+    if (GT == MULAN_GT_PIXEL && has_gb) GB = ld4(p.g_bar, g4);
+    if (need_x) X = ldx4(p.x, g4);
+    float4 AB, BB, CB;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float a = get(A, j), b = get(Bv, j), c = get(C, j);
+      const float e = get(E, j), n = get(N, j);
+      const float f = vi.xval(getx(X, j));
+      const Poly po = poly_eval(a, b, c, rt);
+      const float rS = __frcp_rn(po.S);
+      const float Q = po.q * po.q;
+      const float u = po.P * rS, y = Q * rS;
+      const float gt = p.gmin + (p.delta * po.P) * rS;
+      const float w = (p.delta * Q) * rS;
+      const float v = sigmoid_ref(gt);
+      const float om = 1.0f - v;
+      const float alpha = sqrtf(om), sigma = sqrtf(v);
+      const float dal = -0.5f * v * alpha;      // d alpha / d gamma
+      const float dsg = 0.5f * sigma * om;      // d sigma / d gamma
+
+      float gbar = (GT == MULAN_GT_MEAN) ? gbar_row : get(GB, j);
+      float zb = get(ZB, j);
+      float wbar = 0.f;
+      if (PARAM == MULAN_PARAM_EPS) {
+        const float r = e - n;
+        wbar = 0.5f * gL * (r * r);
+      } else {
+        const float vtg = alpha * e - sigma * f;
+        float vhat = n, eh = 0.f, k = 1.f, zt = 0.f, eg = 0.f;
+        if (PARAM == MULAN_PARAM_VEL_FROM_EPS) {
+          zt = alpha * f + sigma * e;
+          eg = expf(gt);
+          eh = expf(0.5f * gt);
+          k = sqrtf(1.0f + eg);
+          vhat = -eh * zt + k * n;
+        }
+        const float r = vtg - vhat;
+        const float r2 = r * r;
+        const float rb = gL * om * w * r;                // d L / d r
+        wbar = 0.5f * gL * om * r2;
+        gbar += -0.5f * gL * w * r2 * (v * om);          // through (1 - var_t)
+        gbar += rb * (dal * e - dsg * f);                // through v_target
+        if (PARAM == MULAN_PARAM_VEL_FROM_EPS) {
+          zb += rb * eh;                                 // v_hat's direct use of z_t
+          gbar -= rb * (-0.5f * eh * zt + 0.5f * n * __fdiv_rn(eg, k));
+        }
+      }
+      gbar += zb * (dal * f + dsg * e);                  // through z_t = alpha f + sigma eps
+
+      const float gG = p.delta * rS * gbar, gW = p.delta * rS * wbar;
+      const float t = rt.t, t2 = rt.t2, t3_3 = rt.t3_3, t4_2 = rt.t4_2, t5_5 = rt.t5_5;
+      const float two_q = po.q + po.q;
+      // partials of P, S, Q
+      const float Pa = fmaf(a + a, t5_5, fmaf(c + c, t3_3, b * t4_2));
+      const float Sa = fmaf(a + a, kFifth, fmaf(c + c, kThird, 0.5f * b));
+      const float Pb = fmaf(b + b, t3_3, fmaf(a, t4_2, c * t2));
+      const float Sb = fmaf(b + b, kThird, fmaf(a, 0.5f, c));
+      const float Pc = fmaf(a + a, t3_3, fmaf(b, t2, (c + c) * t));
+      const float Sc = fmaf(a + a, kThird, b + (c + c));
+      const float Qa = two_q * t2, Qb = two_q * t, Qc = two_q;
+      put(AB, j, fmaf(gG, fmaf(-u, Sa, Pa), gW * fmaf(-y, Sa, Qa)));
+      put(BB, j, fmaf(gG, fmaf(-u, Sb, Pb), gW * fmaf(-y, Sb, Qb)));
+      put(CB, j, fmaf(gG, fmaf(-u, Sc, Pc), gW * fmaf(-y, Sc, Qc)));
+    }
+    st4(p.a_bar, g4, AB);
+    st4(p.b_bar, g4, BB);
+    st4(p.c_bar, g4, CB);
+  }
+}
+
+template <int PARAM>
+static cudaError_t launch_gt(const BwdPreParams& p, cudaStream_t s) {
+  dim3 grid(p.rows), block(kThreads);
+  if (p.gt_mode == MULAN_GT_MEAN) bwd_pre_kernel<PARAM, MULAN_GT_MEAN><<<grid, block, 0, s>>>(p);
+  else                            bwd_pre_kernel<PARAM, MULAN_GT_PIXEL><<<grid, block, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bwd_pre(const BwdPreParams& p, cudaStream_t s) {
+  if (p.rows == 0) return cudaSuccess;
+  switch (p.param) {
+    case MULAN_PARAM_EPS: return launch_gt<MULAN_PARAM_EPS>(p, s);
+    case MULAN_PARAM_VEL: return launch_gt<MULAN_PARAM_VEL>(p, s);
+    default:              return launch_gt<MULAN_PARAM_VEL_FROM_EPS>(p, s);
+  }
+}
+
+}  // namespace mulan

@@ -1,0 +1,130 @@
+// Shared device helpers for the MuLAN schedule + ELBO kernels (sm_100a).
+//
+// Compiled with -fmad=false: every `a*b+c` written with plain operators rounds twice,
+// exactly like the reference's op-by-op float32 evaluation (and the CPU oracle).  Fused
+// multiply-adds appear only where written explicitly as fmaf(), i.e. where the extra
+// rounding of the reference is pseudo-random per sub-pixel and averages out of the
+// per-example sums (the polynomial), never where a systematic or amplified error would
+// show (1 - sigmoid(g), the reconstruction logits, the prior-KL summand).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mulan {
+
+constexpr int kThreads = 256;            // one CTA per example row
+constexpr int kWarps = kThreads / 32;
+constexpr float kThird = 0.333333343267440796f;  // RN(1/3)
+constexpr float kFifth = 0.200000002980232239f;  // RN(1/5)
+
+// ---------------------------------------------------------------------------------------
+// Memory access: 16-byte vector loads/stores on the read-only / streaming paths.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ld4(const float* __restrict__ p, int i4) {
+  return __ldg(reinterpret_cast<const float4*>(p) + i4);
+}
+__device__ __forceinline__ void st4(float* __restrict__ p, int i4, float4 v) {
+  reinterpret_cast<float4*>(p)[i4] = v;
+}
+__device__ __forceinline__ uchar4 ldx4(const uint8_t* __restrict__ p, int i4) {
+  return __ldg(reinterpret_cast<const uchar4*>(p) + i4);
+}
+__device__ __forceinline__ float get(const float4& v, int j) {
+  return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w));
+}
+__device__ __forceinline__ void put(float4& v, int j, float s) {
+  if (j == 0) v.x = s; else if (j == 1) v.y = s; else if (j == 2) v.z = s; else v.w = s;
+}
+__device__ __forceinline__ int getx(const uchar4& v, int j) {
+  return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w));
+}
+
+// ---------------------------------------------------------------------------------------
+// Reference-faithful scalar math (float32, IEEE-rounded basic ops).
+// ---------------------------------------------------------------------------------------
+// jax.nn.sigmoid == 1/(1+exp(-x)).
+__device__ __forceinline__ float sigmoid_ref(float x) {
+  return __fdiv_rn(1.0f, 1.0f + expf(-x));
+}
+// EncDec.encode (ldm/model_vdm.py:274-280): 2*((x+.5)/vocab) - 1 ; exact for vocab = 2^k.
+__device__ __forceinline__ float encode_ref(int x, float vocab) {
+  return 2.0f * __fdiv_rn((float)x + 0.5f, vocab) - 1.0f;
+}
+
+// Per-example time powers, staged once per row in shared memory.  Integer powers follow
+// XLA's integer_pow lowering (binary exponentiation), see oracle.integer_pow.
+struct RowT {
+  float t, t2, t3, t4, t5;   // t^n
+  float t5_5, t3_3, t4_2;    // t^5/5, t^3/3, t^4/2 (fast polynomial)
+};
+__device__ __forceinline__ RowT make_row_t(float t) {
+  RowT r;
+  r.t = t;
+  r.t2 = t * t;
+  r.t3 = t * r.t2;
+  r.t4 = r.t2 * r.t2;
+  r.t5 = t * r.t4;
+  r.t5_5 = r.t5 * kFifth;
+  r.t3_3 = r.t3 * kThird;
+  r.t4_2 = r.t4 * 0.5f;
+  return r;
+}
+
+// NoiseSchedule_polynomial_fixedend._eval_polynomial (ldm/model_mulan_epsilon.py:514-529)
+// for one sub-pixel: P(t) = int_0^t (a s^2 + b s + c)^2 ds, S = P(1), q = a t^2 + b t + c.
+// FMA form (see file header): differs from the reference's rounding by O(1 ulp) per term,
+// pseudo-randomly per sub-pixel.
+struct Poly {
+  float P, S, q;
+  float a2, b2c, ab, bc, c2;  // a^2, b^2+2ac, ab, bc, c^2
+};
+__device__ __forceinline__ Poly poly_eval(float a, float b, float c, const RowT& r) {
+  Poly o;
+  o.a2 = a * a;
+  o.ab = a * b;
+  o.bc = b * c;
+  o.c2 = c * c;
+  o.b2c = fmaf(a + a, c, b * b);
+  o.S = fmaf(o.a2, kFifth, fmaf(o.b2c, kThird, fmaf(o.ab, 0.5f, o.bc + o.c2)));
+  o.P = fmaf(o.a2, r.t5_5, fmaf(o.b2c, r.t3_3, fmaf(o.ab, r.t4_2, fmaf(o.bc, r.t2, o.c2 * r.t))));
+  o.q = fmaf(fmaf(a, r.t, b), r.t, c);
+  return o;
+}
+
+// ---------------------------------------------------------------------------------------
+// Deterministic per-row reductions: fixed per-thread order, shuffle tree, fixed warp order.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Sum N per-thread accumulators over the CTA; result valid in thread 0.
+template <int N>
+__device__ __forceinline__ void block_sum(float (&acc)[N], float (*smem)[N]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < N; ++k) acc[k] = warp_sum(acc[k]);
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) smem[warp][k] = acc[k];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      float s = smem[0][k];
+      for (int w = 1; w < kWarps; ++w) s += smem[w][k];
+      acc[k] = s;
+    }
+  }
+}
+
+}  // namespace mulan

@@ -1,0 +1,250 @@
+"""PyTorch bindings of the C ABI: raw launches + the autograd pair used by the model.
+
+PyTorch is plumbing here (device memory, streams, autograd bookkeeping); every number is
+produced by libmulan_b200.so.  All ops require contiguous CUDA tensors and raise otherwise:
+there is no CPU path.
+
+Autograd structure (mirrors what ``jax.value_and_grad`` does around the reference's
+``VDM.__call__``, ldm/experiment.py:339): ``mulan_pre`` runs before the denoiser,
+``mulan_post`` after it.  ``mulan_post.backward`` only produces the denoiser cotangent
+``n_bar``; the loss cotangent ``gL`` travels back to ``mulan_pre.backward`` through a
+``link`` tensor, so that ONE kernel (``mulan_bwd_pre``) produces the complete
+``a_bar, b_bar, c_bar`` (paths through z_t, through the denoiser's noise-level input and
+through loss_diff) instead of two kernels plus an add.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import (MULAN_GT_MEAN, MULAN_GT_PIXEL, MULAN_PARAM_EPS, MULAN_PARAM_VEL,
+                   MULAN_PARAM_VEL_FROM_EPS, make_desc)
+
+
+def _p(t: Optional[torch.Tensor]):
+  return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+  return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _req(t: torch.Tensor, dtype, shape, name: str) -> torch.Tensor:
+  if not isinstance(t, torch.Tensor) or not t.is_cuda:
+    raise TypeError(f'{name}: expected a CUDA tensor (libmulan_b200 has no CPU path)')
+  if t.dtype != dtype:
+    raise TypeError(f'{name}: expected dtype {dtype}, got {t.dtype}')
+  if tuple(t.shape) != tuple(shape):
+    raise ValueError(f'{name}: expected shape {tuple(shape)}, got {tuple(t.shape)}')
+  if not t.is_contiguous():
+    raise ValueError(f'{name}: must be contiguous')
+  return t
+
+
+def _opt(t, dtype, shape, name):
+  return None if t is None else _req(t, dtype, shape, name)
+
+
+class Desc:
+  """Python view of mulan_desc (per launch; rows filled from the tensors)."""
+
+  def __init__(self, dim=3072, vocab=256, param=MULAN_PARAM_EPS, gt_mode=MULAN_GT_MEAN,
+               n_timesteps=0, gamma_min=-13.3, gamma_max=5.0):
+    self.dim, self.vocab, self.param, self.gt_mode = dim, vocab, param, gt_mode
+    self.n_timesteps, self.gamma_min, self.gamma_max = n_timesteps, gamma_min, gamma_max
+
+  def c(self, rows: int):
+    return make_desc(rows, self.dim, self.vocab, self.param, self.gt_mode, self.n_timesteps,
+                     self.gamma_min, self.gamma_max)
+
+
+# ------------------------------------------------------------------------------------
+# Raw launches (no autograd)
+# ------------------------------------------------------------------------------------
+
+def fwd_pre(desc: Desc, x, a, b, c, t, eps0, eps, save_w: bool = True):
+  """mulan_fwd_pre. Returns dict(z_t, g_net, w, loss_recon, loss_klz_prior, var_sums)."""
+  B, D = a.shape
+  _req(x, torch.uint8, (B, D), 'x')
+  for n, v in (('a', a), ('b', b), ('c', c), ('eps0', eps0), ('eps', eps)):
+    _req(v, torch.float32, (B, D), n)
+  _req(t, torch.float32, (B,), 't')
+  dev = a.device
+  z_t = torch.empty((B, D), dtype=torch.float32, device=dev)
+  g_net = torch.empty((B,) if desc.gt_mode == MULAN_GT_MEAN else (B, D),
+                      dtype=torch.float32, device=dev)
+  w = torch.empty((B, D), dtype=torch.float32, device=dev) if save_w else None
+  rec = torch.empty((B,), dtype=torch.float32, device=dev)
+  klz = torch.empty((B,), dtype=torch.float32, device=dev)
+  vs = torch.empty((B, 2), dtype=torch.float32, device=dev)
+  d = desc.c(B)
+  _lib.check(_lib.load().mulan_fwd_pre(
+      C.byref(d), _p(x), _p(a), _p(b), _p(c), _p(t), _p(eps0), _p(eps),
+      _p(z_t), _p(g_net), _p(w), _p(rec), _p(klz), _p(vs), _stream()))
+  return dict(z_t=z_t, g_net=g_net, w=w, loss_recon=rec, loss_klz_prior=klz, var_sums=vs)
+
+
+def fwd_post(desc: Desc, x, a, b, c, t, eps, net, w=None):
+  """mulan_fwd_post -> loss_diff[B]."""
+  B, D = eps.shape
+  _req(net, torch.float32, (B, D), 'net')
+  out = torch.empty((B,), dtype=torch.float32, device=eps.device)
+  d = desc.c(B)
+  _lib.check(_lib.load().mulan_fwd_post(
+      C.byref(d), _p(x), _p(a), _p(b), _p(c), _p(t), _p(eps), _p(net), _p(w), _p(out),
+      _stream()))
+  return out
+
+
+def bwd_post(desc: Desc, x, a, b, c, t, eps, net, w, gL):
+  """mulan_bwd_post -> n_bar[B,D]."""
+  B, D = eps.shape
+  _req(gL, torch.float32, (B,), 'gL')
+  out = torch.empty((B, D), dtype=torch.float32, device=eps.device)
+  d = desc.c(B)
+  _lib.check(_lib.load().mulan_bwd_post(
+      C.byref(d), _p(x), _p(a), _p(b), _p(c), _p(t), _p(eps), _p(net), _p(w), _p(gL), _p(out),
+      _stream()))
+  return out
+
+
+def bwd_pre(desc: Desc, x, a, b, c, t, eps, net, z_bar, g_bar, gL):
+  """mulan_bwd_pre -> (a_bar, b_bar, c_bar)."""
+  B, D = a.shape
+  _opt(z_bar, torch.float32, (B, D), 'z_bar')
+  _opt(g_bar, torch.float32, (B,) if desc.gt_mode == MULAN_GT_MEAN else (B, D), 'g_bar')
+  _opt(gL, torch.float32, (B,), 'gL')
+  ab, bb, cb = (torch.empty((B, D), dtype=torch.float32, device=a.device) for _ in range(3))
+  d = desc.c(B)
+  _lib.check(_lib.load().mulan_bwd_pre(
+      C.byref(d), _p(x), _p(a), _p(b), _p(c), _p(t), _p(eps), _p(net), _p(z_bar), _p(g_bar),
+      _p(gL), _p(ab), _p(bb), _p(cb), _stream()))
+  return ab, bb, cb
+
+
+def aux_topk_fwd(logits, gamma_draw, k: int):
+  """mulan_aux_topk_fwd -> (embedding[B,L], kl_z[B])."""
+  B, L = logits.shape
+  _req(logits, torch.float32, (B, L), 'logits')
+  _opt(gamma_draw, torch.float32, (10, B, L), 'gamma_draw')
+  emb = torch.empty((B, L), dtype=torch.float32, device=logits.device)
+  kl = torch.empty((B,), dtype=torch.float32, device=logits.device)
+  _lib.check(_lib.load().mulan_aux_topk_fwd(B, L, k, _p(logits), _p(gamma_draw), _p(emb),
+                                            _p(kl), _stream()))
+  return emb, kl
+
+
+def aux_topk_bwd(logits, gamma_draw, k: int, emb_bar, klz_bar):
+  """mulan_aux_topk_bwd -> logits_bar[B,L]."""
+  B, L = logits.shape
+  _opt(emb_bar, torch.float32, (B, L), 'emb_bar')
+  _opt(klz_bar, torch.float32, (B,), 'klz_bar')
+  out = torch.empty((B, L), dtype=torch.float32, device=logits.device)
+  _lib.check(_lib.load().mulan_aux_topk_bwd(B, L, k, _p(logits), _p(gamma_draw), _p(emb_bar),
+                                            _p(klz_bar), _p(out), _stream()))
+  return out
+
+
+def bpd_reduce(desc: Desc, loss_recon, loss_klz_prior, kl_z, loss_diff, var_sums,
+               want_klz_total: bool = False):
+  """mulan_bpd_reduce -> scalars[6] = bpd, bpd_latent, bpd_recon, bpd_diff, var0, var1."""
+  B = loss_recon.shape[0]
+  sc = torch.empty((6,), dtype=torch.float32, device=loss_recon.device)
+  tot = torch.empty((B,), dtype=torch.float32, device=loss_recon.device) if want_klz_total else None
+  d = desc.c(B)
+  _lib.check(_lib.load().mulan_bpd_reduce(
+      C.byref(d), _p(loss_recon), _p(loss_klz_prior), _p(kl_z), _p(loss_diff), _p(var_sums),
+      _p(sc), _p(tot), _stream()))
+  return (sc, tot) if want_klz_total else sc
+
+
+# ------------------------------------------------------------------------------------
+# Autograd pair
+# ------------------------------------------------------------------------------------
+
+class ElboTape:
+  """Residuals shared by mulan_pre / mulan_post of ONE forward pass."""
+
+  def __init__(self, desc: Desc, save_w: Optional[bool] = None):
+    self.desc = desc
+    # Saving w pays for EPS (post kernels read 12 B instead of 20 B); the velocity models
+    # recompute gamma_t anyway.
+    self.save_w = (desc.param == MULAN_PARAM_EPS) if save_w is None else save_w
+    self.x = self.a = self.b = self.c = self.t = self.eps = self.w = self.net = None
+
+
+class _MulanPre(torch.autograd.Function):
+
+  @staticmethod
+  def forward(ctx, tape: ElboTape, x, a, b, c, t, eps0, eps):
+    a, b, c = a.contiguous(), b.contiguous(), c.contiguous()
+    out = fwd_pre(tape.desc, x, a, b, c, t, eps0, eps, save_w=tape.save_w)
+    tape.x, tape.a, tape.b, tape.c, tape.t, tape.eps, tape.w = x, a, b, c, t, eps, out['w']
+    ctx.tape = tape
+    link = torch.zeros_like(t)
+    ctx.mark_non_differentiable(out['loss_recon'], out['loss_klz_prior'], out['var_sums'])
+    return (out['z_t'], out['g_net'], out['loss_recon'], out['loss_klz_prior'],
+            out['var_sums'], link)
+
+  @staticmethod
+  def backward(ctx, z_bar, g_bar, _r, _k, _v, link_bar):
+    tp = ctx.tape
+    gL = link_bar
+    if gL is not None and tp.net is None:
+      gL = None
+    cont = lambda v: None if v is None else v.contiguous()
+    ab, bb, cb = bwd_pre(tp.desc, tp.x, tp.a, tp.b, tp.c, tp.t, tp.eps, tp.net,
+                         cont(z_bar), cont(g_bar), cont(gL))
+    return None, None, ab, bb, cb, None, None, None
+
+
+class _MulanPost(torch.autograd.Function):
+
+  @staticmethod
+  def forward(ctx, tape: ElboTape, net, link):
+    net_c = net.contiguous()
+    tape.net = net_c.detach()
+    ctx.tape = tape
+    return fwd_post(tape.desc, tape.x, tape.a, tape.b, tape.c, tape.t, tape.eps, net_c, tape.w)
+
+  @staticmethod
+  def backward(ctx, gL):
+    tp = ctx.tape
+    gL = gL.contiguous()
+    n_bar = bwd_post(tp.desc, tp.x, tp.a, tp.b, tp.c, tp.t, tp.eps, tp.net, tp.w, gL)
+    return None, n_bar, gL
+
+
+def mulan_pre(tape: ElboTape, x, a, b, c, t, eps0, eps):
+  """-> z_t[B,D], g_net, loss_recon[B], loss_klz_prior[B], var_sums[B,2], link[B]."""
+  return _MulanPre.apply(tape, x, a, b, c, t, eps0, eps)
+
+
+def mulan_post(tape: ElboTape, net, link):
+  """-> loss_diff[B]."""
+  return _MulanPost.apply(tape, net, link)
+
+
+class _AuxTopK(torch.autograd.Function):
+
+  @staticmethod
+  def forward(ctx, logits, gamma_draw, k: int):
+    logits = logits.contiguous()
+    emb, kl = aux_topk_fwd(logits, gamma_draw, k)
+    ctx.save_for_backward(logits, gamma_draw)
+    ctx.k = k
+    return emb, kl
+
+  @staticmethod
+  def backward(ctx, emb_bar, kl_bar):
+    logits, gamma_draw = ctx.saved_tensors
+    cont = lambda v: None if v is None else v.contiguous()
+    return aux_topk_bwd(logits, gamma_draw, ctx.k, cont(emb_bar), cont(kl_bar)), None, None
+
+
+def aux_topk(logits, gamma_draw, k: int):
+  """_topk_embedding_and_loss (ldm/model_mulan_epsilon.py:233-252) -> (embedding, kl_z)."""
+  return _AuxTopK.apply(logits, gamma_draw, k)

@@ -1,0 +1,420 @@
+"""CPU oracle for the MuLAN schedule + ELBO hot path.  TEST INFRASTRUCTURE ONLY.
+
+This file is a line-by-line CPU restatement (torch on CPU, dtype generic: float32
+for parity, float64 for truth) of the reference's algorithm for the path in
+SURVEY.md section 8a.  Only ``tests/``, ``__graft_entry__.smoke()`` and
+``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import it, and
+only as the checker / CPU baseline.  Nothing under ``mulan_b200/`` imports it.
+
+Pinning status
+--------------
+The reference (s-sahoo/MuLAN) ships no tests, fixtures or golden vectors, and
+JAX/Flax are not installable in this image, so the real reference cannot run
+here.  The oracle is pinned two ways instead (see DESIGN.md "Oracle"):
+
+1. ``tests/golden/make_golden.py`` EXECUTES THE REFERENCE'S OWN SOURCE FILES
+   (``/root/reference/ldm/model_mulan_epsilon.py``, ``model_mulan_velocity.py``,
+   ``model_vdm.py``) on top of a small torch-backed stand-in for the ``jax`` /
+   ``flax`` modules (``tests/golden/jaxshim``) and stores inputs + outputs as
+   ``tests/golden/*.npz``.  ``tests/test_oracle_golden.py`` checks this oracle
+   against those vectors.  That pins the *expression order and semantics* of the
+   reference source; it does not pin XLA's transcendental roundings.
+2. Analytic known-answer tests (``tests/test_oracle_kat.py``).
+
+Until the real JAX reference has been run on the same inputs the parity claim
+versus *XLA numerics* stays "parity unpinned"; versus the reference *source* it
+is pinned by (1).
+
+Conventions
+-----------
+* All random draws (t0, gamma-noise G, eps_0, eps) are INPUTS, so "same inputs
+  and random keys" holds by construction.
+* Expression order follows the reference, including ``(Delta*P)/S``,
+  ``1 - sigmoid(g)``, the jvp-expanded d-gamma/dt, and ``log_softmax`` as
+  shift-by-max then log-sum-exp.
+* Integer powers follow XLA's ``integer_pow`` lowering (binary exponentiation).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Callable, NamedTuple, Optional
+
+import numpy as np
+import torch
+
+MODE_EPS = 0           # ldm/model_mulan_epsilon.py
+MODE_VEL = 1           # ldm/model_mulan_velocity.py, velocity_from_epsilon=False
+MODE_VEL_FROM_EPS = 2  # ldm/model_mulan_velocity.py, velocity_from_epsilon=True
+
+GT_MEAN = 0   # unet_type == 'vdm'  -> per-example mean of g_t  (epsilon.py:275-276)
+GT_PIXEL = 1  # unet_type == 'ldm'  -> per-pixel g_t            (epsilon.py:277-278)
+
+
+@dataclass
+class OracleConfig:
+  """Subset of VDMConfig (model_vdm.py:33-82) the hot path reads."""
+  vocab_size: int = 256
+  gamma_min: float = -13.3
+  gamma_max: float = 5.0
+  sm_n_timesteps: int = 0
+  antithetic_time_sampling: bool = True
+  latent_size: int = 50
+  latent_k: int = 15
+  unet_type: str = 'vdm'
+  velocity_from_epsilon: bool = False
+
+
+class VDMOutput(NamedTuple):
+  """model_vdm.py:86-92."""
+  loss_recon: torch.Tensor  # [B]
+  loss_klz: torch.Tensor    # [B]
+  loss_diff: torch.Tensor   # [B]
+  var_0: torch.Tensor       # scalar
+  var_1: torch.Tensor       # scalar
+
+
+# ----------------------------------------------------------------------------
+# jax.nn primitives restated
+# ----------------------------------------------------------------------------
+
+def sigmoid(x):
+  """jax.nn.sigmoid == lax.logistic == 1 / (1 + exp(-x))."""
+  return 1.0 / (1.0 + torch.exp(-x))
+
+
+def log_softmax(x, axis=-1):
+  """jax.nn.log_softmax: shifted = x - stop_grad(max); shifted - log(sum(exp(shifted)))."""
+  shifted = x - x.max(dim=axis, keepdim=True).values.detach()
+  return shifted - torch.log(torch.sum(torch.exp(shifted), dim=axis, keepdim=True))
+
+
+def softmax(x, axis=-1):
+  """jax.nn.softmax: unnormalized = exp(x - max); unnormalized / sum."""
+  un = torch.exp(x - x.max(dim=axis, keepdim=True).values.detach())
+  return un / torch.sum(un, dim=axis, keepdim=True)
+
+
+def softplus(x):
+  """flax nn.softplus == jnp.logaddexp(x, 0)."""
+  return torch.logaddexp(x, torch.zeros((), dtype=x.dtype))
+
+
+def swish(x):
+  """flax nn.swish == x * sigmoid(x)."""
+  return x * sigmoid(x)
+
+
+def integer_pow(x, n: int):
+  """XLA lowering of lax.integer_pow: binary exponentiation (acc *= x; x *= x)."""
+  assert n >= 1
+  acc = None
+  while n > 0:
+    if n & 1:
+      acc = x if acc is None else acc * x
+    n >>= 1
+    if n > 0:
+      x = x * x
+  return acc
+
+
+# ----------------------------------------------------------------------------
+# EncDec  (model_vdm.py:265-303)
+# ----------------------------------------------------------------------------
+
+def encode(x, vocab_size: int, dtype=torch.float32):
+  """model_vdm.py:274-280: 2*((round(x)+.5)/vocab) - 1."""
+  x = torch.as_tensor(x)
+  xf = x.to(dtype).round()
+  return 2 * ((xf + .5) / vocab_size) - 1
+
+
+def decode(z, g_0, vocab_size: int):
+  """model_vdm.py:282-294: 256-bin Gaussian-kernel logits -> log_softmax. [..., vocab]."""
+  g_0 = g_0[..., None]
+  x_vals = encode(torch.arange(0, vocab_size), vocab_size, z.dtype)  # same for all 3 channels
+  inv_stdev = torch.exp(-0.5 * g_0)
+  logits = -0.5 * torch.square((z[..., None] - x_vals) * inv_stdev)
+  return log_softmax(logits, axis=-1)
+
+
+def logprob(x, z, g_0, vocab_size: int, chunk: int = 32):
+  """model_vdm.py:296-303: sum over all non-batch axes of onehot(x) * logprobs.
+
+  Chunked over the batch so the [B, D, 256] intermediates stay small; each row's
+  arithmetic is unchanged.
+  """
+  B = z.shape[0]
+  xi = torch.as_tensor(x).to(torch.float32).round().to(torch.int64).reshape(B, -1)
+  zf = z.reshape(B, -1)
+  gf = g_0.reshape(B, -1)
+  outs = []
+  for s in range(0, B, chunk):
+    lp = decode(zf[s:s + chunk], gf[s:s + chunk], vocab_size)
+    onehot = torch.nn.functional.one_hot(xi[s:s + chunk], vocab_size).to(lp.dtype)
+    outs.append(torch.sum(onehot * lp, dim=(1, 2)))
+  return torch.cat(outs)
+
+
+# ----------------------------------------------------------------------------
+# NoiseSchedule_polynomial_fixedend  (model_mulan_epsilon.py:481-613)
+# ----------------------------------------------------------------------------
+
+def _delta(cfg: OracleConfig):
+  # epsilon.py:490 -- python double, used as a weak-typed scalar
+  return cfg.gamma_max - cfg.gamma_min
+
+
+def eval_polynomial(a, b, c, t, cfg: OracleConfig):
+  """epsilon.py:514-529 (grad_min_epsilon == 0., :491).  t is [B,1]."""
+  polynomial = (
+      integer_pow(a, 2) * integer_pow(t, 5) / 5.0
+      + (integer_pow(b, 2) + 2 * a * c) * integer_pow(t, 3) / 3.0
+      + a * b * integer_pow(t, 4) / 2.0
+      + b * c * integer_pow(t, 2)
+      + (integer_pow(c, 2) + 0.) * t)
+  scale = (integer_pow(a, 2) / 5.0
+           + (integer_pow(b, 2) + 2 * a * c) / 3.0
+           + a * b / 2.0
+           + b * c
+           + (integer_pow(c, 2) + 0.))
+  return cfg.gamma_min + _delta(cfg) * polynomial / scale
+
+
+def eval_polynomial_dt(a, b, c, t, cfg: OracleConfig):
+  """What jax.jvp(self._get_gamma, (emb, t), (0, 1)) returns (epsilon.py:339-343).
+
+  JAX jvp rules applied term by term to epsilon.py:516-529 with zero tangents on
+  a, b, c and unit tangent on t:  d(t**n) = n * t**(n-1);  d(u/k) = du/k.
+  """
+  dpoly = (
+      integer_pow(a, 2) * (5 * integer_pow(t, 4)) / 5.0
+      + (integer_pow(b, 2) + 2 * a * c) * (3 * integer_pow(t, 2)) / 3.0
+      + a * b * (4 * integer_pow(t, 3)) / 2.0
+      + b * c * (2 * t)
+      + (integer_pow(c, 2) + 0.))
+  scale = (integer_pow(a, 2) / 5.0
+           + (integer_pow(b, 2) + 2 * a * c) / 3.0
+           + a * b / 2.0
+           + b * c
+           + (integer_pow(c, 2) + 0.))
+  return _delta(cfg) * dpoly / scale
+
+
+def compute_coefficients(params: dict, embedding):
+  """epsilon.py:531-538.  params: flax Dense kernels [in,out] / biases, names as :493-512."""
+  def dense(name, h):
+    return h @ params[name + '/kernel'] + params[name + '/bias']
+  h = swish(dense('dense_1', embedding))
+  h = swish(dense('dense_2', h))
+  a = dense('dense_out_a', h)
+  b = dense('dense_out_b', h)
+  c = 1e-3 + softplus(dense('dense_out_c', h))
+  return a, b, c
+
+
+def coefficients_from_raw(c_raw):
+  """The epilogue of epsilon.py:537 alone."""
+  return 1e-3 + softplus(c_raw)
+
+
+# ----------------------------------------------------------------------------
+# Auxiliary latent  (model_mulan_epsilon.py:195-271, model_mulan_velocity.py:68-139)
+# ----------------------------------------------------------------------------
+
+def gumbel_kl_loss(logits, latent_size: int):
+  """epsilon.py:205-210: sum q (log q - log(1/latent_size))."""
+  q_z = softmax(logits)
+  log_q_z = log_softmax(logits)
+  log_unif = torch.log(torch.tensor(1.0 / latent_size, dtype=logits.dtype))
+  return torch.sum(q_z * (log_q_z - log_unif), dim=1)
+
+
+def gamma_noise(G, k: int, gamma_tau: float = 10.0):
+  """epsilon.py:221-231.  G ~ Gamma(1/k), shape [10, B, L] (the draw is an input)."""
+  beta = k / torch.tensor([1.0, 2.0, 3.0, 4.0, 5.0, 6.0, 7.0, 8.0, 9.0, 10.0], dtype=G.dtype)
+  beta = beta[:, None, None]
+  s = G / beta
+  s = torch.sum(s, dim=0)
+  s = s - torch.log(torch.tensor(10.0, dtype=G.dtype))
+  s = gamma_tau * (s / k)
+  return s
+
+
+def topk_embedding_and_loss(logits, G, k: int, latent_size: int):
+  """epsilon.py:233-252 (velocity.py:106-120 computes the same values)."""
+  kl_loss = gumbel_kl_loss(logits, latent_size)
+  logits = logits + gamma_noise(G, k)
+  logits = logits - torch.mean(logits, dim=1, keepdim=True)
+  soft_topk = logits / torch.linalg.norm(logits, dim=1, keepdim=True)
+  top_k_vals = torch.topk(logits, k, dim=1).values
+  hard_topk = (logits >= top_k_vals[:, -1][:, None]).to(logits.dtype)
+  embedding = (hard_topk - soft_topk).detach() + soft_topk
+  return embedding, kl_loss
+
+
+# ----------------------------------------------------------------------------
+# Time sampling (epsilon.py:287-297)
+# ----------------------------------------------------------------------------
+
+def sample_t(t0, n_batch: int, cfg: OracleConfig, dtype=torch.float32):
+  """Antithetic t from the scalar draw t0.  jnp.arange with float args falls back to
+  np.arange (double) and is then cast to the default float type."""
+  ar = torch.from_numpy(np.arange(0., 1., step=1. / n_batch)).to(dtype)
+  t = torch.remainder(torch.as_tensor(t0, dtype=dtype) + ar, 1.)
+  T = cfg.sm_n_timesteps
+  if T > 0:
+    t = torch.ceil(t * T) / T
+  return t
+
+
+# ----------------------------------------------------------------------------
+# VDM.__call__  (model_mulan_epsilon.py:280-363, model_mulan_velocity.py:188-268)
+# ----------------------------------------------------------------------------
+
+def score_model_gt(g_t, cfg: OracleConfig):
+  """epsilon.py:273-278."""
+  if cfg.unet_type == 'vdm':
+    return torch.mean(g_t, dim=tuple(range(1, g_t.ndim))).reshape(-1)
+  return g_t
+
+
+def elbo_terms(x, a, b, c, t, eps_0, eps, score_fn: Callable, mode: int,
+               cfg: OracleConfig, kl_z=None, dtype=torch.float32,
+               return_aux: bool = False):
+  """The glue of VDM.__call__ once (a, b, c) and kl_z exist.
+
+  x uint8 [B, ...]; a,b,c [B, D]; t [B]; eps_0, eps [B, ...];
+  score_fn(z_t, g_for_net) -> network output shaped like z_t.
+  Follows epsilon.py:300-363 (mode EPS) / velocity.py:208-268 (VEL*).
+  """
+  shape = x.shape
+  B = shape[0]
+  orig_f = encode(x, cfg.vocab_size, dtype)                       # epsilon.py:300
+  tt = t.reshape(-1, 1)                                           # epsilon.py:608
+  zeros, ones = torch.zeros_like(tt), torch.ones_like(tt)
+  g_0 = eval_polynomial(a, b, c, zeros, cfg).reshape(shape)       # :307
+  g_1 = eval_polynomial(a, b, c, ones, cfg).reshape(shape)        # :308
+  g_t = eval_polynomial(a, b, c, tt, cfg).reshape(shape)          # :309
+  var_t = sigmoid(g_t)                                            # :311
+  var_0 = sigmoid(g_0)
+  var_1 = sigmoid(g_1)
+  # 1. reconstruction loss                                        # :315-318
+  z_0_rescaled = orig_f + torch.exp(0.5 * g_0) * eps_0
+  loss_recon = -logprob(x, z_0_rescaled, g_0, cfg.vocab_size)
+  # 2. latent loss                                                # :322-325
+  red = tuple(range(1, len(shape)))
+  mean1_sqr = (1. - var_1) * torch.square(orig_f)
+  loss_klz = 0.5 * torch.sum(mean1_sqr + var_1 - torch.log(var_1) - 1., dim=red)
+  # 3. diffusion loss                                             # :327-355
+  z_t = torch.sqrt(1. - var_t) * orig_f + torch.sqrt(var_t) * eps
+  net = score_fn(z_t, score_model_gt(g_t, cfg))
+  T = cfg.sm_n_timesteps
+  if mode == MODE_EPS:
+    eps_hat = net
+    if T == 0:
+      g_t_grad = eval_polynomial_dt(a, b, c, tt, cfg).reshape(shape)
+      loss_diff = .5 * torch.sum(g_t_grad * torch.square(eps - eps_hat), dim=red)
+    else:                                                         # :348-355
+      s = tt - (1. / T)
+      g_s = eval_polynomial(a, b, c, s, cfg).reshape(shape)
+      loss_diff = .5 * T * torch.sum(
+          torch.expm1(g_t - g_s) * torch.square(eps - eps_hat), dim=red)
+      g_t_grad = None
+  else:                                                           # velocity.py:243-260
+    v_hat = net
+    if mode == MODE_VEL_FROM_EPS:
+      v_hat = (-torch.exp(0.5 * g_t) * z_t
+               + torch.sqrt(1 + torch.exp(g_t)) * v_hat)
+    v_target = torch.sqrt(1. - var_t) * eps - torch.sqrt(var_t) * orig_f
+    assert T == 0
+    g_t_grad = eval_polynomial_dt(a, b, c, tt, cfg).reshape(shape)
+    loss_diff = .5 * torch.sum(
+        (1 - var_t) * g_t_grad * torch.square(v_target - v_hat), dim=red)
+  klz_total = loss_klz if kl_z is None else kl_z + loss_klz       # :359
+  out = VDMOutput(loss_recon=loss_recon, loss_klz=klz_total, loss_diff=loss_diff,
+                  var_0=torch.mean(var_0), var_1=torch.mean(var_1))
+  if return_aux:
+    return out, dict(z_t=z_t, g_t=g_t, g_0=g_0, g_1=g_1, g_t_grad=g_t_grad,
+                     net=net, orig_f=orig_f, loss_klz_prior=loss_klz)
+  return out
+
+
+def vdm_call(images, draws: dict, coeff_fn: Callable, encoder_fn: Callable,
+             score_fn: Callable, mode: int, cfg: OracleConfig, dtype=torch.float32,
+             return_aux: bool = False):
+  """Whole VDM.__call__ (epsilon.py:280-363 / velocity.py:188-268) with
+  latent_type='topk', reparam_type='true', z_conditioning=True.
+
+  draws = {'t0': scalar, 'G': [10,B,L], 'eps_0': [B,32,32,3], 'eps': [B,32,32,3]}
+  in the order the reference calls make_rng('sample').
+  coeff_fn(embedding) -> (a, b, c);  encoder_fn(orig_f) -> logits [B, L];
+  score_fn(z_t, g_for_net, conditioning) -> net output.
+  """
+  x = images.reshape(-1, 32, 32, 3)                               # :282
+  n_batch = x.shape[0]
+  t = sample_t(draws['t0'], n_batch, cfg, dtype)                  # :287-297
+  orig_f = encode(x, cfg.vocab_size, dtype)
+  logits = encoder_fn(orig_f)
+  embedding, kl_z = topk_embedding_and_loss(
+      logits, draws['G'], cfg.latent_k, cfg.latent_size)          # :301-303
+  a, b, c = coeff_fn(embedding)
+  return elbo_terms(x, a, b, c, t, draws['eps_0'], draws['eps'],
+                    lambda z, g: score_fn(z, g, embedding),       # :330-337
+                    mode, cfg, kl_z=kl_z, dtype=dtype, return_aux=return_aux)
+
+
+# ----------------------------------------------------------------------------
+# Experiment_VDM.loss_fn  (experiment_vdm.py:62-74)
+# ----------------------------------------------------------------------------
+
+def loss_fn_bpd(out: VDMOutput, image_shape=(32, 32, 3)):
+  rescale_to_bpd = 1. / (np.prod(image_shape) * np.log(2.))
+  bpd_latent = torch.mean(out.loss_klz) * rescale_to_bpd
+  bpd_recon = torch.mean(out.loss_recon) * rescale_to_bpd
+  bpd_diff = torch.mean(out.loss_diff) * rescale_to_bpd
+  bpd = bpd_recon + bpd_latent + bpd_diff
+  scalars = {'bpd': bpd, 'bpd_latent': bpd_latent, 'bpd_recon': bpd_recon,
+             'bpd_diff': bpd_diff, 'var0': out.var_0, 'var': out.var_1}
+  return bpd, scalars
+
+
+# ----------------------------------------------------------------------------
+# eval_bpd_dense_sampling  (notebook_utils.py:176-191)
+# ----------------------------------------------------------------------------
+
+def eval_bpd_dense(images, n_timesteps: int, run_loss_fn: Callable):
+  """For each image: tile it n_timesteps times, call loss_fn once, collect bpd; mean.
+  run_loss_fn(tiled_images[n_timesteps,32,32,3]) -> bpd scalar."""
+  bpds = []
+  for i in range(images.shape[0]):
+    tiled = images[i:i + 1].repeat(n_timesteps, 1, 1, 1)          # :183
+    bpds.append(float(run_loss_fn(tiled)))                        # :185-187
+  return float(np.mean(np.asarray(bpds))), bpds                   # :191
+
+
+# ----------------------------------------------------------------------------
+# Helpers for tests / bench (synthetic inputs)
+# ----------------------------------------------------------------------------
+
+def synth_inputs(B: int, seed: int = 0, D: int = 3072, dtype=torch.float32,
+                 group: Optional[int] = None):
+  """Kernel-level microbench inputs: a,b ~ N(0,1), c = 1e-3+softplus(N(0,1)),
+  antithetic t (per group of `group` rows, default B), eps ~ N(0,1),
+  net_out = eps + 0.3 N(0,1)."""
+  rng = np.random.default_rng(seed)
+  x = rng.integers(0, 256, size=(B, D), dtype=np.uint8)
+  f32 = lambda v: torch.from_numpy(np.asarray(v, dtype=np.float64)).to(dtype)
+  a = f32(rng.standard_normal((B, D)))
+  b = f32(rng.standard_normal((B, D)))
+  c = coefficients_from_raw(f32(rng.standard_normal((B, D))))
+  group = group or B
+  ts = []
+  cfg = OracleConfig()
+  for _ in range(0, B, group):
+    ts.append(sample_t(float(rng.uniform()), min(group, B), cfg, dtype))
+  t = torch.cat(ts)[:B]
+  eps_0 = f32(rng.standard_normal((B, D)))
+  eps = f32(rng.standard_normal((B, D)))
+  net = eps + 0.3 * f32(rng.standard_normal((B, D)))
+  return dict(x=torch.from_numpy(x), a=a, b=b, c=c, t=t, eps_0=eps_0, eps=eps, net=net)

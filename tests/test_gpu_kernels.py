@@ -1,0 +1,366 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same seeded
+inputs.  Tolerances are the north_star's: per-example loss terms 1e-5 relative, gradients
+1e-4 relative (per-example L2), BPD 1e-4 bits/dim, all float32.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mulan_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+LOSS_RTOL = 1e-5
+GRAD_RTOL = 1e-4
+BPD_ATOL = 1e-4
+
+MODES = {'eps': O.MODE_EPS, 'vel': O.MODE_VEL, 'vel_from_eps': O.MODE_VEL_FROM_EPS}
+
+
+def _ops():
+  from mulan_b200 import ops
+  return ops
+
+
+def _dev(d, device):
+  return {k: v.to(device).contiguous() for k, v in d.items()}
+
+
+def _rel(got, want):
+  got, want = got.double().cpu(), want.double().cpu()
+  return ((got - want).abs() / want.abs().clamp_min(1e-30)).max().item()
+
+
+def _rel_l2_rows(got, want):
+  got, want = got.double().cpu(), want.double().cpu()
+  num = (got - want).flatten(1).norm(dim=1)
+  den = want.flatten(1).norm(dim=1).clamp_min(1e-30)
+  return (num / den).max().item()
+
+
+def _oracle(inp, mode, cfg=None, dtype=torch.float32, gt='vdm'):
+  cfg = cfg or O.OracleConfig(unet_type=gt)
+  cast = lambda v: v.to(dtype) if v.is_floating_point() else v
+  i = {k: cast(v) for k, v in inp.items()}
+  return O.elbo_terms(i['x'], i['a'], i['b'], i['c'], i['t'], i['eps_0'], i['eps'],
+                      lambda z, g: i['net'], mode, cfg, dtype=dtype, return_aux=True)
+
+
+@pytest.mark.parametrize('B,seed', [(8, 0), (1, 1), (2, 2), (127, 3), (128, 4)])
+def test_fwd_pre_parity(cuda_device, B, seed):
+  ops = _ops()
+  inp = O.synth_inputs(B, seed)
+  out, aux = _oracle(inp, O.MODE_EPS)
+  g = _dev(inp, cuda_device)
+  desc = ops.Desc()
+  r = ops.fwd_pre(desc, g['x'], g['a'], g['b'], g['c'], g['t'], g['eps_0'], g['eps'])
+  assert _rel(r['loss_recon'], out.loss_recon) < LOSS_RTOL
+  assert _rel(r['loss_klz_prior'], aux['loss_klz_prior']) < LOSS_RTOL
+  # z_t: elementwise, float32 cancellation in P/S makes single pixels differ by a few 1e-6
+  assert (r['z_t'].cpu() - aux['z_t'].reshape(B, -1)).abs().max().item() < 5e-5
+  assert _rel_l2_rows(r['z_t'], aux['z_t'].reshape(B, -1)) < 1e-6
+  g_mean = aux['g_t'].reshape(B, -1).mean(dim=1)
+  assert (r['g_net'].cpu() - g_mean).abs().max().item() < 2e-5
+  # d gamma/dt: q^2 form vs the reference's expanded jvp -> compare per-example sums
+  w_ref = aux['g_t_grad'].reshape(B, -1)
+  assert _rel(r['w'].sum(dim=1), w_ref.sum(dim=1)) < 1e-5
+  assert _rel_l2_rows(r['w'], w_ref) < 1e-5
+  var0 = r['var_sums'][:, 0].sum().item() / (B * 3072)
+  var1 = r['var_sums'][:, 1].sum().item() / (B * 3072)
+  assert abs(var0 - out.var_0.item()) < 1e-6 * out.var_0.item() + 1e-12
+  assert abs(var1 - out.var_1.item()) < 1e-6
+
+
+@pytest.mark.parametrize('mode', list(MODES))
+@pytest.mark.parametrize('B,seed', [(8, 0), (128, 5)])
+def test_fwd_post_parity(cuda_device, mode, B, seed):
+  ops = _ops()
+  inp = O.synth_inputs(B, seed)
+  out, aux = _oracle(inp, MODES[mode])
+  g = _dev(inp, cuda_device)
+  desc = ops.Desc(param=MODES[mode])
+  got = ops.fwd_post(desc, g['x'], g['a'], g['b'], g['c'], g['t'], g['eps'], g['net'], None)
+  assert _rel(got, out.loss_diff) < LOSS_RTOL
+  if mode == 'eps':
+    pre = ops.fwd_pre(desc, g['x'], g['a'], g['b'], g['c'], g['t'], g['eps_0'], g['eps'])
+    got_w = ops.fwd_post(desc, None, None, None, None, None, g['eps'], g['net'], pre['w'])
+    assert _rel(got_w, out.loss_diff) < LOSS_RTOL
+
+
+def test_fwd_gt_pixel(cuda_device):
+  ops = _ops()
+  B = 4
+  inp = O.synth_inputs(B, 11)
+  out, aux = _oracle(inp, O.MODE_EPS, gt='ldm')
+  g = _dev(inp, cuda_device)
+  desc = ops.Desc(gt_mode=1)
+  r = ops.fwd_pre(desc, g['x'], g['a'], g['b'], g['c'], g['t'], g['eps_0'], g['eps'],
+                  save_w=False)
+  assert r['w'] is None
+  assert r['g_net'].shape == (B, 3072)
+  assert (r['g_net'].cpu() - aux['g_t'].reshape(B, -1)).abs().max().item() < 1e-4
+  assert _rel_l2_rows(r['g_net'], aux['g_t'].reshape(B, -1)) < 1e-6
+  assert _rel(r['loss_recon'], out.loss_recon) < LOSS_RTOL
+
+
+def _oracle_grads(inp, mode, gL, zbar, gbar, dtype, gt='vdm'):
+  """Cotangents of (a,b,c,net) for L = sum gL*loss_diff + <zbar, z_t> + <gbar, g_net>."""
+  cfg = O.OracleConfig(unet_type=gt)
+  cast = lambda v: v.to(dtype) if v.is_floating_point() else v
+  i = {k: cast(v) for k, v in inp.items()}
+  a, b, c, net = (i[k].clone().requires_grad_(True) for k in ('a', 'b', 'c', 'net'))
+  out, aux = O.elbo_terms(i['x'], a, b, c, i['t'], i['eps_0'], i['eps'], lambda z, g: net,
+                          mode, cfg, dtype=dtype, return_aux=True)
+  B = a.shape[0]
+  L = (gL.to(dtype) * out.loss_diff).sum()
+  L = L + (zbar.to(dtype) * aux['z_t'].reshape(B, -1)).sum()
+  L = L + (gbar.to(dtype) * O.score_model_gt(aux['g_t'], cfg).reshape(gbar.shape)).sum()
+  # recon and prior KL are part of the loss too; their (a,b,c) gradient is rounding noise
+  L = L + (out.loss_recon + out.loss_klz).sum() * float(gL.mean())
+  return torch.autograd.grad(L, [a, b, c, net])
+
+
+@pytest.mark.parametrize('mode', list(MODES))
+@pytest.mark.parametrize('gt', ['vdm', 'ldm'])
+def test_backward_parity(cuda_device, mode, gt):
+  ops = _ops()
+  B = 8
+  inp = O.synth_inputs(B, 21)
+  rng = np.random.default_rng(99)
+  gL = torch.from_numpy(rng.uniform(0.5, 1.5, B).astype(np.float32)) / (B * 3072 * math.log(2))
+  zbar = torch.from_numpy(rng.standard_normal((B, 3072)).astype(np.float32)) * 1e-4
+  gbar = torch.from_numpy(
+      rng.standard_normal((B,) if gt == 'vdm' else (B, 3072)).astype(np.float32)) * 1e-3
+  want = _oracle_grads(inp, MODES[mode], gL, zbar, gbar, torch.float64, gt)
+  want32 = _oracle_grads(inp, MODES[mode], gL, zbar, gbar, torch.float32, gt)
+  g = _dev(inp, cuda_device)
+  desc = ops.Desc(param=MODES[mode], gt_mode=0 if gt == 'vdm' else 1)
+  gLd, zbd, gbd = gL.to(cuda_device), zbar.to(cuda_device), gbar.to(cuda_device)
+  n_bar = ops.bwd_post(desc, g['x'], g['a'], g['b'], g['c'], g['t'], g['eps'], g['net'], None,
+                       gLd)
+  ab, bb, cb = ops.bwd_pre(desc, g['x'], g['a'], g['b'], g['c'], g['t'], g['eps'], g['net'],
+                           zbd, gbd, gLd)
+  for got, w64, w32, name in ((ab, want[0], want32[0], 'a'), (bb, want[1], want32[1], 'b'),
+                              (cb, want[2], want32[2], 'c'), (n_bar, want[3], want32[3], 'n')):
+    err = _rel_l2_rows(got, w64)
+    err32 = _rel_l2_rows(w32, w64)
+    assert err < GRAD_RTOL, f'{name}_bar: rel l2 {err:.3e} (f32 oracle itself {err32:.3e})'
+    assert _rel_l2_rows(got, w32) < GRAD_RTOL
+  if mode == 'eps':
+    pre = ops.fwd_pre(desc, g['x'], g['a'], g['b'], g['c'], g['t'], g['eps_0'], g['eps'])
+    n2 = ops.bwd_post(desc, None, None, None, None, None, g['eps'], g['net'], pre['w'], gLd)
+    assert _rel_l2_rows(n2, want[3]) < GRAD_RTOL
+
+
+def test_bwd_pre_optional_inputs(cuda_device):
+  """NULL z_bar / g_bar / gL mean zero cotangents."""
+  ops = _ops()
+  B = 4
+  inp = O.synth_inputs(B, 31)
+  g = _dev(inp, cuda_device)
+  desc = ops.Desc()
+  z = torch.zeros((B, 3072), device=cuda_device)
+  zero_g = torch.zeros((B,), device=cuda_device)
+  gL = torch.full((B,), 1e-3, device=cuda_device)
+  full = ops.bwd_pre(desc, g['x'], g['a'], g['b'], g['c'], g['t'], g['eps'], g['net'], z,
+                     zero_g, gL)
+  part = ops.bwd_pre(desc, g['x'], g['a'], g['b'], g['c'], g['t'], g['eps'], g['net'], None,
+                     None, gL)
+  for u, v in zip(full, part):
+    assert torch.equal(u, v)
+  none = ops.bwd_pre(desc, None, g['a'], g['b'], g['c'], g['t'], None, None, None, None, None)
+  for u in none:
+    assert torch.count_nonzero(u).item() == 0
+
+
+def test_edge_cases(cuda_device):
+  """t at the ends, a == 0 (the reference's zero-init head), large |a|,|b|, c -> 1e-3,
+  x at the vocabulary edges with large eps_0."""
+  ops = _ops()
+  B = 8
+  inp = O.synth_inputs(B, 41)
+  inp['t'] = torch.tensor([0.0, 1.0, 1e-6, 1 - 1e-6, 0.5, 0.25, 0.999, 0.001])
+  inp['a'][0] = 0.0
+  inp['a'][1] = 0.0
+  inp['a'][2] *= 30.0
+  inp['b'][3] *= 30.0
+  inp['c'][4] = 1e-3
+  inp['x'][5] = 0
+  inp['x'][6] = 255
+  inp['eps_0'][5] = inp['eps_0'][5] * 3.0
+  inp['eps_0'][6] = inp['eps_0'][6] * 3.0
+  for mode in MODES:
+    out, aux = _oracle(inp, MODES[mode])
+    g = _dev(inp, cuda_device)
+    desc = ops.Desc(param=MODES[mode])
+    r = ops.fwd_pre(desc, g['x'], g['a'], g['b'], g['c'], g['t'], g['eps_0'], g['eps'])
+    assert _rel(r['loss_recon'], out.loss_recon) < LOSS_RTOL
+    assert _rel(r['loss_klz_prior'], aux['loss_klz_prior']) < LOSS_RTOL
+    got = ops.fwd_post(desc, g['x'], g['a'], g['b'], g['c'], g['t'], g['eps'], g['net'], None)
+    # rows with t == 0 have loss_diff ~ c^2-weighted; all rows must match
+    assert _rel(got, out.loss_diff) < LOSS_RTOL, mode
+    assert torch.isfinite(r['z_t']).all()
+
+
+def test_rows_zero_and_errors(cuda_device):
+  ops = _ops()
+  from mulan_b200._lib import MulanError
+  desc = ops.Desc()
+  e = lambda *s, dt=torch.float32: torch.empty(s, dtype=dt, device=cuda_device)
+  r = ops.fwd_pre(desc, e(0, 3072, dt=torch.uint8), e(0, 3072), e(0, 3072), e(0, 3072), e(0),
+                  e(0, 3072), e(0, 3072))
+  assert r['loss_recon'].shape == (0,)
+  with pytest.raises(TypeError):
+    ops.fwd_pre(desc, torch.zeros(2, 3072, dtype=torch.uint8), torch.zeros(2, 3072),
+                torch.zeros(2, 3072), torch.zeros(2, 3072), torch.zeros(2), torch.zeros(2, 3072),
+                torch.zeros(2, 3072))
+  bad = ops.Desc(dim=3070)
+  with pytest.raises(MulanError) as ei:
+    ops.fwd_pre(bad, e(2, 3070, dt=torch.uint8), e(2, 3070), e(2, 3070), e(2, 3070), e(2),
+                e(2, 3070), e(2, 3070))
+  assert ei.value.status == -2
+  with pytest.raises(MulanError) as ei:
+    ops.fwd_pre(ops.Desc(n_timesteps=10), e(2, 3072, dt=torch.uint8), e(2, 3072), e(2, 3072),
+                e(2, 3072), e(2), e(2, 3072), e(2, 3072))
+  assert ei.value.status == -3
+  # misaligned float pointer
+  buf = e(2 * 3072 + 1)
+  mis = buf[1:].view(2, 3072)
+  with pytest.raises(MulanError) as ei:
+    ops.fwd_pre(desc, e(2, 3072, dt=torch.uint8), mis, e(2, 3072), e(2, 3072), e(2), e(2, 3072),
+                e(2, 3072))
+  assert ei.value.status == -2
+
+
+@pytest.mark.parametrize('B,seed', [(8, 0), (3, 1), (128, 2)])
+def test_aux_topk_parity(cuda_device, B, seed):
+  ops = _ops()
+  rng = np.random.default_rng(seed)
+  L, k = 50, 15
+  logits = torch.from_numpy(rng.standard_normal((B, L)).astype(np.float32)) * 2.0
+  G = torch.from_numpy(rng.gamma(1.0 / k, size=(10, B, L)).astype(np.float32))
+  lg = logits.clone().requires_grad_(True)
+  emb, kl = O.topk_embedding_and_loss(lg, G, k, L)
+  eb = torch.from_numpy(rng.standard_normal((B, L)).astype(np.float32))
+  kb = torch.from_numpy(rng.standard_normal((B,)).astype(np.float32))
+  (want_lb,) = torch.autograd.grad((emb * eb).sum() + (kl * kb).sum(), [lg])
+  d = lambda v: v.to(cuda_device).contiguous()
+  got_emb, got_kl = ops.aux_topk_fwd(d(logits), d(G), k)
+  assert torch.equal((got_emb.cpu() > 0.5), (emb.detach() > 0.5))
+  assert (got_emb.cpu().sum(dim=1) - emb.detach().sum(dim=1)).abs().max() < 1e-5
+  assert (got_emb.cpu() - emb.detach()).abs().max().item() < 1e-6
+  assert (got_kl.cpu() - kl.detach()).abs().max().item() < 1e-5 * kl.detach().abs().max().item() + 1e-7
+  got_lb = ops.aux_topk_bwd(d(logits), d(G), k, d(eb), d(kb))
+  assert _rel_l2_rows(got_lb, want_lb) < GRAD_RTOL
+  # KAT: uniform logits -> KL == 0 (no noise -> hard mask is all ones by ties)
+  z = torch.zeros((4, L), device=cuda_device)
+  e0, k0 = ops.aux_topk_fwd(z, None, k)
+  assert k0.abs().max().item() < 1e-6
+
+
+def test_bpd_reduce_and_loss_fn(cuda_device):
+  ops = _ops()
+  B = 16
+  inp = O.synth_inputs(B, 7)
+  rng = np.random.default_rng(5)
+  kl_z = torch.from_numpy(rng.uniform(0, 2, B).astype(np.float32))
+  out, aux = _oracle(inp, O.MODE_EPS)
+  out = O.VDMOutput(out.loss_recon, kl_z + aux['loss_klz_prior'], out.loss_diff, out.var_0,
+                    out.var_1)
+  bpd, sc = O.loss_fn_bpd(out)
+  g = _dev(inp, cuda_device)
+  desc = ops.Desc()
+  r = ops.fwd_pre(desc, g['x'], g['a'], g['b'], g['c'], g['t'], g['eps_0'], g['eps'])
+  diff = ops.fwd_post(desc, None, None, None, None, None, g['eps'], g['net'], r['w'])
+  got, tot = ops.bpd_reduce(desc, r['loss_recon'], r['loss_klz_prior'], kl_z.to(cuda_device), diff,
+                            r['var_sums'], want_klz_total=True)
+  got = got.cpu()
+  assert abs(got[0].item() - bpd.item()) < BPD_ATOL
+  for i, key in enumerate(['bpd', 'bpd_latent', 'bpd_recon', 'bpd_diff']):
+    assert abs(got[i].item() - sc[key].item()) < 1e-5 * abs(sc[key].item()) + 1e-7, key
+  assert abs(got[4].item() - sc['var0'].item()) < 1e-9
+  assert abs(got[5].item() - sc['var'].item()) < 1e-6
+  assert _rel(tot, out.loss_klz) < LOSS_RTOL
+
+
+@pytest.mark.parametrize('mode', list(MODES))
+def test_autograd_pair_with_denoiser(cuda_device, mode):
+  """End to end through mulan_pre -> torch denoiser -> mulan_post, gradients w.r.t. the
+  coefficient heads and the denoiser weights, against oracle autograd."""
+  ops = _ops()
+  B = 8
+  inp = O.synth_inputs(B, 51)
+  w1 = torch.tensor(0.7)
+  w2 = torch.tensor(0.05)
+
+  def net_fn(z, g, w1, w2, noise):
+    return w1 * z.reshape(z.shape[0], -1) + w2 * g.reshape(-1, 1) + noise
+
+  for dtype, store in ((torch.float64, 'w64'), (torch.float32, 'w32')):
+    cast = lambda v: v.to(dtype) if v.is_floating_point() else v
+    i = {k: cast(v) for k, v in inp.items()}
+    a, b, c = (i[k].clone().requires_grad_(True) for k in ('a', 'b', 'c'))
+    p1, p2 = w1.to(dtype).requires_grad_(True), w2.to(dtype).requires_grad_(True)
+    out = O.elbo_terms(i['x'], a, b, c, i['t'], i['eps_0'], i['eps'],
+                       lambda z, g: net_fn(z, g, p1, p2, 0.3 * i['net']), MODES[mode],
+                       O.OracleConfig(), dtype=dtype)
+    bpd, _ = O.loss_fn_bpd(out)
+    grads = torch.autograd.grad(bpd, [a, b, c, p1, p2])
+    if store == 'w64':
+      want, want_bpd = grads, bpd.item()
+  g = _dev(inp, cuda_device)
+  a, b, c = (g[k].clone().requires_grad_(True) for k in ('a', 'b', 'c'))
+  p1 = w1.to(cuda_device).requires_grad_(True)
+  p2 = w2.to(cuda_device).requires_grad_(True)
+  desc = ops.Desc(param=MODES[mode])
+  tape = ops.ElboTape(desc)
+  z_t, g_net, rec, klz, vs, link = ops.mulan_pre(tape, g['x'], a, b, c, g['t'], g['eps_0'],
+                                                 g['eps'])
+  net = net_fn(z_t, g_net, p1, p2, 0.3 * g['net'])
+  diff = ops.mulan_post(tape, net, link)
+  bpd = (rec.mean() + klz.mean() + diff.mean()) / (3072 * math.log(2.0))
+  assert abs(bpd.item() - want_bpd) < BPD_ATOL
+  bpd.backward()
+  assert _rel_l2_rows(a.grad, want[0]) < GRAD_RTOL
+  assert _rel_l2_rows(b.grad, want[1]) < GRAD_RTOL
+  assert _rel_l2_rows(c.grad, want[2]) < GRAD_RTOL
+  assert abs(p1.grad.item() - want[3].item()) < GRAD_RTOL * abs(want[3].item())
+  assert abs(p2.grad.item() - want[4].item()) < GRAD_RTOL * abs(want[4].item()) + 1e-9
+
+
+def test_full_size_properties(cuda_device):
+  """At BASELINE's full per-GPU sizes (and beyond L2): size-independent properties.
+  - determinism (bitwise identical reruns),
+  - row independence (a row's outputs do not depend on its neighbours / batch size),
+  - v-from-eps loss == eps loss (algebraic identity),
+  - gamma monotone: w >= 0, and the prior KL / recon terms are >= 0.
+  """
+  ops = _ops()
+  B = 2048
+  inp = O.synth_inputs(B, 61, group=128)
+  g = _dev(inp, cuda_device)
+  desc = ops.Desc()
+  r1 = ops.fwd_pre(desc, g['x'], g['a'], g['b'], g['c'], g['t'], g['eps_0'], g['eps'])
+  r2 = ops.fwd_pre(desc, g['x'], g['a'], g['b'], g['c'], g['t'], g['eps_0'], g['eps'])
+  for k in ('z_t', 'g_net', 'w', 'loss_recon', 'loss_klz_prior', 'var_sums'):
+    assert torch.equal(r1[k], r2[k]), k
+  sl = slice(700, 716)
+  sub = {k: v[sl].contiguous() for k, v in g.items()}
+  rs = ops.fwd_pre(desc, sub['x'], sub['a'], sub['b'], sub['c'], sub['t'], sub['eps_0'],
+                   sub['eps'])
+  for k in ('z_t', 'g_net', 'w', 'loss_recon', 'loss_klz_prior'):
+    assert torch.equal(r1[k][sl], rs[k]), k
+  assert (r1['w'] >= 0).all()
+  assert (r1['loss_recon'] >= 0).all() and (r1['loss_klz_prior'] >= 0).all()
+  d_eps = ops.fwd_post(ops.Desc(param=0), g['x'], g['a'], g['b'], g['c'], g['t'], g['eps'],
+                       g['net'], None)
+  d_vfe = ops.fwd_post(ops.Desc(param=2), g['x'], g['a'], g['b'], g['c'], g['t'], g['eps'],
+                       g['net'], None)
+  assert _rel(d_vfe, d_eps) < 2e-5
+  # spot-check 16 rows of the big batch against the oracle
+  osub = {k: v[sl] for k, v in inp.items()}
+  out, aux = _oracle(osub, O.MODE_EPS)
+  assert _rel(r1['loss_recon'][sl], out.loss_recon) < LOSS_RTOL
+  assert _rel(d_eps[sl], out.loss_diff) < LOSS_RTOL

@@ -1,0 +1,416 @@
+#!/usr/bin/env python
+"""bench.py -- MuLAN schedule + ELBO hot path on B200 (see DESIGN.md "Measurement").
+
+A "step" is one pass of the hot path (fwd_pre -> fwd_post -> bpd_reduce -> bwd_post ->
+bwd_pre, i.e. ELBO loss + gradients w.r.t. the schedule coefficients and the denoiser
+output) over one batch of synthetic uint8 32x32x3 examples per GPU.  The denoiser (U-Net)
+is NOT part of the path: its output and its backward cotangents are supplied
+as resident tensors.
+
+  python bench.py [--gpus N --steps K --warmup W]           # this repo's CUDA path
+  python bench.py --impl reference [...]                     # reference algorithm on host cores
+
+Prints ONE JSON line (rank 0).  Never run under a profiler for a bench value.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+  sys.path.insert(0, ROOT)
+
+D = 3072
+GROUP = 128          # per-GPU batch of configs[1]; antithetic t is drawn per group
+PARAMS = {'eps': 0, 'vel': 1, 'vel_from_eps': 2}
+# algorithmic bytes per sub-pixel, kernel -> bytes (DESIGN.md "Kernels"; SURVEY.md 8d rule:
+# every declared input read once, every output written once)
+ALGO_BYTES = {
+    'eps': {'fwd_pre': 29, 'fwd_post': 12, 'bwd_post': 16, 'bwd_pre': 37},
+    'vel': {'fwd_pre': 25, 'fwd_post': 21, 'bwd_post': 25, 'bwd_pre': 37},
+    'vel_from_eps': {'fwd_pre': 25, 'fwd_post': 21, 'bwd_post': 25, 'bwd_pre': 37},
+}
+
+
+def parse_args():
+  ap = argparse.ArgumentParser()
+  ap.add_argument('--gpus', type=int, default=1)
+  ap.add_argument('--steps', type=int, default=20)
+  ap.add_argument('--warmup', type=int, default=3)
+  ap.add_argument('--impl', choices=['native', 'reference'], default='native')
+  ap.add_argument('--rows', type=int, default=128 * GROUP,
+                  help='examples per GPU per step (default 128 stacked batches of 128)')
+  ap.add_argument('--param', choices=list(PARAMS), default='eps')
+  ap.add_argument('--ref-rows', type=int, default=GROUP,
+                  help='rows of the bounded CPU sample (cpu_baseline / --impl reference)')
+  ap.add_argument('--no-e2e', action='store_true')
+  ap.add_argument('--no-cpu-baseline', action='store_true')
+  return ap.parse_args()
+
+
+def workload_name(args):
+  model = {'eps': 'mulan_epsilon', 'vel': 'mulan_velocity',
+           'vel_from_eps': 'mulan_velocity(velocity_from_epsilon)'}[args.param]
+  return (f'cifar10-conditioned {model} ELBO loss+grad hot path, per-GPU batch {GROUP} x '
+          f'{args.rows // GROUP} stacked batches = {args.rows} rows/step/GPU, synthetic uint8 '
+          f'32x32x3, denoiser output supplied')
+
+
+# ----------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------
+class ClockSampler:
+  Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+       'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+       'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+  def __init__(self, index: int):
+    self.index, self.lines, self.proc = index, [], None
+
+  def start(self):
+    try:
+      self.proc = subprocess.Popen(
+          ['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.Q}',
+           '--format=csv,noheader,nounits', '-lms', '100'],
+          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+      threading.Thread(target=self._pump, daemon=True).start()
+    except OSError:
+      self.proc = None
+
+  def _pump(self):
+    for line in self.proc.stdout:
+      self.lines.append(line.strip())
+
+  def stop(self):
+    if self.proc is None:
+      return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+    self.proc.terminate()
+    try:
+      self.proc.wait(timeout=2)
+    except subprocess.TimeoutExpired:
+      self.proc.kill()
+    sm, smax, reasons = [], None, set()
+    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+    for ln in self.lines:
+      f = [s.strip() for s in ln.split(',')]
+      if len(f) < 9:
+        continue
+      try:
+        sm.append(float(f[1])); smax = float(f[2])
+      except ValueError:
+        continue
+      for n, v in zip(names, f[5:9]):
+        if v.lower().startswith('active'):
+          reasons.add(n)
+    sm.sort()
+    return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': smax,
+            'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------
+# synthetic inputs generated on the device
+# ----------------------------------------------------------------------------------------
+def make_inputs(rows, device, seed):
+  import torch
+  g = torch.Generator(device=device).manual_seed(seed)
+  rn = lambda: torch.randn((rows, D), generator=g, device=device, dtype=torch.float32)
+  x = torch.randint(0, 256, (rows, D), generator=g, device=device, dtype=torch.uint8)
+  a, b = rn(), rn()
+  c = 1e-3 + torch.nn.functional.softplus(rn())
+  eps0, eps = rn(), rn()
+  net = eps + 0.3 * rn()
+  ngroups = (rows + GROUP - 1) // GROUP
+  t0 = torch.rand((ngroups, 1), generator=g, device=device)
+  t = torch.remainder(t0 + torch.arange(GROUP, device=device) / GROUP, 1.0).reshape(-1)[:rows]
+  z_bar = 1e-4 * rn()
+  g_bar = 1e-3 * torch.randn((rows,), generator=g, device=device)
+  return dict(x=x, a=a, b=b, c=c, t=t.contiguous(), eps0=eps0, eps=eps, net=net, z_bar=z_bar,
+              g_bar=g_bar)
+
+
+# ----------------------------------------------------------------------------------------
+# native arm
+# ----------------------------------------------------------------------------------------
+def run_native(args):
+  import torch
+  import torch.distributed as dist
+  from mulan_b200 import ops, host, _lib
+
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  rank = int(os.environ.get('RANK', '0'))
+  local = int(os.environ.get('LOCAL_RANK', '0'))
+  if world > 1:
+    dist.init_process_group('nccl', device_id=torch.device(f'cuda:{local}'))
+  assert world == args.gpus, f'--gpus {args.gpus} but WORLD_SIZE={world}'
+  torch.cuda.set_device(local)
+  dev = torch.device(f'cuda:{local}')
+  _lib.load()   # loud failure if the CUDA library is missing
+
+  rows, K, W = args.rows, args.steps, args.warmup
+  param = PARAMS[args.param]
+  desc = ops.Desc(param=param)
+  save_w = args.param == 'eps'
+  inp = make_inputs(rows, dev, seed=1234 + rank)
+  gL = torch.full((rows,), 1.0 / (rows * D * math.log(2.0)), device=dev)
+  names = ['fwd_pre', 'fwd_post', 'bpd_reduce', 'bwd_post', 'bwd_pre']
+  launches = 0
+
+  def step(ev=None):
+    nonlocal launches
+    i = inp
+    if ev: ev[0].record()
+    pre = ops.fwd_pre(desc, i['x'], i['a'], i['b'], i['c'], i['t'], i['eps0'], i['eps'],
+                      save_w=save_w)
+    if ev: ev[1].record()
+    diff = ops.fwd_post(desc, i['x'], i['a'], i['b'], i['c'], i['t'], i['eps'], i['net'],
+                        pre['w'])
+    if ev: ev[2].record()
+    sc = ops.bpd_reduce(desc, pre['loss_recon'], pre['loss_klz_prior'], None, diff,
+                        pre['var_sums'])
+    if ev: ev[3].record()
+    n_bar = ops.bwd_post(desc, i['x'], i['a'], i['b'], i['c'], i['t'], i['eps'], i['net'],
+                         pre['w'], gL)
+    if ev: ev[4].record()
+    grads = ops.bwd_pre(desc, i['x'], i['a'], i['b'], i['c'], i['t'], i['eps'], i['net'],
+                        i['z_bar'], i['g_bar'], gL)
+    if ev: ev[5].record()
+    launches += 5
+    if world > 1:
+      # the one exchange that follows the path: pmean of the loss scalars
+      # (ldm/experiment.py:347-348)
+      dist.all_reduce(sc, op=dist.ReduceOp.AVG)
+    return sc, n_bar, grads
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  for _ in range(W):
+    step()
+  barrier()
+  launches = 0
+  evs = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(K)]
+  sampler = ClockSampler(local)
+  if rank == 0:
+    sampler.start()
+  t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  barrier()
+  t_start.record()
+  for k in range(K):
+    sc, _, _ = step(evs[k])
+  t_end.record()
+  barrier()
+  clocks = sampler.stop() if rank == 0 else None
+  elapsed_ms = t_start.elapsed_time(t_end)
+  tmax = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+  if world > 1:
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+  elapsed_ms = tmax.item()
+  timed_launches = launches
+  kern_ms = {n: sum(evs[k][j].elapsed_time(evs[k][j + 1]) for k in range(K)) / K
+             for j, n in enumerate(names)}
+  bpd = sc[0].item()
+
+  # ---- e2e: host buffers through the C ABI (mulan_elbo_host), copies inside the timing ----
+  e2e = None
+  if not args.no_e2e:
+    pin = lambda v: v.cpu().pin_memory()
+    h = {k: pin(inp[k]) for k in ('x', 'a', 'b', 'c', 't', 'eps0', 'eps', 'net')}
+    out = host.HostOutputs(rows, D, want_grad=True, pinned=True)
+    call = lambda: host.elbo_host(h['x'], h['a'], h['b'], h['c'], h['t'], h['eps0'], h['eps'],
+                                  h['net'], param=param, want_grad=True, out=out)
+    ke = max(2, min(K, 5))
+    call(); call()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(ke):
+      r = call()           # synchronises before returning
+    t1 = time.perf_counter()
+    te = torch.tensor([t1 - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+      dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    h2d = rows * D * (1 + 6 * 4) + rows * 4
+    d2h = rows * D * 4 * 4 + (3 * rows + 6) * 4
+    e2e = {'value': world * rows * ke / te.item(), 'unit': 'samples/s', 'steps': ke,
+           'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+           'api': 'mulan_elbo_host (C ABI, pinned host buffers)',
+           'bpd': float(r['scalars'][0])}
+    _lib.load().mulan_host_workspace_release()
+
+  # ---- latency of configs[1]'s literal size (one batch of 128 rows, CUDA graph) ----
+  lat = None
+  if rank == 0:
+    small = {k: (v[:GROUP].contiguous()) for k, v in inp.items()}
+    gLs = torch.full((GROUP,), 1.0 / (GROUP * D * math.log(2.0)), device=dev)
+    def small_step():
+      pre = ops.fwd_pre(desc, small['x'], small['a'], small['b'], small['c'], small['t'],
+                        small['eps0'], small['eps'], save_w=save_w)
+      diff = ops.fwd_post(desc, small['x'], small['a'], small['b'], small['c'], small['t'],
+                          small['eps'], small['net'], pre['w'])
+      ops.bpd_reduce(desc, pre['loss_recon'], pre['loss_klz_prior'], None, diff, pre['var_sums'])
+      ops.bwd_post(desc, small['x'], small['a'], small['b'], small['c'], small['t'],
+                   small['eps'], small['net'], pre['w'], gLs)
+      ops.bwd_pre(desc, small['x'], small['a'], small['b'], small['c'], small['t'], small['eps'],
+                  small['net'], small['z_bar'], small['g_bar'], gLs)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+      for _ in range(3):
+        small_step()
+      torch.cuda.synchronize()
+      graph = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(graph, stream=s):
+        small_step()
+      for _ in range(5):
+        graph.replay()
+      e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      e0.record(s)
+      for _ in range(200):
+        graph.replay()
+      e1.record(s)
+      torch.cuda.synchronize()
+      lat = {'rows': GROUP, 'us_per_step': e0.elapsed_time(e1) * 1000 / 200,
+             'how': 'CUDA graph of the 5 launches, 200 replays, L2-resident'}
+
+  # ---- cpu baseline (oracle port on host cores; rank 0, N=1 only) ----
+  cpu = None
+  if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    cpu = cpu_reference(args, steps=2, warmup=1)
+
+  if rank != 0:
+    if world > 1:
+      dist.destroy_process_group()
+    return
+
+  nsub = rows * D
+  dom = max((n for n in names if n != 'bpd_reduce'), key=lambda n: kern_ms[n])
+  ab = ALGO_BYTES[args.param]
+  peaks, peak_src = load_peak()
+  kernels = {}
+  for n in names:
+    if n == 'bpd_reduce':
+      kernels[n] = {'ms': kern_ms[n]}
+      continue
+    gbs = ab[n] * nsub / (kern_ms[n] * 1e-3) / 1e9
+    kernels[n] = {'ms': kern_ms[n], 'algo_bytes_per_subpixel': ab[n], 'gbs': gbs,
+                  'frac_of_measured': gbs / peaks, 'frac_of_8TBs': gbs / 8000.0}
+  total_algo = sum(ab.values()) * nsub
+  traffic = load_traffic(dom, rows)
+  line = {
+      'metric': 'mulan_elbo_train_samples_per_s', 'value': world * rows * K / (elapsed_ms * 1e-3),
+      'unit': 'samples/s', 'n_gpus': world, 'steps': K, 'warmup': W,
+      'ms_per_step': elapsed_ms / K, 'higher_is_better': True, 'scaling': 'weak',
+      'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+      'config': {'workload': workload_name(args), 'rows_per_gpu': rows, 'dim': D,
+                 'param': args.param, 'l2': 'inputs larger than L2 (%.2f GB read per step)'
+                 % (sum(ab.values()) * nsub / 1e9), 'parallelism': f'dp{world} (rows sharded)'},
+      'roofline': {'bound': 'hbm', 'kernel': dom, 'achieved': kernels[dom]['gbs'],
+                   'peak': peaks, 'peak_source': peak_src, 'unit': 'GB/s',
+                   'frac': kernels[dom]['gbs'] / peaks, 'traffic': traffic,
+                   'algo_bytes_per_launch': ab[dom] * nsub},
+      'step_hbm': {'algo_bytes_per_step': total_algo,
+                   'gbs': total_algo / (elapsed_ms / K * 1e-3) / 1e9,
+                   'frac_of_measured': total_algo / (elapsed_ms / K * 1e-3) / 1e9 / peaks},
+      'kernels': kernels, 'gpu_launches': timed_launches, 'clocks': clocks, 'e2e': e2e,
+      'latency_b128': lat, 'cpu_baseline': cpu, 'bpd': bpd,
+  }
+  print(json.dumps(line))
+  if world > 1:
+    dist.destroy_process_group()
+
+
+def load_peak():
+  p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+  if os.path.exists(p):
+    try:
+      return float(json.load(open(p))['hbm_gbs']), 'MEASURED_PEAKS.json hbm_gbs (of measured)'
+    except Exception:
+      pass
+  return 6650.0, 'B200_PROFILING.md fallback 6.65 TB/s (of fallback)'
+
+
+def load_traffic(kernel, rows):
+  """dram bytes per launch from the committed ncu --set full capture (profiles/), or None."""
+  p = os.path.join(ROOT, 'profiles', 'traffic.json')
+  if not os.path.exists(p):
+    return None
+  try:
+    t = json.load(open(p)).get(kernel)
+    if t and t.get('rows') == rows:
+      return t['dram_bytes_per_launch']
+  except Exception:
+    return None
+  return None
+
+
+# ----------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference on the host cores
+# ----------------------------------------------------------------------------------------
+def cpu_reference(args, steps, warmup):
+  import torch
+  from oracle import mulan_oracle as O   # CPU baseline leg: allowed to execute oracle/
+  cores = os.cpu_count() or 1
+  torch.set_num_threads(cores)
+  B = args.ref_rows
+  mode = PARAMS[args.param]
+  inp = O.synth_inputs(B, seed=0)
+  cfg = O.OracleConfig()
+
+  def one():
+    a, b, c, net = (inp[k].clone().requires_grad_(True) for k in ('a', 'b', 'c', 'net'))
+    out = O.elbo_terms(inp['x'], a, b, c, inp['t'], inp['eps_0'], inp['eps'],
+                       lambda z, g: net, mode, cfg)
+    bpd, _ = O.loss_fn_bpd(out)
+    torch.autograd.grad(bpd, [a, b, c, net])
+    return bpd.item()
+
+  for _ in range(warmup):
+    one()
+  t0 = time.perf_counter()
+  for _ in range(steps):
+    one()
+  dt = time.perf_counter() - t0
+  return {'value': B * steps / dt, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
+          'ms_per_step': dt / steps * 1e3,
+          'sample': f'{steps} steps of {B} rows (one per-GPU batch of the workload), oracle '
+                    f'float32 loss+grad with torch CPU, {cores} threads'}
+
+
+def run_reference(args):
+  rank = int(os.environ.get('RANK', '0'))
+  if rank != 0:
+    return
+  cpu = cpu_reference(args, steps=args.steps, warmup=args.warmup)
+  line = {
+      'impl': 'reference', 'metric': 'mulan_elbo_train_samples_per_s', 'value': cpu['value'],
+      'unit': 'samples/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+      'ms_per_step': cpu['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
+      'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+      'config': {'workload': workload_name(args), 'param': args.param,
+                 'note': 'reference algorithm (CPU oracle port; JAX is not installable in this '
+                         'image) on the host cores, bounded sample per step'},
+      'cpu_baseline': cpu,
+      'e2e': {'value': cpu['value'], 'unit': 'samples/s', 'h2d_bytes_per_step': 0,
+              'd2h_bytes_per_step': 0},
+      'gpu_launches': 0,
+  }
+  print(json.dumps(line))
+
+
+def main():
+  args = parse_args()
+  if args.impl == 'reference':
+    run_reference(args)
+  else:
+    run_native(args)
+
+
+if __name__ == '__main__':
+  main()

@@ -109,7 +109,9 @@ int mulan_fwd_pre(const mulan_desc* d, const uint8_t* x, const float* a, const f
   p.rows = d->rows; p.dim4 = d->dim / 4; p.gt_mode = d->gt_mode;
   p.W = recon_window(d);
   p.gmin = f32_gmin(d); p.delta = f32_delta(d);
+  p.k = mulan::make_end_consts(p.gmin, p.delta);
   p.vi = mulan::make_vocab(d->vocab);
+  p.recon_s = (2.0f / (float)d->vocab) * p.k.inv0;
   cudaError_t e = mulan::launch_fwd_pre(p, (cudaStream_t)stream);
   return e == cudaSuccess ? 0 : cuda_fail(fn, e);
 }
@@ -233,6 +235,7 @@ int mulan_bpd_reduce(const mulan_desc* d, const float* loss_recon, const float* 
 // ---------------------------------------------------------------------------------------
 namespace {
 
+// Device-side workspace of mulan_elbo_host, cached per host thread (one thread per device).
 struct HostWs {
   int device = -1;
   size_t cap_rows = 0;
@@ -241,16 +244,12 @@ struct HostWs {
   uint8_t* d_x = nullptr;
   float* d_f = nullptr;      // one slab: a,b,c,eps0,eps,net,z_t,w,nbar,abar,bbar,cbar [12][B,D]
   float* d_row = nullptr;    // t, g_net, recon, klz, diff, gL, var_sums[2] -> 8*B, + 8 scalars
-  uint8_t* h_x = nullptr;    // pinned staging
-  float* h_f = nullptr;      // pinned: 6 inputs + 4 grads
-  float* h_row = nullptr;
+  float* h_gl = nullptr;     // pinned [B]: the uniform loss cotangent
   void release() {
     if (d_x) cudaFree(d_x);
     if (d_f) cudaFree(d_f);
     if (d_row) cudaFree(d_row);
-    if (h_x) cudaFreeHost(h_x);
-    if (h_f) cudaFreeHost(h_f);
-    if (h_row) cudaFreeHost(h_row);
+    if (h_gl) cudaFreeHost(h_gl);
     if (stream) cudaStreamDestroy(stream);
     *this = HostWs();
   }
@@ -272,6 +271,8 @@ int mulan_elbo_host(const mulan_desc* d, const uint8_t* x, const float* a, const
   REQ_PTR(x, fn); REQ_PTR(a, fn); REQ_PTR(b, fn); REQ_PTR(c, fn); REQ_PTR(t, fn);
   REQ_PTR(eps0, fn); REQ_PTR(eps, fn); REQ_PTR(losses, fn); REQ_PTR(scalars, fn);
   if (denoiser == nullptr) REQ_PTR(net, fn);
+  if (d->gt_mode == MULAN_GT_PIXEL)
+    return fail(MULAN_ERR_UNSUPPORTED, "%s: gt_mode=PIXEL is served by the device-pointer API", fn);
   const size_t B = (size_t)d->rows, D = (size_t)d->dim, N = B * D;
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
@@ -284,9 +285,7 @@ int mulan_elbo_host(const mulan_desc* d, const uint8_t* x, const float* a, const
         (e = cudaMalloc(&ws.d_x, N)) != cudaSuccess ||
         (e = cudaMalloc(&ws.d_f, 12 * N * sizeof(float))) != cudaSuccess ||
         (e = cudaMalloc(&ws.d_row, (8 * B + 8) * sizeof(float))) != cudaSuccess ||
-        (e = cudaMallocHost(&ws.h_x, N)) != cudaSuccess ||
-        (e = cudaMallocHost(&ws.h_f, 10 * N * sizeof(float))) != cudaSuccess ||
-        (e = cudaMallocHost(&ws.h_row, (8 * B + 8) * sizeof(float))) != cudaSuccess) {
+        (e = cudaMallocHost(&ws.h_gl, B * sizeof(float))) != cudaSuccess) {
       ws.release();
       return cuda_fail("mulan_elbo_host workspace", e);
     }
@@ -299,22 +298,16 @@ int mulan_elbo_host(const mulan_desc* d, const uint8_t* x, const float* a, const
   float* dT = ws.d_row; float* dG = ws.d_row + B; float* dRec = ws.d_row + 2 * B;
   float* dKlz = ws.d_row + 3 * B; float* dDiff = ws.d_row + 4 * B; float* dGL = ws.d_row + 5 * B;
   float* dVar = ws.d_row + 6 * B; float* dSc = ws.d_row + 8 * B;
-  if (d->gt_mode == MULAN_GT_PIXEL)
-    return fail(MULAN_ERR_UNSUPPORTED, "%s: gt_mode=PIXEL is served by the device-pointer API", fn);
 
-  // Stage through pinned memory so the copies are truly asynchronous DMA.
-  const float* srcs[6] = {a, b, c, eps0, eps, net};
+  // H2D straight from the caller's buffers: true async DMA when they are page-locked
+  // (cudaHostAlloc / torch pin_memory), driver-staged otherwise.
+  e = cudaMemcpyAsync(ws.d_x, x, N, cudaMemcpyHostToDevice, s);
+  const float* srcs[6] = {a, b, c, eps0, eps, denoiser == nullptr ? net : nullptr};
   float* dsts[6] = {dA, dB, dC, dE0, dE, dN};
-  memcpy(ws.h_x, x, N);
-  e = cudaMemcpyAsync(ws.d_x, ws.h_x, N, cudaMemcpyHostToDevice, s);
-  for (int i = 0; i < 6 && e == cudaSuccess; ++i) {
-    if (srcs[i] == nullptr) continue;
-    memcpy(ws.h_f + i * N, srcs[i], N * sizeof(float));
-    e = cudaMemcpyAsync(dsts[i], ws.h_f + i * N, N * sizeof(float), cudaMemcpyHostToDevice, s);
-  }
-  if (e != cudaSuccess) return cuda_fail(fn, e);
-  memcpy(ws.h_row, t, B * sizeof(float));
-  e = cudaMemcpyAsync(dT, ws.h_row, B * sizeof(float), cudaMemcpyHostToDevice, s);
+  for (int i = 0; i < 6 && e == cudaSuccess; ++i)
+    if (srcs[i] != nullptr)
+      e = cudaMemcpyAsync(dsts[i], srcs[i], N * sizeof(float), cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dT, t, B * sizeof(float), cudaMemcpyHostToDevice, s);
   if (e != cudaSuccess) return cuda_fail(fn, e);
 
   float* w_save = d->param == MULAN_PARAM_EPS ? dW : nullptr;
@@ -331,36 +324,28 @@ int mulan_elbo_host(const mulan_desc* d, const uint8_t* x, const float* a, const
   if (want_grad) {
     // d bpd / d loss_diff_b = 1 / (B * D * ln 2)   (ldm/experiment_vdm.py:62-66)
     const float g = (float)(1.0 / ((double)B * (double)D * 0.6931471805599453));
-    float* hg = ws.h_row + B;
-    for (size_t i = 0; i < B; ++i) hg[i] = g;
-    e = cudaMemcpyAsync(dGL, hg, B * sizeof(float), cudaMemcpyHostToDevice, s);
+    for (size_t i = 0; i < B; ++i) ws.h_gl[i] = g;
+    e = cudaMemcpyAsync(dGL, ws.h_gl, B * sizeof(float), cudaMemcpyHostToDevice, s);
     if (e != cudaSuccess) return cuda_fail(fn, e);
     r = mulan_bwd_post(d, ws.d_x, dA, dB, dC, dT, dE, dN, w_save, dGL, dNB, s);
     if (r) return r;
     r = mulan_bwd_pre(d, ws.d_x, dA, dB, dC, dT, dE, dN, nullptr, nullptr, dGL, dAB, dBB, dCB, s);
     if (r) return r;
   }
-  // D2H
-  float* hl = ws.h_row + 2 * B;
-  e = cudaMemcpyAsync(hl, dRec, 3 * B * sizeof(float), cudaMemcpyDeviceToHost, s);
+  // D2H: recon | klz_prior | diff are contiguous in d_row
+  e = cudaMemcpyAsync(losses, dRec, 3 * B * sizeof(float), cudaMemcpyDeviceToHost, s);
   if (e == cudaSuccess)
-    e = cudaMemcpyAsync(hl + 3 * B, dSc, 6 * sizeof(float), cudaMemcpyDeviceToHost, s);
-  float* gdst[4] = {a_bar, b_bar, c_bar, n_bar};
-  float* gsrc[4] = {dAB, dBB, dCB, dNB};
+    e = cudaMemcpyAsync(scalars, dSc, 6 * sizeof(float), cudaMemcpyDeviceToHost, s);
   if (want_grad) {
+    float* gdst[4] = {a_bar, b_bar, c_bar, n_bar};
+    float* gsrc[4] = {dAB, dBB, dCB, dNB};
     for (int i = 0; i < 4 && e == cudaSuccess; ++i)
       if (gdst[i] != nullptr)
-        e = cudaMemcpyAsync(ws.h_f + (6 + i) * N, gsrc[i], N * sizeof(float),
-                            cudaMemcpyDeviceToHost, s);
+        e = cudaMemcpyAsync(gdst[i], gsrc[i], N * sizeof(float), cudaMemcpyDeviceToHost, s);
   }
   if (e != cudaSuccess) return cuda_fail(fn, e);
   e = cudaStreamSynchronize(s);
   if (e != cudaSuccess) return cuda_fail(fn, e);
-  memcpy(losses, hl, 3 * B * sizeof(float));
-  memcpy(scalars, hl + 3 * B, 6 * sizeof(float));
-  if (want_grad)
-    for (int i = 0; i < 4; ++i)
-      if (gdst[i] != nullptr) memcpy(gdst[i], ws.h_f + (6 + i) * N, N * sizeof(float));
   return 0;
 }
 

@@ -55,14 +55,14 @@ bwd_pre_kernel(const BwdPreParams p) {
       const float e = get(E, j), n = get(N, j);
       const float f = vi.xval(getx(X, j));
       const Poly po = poly_eval(a, b, c, rt);
-      const float rS = __frcp_rn(po.S);
+      const float rS = rcp_scale(po.S);
       const float Q = po.q * po.q;
       const float u = po.P * rS, y = Q * rS;
       const float gt = p.gmin + (p.delta * po.P) * rS;
       const float w = (p.delta * Q) * rS;
-      const float v = sigmoid_ref(gt);
+      const float v = sigmoid_fast(gt);
       const float om = 1.0f - v;
-      const float alpha = sqrtf(om), sigma = sqrtf(v);
+      const float alpha = sqrt_nr(om), sigma = sqrt_nr(v);
       const float dal = -0.5f * v * alpha;      // d alpha / d gamma
       const float dsg = 0.5f * sigma * om;      // d sigma / d gamma
 
@@ -77,9 +77,9 @@ bwd_pre_kernel(const BwdPreParams p) {
         float vhat = n, eh = 0.f, k = 1.f, zt = 0.f, eg = 0.f;
         if (PARAM == MULAN_PARAM_VEL_FROM_EPS) {
           zt = alpha * f + sigma * e;
-          eg = expf(gt);
-          eh = expf(0.5f * gt);
-          k = sqrtf(1.0f + eg);
+          eg = exp_fast(gt);
+          eh = exp_fast(0.5f * gt);
+          k = sqrt_nr(1.0f + eg);
           vhat = -eh * zt + k * n;
         }
         const float r = vtg - vhat;

@@ -52,6 +52,62 @@ __device__ __forceinline__ float encode_ref(int x, float vocab) {
   return 2.0f * __fdiv_rn((float)x + 0.5f, vocab) - 1.0f;
 }
 
+// ---------------------------------------------------------------------------------------
+// Fast scalar math: bare MUFU + Newton, no slow-path branches.  Each is within ~1 ulp of the
+// IEEE result on the stated domain; the residual differs from the reference's rounding
+// pseudo-randomly per sub-pixel, so per-example sums are unaffected at the 1e-7 level
+// (tests/test_gpu_kernels.py holds them to 1e-5).
+// ---------------------------------------------------------------------------------------
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
+}
+__device__ __forceinline__ float rsqrt_approx(float x) {
+  float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
+}
+// 1/x, x normal and finite: MUFU.RCP + one Newton step.
+__device__ __forceinline__ float rcp_nr(float x) {
+  const float r = rcp_approx(x);
+  return fmaf(fmaf(-x, r, 1.0f), r, r);
+}
+// 1/S for the polynomial scale: Newton on the normal range, IEEE otherwise (S == 0, denormal,
+// huge, NaN are possible for adversarial coefficients and must behave like the reference).
+__device__ __forceinline__ bool scale_in_range(float S) {
+  const float aS = fabsf(S);
+  return aS > 1e-30f && aS < 1e30f;
+}
+__device__ __forceinline__ float rcp_scale(float S) {
+  return scale_in_range(S) ? rcp_nr(S) : __frcp_rn(S);
+}
+// sqrt(x), 0 <= x < 2^100: x * rsqrt(x) + one Newton step; sqrt(0) = 0.
+__device__ __forceinline__ float sqrt_nr(float x) {
+  const float y = rsqrt_approx(x);
+  float s = x * y;
+  s = fmaf(fmaf(-s, s, x), 0.5f * y, s);
+  return x > 0.0f ? s : 0.0f;
+}
+__device__ __forceinline__ float exp_fast(float x) { return ex2_approx(x * kLog2e); }
+// sigmoid with the reference's structure 1/(1+exp(-x)): for x >~ 3 (where 1 - sigmoid is
+// amplified) the rounding of 1+e dominates and the result equals the IEEE one.
+__device__ __forceinline__ float sigmoid_fast(float x) {
+  return rcp_nr(1.0f + exp_fast(fminf(-x, 80.0f)));
+}
+// log(s) for s = 1 + d in [1, 4): series for tiny d (MUFU.LG2 has ~2^-22 ABSOLUTE error,
+// useless next to log(1+d) ~ d), MUFU.LG2 otherwise.
+__device__ __forceinline__ float log_1p_sum(float s) {
+  const float d = s - 1.0f;
+  const float small = d * fmaf(d, fmaf(d, kThird, -0.5f), 1.0f);
+  const float big = lg2_approx(s) * kLn2;
+  return d < 0.0078125f ? small : big;
+}
+
 // Per-example time powers, staged once per row in shared memory.  Integer powers follow
 // XLA's integer_pow lowering (binary exponentiation), see oracle.integer_pow.
 struct RowT {

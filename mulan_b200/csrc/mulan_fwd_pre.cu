@@ -1,5 +1,6 @@
 // mulan_fwd_pre: schedule eval + noising + reconstruction + prior KL, one pass over
-// [B, D] (25 B/sub-pixel algorithmic: x1 + a,b,c 12 + eps0 4 + eps 4 -> z_t 4).
+// [B, D] (25 B/sub-pixel algorithmic: x1 + a,b,c 12 + eps0 4 + eps 4 -> z_t 4; +4 when the
+// loss weight w is saved for the post kernels, +4 for per-pixel g_t).
 //
 // Reference statements fused here (ldm/model_mulan_epsilon.py; the velocity model runs the
 // same lines, ldm/model_mulan_velocity.py:208-236):
@@ -15,118 +16,133 @@
 //
 // Layout: one CTA (256 threads) per example row; each thread owns float4 columns
 // tid, tid+256, ... of the row (coalesced 16-B accesses, uchar4 for x).  Per-row t powers
-// and the gamma-bound constants (gamma_0 = gamma_min exactly for the fixed-end polynomial,
-// so exp(+-gamma_0/2), sigmoid(gamma_0), sigmoid(gamma_1), log sigmoid(gamma_1) are
-// constants) are computed once by thread 0 and staged in shared memory.  Per-row sums use
-// a fixed-order shuffle tree (deterministic; no atomics).
+// are staged in shared memory by thread 0.  The gamma-bound constants (gamma_0 = gamma_min
+// exactly for the fixed-end polynomial, so exp(+-gamma_0/2), sigmoid(gamma_0),
+// sigmoid(gamma_1), log sigmoid(gamma_1) are constants) are computed once per launch on
+// the host, correctly rounded, and travel in the kernel parameter block: the reconstruction
+// term is sensitive to a 1-ulp change of exp(gamma_0/2) at the 1e-5 level (it decides how
+// z_0 rounds), so these constants must not depend on which exp implementation evaluates
+// them.  Per-row sums use a fixed-order shuffle tree (deterministic; no atomics).
+//
+// The kernel is instruction-issue bound, not HBM bound, unless the per-sub-pixel instruction
+// count stays near ~110 (profiles/): hence the 3-bin reconstruction window in closed form
+// and the branch-free MUFU+Newton math of mulan_common.cuh on the hot path.  Everything
+// that decides HOW the reference rounds where it matters (z_0, u = (z_0 - x_k) e^{-g0/2},
+// 1 - sigmoid, the prior-KL summand) keeps the reference's op order.
 #include "mulan_kernels.h"
 
 namespace mulan {
 
-struct PreStage {
-  RowT rt;
-  float g0, s0, inv0, v0;   // gamma_0 == f32(gamma_min); exp(.5 g0); exp(-.5 g0); sigmoid(g0)
-  float v1, om1, lv1;       // sigmoid(g1), 1 - v1, log(v1) when uniform
-  int v1_uniform;           // sigmoid(gmin + r) identical for r in {D-ulp, D, D+ulp}
-  float s_lo, s_hi;         // |S| range for which the fixed-end constants are exact
-};
-
-// log-softmax over the vocab bins, evaluated only on a window of +-W bins around the bin
-// nearest to z: every bin outside the window has exp(logit - max) < e^-30 (cannot move a
-// float32 sum that is >= 1).  Returns log p(x | z).
-template <int WCT>
-__device__ __forceinline__ float recon_logprob(int xi, float z, float inv0, int Wrt,
-                                               const VocabInfo& vi) {
-  const int W = WCT > 0 ? WCT : Wrt;
-  // nearest bin: centres at (2k+1)/vocab - 1
-  float kf = rintf((z + 1.0f) * vi.half_vocab - 0.5f);
+// ---------------------------------------------------------------------------------------
+// Generic reconstruction term: log-softmax over the vocab bins evaluated on a window of
+// +-W bins around the bin nearest to z (bins further away have exp(logit - max) < e^-30 and
+// cannot move a float32 sum >= 1).  IEEE expf/logf.  Used when W != 1, vocab is not a power
+// of two, or the fixed ends do not hold for a sub-pixel.  Returns log p(x | z).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float recon_logprob_generic(int xi, float z, float inv0, int W,
+                                                       const VocabInfo& vi) {
+  float kf = rintf((z + 1.0f) * vi.half_vocab - 0.5f);   // nearest bin centre (2k+1)/vocab-1
   kf = fminf(fmaxf(kf, 0.0f), vi.vocab_m1);
   const int kc = (int)kf;
   auto logit = [&](int k) {
-    const float xv = vi.xval(k);
-    const float u = (z - xv) * inv0;
+    const float u = (z - vi.xval(k)) * inv0;
     return -0.5f * (u * u);
   };
   const float lc = logit(kc);
   const float lm = kc > 0 ? logit(kc - 1) : -INFINITY;
   const float lp = kc < vi.vocab - 1 ? logit(kc + 1) : -INFINITY;
   const float m = fmaxf(lc, fmaxf(lm, lp));
-  float sum;
-  if (WCT == 1) {
-    sum = expf(lm - m) + expf(lc - m) + expf(lp - m);
-  } else {
-    sum = 0.0f;
-    const int k0 = max(kc - W, 0), k1 = min(kc + W, vi.vocab - 1);
-    for (int k = k0; k <= k1; ++k) sum += expf(logit(k) - m);
-  }
-  const float lx = logit(xi);
-  // z NaN -> everything NaN, as in the reference.
-  return (lx - m) - logf(sum);
+  float sum = 0.0f;
+  const int k0 = max(kc - W, 0), k1 = min(kc + W, vi.vocab - 1);
+  for (int k = k0; k <= k1; ++k) sum += expf(logit(k) - m);
+  return (logit(xi) - m) - logf(sum);   // z NaN -> NaN, as in the reference
+}
+
+// Fast reconstruction term for W == 1 and vocab a power of two (the shipped configs:
+// gamma_0 = -13.3 puts neighbouring bins 6.04 decoder-sigmas apart).
+//   u_c = (z - x_c) e^{-g0/2}           reference op order (x_c exact, subtraction, product)
+//   l_{c+-1} - l_c = -+ s u_c - s^2/2    closed form, s = (2/vocab) e^{-g0/2}
+//   log p(x) = (l_x - l_c) - log(1 + e^{l_{c-1}-l_c} + e^{l_{c+1}-l_c})
+// The centre bin is the max up to rounding ties, where log-sum-exp is shift invariant.
+struct ReconFast {
+  float inv0, s2, c0;   // e^{-g0/2}; s log2(e); -s^2/2 log2(e)
+  float two_iv, off;    // 2/vocab; 1/vocab - 1
+  float half_vocab, vocab_m1;
+};
+__device__ __forceinline__ float recon_logprob_fast(float f, float z, const ReconFast& rc) {
+  float kf = rintf(fmaf(z, rc.half_vocab, rc.half_vocab - 0.5f));
+  kf = fminf(fmaxf(kf, 0.0f), rc.vocab_m1);
+  const float xc = fmaf(kf, rc.two_iv, rc.off);           // exact bin centre
+  const float uc = (z - xc) * rc.inv0;
+  const float em = kf > 0.0f ? ex2_approx(fmaf(-rc.s2, uc, rc.c0)) : 0.0f;
+  const float ep = kf < rc.vocab_m1 ? ex2_approx(fmaf(rc.s2, uc, rc.c0)) : 0.0f;
+  const float sum = (1.0f + em) + ep;
+  const float ux = (z - f) * rc.inv0;
+  const float lx = -0.5f * (ux * ux), lc = -0.5f * (uc * uc);
+  return (lx - lc) - log_1p_sum(sum);
 }
 
 // Rare path: S is zero / denormal / huge / NaN so gamma(0), gamma(1) are not the fixed-end
-// constants.  Evaluate them per sub-pixel exactly as the reference does.
-__device__ __noinline__ void slow_ends(float S, float gmin, float delta, int xi, float f,
-                                       float e0, const VocabInfo& vi,
-                                       float* lp, float* kl, float* v0o, float* v1o) {
+// constants.  Evaluate this sub-pixel exactly as the reference does (IEEE ops).
+struct SlowPix { float gt, wt, lp, kl, v0, v1; };
+__device__ __noinline__ SlowPix slow_pixel(const Poly po, float gmin, float delta, int xi,
+                                           float f, float e0, const VocabInfo vi) {
+  SlowPix o;
+  const float S = po.S;
+  o.gt = gmin + __fdiv_rn(delta * po.P, S);
+  o.wt = __fdiv_rn(delta * (po.q * po.q), S);
   const float g0 = gmin + __fdiv_rn(delta * 0.0f, S);
   const float g1 = gmin + __fdiv_rn(delta * S, S);
-  const float v0 = sigmoid_ref(g0), v1 = sigmoid_ref(g1);
+  o.v0 = sigmoid_ref(g0);
+  o.v1 = sigmoid_ref(g1);
   const float s0 = expf(0.5f * g0), inv0 = expf(-0.5f * g0);
   const float z = f + s0 * e0;
-  *lp = recon_logprob<0>(xi, z, inv0, vi.vocab, vi);  // full vocab
-  *kl = (1.0f - v1) * (f * f) + v1 - logf(v1) - 1.0f;
-  *v0o = v0;
-  *v1o = v1;
+  o.lp = recon_logprob_generic(xi, z, inv0, vi.vocab, vi);  // full vocab
+  o.kl = (1.0f - o.v1) * (f * f) + o.v1 - logf(o.v1) - 1.0f;
+  return o;
 }
 
-template <int GT, bool SAVEW, int WCT>
+// Prior-KL summand when sigmoid(gamma_1) is not the same float for the three possible
+// roundings of (delta*S)/S (never the case for the shipped gamma range).
+__device__ __noinline__ float2 prior_general(float S, float gmin, float delta, float f) {
+  const float g1 = gmin + __fdiv_rn(delta * S, S);
+  const float v1 = sigmoid_ref(g1);
+  return make_float2((1.0f - v1) * (f * f) + v1 - logf(v1) - 1.0f, v1);
+}
+
+template <int GT, bool SAVEW, bool FAST>
 __global__ void __launch_bounds__(kThreads)
 fwd_pre_kernel(const FwdPreParams p) {
-  __shared__ PreStage st;
+  __shared__ RowT s_rt;
   __shared__ float red[kWarps][5];
   const int row = blockIdx.x;
   const int tid = threadIdx.x;
 
-  if (tid == 0) {
-    st.rt = make_row_t(__ldg(p.t + row));
-    const float g0 = p.gmin;
-    st.g0 = g0;
-    st.s0 = expf(0.5f * g0);
-    st.inv0 = expf(-0.5f * g0);
-    st.v0 = sigmoid_ref(g0);
-    // gamma(1) = gmin + (delta*S)/S is gmin + {delta-ulp, delta, delta+ulp}
-    const float d0 = p.delta;
-    const float va = sigmoid_ref(p.gmin + nextafterf(d0, -INFINITY));
-    const float vb = sigmoid_ref(p.gmin + d0);
-    const float vc = sigmoid_ref(p.gmin + nextafterf(d0, INFINITY));
-    st.v1_uniform = (va == vb) && (vb == vc);
-    st.v1 = vb;
-    st.om1 = 1.0f - vb;
-    st.lv1 = logf(vb);
-    st.s_lo = 1e-30f;
-    st.s_hi = 1e30f;
-  }
+  if (tid == 0) s_rt = make_row_t(__ldg(p.t + row));
   __syncthreads();
-  const RowT rt = st.rt;
-  const float s0 = st.s0, inv0 = st.inv0, v0c = st.v0;
-  const float v1c = st.v1, om1 = st.om1, lv1 = st.lv1;
-  const bool v1_uniform = st.v1_uniform != 0;
+  const RowT rt = s_rt;
+  const float s0 = p.k.s0, inv0 = p.k.inv0, v0c = p.k.v0;
+  const float v1c = p.k.v1, om1 = p.k.om1;
+  const float lv1 = p.k.lv1;
+  const bool v1_uniform = p.k.v1_uniform != 0;
   const VocabInfo vi = p.vi;
+  ReconFast rc;
+  rc.inv0 = inv0;
+  rc.s2 = p.recon_s * kLog2e;
+  rc.c0 = -0.5f * p.recon_s * p.recon_s * kLog2e;
+  rc.two_iv = 2.0f * vi.inv_vocab;
+  rc.off = vi.inv_vocab - 1.0f;
+  rc.half_vocab = vi.half_vocab;
+  rc.vocab_m1 = vi.vocab_m1;
 
   const size_t base4 = (size_t)row * p.dim4;
-  const float* __restrict__ pa = p.a;
-  const float* __restrict__ pb = p.b;
-  const float* __restrict__ pc = p.c;
-  const float* __restrict__ pe0 = p.eps0;
-  const float* __restrict__ pe = p.eps;
-
-  float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};  // logprob, klz summand, g_t, var0, var1
+  // logprob, klz summand, g_t, and (only off the fixed-end path) var0 / var1 corrections
+  float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
 
   for (int i4 = tid; i4 < p.dim4; i4 += kThreads) {
     const size_t g4 = base4 + i4;
-    const float4 A = ld4(pa, g4), Bv = ld4(pb, g4), C = ld4(pc, g4);
-    const float4 E0 = ld4(pe0, g4), E = ld4(pe, g4);
+    const float4 A = ld4(p.a, g4), Bv = ld4(p.b, g4), C = ld4(p.c, g4);
+    const float4 E0 = ld4(p.eps0, g4), E = ld4(p.eps, g4);
     const uchar4 X = ldx4(p.x, g4);
     float4 Z, Wv, G;
 #pragma unroll
@@ -136,35 +152,34 @@ fwd_pre_kernel(const FwdPreParams p) {
       const int xi = getx(X, j);
       const float f = vi.xval(xi);                        // encode(x)
       const Poly po = poly_eval(a, b, c, rt);
-      const float rS = __frcp_rn(po.S);
-      const float gt = p.gmin + (p.delta * po.P) * rS;    // gamma_t
-      const float wt = (p.delta * (po.q * po.q)) * rS;    // d gamma / dt
-      const float vt = sigmoid_ref(gt);
-      const float alpha = sqrtf(1.0f - vt), sigma = sqrtf(vt);
-      put(Z, j, alpha * f + sigma * e);                   // z_t (two roundings + add)
+      float gt, wt;
+      if (scale_in_range(po.S)) {                         // fixed ends are exact constants
+        const float rS = rcp_nr(po.S);
+        gt = p.gmin + (p.delta * po.P) * rS;              // gamma_t
+        wt = (p.delta * (po.q * po.q)) * rS;              // d gamma / dt
+        const float z0 = f + s0 * e0;                     // z_0_rescaled (two roundings)
+        acc[0] += FAST ? recon_logprob_fast(f, z0, rc)
+                       : recon_logprob_generic(xi, z0, inv0, p.W, vi);
+        if (v1_uniform) {
+          acc[1] += om1 * (f * f) + v1c - lv1 - 1.0f;     // reference op order
+        } else {
+          const float2 pg = prior_general(po.S, p.gmin, p.delta, f);
+          acc[1] += pg.x;
+          acc[4] += pg.y - v1c;
+        }
+      } else {
+        const SlowPix sp = slow_pixel(po, p.gmin, p.delta, xi, f, e0, vi);
+        gt = sp.gt; wt = sp.wt;
+        acc[0] += sp.lp; acc[1] += sp.kl;
+        acc[3] += sp.v0 - v0c; acc[4] += sp.v1 - v1c;
+      }
+      const float vt = sigmoid_fast(gt);
+      const float om = 1.0f - vt;
+      const float alpha = sqrt_nr(om), sigma = sqrt_nr(vt);
+      put(Z, j, alpha * f + sigma * e);                   // z_t (two products, one add)
       if (SAVEW) put(Wv, j, wt);
       if (GT == MULAN_GT_PIXEL) put(G, j, gt);
       acc[2] += gt;
-
-      const float aS = fabsf(po.S);
-      if (aS > st.s_lo && aS < st.s_hi) {                 // fixed ends are exact constants
-        const float z0 = f + s0 * e0;                     // z_0_rescaled
-        acc[0] += recon_logprob<WCT>(xi, z0, inv0, p.W, vi);
-        acc[3] += v0c;
-        if (v1_uniform) {
-          acc[1] += om1 * (f * f) + v1c - lv1 - 1.0f;
-          acc[4] += v1c;
-        } else {
-          const float g1 = p.gmin + __fdiv_rn(p.delta * po.S, po.S);
-          const float v1 = sigmoid_ref(g1);
-          acc[1] += (1.0f - v1) * (f * f) + v1 - logf(v1) - 1.0f;
-          acc[4] += v1;
-        }
-      } else {
-        float lp, kl, v0, v1;
-        slow_ends(po.S, p.gmin, p.delta, xi, f, e0, vi, &lp, &kl, &v0, &v1);
-        acc[0] += lp; acc[1] += kl; acc[3] += v0; acc[4] += v1;
-      }
     }
     st4(p.z_t, g4, Z);
     if (SAVEW) st4(p.w_save, g4, Wv);
@@ -173,19 +188,21 @@ fwd_pre_kernel(const FwdPreParams p) {
 
   block_sum<5>(acc, red);
   if (tid == 0) {
+    const float dimf = (float)(p.dim4 * 4);
     p.loss_recon[row] = -acc[0];
     p.loss_klz[row] = 0.5f * acc[1];
-    if (GT == MULAN_GT_MEAN) p.g_net[row] = __fdiv_rn(acc[2], (float)(p.dim4 * 4));
-    p.var_sums[2 * row + 0] = acc[3];
-    p.var_sums[2 * row + 1] = acc[4];
+    if (GT == MULAN_GT_MEAN) p.g_net[row] = __fdiv_rn(acc[2], dimf);
+    // sum over the row of sigmoid(g_0), sigmoid(g_1): D * constant + corrections
+    p.var_sums[2 * row + 0] = dimf * v0c + acc[3];
+    p.var_sums[2 * row + 1] = dimf * v1c + acc[4];
   }
 }
 
 template <int GT, bool SAVEW>
 static cudaError_t launch_w(const FwdPreParams& p, cudaStream_t s) {
   dim3 grid(p.rows), block(kThreads);
-  if (p.W == 1) fwd_pre_kernel<GT, SAVEW, 1><<<grid, block, 0, s>>>(p);
-  else          fwd_pre_kernel<GT, SAVEW, 0><<<grid, block, 0, s>>>(p);
+  if (p.W == 1 && p.vi.pow2) fwd_pre_kernel<GT, SAVEW, true><<<grid, block, 0, s>>>(p);
+  else                       fwd_pre_kernel<GT, SAVEW, false><<<grid, block, 0, s>>>(p);
   return cudaGetLastError();
 }
 

@@ -34,13 +34,45 @@ inline VocabInfo make_vocab(int vocab) {
   return v;
 }
 
+// Constants of the fixed-end schedule: gamma(0) == f32(gamma_min) exactly, gamma(1) ==
+// gmin + (delta*S)/S in {delta-ulp, delta, delta+ulp}.  Evaluated on the host in the
+// reference's float32 op order with correctly rounded exp/log (double, then one rounding).
+struct EndConsts {
+  float s0, inv0, v0;       // exp(.5 g0), exp(-.5 g0), sigmoid(g0)
+  float v1, om1, lv1;       // sigmoid(g1), 1 - v1, log(v1)
+  int v1_uniform;           // sigmoid(gmin + r) identical for the three candidate r
+};
+
+inline float host_exp_f32(float x) { return (float)exp((double)x); }
+inline float host_sigmoid_f32(float x) {
+  const float e = host_exp_f32(-x);
+  const float d = 1.0f + e;
+  return 1.0f / d;
+}
+inline EndConsts make_end_consts(float gmin, float delta) {
+  EndConsts k;
+  k.s0 = host_exp_f32(0.5f * gmin);
+  k.inv0 = host_exp_f32(-0.5f * gmin);
+  k.v0 = host_sigmoid_f32(gmin);
+  const float lo = nextafterf(delta, -INFINITY), hi = nextafterf(delta, INFINITY);
+  const float g1a = gmin + lo, g1b = gmin + delta, g1c = gmin + hi;
+  const float va = host_sigmoid_f32(g1a), vb = host_sigmoid_f32(g1b), vc = host_sigmoid_f32(g1c);
+  k.v1_uniform = (va == vb) && (vb == vc);
+  k.v1 = vb;
+  k.om1 = 1.0f - vb;
+  k.lv1 = (float)log((double)vb);
+  return k;
+}
+
 struct FwdPreParams {
   const uint8_t* x;
   const float *a, *b, *c, *t, *eps0, *eps;
   float *z_t, *g_net, *w_save, *loss_recon, *loss_klz, *var_sums;
   int rows, dim4, gt_mode;
   int W;              // reconstruction window half-width for gamma_0 = gamma_min
+  float recon_s;      // bin spacing in decoder sigmas: (2/vocab) exp(-gamma_0/2)
   float gmin, delta;  // f32(gamma_min), f32(gamma_max - gamma_min)
+  EndConsts k;
   VocabInfo vi;
 };
 

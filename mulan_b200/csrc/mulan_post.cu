@@ -34,7 +34,7 @@ __device__ __forceinline__ PostPix post_pixel(float a, float b, float c, int xi,
     w = wsaved;
   } else {
     const Poly po = poly_eval(a, b, c, rt);
-    const float rS = __frcp_rn(po.S);
+    const float rS = rcp_scale(po.S);
     gt = gmin + (delta * po.P) * rS;
     w = (delta * (po.q * po.q)) * rS;
   }
@@ -44,15 +44,15 @@ __device__ __forceinline__ PostPix post_pixel(float a, float b, float c, int xi,
     if (BWD) o.dnet = -2.0f * (w * r);
   } else {
     const float f = vi.xval(xi);
-    const float vt = sigmoid_ref(gt);
+    const float vt = sigmoid_fast(gt);
     const float om = 1.0f - vt;
-    const float alpha = sqrtf(om), sigma = sqrtf(vt);
+    const float alpha = sqrt_nr(om), sigma = sqrt_nr(vt);
     const float vtg = alpha * e - sigma * f;
     float vhat = n, k = 1.0f;
     if (PARAM == MULAN_PARAM_VEL_FROM_EPS) {
       const float zt = alpha * f + sigma * e;
-      k = sqrtf(1.0f + expf(gt));
-      vhat = -expf(0.5f * gt) * zt + k * n;
+      k = sqrt_nr(1.0f + exp_fast(gt));
+      vhat = -exp_fast(0.5f * gt) * zt + k * n;
     }
     const float r = vtg - vhat;
     const float omw = om * w;

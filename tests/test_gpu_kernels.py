@@ -58,9 +58,14 @@ def test_fwd_pre_parity(cuda_device, B, seed):
   r = ops.fwd_pre(desc, g['x'], g['a'], g['b'], g['c'], g['t'], g['eps_0'], g['eps'])
   assert _rel(r['loss_recon'], out.loss_recon) < LOSS_RTOL
   assert _rel(r['loss_klz_prior'], aux['loss_klz_prior']) < LOSS_RTOL
-  # z_t: elementwise, float32 cancellation in P/S makes single pixels differ by a few 1e-6
-  assert (r['z_t'].cpu() - aux['z_t'].reshape(B, -1)).abs().max().item() < 5e-5
-  assert _rel_l2_rows(r['z_t'], aux['z_t'].reshape(B, -1)) < 1e-6
+  # z_t elementwise: float32 cancellation in P/S makes single pixels of the float32 reference
+  # itself differ from exact arithmetic by ~1e-5..1e-4; bound the CUDA error by the oracle's.
+  _, aux64 = _oracle(inp, O.MODE_EPS, dtype=torch.float64)
+  z64 = aux64['z_t'].reshape(B, -1)
+  err_ref = (aux['z_t'].reshape(B, -1).double() - z64).abs().max().item()
+  err_got = (r['z_t'].cpu().double() - z64).abs().max().item()
+  assert err_got <= 4 * err_ref + 2e-6, (err_got, err_ref)
+  assert _rel_l2_rows(r['z_t'], aux['z_t'].reshape(B, -1)) < 1e-5
   g_mean = aux['g_t'].reshape(B, -1).mean(dim=1)
   assert (r['g_net'].cpu() - g_mean).abs().max().item() < 2e-5
   # d gamma/dt: q^2 form vs the reference's expanded jvp -> compare per-example sums
@@ -100,8 +105,13 @@ def test_fwd_gt_pixel(cuda_device):
                   save_w=False)
   assert r['w'] is None
   assert r['g_net'].shape == (B, 3072)
-  assert (r['g_net'].cpu() - aux['g_t'].reshape(B, -1)).abs().max().item() < 1e-4
-  assert _rel_l2_rows(r['g_net'], aux['g_t'].reshape(B, -1)) < 1e-6
+  # per-pixel gamma_t: bound the error against float64 by the float32 oracle's own error
+  _, aux64 = _oracle(inp, O.MODE_EPS, dtype=torch.float64, gt='ldm')
+  g64 = aux64['g_t'].reshape(B, -1)
+  err_ref = (aux['g_t'].reshape(B, -1).double() - g64).abs().max().item()
+  err_got = (r['g_net'].cpu().double() - g64).abs().max().item()
+  assert err_got <= 4 * err_ref + 4e-6, (err_got, err_ref)
+  assert _rel_l2_rows(r['g_net'], aux['g_t'].reshape(B, -1)) < 1e-5
   assert _rel(r['loss_recon'], out.loss_recon) < LOSS_RTOL
 
 
@@ -302,7 +312,8 @@ def test_autograd_pair_with_denoiser(cuda_device, mode):
     cast = lambda v: v.to(dtype) if v.is_floating_point() else v
     i = {k: cast(v) for k, v in inp.items()}
     a, b, c = (i[k].clone().requires_grad_(True) for k in ('a', 'b', 'c'))
-    p1, p2 = w1.to(dtype).requires_grad_(True), w2.to(dtype).requires_grad_(True)
+    p1 = w1.detach().clone().to(dtype).requires_grad_(True)
+    p2 = w2.detach().clone().to(dtype).requires_grad_(True)
     out = O.elbo_terms(i['x'], a, b, c, i['t'], i['eps_0'], i['eps'],
                        lambda z, g: net_fn(z, g, p1, p2, 0.3 * i['net']), MODES[mode],
                        O.OracleConfig(), dtype=dtype)
@@ -312,8 +323,8 @@ def test_autograd_pair_with_denoiser(cuda_device, mode):
       want, want_bpd = grads, bpd.item()
   g = _dev(inp, cuda_device)
   a, b, c = (g[k].clone().requires_grad_(True) for k in ('a', 'b', 'c'))
-  p1 = w1.to(cuda_device).requires_grad_(True)
-  p2 = w2.to(cuda_device).requires_grad_(True)
+  p1 = w1.detach().clone().to(cuda_device).requires_grad_(True)
+  p2 = w2.detach().clone().to(cuda_device).requires_grad_(True)
   desc = ops.Desc(param=MODES[mode])
   tape = ops.ElboTape(desc)
   z_t, g_net, rec, klz, vs, link = ops.mulan_pre(tape, g['x'], a, b, c, g['t'], g['eps_0'],

@@ -111,7 +111,7 @@ int mulan_fwd_pre(const mulan_desc* d, const uint8_t* x, const float* a, const f
   p.gmin = f32_gmin(d); p.delta = f32_delta(d);
   p.k = mulan::make_end_consts(p.gmin, p.delta);
   p.vi = mulan::make_vocab(d->vocab);
-  p.recon_s = (2.0f / (float)d->vocab) * p.k.inv0;
+  p.rc = mulan::make_recon_fast(p.k, p.vi);
   cudaError_t e = mulan::launch_fwd_pre(p, (cudaStream_t)stream);
   return e == cudaSuccess ? 0 : cuda_fail(fn, e);
 }

@@ -93,6 +93,14 @@ __device__ __forceinline__ float sqrt_nr(float x) {
   s = fmaf(fmaf(-s, s, x), 0.5f * y, s);
   return x > 0.0f ? s : 0.0f;
 }
+// sqrt(x) = x * rsqrt(x) straight off the MUFU (~2^-22 relative): for alpha/sigma, whose
+// rounding in the reference is itself pseudo-random per sub-pixel.  x > 0.
+__device__ __forceinline__ float sqrt_fast(float x) { return x * rsqrt_approx(x); }
+// same, with sqrt(0) = 0 (1 - sigmoid can round to 0)
+__device__ __forceinline__ float sqrt_fast0(float x) {
+  const float s = x * rsqrt_approx(x);
+  return x > 0.0f ? s : 0.0f;
+}
 __device__ __forceinline__ float exp_fast(float x) { return ex2_approx(x * kLog2e); }
 // sigmoid with the reference's structure 1/(1+exp(-x)): for x >~ 3 (where 1 - sigmoid is
 // amplified) the rounding of 1+e dominates and the result equals the IEEE one.

@@ -64,12 +64,8 @@ __device__ __forceinline__ float recon_logprob_generic(int xi, float z, float in
 //   l_{c+-1} - l_c = -+ s u_c - s^2/2    closed form, s = (2/vocab) e^{-g0/2}
 //   log p(x) = (l_x - l_c) - log(1 + e^{l_{c-1}-l_c} + e^{l_{c+1}-l_c})
 // The centre bin is the max up to rounding ties, where log-sum-exp is shift invariant.
-struct ReconFast {
-  float inv0, s2, c0;   // e^{-g0/2}; s log2(e); -s^2/2 log2(e)
-  float two_iv, off;    // 2/vocab; 1/vocab - 1
-  float half_vocab, vocab_m1;
-};
-__device__ __forceinline__ float recon_logprob_fast(float f, float z, const ReconFast& rc) {
+__device__ __forceinline__ float recon_logprob_fast(float xf, float f, float z,
+                                                    const ReconFast& rc) {
   float kf = rintf(fmaf(z, rc.half_vocab, rc.half_vocab - 0.5f));
   kf = fminf(fmaxf(kf, 0.0f), rc.vocab_m1);
   const float xc = fmaf(kf, rc.two_iv, rc.off);           // exact bin centre
@@ -77,9 +73,11 @@ __device__ __forceinline__ float recon_logprob_fast(float f, float z, const Reco
   const float em = kf > 0.0f ? ex2_approx(fmaf(-rc.s2, uc, rc.c0)) : 0.0f;
   const float ep = kf < rc.vocab_m1 ? ex2_approx(fmaf(rc.s2, uc, rc.c0)) : 0.0f;
   const float sum = (1.0f + em) + ep;
-  const float ux = (z - f) * rc.inv0;
-  const float lx = -0.5f * (ux * ux), lc = -0.5f * (uc * uc);
-  return (lx - lc) - log_1p_sum(sum);
+  // l_x - l_c = -(u_x - u_c)(u_x + u_c)/2 with u_x - u_c = (k_c - x) s exactly; 0 when x is
+  // the nearest bin (all but the |eps_0| > 3 tail)
+  const float ds = (kf - xf) * rc.s;
+  const float lxc = -ds * fmaf(0.5f, ds, uc);
+  return lxc - log_1p_sum(sum);
 }
 
 // Rare path: S is zero / denormal / huge / NaN so gamma(0), gamma(1) are not the fixed-end
@@ -111,7 +109,7 @@ __device__ __noinline__ float2 prior_general(float S, float gmin, float delta, f
 }
 
 template <int GT, bool SAVEW, bool FAST>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 fwd_pre_kernel(const FwdPreParams p) {
   __shared__ RowT s_rt;
   __shared__ float red[kWarps][5];
@@ -121,19 +119,14 @@ fwd_pre_kernel(const FwdPreParams p) {
   if (tid == 0) s_rt = make_row_t(__ldg(p.t + row));
   __syncthreads();
   const RowT rt = s_rt;
+  // everything below lives in the kernel parameter (constant) bank: no registers
   const float s0 = p.k.s0, inv0 = p.k.inv0, v0c = p.k.v0;
   const float v1c = p.k.v1, om1 = p.k.om1;
   const float lv1 = p.k.lv1;
   const bool v1_uniform = p.k.v1_uniform != 0;
-  const VocabInfo vi = p.vi;
-  ReconFast rc;
-  rc.inv0 = inv0;
-  rc.s2 = p.recon_s * kLog2e;
-  rc.c0 = -0.5f * p.recon_s * p.recon_s * kLog2e;
-  rc.two_iv = 2.0f * vi.inv_vocab;
-  rc.off = vi.inv_vocab - 1.0f;
-  rc.half_vocab = vi.half_vocab;
-  rc.vocab_m1 = vi.vocab_m1;
+  const VocabInfo& vi = p.vi;
+  const ReconFast& rc = p.rc;
+  const float gmin = p.gmin, delta = p.delta;
 
   const size_t base4 = (size_t)row * p.dim4;
   // logprob, klz summand, g_t, and (only off the fixed-end path) var0 / var1 corrections
@@ -150,32 +143,34 @@ fwd_pre_kernel(const FwdPreParams p) {
       const float a = get(A, j), b = get(Bv, j), c = get(C, j);
       const float e0 = get(E0, j), e = get(E, j);
       const int xi = getx(X, j);
-      const float f = vi.xval(xi);                        // encode(x)
+      const float xf = (float)xi;
+      const float f = FAST ? fmaf(xf, rc.two_iv, rc.off)  // encode(x), exact for 2^k vocab
+                           : vi.xval(xi);
       const Poly po = poly_eval(a, b, c, rt);
       float gt, wt;
       if (scale_in_range(po.S)) {                         // fixed ends are exact constants
-        const float rS = rcp_nr(po.S);
-        gt = p.gmin + (p.delta * po.P) * rS;              // gamma_t
-        wt = (p.delta * (po.q * po.q)) * rS;              // d gamma / dt
+        const float rSd = delta * rcp_nr(po.S);
+        gt = fmaf(po.P, rSd, gmin);                       // gamma_t
+        wt = (po.q * po.q) * rSd;                         // d gamma / dt
         const float z0 = f + s0 * e0;                     // z_0_rescaled (two roundings)
-        acc[0] += FAST ? recon_logprob_fast(f, z0, rc)
+        acc[0] += FAST ? recon_logprob_fast(xf, f, z0, rc)
                        : recon_logprob_generic(xi, z0, inv0, p.W, vi);
         if (v1_uniform) {
           acc[1] += om1 * (f * f) + v1c - lv1 - 1.0f;     // reference op order
         } else {
-          const float2 pg = prior_general(po.S, p.gmin, p.delta, f);
+          const float2 pg = prior_general(po.S, gmin, delta, f);
           acc[1] += pg.x;
           acc[4] += pg.y - v1c;
         }
       } else {
-        const SlowPix sp = slow_pixel(po, p.gmin, p.delta, xi, f, e0, vi);
+        const SlowPix sp = slow_pixel(po, gmin, delta, xi, f, e0, vi);
         gt = sp.gt; wt = sp.wt;
         acc[0] += sp.lp; acc[1] += sp.kl;
         acc[3] += sp.v0 - v0c; acc[4] += sp.v1 - v1c;
       }
       const float vt = sigmoid_fast(gt);
       const float om = 1.0f - vt;
-      const float alpha = sqrt_nr(om), sigma = sqrt_nr(vt);
+      const float alpha = sqrt_fast0(om), sigma = sqrt_fast(vt);
       put(Z, j, alpha * f + sigma * e);                   // z_t (two products, one add)
       if (SAVEW) put(Wv, j, wt);
       if (GT == MULAN_GT_PIXEL) put(G, j, gt);

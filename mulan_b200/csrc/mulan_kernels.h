@@ -64,15 +64,35 @@ inline EndConsts make_end_consts(float gmin, float delta) {
   return k;
 }
 
+// Constants of the closed-form 3-bin reconstruction term (mulan_fwd_pre.cu).
+struct ReconFast {
+  float inv0, s, s2, c0;   // e^{-g0/2}; s = (2/vocab) e^{-g0/2}; s log2(e); -s^2/2 log2(e)
+  float two_iv, off;       // 2/vocab; 1/vocab - 1
+  float half_vocab, vocab_m1;
+};
+inline ReconFast make_recon_fast(const EndConsts& k, const VocabInfo& vi) {
+  ReconFast rc;
+  const double s = (2.0 / (double)vi.vocab) * (double)k.inv0;
+  rc.inv0 = k.inv0;
+  rc.s = (float)s;
+  rc.s2 = (float)(s * 1.4426950408889634);
+  rc.c0 = (float)(-0.5 * s * s * 1.4426950408889634);
+  rc.two_iv = 2.0f * vi.inv_vocab;
+  rc.off = vi.inv_vocab - 1.0f;
+  rc.half_vocab = vi.half_vocab;
+  rc.vocab_m1 = vi.vocab_m1;
+  return rc;
+}
+
 struct FwdPreParams {
   const uint8_t* x;
   const float *a, *b, *c, *t, *eps0, *eps;
   float *z_t, *g_net, *w_save, *loss_recon, *loss_klz, *var_sums;
   int rows, dim4, gt_mode;
   int W;              // reconstruction window half-width for gamma_0 = gamma_min
-  float recon_s;      // bin spacing in decoder sigmas: (2/vocab) exp(-gamma_0/2)
   float gmin, delta;  // f32(gamma_min), f32(gamma_max - gamma_min)
   EndConsts k;
+  ReconFast rc;
   VocabInfo vi;
 };
 

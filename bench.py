@@ -67,19 +67,52 @@ def workload_name(args):
 # clocks
 # ----------------------------------------------------------------------------------------
 class ClockSampler:
+  """SM clock + throttle reasons sampled DURING the timed region: NVML in a thread (2 ms
+  period, so even a 20 ms region gets samples); nvidia-smi -lms as the fallback."""
   Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
        'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
-  def __init__(self, index: int):
-    self.index, self.lines, self.proc = index, [], None
+  def __init__(self, index: int, uuid=None):
+    self.index, self.uuid = index, uuid
+    self.samples, self.lines, self.proc = [], [], None
+    self.smax, self.stop_flag, self.thread, self.how = None, False, None, None
 
   def start(self):
     try:
+      import pynvml as nv
+      nv.nvmlInit()
+      h = None
+      if self.uuid is not None:
+        try:
+          h = nv.nvmlDeviceGetHandleByUUID(('GPU-' + str(self.uuid)).encode())
+        except Exception:
+          h = None
+      if h is None:
+        h = nv.nvmlDeviceGetHandleByIndex(self.index)
+      self.smax = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+      self.how = 'nvml'
+
+      def loop():
+        while not self.stop_flag:
+          try:
+            self.samples.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)),
+                                 int(nv.nvmlDeviceGetCurrentClocksEventReasons(h)),
+                                 nv.nvmlDeviceGetPowerUsage(h) / 1000.0))
+          except Exception:
+            pass
+          time.sleep(0.002)
+      self.thread = threading.Thread(target=loop, daemon=True)
+      self.thread.start()
+      return
+    except Exception:
+      self.how = None
+    try:
       self.proc = subprocess.Popen(
           ['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.Q}',
-           '--format=csv,noheader,nounits', '-lms', '100'],
+           '--format=csv,noheader,nounits', '-lms', '20'],
           stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+      self.how = 'nvidia-smi'
       threading.Thread(target=self._pump, daemon=True).start()
     except OSError:
       self.proc = None
@@ -88,30 +121,46 @@ class ClockSampler:
     for line in self.proc.stdout:
       self.lines.append(line.strip())
 
-  def stop(self):
-    if self.proc is None:
-      return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-    self.proc.terminate()
-    try:
-      self.proc.wait(timeout=2)
-    except subprocess.TimeoutExpired:
-      self.proc.kill()
-    sm, smax, reasons = [], None, set()
+  def mark(self):
+    """Number of samples so far (to slice out the timed region)."""
+    return len(self.samples) if self.how == 'nvml' else len(self.lines)
+
+  def stop(self, lo=0, hi=None):
     names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-    for ln in self.lines:
-      f = [s.strip() for s in ln.split(',')]
-      if len(f) < 9:
-        continue
+    sm, reasons, power = [], set(), []
+    if self.how == 'nvml':
+      self.stop_flag = True
+      self.thread.join(timeout=1)
+      bits = {'hw_slowdown': 0x8, 'hw_thermal_slowdown': 0x40, 'sw_thermal_slowdown': 0x20,
+              'sw_power_cap': 0x4}
+      for clk, r, pw in self.samples[lo:hi]:
+        sm.append(clk); power.append(pw)
+        for n, bit in bits.items():
+          if r & bit:
+            reasons.add(n)
+    elif self.proc is not None:
+      self.proc.terminate()
       try:
-        sm.append(float(f[1])); smax = float(f[2])
-      except ValueError:
-        continue
-      for n, v in zip(names, f[5:9]):
-        if v.lower().startswith('active'):
-          reasons.add(n)
+        self.proc.wait(timeout=2)
+      except subprocess.TimeoutExpired:
+        self.proc.kill()
+      for ln in self.lines[lo:hi]:
+        f = [x.strip() for x in ln.split(',')]
+        if len(f) < 9:
+          continue
+        try:
+          sm.append(float(f[1])); self.smax = float(f[2]); power.append(float(f[3]))
+        except ValueError:
+          continue
+        for n, v in zip(names, f[5:9]):
+          if v.lower().startswith('active'):
+            reasons.add(n)
+    else:
+      return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no NVML / nvidia-smi']}
     sm.sort()
-    return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': smax,
-            'samples': len(sm), 'reasons': sorted(reasons)}
+    return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': self.smax,
+            'power_w_max': max(power) if power else None, 'samples': len(sm),
+            'reasons': sorted(reasons), 'how': self.how}
 
 
 # ----------------------------------------------------------------------------------------
@@ -198,17 +247,23 @@ def run_native(args):
   barrier()
   launches = 0
   evs = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(K)]
-  sampler = ClockSampler(local)
+  try:
+    uuid = torch.cuda.get_device_properties(local).uuid
+  except Exception:
+    uuid = None
+  sampler = ClockSampler(local, uuid)
   if rank == 0:
     sampler.start()
   t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   barrier()
+  mark0 = sampler.mark()
   t_start.record()
   for k in range(K):
     sc, _, _ = step(evs[k])
   t_end.record()
   barrier()
-  clocks = sampler.stop() if rank == 0 else None
+  mark1 = sampler.mark()
+  clocks = sampler.stop(mark0, max(mark1, mark0 + 1)) if rank == 0 else None
   elapsed_ms = t_start.elapsed_time(t_end)
   tmax = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
   if world > 1:

@@ -1,0 +1,221 @@
+"""Host-side mirror of the reference's model interface for the hot path.
+
+Same names, argument meaning and outputs as the reference's Flax modules, so a restated
+training / evaluation loop stays drop-in:
+
+  VDMConfig, VDMOutput                      ldm/model_vdm.py:33-92
+  EncDec.encode                             ldm/model_vdm.py:274-280
+  NoiseSchedule_polynomial_fixedend         ldm/model_mulan_epsilon.py:481-613
+  VDM.__call__                              ldm/model_mulan_epsilon.py:280-363,
+                                            ldm/model_mulan_velocity.py:188-268
+  Experiment_VDM.loss_fn                    ldm/experiment_vdm.py:47-78
+
+The encoder and the denoiser (U-Net) are NOT part of the path: they are
+constructor arguments (any torch callables).  The five Dense layers of the schedule head are
+cuBLAS GEMMs (torch.nn.Linear, float32 -- the reference runs with
+JAX_DEFAULT_MATMUL_PRECISION=float32).  Everything between those networks runs in
+libmulan_b200.so; there is no PyTorch fallback for it.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Callable, NamedTuple, Optional
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import ops
+from ._lib import (MULAN_GT_MEAN, MULAN_GT_PIXEL, MULAN_PARAM_EPS, MULAN_PARAM_VEL,
+                   MULAN_PARAM_VEL_FROM_EPS)
+
+
+@dataclass
+class VDMConfig:
+  """The fields of ldm/model_vdm.py:33-82 that the hot path reads (same names)."""
+  vocab_size: int = 256
+  antithetic_time_sampling: bool = True
+  gamma_type: str = 'poly_fixedend'
+  gamma_min: float = -13.3
+  gamma_max: float = 5.0
+  sm_n_timesteps: int = 0
+  latent_size: int = 50
+  latent_type: str = 'topk'
+  latent_k: int = 15
+  topk_noise_type: str = 'gamma'
+  reparam_type: str = 'true'
+  z_conditioning: bool = True
+  velocity_from_epsilon: bool = False
+  unet_type: str = 'vdm'
+  vdm_type: str = 'mulan_epsilon'     # ldm/experiment_vdm.py:32-38 selects the module by this
+
+
+class VDMOutput(NamedTuple):
+  """ldm/model_vdm.py:86-92."""
+  loss_recon: torch.Tensor  # [B]
+  loss_klz: torch.Tensor    # [B]
+  loss_diff: torch.Tensor   # [B]
+  var_0: torch.Tensor       # scalar
+  var_1: torch.Tensor       # scalar
+
+
+class EncDec:
+  """ldm/model_vdm.py:265-303.  Only `encode` is needed outside the kernels (it feeds the
+  encoder network); decode/logprob live inside mulan_fwd_pre."""
+
+  def __init__(self, config: VDMConfig):
+    self.config = config
+
+  def encode(self, x: torch.Tensor) -> torch.Tensor:
+    return 2 * ((x.to(torch.float32).round() + .5) / self.config.vocab_size) - 1
+
+
+class NoiseSchedule_polynomial_fixedend(nn.Module):
+  """ldm/model_mulan_epsilon.py:481-613: MLP 50 -> 3072 -> 3072 -> 3 x 3072 producing the
+  per-pixel polynomial coefficients.  Parameter names follow the Flax module
+  (dense_1, dense_2, dense_out_a/b/c); `dense_out_a` is zero-initialised (:495-500)."""
+
+  def __init__(self, config: VDMConfig, n_features: int = 32 * 32 * 3):
+    super().__init__()
+    self.config = config
+    n_out = 32 * 32 * 3
+    self.dense_1 = nn.Linear(config.latent_size, n_features)
+    self.dense_2 = nn.Linear(n_features, n_features)
+    self.dense_out_a = nn.Linear(n_features, n_out)
+    self.dense_out_b = nn.Linear(n_features, n_out)
+    self.dense_out_c = nn.Linear(n_features, n_out)
+    for lin in (self.dense_1, self.dense_2, self.dense_out_b, self.dense_out_c):
+      nn.init.normal_(lin.weight, std=1.0 / math.sqrt(lin.in_features))  # flax lecun_normal
+      nn.init.zeros_(lin.bias)
+    nn.init.zeros_(self.dense_out_a.weight)
+    nn.init.zeros_(self.dense_out_a.bias)
+
+  def load_flax(self, params: dict):
+    """params: {'dense_1/kernel': [in,out], 'dense_1/bias': [out], ...} (Flax layout)."""
+    with torch.no_grad():
+      for name in ('dense_1', 'dense_2', 'dense_out_a', 'dense_out_b', 'dense_out_c'):
+        lin = getattr(self, name)
+        lin.weight.copy_(torch.as_tensor(params[name + '/kernel']).t())
+        lin.bias.copy_(torch.as_tensor(params[name + '/bias']))
+
+  def _compute_coefficients(self, embedding):
+    """:531-538.  swish == SiLU; softplus == logaddexp(x, 0)."""
+    h = nn.functional.silu(self.dense_1(embedding))
+    h = nn.functional.silu(self.dense_2(h))
+    a = self.dense_out_a(h)
+    b = self.dense_out_b(h)
+    c = 1e-3 + nn.functional.softplus(self.dense_out_c(h))
+    return a, b, c
+
+
+def sample_t(t0: torch.Tensor, n_batch: int, config: VDMConfig) -> torch.Tensor:
+  """ldm/model_mulan_epsilon.py:287-297: antithetic t from the scalar draw t0
+  (jnp.arange with float arguments is np.arange in double, cast to float32)."""
+  ar = torch.from_numpy(np.arange(0., 1., step=1. / n_batch).astype(np.float32)).to(t0.device)
+  t = torch.remainder(t0.to(torch.float32) + ar, 1.)
+  T = config.sm_n_timesteps
+  if T > 0:
+    t = torch.ceil(t * T) / T
+  return t.contiguous()
+
+
+def gamma_draw(shape, k: int, generator: Optional[torch.Generator], device) -> torch.Tensor:
+  """jax.random.gamma(key, 1/k, shape) stand-in (ldm/model_mulan_epsilon.py:222-223)."""
+  conc = torch.full(shape, 1.0 / k, dtype=torch.float32, device=device)
+  return torch._standard_gamma(conc, generator=generator)
+
+
+class VDM(nn.Module):
+  """MuLAN model wrapper: the epsilon (`vdm_type='mulan_epsilon'`) and velocity
+  (`'mulan_velocity'`, optionally `velocity_from_epsilon`) parameterisations share this class.
+
+  encoder_model(orig_f[B,32,32,3], deterministic) -> logits [B, latent_size]
+  score_model(z_t[B,32,32,3], g_t ([B] or [B,32,32,3]), conditioning[B,latent], deterministic)
+      -> network output [B,32,32,3]
+  """
+
+  def __init__(self, config: VDMConfig, encoder_model: Callable, score_model: Callable,
+               gamma: Optional[nn.Module] = None):
+    super().__init__()
+    if config.gamma_type != 'poly_fixedend':
+      raise NotImplementedError('only gamma_type="poly_fixedend" (both shipped configs) is on '
+                                'the kernel path')
+    if config.latent_type != 'topk' or config.reparam_type != 'true':
+      raise NotImplementedError('only latent_type="topk", reparam_type="true" is on the kernel path')
+    if config.topk_noise_type != 'gamma':
+      raise NotImplementedError('only topk_noise_type="gamma" is on the kernel path')
+    self.config = config
+    self.encdec = EncDec(config)
+    self.encoder_model = encoder_model
+    self.score_model = score_model
+    self.gamma = gamma if gamma is not None else NoiseSchedule_polynomial_fixedend(config)
+    if config.vdm_type == 'mulan_epsilon':
+      param = MULAN_PARAM_EPS
+    elif config.vdm_type == 'mulan_velocity':
+      param = MULAN_PARAM_VEL_FROM_EPS if config.velocity_from_epsilon else MULAN_PARAM_VEL
+    else:
+      raise NotImplementedError(f'vdm_type={config.vdm_type!r} is not a MuLAN model')
+    gt = MULAN_GT_MEAN if config.unet_type == 'vdm' else MULAN_GT_PIXEL
+    self.desc = ops.Desc(dim=32 * 32 * 3, vocab=config.vocab_size, param=param, gt_mode=gt,
+                         n_timesteps=config.sm_n_timesteps, gamma_min=config.gamma_min,
+                         gamma_max=config.gamma_max)
+    self._generator = None
+
+  def make_draws(self, n_batch: int, device, generator: Optional[torch.Generator] = None):
+    """The four make_rng('sample') draws of __call__, in the reference's order."""
+    g = generator
+    L = self.config.latent_size
+    return dict(
+        t0=torch.rand((), generator=g, device=device),
+        G=gamma_draw((10, n_batch, L), self.config.latent_k, g, device),
+        eps_0=torch.randn((n_batch, 32, 32, 3), generator=g, device=device),
+        eps=torch.randn((n_batch, 32, 32, 3), generator=g, device=device))
+
+  def forward(self, images, labels=None, conditioning=None, step=0, deterministic: bool = True,
+              draws: Optional[dict] = None, generator: Optional[torch.Generator] = None):
+    cfg = self.config
+    x = images.reshape(-1, 32, 32, 3)
+    n_batch = x.shape[0]
+    dev = x.device
+    if draws is None:
+      draws = self.make_draws(n_batch, dev, generator)
+    D = 32 * 32 * 3
+    if cfg.antithetic_time_sampling:
+      t = sample_t(draws['t0'], n_batch, cfg)
+    else:
+      t = draws['t0'].to(torch.float32).reshape(n_batch).contiguous()
+
+    x_u8 = x.to(torch.uint8).reshape(n_batch, D).contiguous()
+    orig_f = self.encdec.encode(x)
+    logits = self.encoder_model(orig_f, deterministic)
+    embedding, kl_z = ops.aux_topk(logits, draws['G'].contiguous(), cfg.latent_k)
+    a, b, c = self.gamma._compute_coefficients(embedding)
+
+    tape = ops.ElboTape(self.desc)
+    z_t, g_net, loss_recon, klz_prior, var_sums, link = ops.mulan_pre(
+        tape, x_u8, a, b, c, t, draws['eps_0'].reshape(n_batch, D).contiguous(),
+        draws['eps'].reshape(n_batch, D).contiguous())
+    cond = embedding if cfg.z_conditioning else conditioning[:, None]
+    g_in = g_net if cfg.unet_type == 'vdm' else g_net.reshape(n_batch, 32, 32, 3)
+    net = self.score_model(z_t.reshape(n_batch, 32, 32, 3), g_in, cond, deterministic)
+    loss_diff = ops.mulan_post(tape, net.reshape(n_batch, D), link)
+    n = float(n_batch * D)
+    return VDMOutput(loss_recon=loss_recon, loss_klz=kl_z + klz_prior, loss_diff=loss_diff,
+                     var_0=var_sums[:, 0].sum() / n, var_1=var_sums[:, 1].sum() / n)
+
+
+def loss_fn(model: VDM, inputs: dict, step=0, is_train: bool = True, draws=None,
+            generator=None):
+  """Experiment_VDM.loss_fn (ldm/experiment_vdm.py:47-78): -> (bpd, metrics)."""
+  outputs = model(**inputs, step=step, deterministic=not is_train, draws=draws,
+                  generator=generator)
+  rescale_to_bpd = 1. / (np.prod(inputs['images'].shape[1:]) * np.log(2.))
+  bpd_latent = torch.mean(outputs.loss_klz) * rescale_to_bpd
+  bpd_recon = torch.mean(outputs.loss_recon) * rescale_to_bpd
+  bpd_diff = torch.mean(outputs.loss_diff) * rescale_to_bpd
+  bpd = bpd_recon + bpd_latent + bpd_diff
+  scalar_dict = {'bpd': bpd, 'bpd_latent': bpd_latent, 'bpd_recon': bpd_recon,
+                 'bpd_diff': bpd_diff, 'var0': outputs.var_0, 'var': outputs.var_1}
+  metrics = {'scalars': scalar_dict, 'images': {'inputs': inputs['images']}}
+  return bpd, metrics

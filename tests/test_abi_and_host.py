@@ -1,0 +1,260 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/mulan_b200.h
+declares (no compute calls without a GPU), argument validation works, the bindings refuse
+CPU tensors, and the host-side logic (t sampling, sharding, flat gradient bucket over gloo
+with world_size 2, dense-eval sharding) is right."""
+import ctypes as C
+import os
+import re
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, 'include', 'mulan_b200.h')
+
+
+@pytest.fixture(scope='module')
+def lib():
+  from mulan_b200.build import build_library
+  build_library()
+  from mulan_b200 import _lib
+  return _lib
+
+
+def header_symbols():
+  src = open(HEADER).read()
+  src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+  return sorted(set(re.findall(r'^\s*(?:const\s+char\s*\*|int|void)\s+(mulan_\w+)\s*\(', src,
+                               flags=re.M)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+  syms = header_symbols()
+  assert len(syms) >= 11, syms
+  handle = lib.load()
+  for s in syms:
+    assert hasattr(handle, s), f'libmulan_b200.so does not export {s}'
+  assert set(syms) == set(lib.SIGNATURES), (set(syms) ^ set(lib.SIGNATURES))
+  assert handle.mulan_abi_version() == 1
+
+
+def test_desc_layout_matches_header(lib):
+  # 6 x int32 + 2 x double, no padding surprises
+  assert C.sizeof(lib.MulanDesc) == 40
+  assert lib.MulanDesc.gamma_min.offset == 24 and lib.MulanDesc.gamma_max.offset == 32
+
+
+def test_argument_validation_without_gpu(lib):
+  h = lib.load()
+  assert h.mulan_fwd_pre(None, *([None] * 14)) == -1
+  assert b'desc is NULL' in h.mulan_last_error()
+  d = lib.make_desc(rows=2, dim=3070)
+  assert h.mulan_fwd_pre(C.byref(d), *([None] * 14)) == -2
+  d = lib.make_desc(rows=2, vocab=1)
+  assert h.mulan_fwd_post(C.byref(d), *([None] * 10)) == -1
+  d = lib.make_desc(rows=2, param=7)
+  assert h.mulan_bwd_post(C.byref(d), *([None] * 11)) == -1
+  d = lib.make_desc(rows=2, n_timesteps=1000)
+  assert h.mulan_bwd_pre(C.byref(d), *([None] * 14)) == -3
+  assert b'discrete-time' in h.mulan_last_error()
+  d = lib.make_desc(rows=2, gamma_min=5.0, gamma_max=-13.3)
+  assert h.mulan_fwd_pre(C.byref(d), *([None] * 14)) == -1
+  d = lib.make_desc(rows=2)
+  assert h.mulan_fwd_pre(C.byref(d), *([None] * 14)) == -1     # x is NULL
+  assert b'x is NULL' in h.mulan_last_error()
+  assert h.mulan_aux_topk_fwd(4, 65, 15, None, None, None, None, None) == -1
+  assert h.mulan_aux_topk_fwd(4, 50, 51, None, None, None, None, None) == -1
+  # rows == 0 is a no-op that needs no pointers and no device
+  d = lib.make_desc(rows=0)
+  assert h.mulan_fwd_pre(C.byref(d), *([None] * 14)) == 0
+  assert h.mulan_aux_topk_fwd(0, 50, 15, None, None, None, None, None) == 0
+
+
+def test_ops_refuse_cpu_tensors(lib):
+  from mulan_b200 import ops
+  z = torch.zeros(2, 3072)
+  with pytest.raises(TypeError, match='no CPU path'):
+    ops.fwd_pre(ops.Desc(), torch.zeros(2, 3072, dtype=torch.uint8), z, z, z, torch.zeros(2), z, z)
+  with pytest.raises(TypeError):
+    ops.aux_topk_fwd(torch.zeros(2, 50), None, 15)
+
+
+def test_product_path_does_not_import_oracle():
+  for fn in os.listdir(os.path.join(ROOT, 'mulan_b200')):
+    if fn.endswith('.py'):
+      src = open(os.path.join(ROOT, 'mulan_b200', fn)).read()
+      assert 'import oracle' not in src and 'from oracle' not in src, fn
+
+
+def test_sample_t_matches_oracle():
+  from mulan_b200.model import VDMConfig, sample_t
+  from oracle import mulan_oracle as O
+  for B in (1, 2, 8, 127, 128):
+    for t0 in (0.0, 0.123456, 0.999):
+      got = sample_t(torch.tensor(t0), B, VDMConfig())
+      want = O.sample_t(t0, B, O.OracleConfig())
+      assert torch.equal(got, want)
+  got = sample_t(torch.tensor(0.37), 8, VDMConfig(sm_n_timesteps=10))
+  assert torch.equal(got, O.sample_t(0.37, 8, O.OracleConfig(sm_n_timesteps=10)))
+
+
+def test_model_rejects_off_path_configs():
+  from mulan_b200.model import VDM, VDMConfig
+  f = lambda *a, **k: None
+  with pytest.raises(NotImplementedError):
+    VDM(VDMConfig(gamma_type='learnable_nnet'), f, f)
+  with pytest.raises(NotImplementedError):
+    VDM(VDMConfig(latent_type='gaussian'), f, f)
+  with pytest.raises(NotImplementedError):
+    VDM(VDMConfig(vdm_type='vdm'), f, f)
+
+
+def test_schedule_head_matches_oracle_coefficients():
+  """The cuBLAS-side MLP (torch Linear) restates _compute_coefficients; check on CPU."""
+  from mulan_b200.model import NoiseSchedule_polynomial_fixedend, VDMConfig
+  from oracle import mulan_oracle as O
+  sys.path.insert(0, os.path.join(ROOT, 'tests', 'golden'))
+  import golden_inputs as GI
+  W = GI.mlp_weights(5)
+  head = NoiseSchedule_polynomial_fixedend(VDMConfig())
+  assert torch.count_nonzero(head.dense_out_a.weight) == 0      # zero-init like the reference
+  head.load_flax(W)
+  emb = torch.randn(3, 50)
+  a, b, c = head._compute_coefficients(emb)
+  oa, ob, oc = O.compute_coefficients({k: torch.from_numpy(v) for k, v in W.items()}, emb)
+  for u, v in ((a, oa), (b, ob), (c, oc)):
+    assert (u - v).abs().max().item() < 2e-4 * v.abs().max().item()
+  assert torch.all(c > 1e-3)
+
+
+def test_shard_rows():
+  from mulan_b200.dist import shard_rows
+  for n in (0, 1, 7, 128, 1000):
+    for w in (1, 2, 3, 8):
+      got = []
+      for r in range(w):
+        s = shard_rows(n, r, w)
+        got += list(range(n))[s]
+      assert got == list(range(n))
+
+
+def _free_port():
+  s = socket.socket()
+  s.bind(('127.0.0.1', 0))
+  p = s.getsockname()[1]
+  s.close()
+  return p
+
+
+class _CpuStubVDM(torch.nn.Module):
+  """VDM-shaped CPU model built on the ORACLE (test-only), to exercise the multi-process
+  host logic without a GPU."""
+
+  def __init__(self):
+    super().__init__()
+    from mulan_b200.model import VDMConfig
+    self.config = VDMConfig()
+    self.w = torch.nn.Parameter(torch.tensor(0.5))
+    self.head = torch.nn.Linear(4, 3, bias=False)
+
+  def make_draws(self, n, device, gen):
+    return dict(t0=torch.rand((), generator=gen), G=torch.zeros(10, n, 50),
+                eps_0=torch.randn((n, 32, 32, 3), generator=gen),
+                eps=torch.randn((n, 32, 32, 3), generator=gen))
+
+  def forward(self, images, labels=None, conditioning=None, step=0, deterministic=True,
+              draws=None, generator=None):
+    from mulan_b200.model import VDMOutput, sample_t
+    from oracle import mulan_oracle as O
+    B = images.shape[0]
+    if draws is None:
+      draws = self.make_draws(B, images.device, generator)
+    t = (sample_t(draws['t0'], B, self.config) if self.config.antithetic_time_sampling
+         else draws['t0'].reshape(B))
+    pix = images.reshape(B, -1).float() / 255.0
+    a = pix * self.head.weight[0, 0] + 0.3
+    b = pix * self.head.weight[1, 1] - 0.2
+    c = 1e-3 + torch.nn.functional.softplus(pix * self.head.weight[2, 2])
+    out = O.elbo_terms(images.reshape(B, -1), a, b, c, t, draws['eps_0'].reshape(B, -1),
+                       draws['eps'].reshape(B, -1), lambda z, g: self.w * z, O.MODE_EPS,
+                       O.OracleConfig())
+    return VDMOutput(*out)
+
+
+def _worker(rank, world, port, q):
+  os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank),
+                    WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+  torch.set_num_threads(2)
+  from mulan_b200 import dist as md
+  r, w, _ = md.init_distributed('gloo')
+  assert (r, w) == (rank, world)
+  torch.manual_seed(0)
+  model = _CpuStubVDM()
+  rng = np.random.default_rng(0)
+  images = torch.from_numpy(rng.integers(0, 256, (8, 32, 32, 3), dtype=np.uint8))
+  # --- train step: each rank sees its shard; gradients and scalars are pmean'ed
+  bucket = md.FlatGradBucket(model.parameters(), extra=6)
+  opt = torch.optim.SGD(model.parameters(), lr=0.0)
+  sl = md.shard_rows(8, rank, world)
+  gen = torch.Generator().manual_seed(100 + rank)
+  draws = model.make_draws(sl.stop - sl.start, 'cpu', gen)
+  scalars = md.train_step(model, opt, bucket, {'images': images[sl]}, 0, draws=draws)
+  # --- dense eval, sharded by image
+  mean_bpd, mine = md.eval_bpd_dense_sampling(model, images[:4], n_timesteps=4,
+                                              images_per_launch=2, seed=3)
+  q.put((rank, bucket.flat.numpy().copy(), {k: float(v) for k, v in scalars.items()}, mean_bpd,
+         mine.numpy().copy(), {k: v.numpy().copy() for k, v in draws.items()}))
+  dist.barrier()
+  dist.destroy_process_group()
+
+
+def test_world_size_2_gloo():
+  """N>1 host path on CPU: flat-bucket gradient pmean + scalar pmean (ldm/experiment.py:341,
+  347) and the example-sharded dense evaluation reduction."""
+  from mulan_b200 import dist as md
+  from mulan_b200.model import loss_fn
+  ctx = mp.get_context('spawn')
+  q = ctx.Queue()
+  port = _free_port()
+  procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+  for p in procs:
+    p.start()
+  res = sorted([q.get(timeout=300) for _ in procs], key=lambda r: r[0])
+  for p in procs:
+    p.join(timeout=60)
+    assert p.exitcode == 0
+  (r0, flat0, sc0, bpd0, mine0, d0), (r1, flat1, sc1, bpd1, mine1, d1) = res
+  flat0, flat1 = torch.from_numpy(flat0), torch.from_numpy(flat1)
+  d0 = {k: torch.from_numpy(v) for k, v in d0.items()}
+  d1 = {k: torch.from_numpy(v) for k, v in d1.items()}
+  assert torch.equal(flat0, flat1)                      # all-reduced bucket is replicated
+  assert sc0 == sc1 and bpd0 == bpd1
+  # single-process reference of the same computation
+  torch.manual_seed(0)
+  model = _CpuStubVDM()
+  rng = np.random.default_rng(0)
+  images = torch.from_numpy(rng.integers(0, 256, (8, 32, 32, 3), dtype=np.uint8))
+  grads, bpds = [], []
+  for rank, draws in ((0, d0), (1, d1)):
+    sl = md.shard_rows(8, rank, 2)
+    model.zero_grad()
+    for p_ in model.parameters():
+      p_.grad = None
+    bpd, _ = loss_fn(model, {'images': images[sl]}, draws=draws)
+    bpd.backward()
+    grads.append(torch.cat([p_.grad.reshape(-1) for p_ in model.parameters()]))
+    bpds.append(bpd.item())
+  want = (grads[0] + grads[1]) / 2
+  n = want.numel()
+  assert torch.allclose(flat0[:n], want, rtol=1e-5, atol=1e-9)
+  assert abs(sc0['bpd'] - (bpds[0] + bpds[1]) / 2) < 1e-5 * abs(sc0['bpd'])
+  # dense eval: ranks took images[0::2], images[1::2]; the mean covers all four
+  all_bpd, _ = md.eval_bpd_dense_sampling(model, images[:4], n_timesteps=4, images_per_launch=2,
+                                          seed=3)
+  assert abs(bpd0 - all_bpd) < 1e-6 * abs(all_bpd)
+  assert mine0.size == 2 and mine1.size == 2

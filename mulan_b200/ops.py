@@ -161,6 +161,53 @@ def bpd_reduce(desc: Desc, loss_recon, loss_klz_prior, kl_z, loss_diff, var_sums
   return (sc, tot) if want_klz_total else sc
 
 
+class ElboWorkspace:
+  """Preallocated outputs of the whole path for a fixed shard size: every launch writes into
+  the same buffers, so a step makes no allocation and can be captured in a CUDA graph
+  (the reference's `pmap(scan(train_step))` keeps the 1000 sub-steps on the device the same
+  way, ldm/experiment.py:89-91)."""
+
+  def __init__(self, desc: Desc, rows: int, device, save_w: Optional[bool] = None):
+    self.desc, self.rows = desc, rows
+    self.save_w = (desc.param == MULAN_PARAM_EPS) if save_w is None else save_w
+    D = desc.dim
+    f = lambda *s: torch.empty(s, dtype=torch.float32, device=device)
+    self.z_t = f(rows, D)
+    self.g_net = f(rows) if desc.gt_mode == MULAN_GT_MEAN else f(rows, D)
+    self.w = f(rows, D) if self.save_w else None
+    self.loss_recon, self.loss_klz_prior, self.loss_diff = f(rows), f(rows), f(rows)
+    self.var_sums, self.scalars, self.loss_klz = f(rows, 2), f(6), f(rows)
+    self.n_bar, self.a_bar, self.b_bar, self.c_bar = f(rows, D), f(rows, D), f(rows, D), f(rows, D)
+    self._d = desc.c(rows)
+    self._lib = _lib.load()
+
+  def fwd_pre(self, x, a, b, c, t, eps0, eps):
+    _lib.check(self._lib.mulan_fwd_pre(
+        C.byref(self._d), _p(x), _p(a), _p(b), _p(c), _p(t), _p(eps0), _p(eps), _p(self.z_t),
+        _p(self.g_net), _p(self.w), _p(self.loss_recon), _p(self.loss_klz_prior),
+        _p(self.var_sums), _stream()))
+
+  def fwd_post(self, x, a, b, c, t, eps, net):
+    _lib.check(self._lib.mulan_fwd_post(
+        C.byref(self._d), _p(x), _p(a), _p(b), _p(c), _p(t), _p(eps), _p(net), _p(self.w),
+        _p(self.loss_diff), _stream()))
+
+  def bpd_reduce(self, kl_z=None):
+    _lib.check(self._lib.mulan_bpd_reduce(
+        C.byref(self._d), _p(self.loss_recon), _p(self.loss_klz_prior), _p(kl_z),
+        _p(self.loss_diff), _p(self.var_sums), _p(self.scalars), _p(self.loss_klz), _stream()))
+
+  def bwd_post(self, x, a, b, c, t, eps, net, gL):
+    _lib.check(self._lib.mulan_bwd_post(
+        C.byref(self._d), _p(x), _p(a), _p(b), _p(c), _p(t), _p(eps), _p(net), _p(self.w), _p(gL),
+        _p(self.n_bar), _stream()))
+
+  def bwd_pre(self, x, a, b, c, t, eps, net, z_bar, g_bar, gL):
+    _lib.check(self._lib.mulan_bwd_pre(
+        C.byref(self._d), _p(x), _p(a), _p(b), _p(c), _p(t), _p(eps), _p(net), _p(z_bar),
+        _p(g_bar), _p(gL), _p(self.a_bar), _p(self.b_bar), _p(self.c_bar), _stream()))
+
+
 # ------------------------------------------------------------------------------------
 # Autograd pair
 # ------------------------------------------------------------------------------------

@@ -50,6 +50,11 @@ def parse_args():
   ap.add_argument('--param', choices=list(PARAMS), default='eps')
   ap.add_argument('--ref-rows', type=int, default=GROUP,
                   help='rows of the bounded CPU sample (cpu_baseline / --impl reference)')
+  ap.add_argument('--workload', choices=['train', 'dense_vlb'], default='train',
+                  help='train: ELBO loss+grad (configs[1..3]); dense_vlb: forward-only VLB '
+                       'evaluation, 16 images x 128 timesteps per launch (configs[4])')
+  ap.add_argument('--launch-rows', type=int, default=2048,
+                  help='dense_vlb: rows per launch (16 images x 128 antithetic timesteps)')
   ap.add_argument('--no-e2e', action='store_true')
   ap.add_argument('--no-cpu-baseline', action='store_true')
   return ap.parse_args()
@@ -58,6 +63,10 @@ def parse_args():
 def workload_name(args):
   model = {'eps': 'mulan_epsilon', 'vel': 'mulan_velocity',
            'vel_from_eps': 'mulan_velocity(velocity_from_epsilon)'}[args.param]
+  if args.workload == 'dense_vlb':
+    return (f'eval_bpd dense VLB forward ({model}: recon + prior + diffusion terms), '
+            f'{args.launch_rows // GROUP} images x {GROUP} timesteps per launch, '
+            f'{args.rows} rows/step/GPU, synthetic uint8 32x32x3, denoiser output supplied')
   return (f'cifar10-conditioned {model} ELBO loss+grad hot path, per-GPU batch {GROUP} x '
           f'{args.rows // GROUP} stacked batches = {args.rows} rows/step/GPU, synthetic uint8 '
           f'32x32x3, denoiser output supplied')
@@ -206,19 +215,36 @@ def run_native(args):
   param = PARAMS[args.param]
   desc = ops.Desc(param=param)
   inp = make_inputs(rows, dev, seed=1234 + rank)
-  gL = torch.full((rows,), 1.0 / (rows * D * math.log(2.0)), device=dev)
-  ws = ops.ElboWorkspace(desc, rows, dev)
-  i = inp
-  kernels = {   # name -> launch closure (all write into the preallocated workspace)
-      'fwd_pre': lambda: ws.fwd_pre(i['x'], i['a'], i['b'], i['c'], i['t'], i['eps0'], i['eps']),
-      'fwd_post': lambda: ws.fwd_post(i['x'], i['a'], i['b'], i['c'], i['t'], i['eps'], i['net']),
-      'bpd_reduce': lambda: ws.bpd_reduce(None),
-      'bwd_post': lambda: ws.bwd_post(i['x'], i['a'], i['b'], i['c'], i['t'], i['eps'], i['net'],
-                                      gL),
-      'bwd_pre': lambda: ws.bwd_pre(i['x'], i['a'], i['b'], i['c'], i['t'], i['eps'], i['net'],
-                                    i['z_bar'], i['g_bar'], gL),
+  train = args.workload == 'train'
+  lrows = rows if train else min(args.launch_rows, rows)   # rows per launch
+  assert rows % lrows == 0
+  chunks = []
+  for s0 in range(0, rows, lrows):
+    ci = {k: v[s0:s0 + lrows] for k, v in inp.items()}
+    chunks.append((ops.ElboWorkspace(desc, lrows, dev, save_w=(train and args.param == 'eps')),
+                   ci, torch.full((lrows,), 1.0 / (lrows * D * math.log(2.0)), device=dev)))
+  ws = chunks[0][0]
+
+  def each(fn):
+    def run():
+      for w_, i, g in chunks:
+        fn(w_, i, g)
+    return run
+  kernels = {   # name -> launch closure (all write into the preallocated workspaces)
+      'fwd_pre': each(lambda w_, i, g: w_.fwd_pre(i['x'], i['a'], i['b'], i['c'], i['t'],
+                                                  i['eps0'], i['eps'])),
+      'fwd_post': each(lambda w_, i, g: w_.fwd_post(i['x'], i['a'], i['b'], i['c'], i['t'],
+                                                    i['eps'], i['net'])),
+      'bpd_reduce': each(lambda w_, i, g: w_.bpd_reduce(None)),
   }
+  if train:
+    kernels['bwd_post'] = each(lambda w_, i, g: w_.bwd_post(i['x'], i['a'], i['b'], i['c'], i['t'],
+                                                            i['eps'], i['net'], g))
+    kernels['bwd_pre'] = each(lambda w_, i, g: w_.bwd_pre(i['x'], i['a'], i['b'], i['c'], i['t'],
+                                                          i['eps'], i['net'], i['z_bar'],
+                                                          i['g_bar'], g))
   names = list(kernels)
+  launches_per_step = len(names) * len(chunks)
 
   def step():
     for n in names:
@@ -271,7 +297,7 @@ def run_native(args):
   if world > 1:
     dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
   elapsed_ms = tmax.item()
-  timed_launches = len(names) * K
+  timed_launches = launches_per_step * K
   bpd = ws.scalars[0].item()
 
   # ---- per-kernel durations, live, CUDA events on the launching stream: each kernel K times
@@ -292,7 +318,7 @@ def run_native(args):
 
   # ---- e2e: host buffers through the C ABI (mulan_elbo_host), copies inside the timing ----
   e2e = None
-  if not args.no_e2e:
+  if not args.no_e2e and train:
     pin = lambda v: v.cpu().pin_memory()
     h = {k: pin(inp[k]) for k in ('x', 'a', 'b', 'c', 't', 'eps0', 'eps', 'net')}
     out = host.HostOutputs(rows, D, want_grad=True, pinned=True)
@@ -318,7 +344,7 @@ def run_native(args):
 
   # ---- latency of configs[1]'s literal size (one batch of 128 rows, CUDA graph) ----
   lat = None
-  if rank == 0:
+  if rank == 0 and train:
     sm = {k: (v[:GROUP].contiguous()) for k, v in inp.items()}
     gLs = torch.full((GROUP,), 1.0 / (GROUP * D * math.log(2.0)), device=dev)
     wss = ops.ElboWorkspace(desc, GROUP, dev)
@@ -360,7 +386,12 @@ def run_native(args):
 
   nsub = rows * D
   dom = max((n for n in names if n != 'bpd_reduce'), key=lambda n: kern_ms[n])
-  ab = ALGO_BYTES[args.param]
+  ab = dict(ALGO_BYTES[args.param])
+  if not train:
+    ab['fwd_pre'] = 25        # no saved w
+    if args.param == 'eps':
+      ab['fwd_post'] = 20     # w recomputed from a, b, c
+  ab = {k: v for k, v in ab.items() if k in names}
   peaks, peak_src = load_peak()
   kinfo = {}
   for n in names:
@@ -371,17 +402,19 @@ def run_native(args):
     kinfo[n] = {'ms': kern_ms[n], 'algo_bytes_per_subpixel': ab[n], 'gbs': gbs,
                 'frac_of_measured': gbs / peaks, 'frac_of_8TBs': gbs / 8000.0}
   total_algo = sum(ab.values()) * nsub
-  traffic = load_traffic(dom, rows)
+  traffic = load_traffic(dom, rows) if train else None
   ms_step = elapsed_ms / K
   line = {
-      'metric': 'mulan_elbo_train_samples_per_s', 'value': world * rows * K / (elapsed_ms * 1e-3),
+      'metric': 'mulan_elbo_train_samples_per_s' if train else 'mulan_dense_vlb_rows_per_s',
+      'value': world * rows * K / (elapsed_ms * 1e-3),
       'unit': 'samples/s', 'n_gpus': world, 'steps': K, 'warmup': max(W, 3),
       'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak',
       'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
       'config': {'workload': workload_name(args), 'rows_per_gpu': rows, 'dim': D,
                  'param': args.param, 'l2': 'inputs larger than L2 (%.2f GB of HBM traffic per '
                  'step)' % (total_algo / 1e9), 'parallelism': f'dp{world} (rows sharded)',
-                 'timed_loop': 'CUDA-graph replay of one step (5 kernels)'},
+                 'timed_loop': 'CUDA-graph replay of one step (%d launches)' % launches_per_step,
+                 'rows_per_launch': lrows},
       'roofline': {'bound': 'hbm', 'kernel': dom, 'achieved': kinfo[dom]['gbs'],
                    'peak': peaks, 'peak_source': peak_src, 'unit': 'GB/s',
                    'frac': kinfo[dom]['gbs'] / peaks, 'traffic': traffic,
@@ -394,7 +427,7 @@ def run_native(args):
       'kernels': kinfo, 'gpu_launches': timed_launches, 'clocks': clocks, 'e2e': e2e,
       'latency_b128': lat, 'cpu_baseline': cpu, 'bpd': bpd,
   }
-  print(json.dumps(line))
+  emit(line)
   if world > 1:
     dist.destroy_process_group()
 
@@ -474,11 +507,29 @@ def run_reference(args):
               'd2h_bytes_per_step': 0},
       'gpu_launches': 0,
   }
-  print(json.dumps(line))
+  emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+  """The ONE JSON line, on the real stdout (libraries such as NCCL print banners to fd 1;
+  main() points fd 1 at stderr for the duration of the run)."""
+  data = (json.dumps(line) + '\n').encode()
+  if _REAL_STDOUT is not None:
+    os.write(_REAL_STDOUT, data)
+  else:
+    sys.stdout.write(data.decode())
+    sys.stdout.flush()
 
 
 def main():
+  global _REAL_STDOUT
   args = parse_args()
+  sys.stdout.flush()
+  _REAL_STDOUT = os.dup(1)
+  os.dup2(2, 1)
   if args.impl == 'reference':
     run_reference(args)
   else:

@@ -116,6 +116,18 @@ struct BwdPreParams {
   VocabInfo vi;
 };
 
+// Number of CTAs of `kernel` (kThreads threads, static shared memory only) that are resident
+// on the current device at once: the grid size of the persistent kernels.
+inline int resident_ctas(const void* kernel) {
+  int dev = 0, sms = 148, per_sm = 1;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0) != cudaSuccess ||
+      per_sm < 1)
+    per_sm = 1;
+  return sms * per_sm;
+}
+
 cudaError_t launch_fwd_pre(const FwdPreParams& p, cudaStream_t s);
 cudaError_t launch_fwd_post(const PostParams& p, cudaStream_t s);
 cudaError_t launch_bwd_post(const PostParams& p, cudaStream_t s);

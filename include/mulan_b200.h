@@ -86,8 +86,9 @@ int mulan_abi_version(void);
  *   in : x[B,D] u8; a,b,c[B,D] polynomial coefficients (c already 1e-3+softplus);
  *        t[B]; eps0[B,D]; eps[B,D]
  *   out: z_t[B,D]; g_net ([B] for GT_MEAN, [B,D] for GT_PIXEL);
- *        w_save[B,D] or NULL -- the loss weight d-gamma/dt (T==0) or T*expm1(g_t-g_s)
- *        (T>0, epsilon model only), reusable by mulan_fwd_post / mulan_bwd_post;
+ *        w_save[B,D] or NULL -- the loss weight d-gamma/dt (T==0) or expm1(g_t-g_s) with
+ *        s = t - 1/T (T>0: epsilon model only, w_save REQUIRED, t already discretised by the
+ *        caller as ceil(t*T)/T), consumed by mulan_fwd_post / mulan_bwd_post;
  *        loss_recon[B]; loss_klz_prior[B]; var_sums[B,2] = per-row sum of sigmoid(g_0),
  *        sigmoid(g_1).
  */

@@ -40,10 +40,11 @@ int check_desc(const mulan_desc* d, const char* fn) {
     return fail(MULAN_ERR_INVALID_ARG, "%s: n_timesteps=%d < 0", fn, d->n_timesteps);
   if (!(d->gamma_max > d->gamma_min))
     return fail(MULAN_ERR_INVALID_ARG, "%s: gamma_max must exceed gamma_min", fn);
-  if (d->n_timesteps > 0)
+  if (d->n_timesteps > 0 && d->param != MULAN_PARAM_EPS)
     return fail(MULAN_ERR_UNSUPPORTED,
-                "%s: discrete-time loss (sm_n_timesteps=%d > 0) is not implemented; both shipped "
-                "configs use 0 and the velocity model asserts it", fn, d->n_timesteps);
+                "%s: discrete time (sm_n_timesteps=%d > 0) exists only for the epsilon model; the "
+                "reference's velocity model asserts T == 0 (ldm/model_mulan_velocity.py:255)", fn,
+                d->n_timesteps);
   return 0;
 }
 
@@ -112,7 +113,17 @@ int mulan_fwd_pre(const mulan_desc* d, const uint8_t* x, const float* a, const f
   p.k = mulan::make_end_consts(p.gmin, p.delta);
   p.vi = mulan::make_vocab(d->vocab);
   p.rc = mulan::make_recon_fast(p.k, p.vi);
+  if (d->n_timesteps > 0 && w_save == nullptr)
+    return fail(MULAN_ERR_INVALID_ARG, "%s: sm_n_timesteps > 0 needs w_save (the discrete-time "
+                "loss weight is produced here and consumed by the post kernels)", fn);
   cudaError_t e = mulan::launch_fwd_pre(p, (cudaStream_t)stream);
+  if (e == cudaSuccess && d->n_timesteps > 0) {
+    mulan::DiscreteWParams q;
+    q.a = a; q.b = b; q.c = c; q.t = t; q.w = w_save;
+    q.rows = d->rows; q.dim4 = d->dim / 4; q.gmin = p.gmin; q.delta = p.delta;
+    q.inv_T = (float)(1.0 / (double)d->n_timesteps);
+    e = mulan::launch_discrete_w(q, (cudaStream_t)stream);
+  }
   return e == cudaSuccess ? 0 : cuda_fail(fn, e);
 }
 
@@ -128,7 +139,11 @@ static int fill_post(const char* fn, const mulan_desc* d, const uint8_t* x, cons
   p->gL = nullptr; p->loss_diff = nullptr; p->n_bar = nullptr;
   p->rows = d->rows; p->dim4 = d->dim / 4; p->param = d->param;
   p->gmin = f32_gmin(d); p->delta = f32_delta(d);
-  p->scale = 0.5f;
+  // .5 * sum(...)  |  .5 * T * sum(...)   (ldm/model_mulan_epsilon.py:345, :353)
+  p->scale = d->n_timesteps > 0 ? (float)(0.5 * (double)d->n_timesteps) : 0.5f;
+  if (d->n_timesteps > 0 && w_save == nullptr)
+    return fail(MULAN_ERR_INVALID_ARG, "%s: sm_n_timesteps > 0 needs the w_save written by "
+                "mulan_fwd_pre", fn);
   p->vi = mulan::make_vocab(d->vocab);
   return 0;
 }
@@ -181,6 +196,8 @@ int mulan_bwd_pre(const mulan_desc* d, const uint8_t* x, const float* a, const f
   p.a_bar = a_bar; p.b_bar = b_bar; p.c_bar = c_bar;
   p.rows = d->rows; p.dim4 = d->dim / 4; p.param = d->param; p.gt_mode = d->gt_mode;
   p.gmin = f32_gmin(d); p.delta = f32_delta(d);
+  p.T = d->n_timesteps;
+  p.inv_T = d->n_timesteps > 0 ? (float)(1.0 / (double)d->n_timesteps) : 0.f;
   p.vi = mulan::make_vocab(d->vocab);
   cudaError_t e = mulan::launch_bwd_pre(p, (cudaStream_t)stream);
   return e == cudaSuccess ? 0 : cuda_fail(fn, e);

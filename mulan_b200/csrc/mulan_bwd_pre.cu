@@ -15,10 +15,11 @@
 
 namespace mulan {
 
-template <int PARAM, int GT>
+template <int PARAM, int GT, bool DISC>
 __global__ void __launch_bounds__(kThreads)
 bwd_pre_kernel(const BwdPreParams p) {
   __shared__ RowT s_rt;
+  __shared__ RowD s_rd;
   __shared__ float s_gL, s_gbar;
   const int row = blockIdx.x, tid = threadIdx.x;
   const bool has_gL = p.gL != nullptr;
@@ -26,6 +27,7 @@ bwd_pre_kernel(const BwdPreParams p) {
   const bool has_gb = p.g_bar != nullptr;
   if (tid == 0) {
     s_rt = make_row_t(__ldg(p.t + row));
+    if (DISC) s_rd = make_row_d(__ldg(p.t + row), __ldg(p.t + row) - p.inv_T);   // s = t - 1/T
     s_gL = has_gL ? __ldg(p.gL + row) : 0.f;
     // jnp.mean backward: cotangent / D broadcast to every sub-pixel
     s_gbar = (GT == MULAN_GT_MEAN && has_gb)
@@ -33,6 +35,8 @@ bwd_pre_kernel(const BwdPreParams p) {
   }
   __syncthreads();
   const RowT rt = s_rt;
+  RowD rd;
+  if (DISC) rd = s_rd;
   const float gL = s_gL, gbar_row = s_gbar;
   const VocabInfo vi = p.vi;
   const size_t base4 = (size_t)row * p.dim4;
@@ -69,7 +73,16 @@ bwd_pre_kernel(const BwdPreParams p) {
       float gbar = (GT == MULAN_GT_MEAN) ? gbar_row : get(GB, j);
       float zb = get(ZB, j);
       float wbar = 0.f;
-      if (PARAM == MULAN_PARAM_EPS) {
+      float gD = 0.f, du = 0.f;         // DISC: cotangent of gamma(t) - gamma(s), (P(t)-P(s))/S
+      if (PARAM == MULAN_PARAM_EPS && DISC) {
+        // loss = .5 T sum expm1(dg) r^2, dg = gamma(t) - gamma(s) = Delta (P(t) - P(s)) / S
+        const float r = e - n;
+        const float dP = fmaf(po.a2, rd.d5_5, fmaf(po.b2c, rd.d3_3, fmaf(po.ab, rd.d4_2,
+                         fmaf(po.bc, rd.d2, po.c2 * rd.d1))));
+        du = dP * rS;
+        const float dexp = expf(p.delta * du);
+        gD = p.delta * rS * (0.5f * (float)p.T * gL * (r * r) * dexp);
+      } else if (PARAM == MULAN_PARAM_EPS) {
         const float r = e - n;
         wbar = 0.5f * gL * (r * r);
       } else {
@@ -106,9 +119,20 @@ bwd_pre_kernel(const BwdPreParams p) {
       const float Pc = fmaf(a + a, t3_3, fmaf(b, t2, (c + c) * t));
       const float Sc = fmaf(a + a, kThird, b + (c + c));
       const float Qa = two_q * t2, Qb = two_q * t, Qc = two_q;
-      put(AB, j, fmaf(gG, fmaf(-u, Sa, Pa), gW * fmaf(-y, Sa, Qa)));
-      put(BB, j, fmaf(gG, fmaf(-u, Sb, Pb), gW * fmaf(-y, Sb, Qb)));
-      put(CB, j, fmaf(gG, fmaf(-u, Sc, Pc), gW * fmaf(-y, Sc, Qc)));
+      float ab_ = fmaf(gG, fmaf(-u, Sa, Pa), gW * fmaf(-y, Sa, Qa));
+      float bb_ = fmaf(gG, fmaf(-u, Sb, Pb), gW * fmaf(-y, Sb, Qb));
+      float cb_ = fmaf(gG, fmaf(-u, Sc, Pc), gW * fmaf(-y, Sc, Qc));
+      if (DISC) {                               // path through gamma(t) - gamma(s)
+        const float dPa = fmaf(a + a, rd.d5_5, fmaf(c + c, rd.d3_3, b * rd.d4_2));
+        const float dPb = fmaf(b + b, rd.d3_3, fmaf(a, rd.d4_2, c * rd.d2));
+        const float dPc = fmaf(a + a, rd.d3_3, fmaf(b, rd.d2, (c + c) * rd.d1));
+        ab_ = fmaf(gD, fmaf(-du, Sa, dPa), ab_);
+        bb_ = fmaf(gD, fmaf(-du, Sb, dPb), bb_);
+        cb_ = fmaf(gD, fmaf(-du, Sc, dPc), cb_);
+      }
+      put(AB, j, ab_);
+      put(BB, j, bb_);
+      put(CB, j, cb_);
     }
     st4(p.a_bar, g4, AB);
     st4(p.b_bar, g4, BB);
@@ -119,8 +143,54 @@ bwd_pre_kernel(const BwdPreParams p) {
 template <int PARAM>
 static cudaError_t launch_gt(const BwdPreParams& p, cudaStream_t s) {
   dim3 grid(p.rows), block(kThreads);
-  if (p.gt_mode == MULAN_GT_MEAN) bwd_pre_kernel<PARAM, MULAN_GT_MEAN><<<grid, block, 0, s>>>(p);
-  else                            bwd_pre_kernel<PARAM, MULAN_GT_PIXEL><<<grid, block, 0, s>>>(p);
+  if (PARAM == MULAN_PARAM_EPS && p.T > 0) {
+    if (p.gt_mode == MULAN_GT_MEAN)
+      bwd_pre_kernel<MULAN_PARAM_EPS, MULAN_GT_MEAN, true><<<grid, block, 0, s>>>(p);
+    else
+      bwd_pre_kernel<MULAN_PARAM_EPS, MULAN_GT_PIXEL, true><<<grid, block, 0, s>>>(p);
+  } else if (p.gt_mode == MULAN_GT_MEAN) {
+    bwd_pre_kernel<PARAM, MULAN_GT_MEAN, false><<<grid, block, 0, s>>>(p);
+  } else {
+    bwd_pre_kernel<PARAM, MULAN_GT_PIXEL, false><<<grid, block, 0, s>>>(p);
+  }
+  return cudaGetLastError();
+}
+
+// w = expm1(gamma(t) - gamma(t - 1/T)): the discrete-time weight of the epsilon loss
+// (ldm/model_mulan_epsilon.py:350-354), written over the d-gamma/dt that fwd_pre saved.
+__global__ void __launch_bounds__(kThreads)
+discrete_w_kernel(const DiscreteWParams p) {
+  __shared__ RowT s_rt;
+  __shared__ RowD s_rd;
+  const int row = blockIdx.x, tid = threadIdx.x;
+  if (tid == 0) {
+    const float t = __ldg(p.t + row);
+    s_rt = make_row_t(t);
+    s_rd = make_row_d(t, t - p.inv_T);
+  }
+  __syncthreads();
+  const RowT rt = s_rt;
+  const RowD rd = s_rd;
+  const size_t base4 = (size_t)row * p.dim4;
+  for (int i4 = tid; i4 < p.dim4; i4 += kThreads) {
+    const size_t g4 = base4 + i4;
+    const float4 A = ld4(p.a, g4), Bv = ld4(p.b, g4), C = ld4(p.c, g4);
+    float4 Wv;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const Poly po = poly_eval(get(A, j), get(Bv, j), get(C, j), rt);
+      const float rS = rcp_scale(po.S);
+      const float dP = fmaf(po.a2, rd.d5_5, fmaf(po.b2c, rd.d3_3, fmaf(po.ab, rd.d4_2,
+                       fmaf(po.bc, rd.d2, po.c2 * rd.d1))));
+      put(Wv, j, expm1f((p.delta * dP) * rS));
+    }
+    st4(p.w, g4, Wv);
+  }
+}
+
+cudaError_t launch_discrete_w(const DiscreteWParams& p, cudaStream_t s) {
+  if (p.rows == 0) return cudaSuccess;
+  discrete_w_kernel<<<p.rows, kThreads, 0, s>>>(p);
   return cudaGetLastError();
 }
 

@@ -135,6 +135,24 @@ __device__ __forceinline__ RowT make_row_t(float t) {
   return r;
 }
 
+// Discrete time (sm_n_timesteps = T > 0): differences of the time powers between t and
+// s = t - 1/T in factored form, so that gamma(t) - gamma(s) = Delta (P(t) - P(s)) / S keeps full
+// float32 precision (the reference subtracts two rounded gammas and loses ~T ulps; being
+// closer to exact arithmetic than the reference's own float32 is within every tolerance).
+struct RowD {
+  float d1, d2, d3_3, d4_2, d5_5;   // (t^n - s^n)/{1,1,3,2,5}
+};
+__device__ __forceinline__ RowD make_row_d(float t, float s) {
+  RowD r;
+  const float d = t - s, p = t + s, t2 = t * t, s2 = s * s, ts = t * s;
+  r.d1 = d;
+  r.d2 = d * p;
+  r.d3_3 = d * (t2 + ts + s2) * kThird;
+  r.d4_2 = d * p * (t2 + s2) * 0.5f;
+  r.d5_5 = d * (t2 * t2 + t2 * ts + t2 * s2 + ts * s2 + s2 * s2) * kFifth;
+  return r;
+}
+
 // NoiseSchedule_polynomial_fixedend._eval_polynomial (ldm/model_mulan_epsilon.py:514-529)
 // for one sub-pixel: P(t) = int_0^t (a s^2 + b s + c)^2 ds, S = P(1), q = a t^2 + b t + c.
 // FMA form (see file header): differs from the reference's rounding by O(1 ulp) per term,

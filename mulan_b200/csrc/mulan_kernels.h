@@ -113,7 +113,17 @@ struct BwdPreParams {
   float *a_bar, *b_bar, *c_bar;
   int rows, dim4, param, gt_mode;
   float gmin, delta;
+  int T;              // sm_n_timesteps (0 = continuous)
+  float inv_T;        // f32(1/T): s = t - 1/T  (ldm/model_mulan_epsilon.py:350)
   VocabInfo vi;
+};
+
+// Discrete-time loss weight expm1(gamma(t) - gamma(t - 1/T)) (ldm/model_mulan_epsilon.py:350-354)
+struct DiscreteWParams {
+  const float *a, *b, *c, *t;
+  float* w;
+  int rows, dim4;
+  float gmin, delta, inv_T;
 };
 
 // Number of CTAs of `kernel` (kThreads threads, static shared memory only) that are resident
@@ -132,6 +142,7 @@ cudaError_t launch_fwd_pre(const FwdPreParams& p, cudaStream_t s);
 cudaError_t launch_fwd_post(const PostParams& p, cudaStream_t s);
 cudaError_t launch_bwd_post(const PostParams& p, cudaStream_t s);
 cudaError_t launch_bwd_pre(const BwdPreParams& p, cudaStream_t s);
+cudaError_t launch_discrete_w(const DiscreteWParams& p, cudaStream_t s);
 cudaError_t launch_aux_topk_fwd(int rows, int latent, int k, const float* logits,
                                 const float* gamma_draw, float* embedding, float* kl_z,
                                 cudaStream_t s);

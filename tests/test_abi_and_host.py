@@ -59,9 +59,9 @@ def test_argument_validation_without_gpu(lib):
   assert h.mulan_fwd_post(C.byref(d), *([None] * 10)) == -1
   d = lib.make_desc(rows=2, param=7)
   assert h.mulan_bwd_post(C.byref(d), *([None] * 11)) == -1
-  d = lib.make_desc(rows=2, n_timesteps=1000)
-  assert h.mulan_bwd_pre(C.byref(d), *([None] * 14)) == -3
-  assert b'discrete-time' in h.mulan_last_error()
+  d = lib.make_desc(rows=2, n_timesteps=1000, param=lib.MULAN_PARAM_VEL)
+  assert h.mulan_bwd_pre(C.byref(d), *([None] * 14)) == -3     # velocity model asserts T == 0
+  assert b'discrete time' in h.mulan_last_error()
   d = lib.make_desc(rows=2, gamma_min=5.0, gamma_max=-13.3)
   assert h.mulan_fwd_pre(C.byref(d), *([None] * 14)) == -1
   d = lib.make_desc(rows=2)

@@ -232,9 +232,13 @@ def test_rows_zero_and_errors(cuda_device):
                 e(2, 3070), e(2, 3070))
   assert ei.value.status == -2
   with pytest.raises(MulanError) as ei:
-    ops.fwd_pre(ops.Desc(n_timesteps=10), e(2, 3072, dt=torch.uint8), e(2, 3072), e(2, 3072),
-                e(2, 3072), e(2), e(2, 3072), e(2, 3072))
+    ops.fwd_pre(ops.Desc(n_timesteps=10, param=1), e(2, 3072, dt=torch.uint8), e(2, 3072),
+                e(2, 3072), e(2, 3072), e(2), e(2, 3072), e(2, 3072))
   assert ei.value.status == -3
+  with pytest.raises(MulanError) as ei:   # discrete time needs the saved weight
+    ops.fwd_pre(ops.Desc(n_timesteps=10), e(2, 3072, dt=torch.uint8), e(2, 3072), e(2, 3072),
+                e(2, 3072), e(2), e(2, 3072), e(2, 3072), save_w=False)
+  assert ei.value.status == -1
   # misaligned float pointer
   buf = e(2 * 3072 + 1)
   mis = buf[1:].view(2, 3072)
@@ -242,6 +246,44 @@ def test_rows_zero_and_errors(cuda_device):
     ops.fwd_pre(desc, e(2, 3072, dt=torch.uint8), mis, e(2, 3072), e(2, 3072), e(2), e(2, 3072),
                 e(2, 3072))
   assert ei.value.status == -2
+
+
+@pytest.mark.parametrize('T', [10, 1000])
+def test_discrete_time_epsilon(cuda_device, T):
+  """sm_n_timesteps > 0 (ldm/model_mulan_epsilon.py:348-355): loss and gradients."""
+  ops = _ops()
+  B = 8
+  cfg = O.OracleConfig(sm_n_timesteps=T)
+  inp = O.synth_inputs(B, 71)
+  inp['t'] = O.sample_t(0.321, B, cfg)
+  rng = np.random.default_rng(5)
+  gL = torch.from_numpy(rng.uniform(0.5, 1.5, B).astype(np.float32)) / (B * 3072 * math.log(2))
+  res = {}
+  for dtype in (torch.float32, torch.float64):
+    cast = lambda v: v.to(dtype) if v.is_floating_point() else v
+    i = {k: cast(v) for k, v in inp.items()}
+    a, b, c, net = (i[k].clone().requires_grad_(True) for k in ('a', 'b', 'c', 'net'))
+    out = O.elbo_terms(i['x'], a, b, c, i['t'], i['eps_0'], i['eps'], lambda z, g: net,
+                       O.MODE_EPS, cfg, dtype=dtype)
+    grads = torch.autograd.grad((gL.to(dtype) * out.loss_diff).sum(), [a, b, c, net])
+    res[dtype] = (out.loss_diff.detach(), grads)
+  g = _dev(inp, cuda_device)
+  desc = ops.Desc(n_timesteps=T)
+  gLd = gL.to(cuda_device)
+  pre = ops.fwd_pre(desc, g['x'], g['a'], g['b'], g['c'], g['t'], g['eps_0'], g['eps'])
+  diff = ops.fwd_post(desc, None, None, None, None, None, g['eps'], g['net'], pre['w'])
+  # float32 cancellation in g_t - g_s: hold the CUDA loss to the float32 oracle at 1e-5 when
+  # the oracle itself is that close to float64, else to a multiple of the oracle's own error
+  l32, l64 = res[torch.float32][0], res[torch.float64][0]
+  ref_err = _rel(l32, l64)
+  assert _rel(diff, l64) < max(LOSS_RTOL, 4 * ref_err), (_rel(diff, l64), ref_err)
+  n_bar = ops.bwd_post(desc, None, None, None, None, None, g['eps'], g['net'], pre['w'], gLd)
+  ab, bb, cb = ops.bwd_pre(desc, g['x'], g['a'], g['b'], g['c'], g['t'], g['eps'], g['net'],
+                           None, None, gLd)
+  for got, k in ((ab, 0), (bb, 1), (cb, 2), (n_bar, 3)):
+    w64, w32 = res[torch.float64][1][k], res[torch.float32][1][k]
+    ref = _rel_l2_rows(w32, w64)
+    assert _rel_l2_rows(got, w64) < max(GRAD_RTOL, 4 * ref), (k, _rel_l2_rows(got, w64), ref)
 
 
 @pytest.mark.parametrize('B,seed', [(8, 0), (3, 1), (128, 2)])

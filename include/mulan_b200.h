@@ -173,14 +173,17 @@ int mulan_bpd_reduce(const mulan_desc* desc,
  * the denoiser callback (or the supplied `net`), fwd_post, bwd_post, bwd_pre, bpd_reduce and
  * D2H of the results, on the current device.  This is the call a ctypes/cgo-style binding
  * with host arrays would make; it allocates a workspace internally (cached per thread) and
- * synchronises before returning.
- *   denoiser(user, z_t_dev, g_net_dev, net_dev, stream): fills net_dev[B,D]; may be NULL, in
- *   which case `net` (host, [B,D]) is used.  When want_grad != 0 and the denoiser is NULL,
- *   z_bar is taken as zero (the supplied net does not depend on z_t).
+ * synchronises before returning.  The batch flows through copy-in / compute / copy-out
+ * streams in row chunks, so transfers in both directions overlap each other and the
+ * kernels; page-locked host buffers make the copies true DMA.
+ *   denoiser(user, rows, z_t_dev, g_net_dev, net_dev, stream): fills net_dev[rows,D] for
+ *   one chunk of `rows` examples (called once per chunk, in row order); may be NULL, in
+ *   which case `net` (host, [B,D]) is used.  z_bar is taken as zero (the path through the
+ *   denoiser's own backward is the caller's).
  *   out (host): losses[3*B] = recon | klz_prior | diff; scalars[6];
  *               grads (want_grad): a_bar,b_bar,c_bar,n_bar [B,D] each (NULL to skip copy-out)
  */
-typedef int (*mulan_denoiser_fn)(void* user, const float* z_t, const float* g_net,
+typedef int (*mulan_denoiser_fn)(void* user, int32_t rows, const float* z_t, const float* g_net,
                                  float* net, void* stream);
 int mulan_elbo_host(const mulan_desc* desc,
                     const uint8_t* x, const float* a, const float* b, const float* c,

@@ -33,7 +33,8 @@ class MulanError(RuntimeError):
     self.status = status
 
 
-DENOISER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p)
+DENOISER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                          C.c_void_p)
 
 _P = C.c_void_p
 _D = C.POINTER(MulanDesc)

@@ -85,6 +85,10 @@ int recon_window(const mulan_desc* d) {
 
 }  // namespace
 
+namespace mulan {
+void set_last_error(const char* msg) { snprintf(g_err, sizeof(g_err), "%s", msg); }
+}  // namespace mulan
+
 extern "C" {
 
 const char* mulan_last_error(void) { return g_err; }
@@ -245,125 +249,6 @@ int mulan_bpd_reduce(const mulan_desc* d, const float* loss_recon, const float* 
                                            loss_diff, var_sums, scalars, loss_klz_total,
                                            (cudaStream_t)stream);
   return e == cudaSuccess ? 0 : cuda_fail(fn, e);
-}
-
-// ---------------------------------------------------------------------------------------
-// Host-buffer entry
-// ---------------------------------------------------------------------------------------
-namespace {
-
-// Device-side workspace of mulan_elbo_host, cached per host thread (one thread per device).
-struct HostWs {
-  int device = -1;
-  size_t cap_rows = 0;
-  int dim = 0;
-  cudaStream_t stream = nullptr;
-  uint8_t* d_x = nullptr;
-  float* d_f = nullptr;      // one slab: a,b,c,eps0,eps,net,z_t,w,nbar,abar,bbar,cbar [12][B,D]
-  float* d_row = nullptr;    // t, g_net, recon, klz, diff, gL, var_sums[2] -> 8*B, + 8 scalars
-  float* h_gl = nullptr;     // pinned [B]: the uniform loss cotangent
-  void release() {
-    if (d_x) cudaFree(d_x);
-    if (d_f) cudaFree(d_f);
-    if (d_row) cudaFree(d_row);
-    if (h_gl) cudaFreeHost(h_gl);
-    if (stream) cudaStreamDestroy(stream);
-    *this = HostWs();
-  }
-};
-thread_local HostWs g_ws;
-
-}  // namespace
-
-void mulan_host_workspace_release(void) { g_ws.release(); }
-
-int mulan_elbo_host(const mulan_desc* d, const uint8_t* x, const float* a, const float* b,
-                    const float* c, const float* t, const float* eps0, const float* eps,
-                    const float* net, mulan_denoiser_fn denoiser, void* user, int32_t want_grad,
-                    float* losses, float* scalars, float* a_bar, float* b_bar, float* c_bar,
-                    float* n_bar) {
-  const char* fn = "mulan_elbo_host";
-  if (int r = check_desc(d, fn)) return r;
-  if (d->rows == 0) return fail(MULAN_ERR_INVALID_ARG, "%s: rows=0", fn);
-  REQ_PTR(x, fn); REQ_PTR(a, fn); REQ_PTR(b, fn); REQ_PTR(c, fn); REQ_PTR(t, fn);
-  REQ_PTR(eps0, fn); REQ_PTR(eps, fn); REQ_PTR(losses, fn); REQ_PTR(scalars, fn);
-  if (denoiser == nullptr) REQ_PTR(net, fn);
-  if (d->gt_mode == MULAN_GT_PIXEL)
-    return fail(MULAN_ERR_UNSUPPORTED, "%s: gt_mode=PIXEL is served by the device-pointer API", fn);
-  const size_t B = (size_t)d->rows, D = (size_t)d->dim, N = B * D;
-  int dev = 0;
-  cudaError_t e = cudaGetDevice(&dev);
-  if (e != cudaSuccess) return cuda_fail(fn, e);
-  HostWs& ws = g_ws;
-  if (ws.device != dev || ws.cap_rows < B || ws.dim != d->dim) {
-    ws.release();
-    ws.device = dev; ws.cap_rows = B; ws.dim = d->dim;
-    if ((e = cudaStreamCreateWithFlags(&ws.stream, cudaStreamNonBlocking)) != cudaSuccess ||
-        (e = cudaMalloc(&ws.d_x, N)) != cudaSuccess ||
-        (e = cudaMalloc(&ws.d_f, 12 * N * sizeof(float))) != cudaSuccess ||
-        (e = cudaMalloc(&ws.d_row, (8 * B + 8) * sizeof(float))) != cudaSuccess ||
-        (e = cudaMallocHost(&ws.h_gl, B * sizeof(float))) != cudaSuccess) {
-      ws.release();
-      return cuda_fail("mulan_elbo_host workspace", e);
-    }
-  }
-  cudaStream_t s = ws.stream;
-  float* dA = ws.d_f + 0 * N; float* dB = ws.d_f + 1 * N; float* dC = ws.d_f + 2 * N;
-  float* dE0 = ws.d_f + 3 * N; float* dE = ws.d_f + 4 * N; float* dN = ws.d_f + 5 * N;
-  float* dZ = ws.d_f + 6 * N; float* dW = ws.d_f + 7 * N; float* dNB = ws.d_f + 8 * N;
-  float* dAB = ws.d_f + 9 * N; float* dBB = ws.d_f + 10 * N; float* dCB = ws.d_f + 11 * N;
-  float* dT = ws.d_row; float* dG = ws.d_row + B; float* dRec = ws.d_row + 2 * B;
-  float* dKlz = ws.d_row + 3 * B; float* dDiff = ws.d_row + 4 * B; float* dGL = ws.d_row + 5 * B;
-  float* dVar = ws.d_row + 6 * B; float* dSc = ws.d_row + 8 * B;
-
-  // H2D straight from the caller's buffers: true async DMA when they are page-locked
-  // (cudaHostAlloc / torch pin_memory), driver-staged otherwise.
-  e = cudaMemcpyAsync(ws.d_x, x, N, cudaMemcpyHostToDevice, s);
-  const float* srcs[6] = {a, b, c, eps0, eps, denoiser == nullptr ? net : nullptr};
-  float* dsts[6] = {dA, dB, dC, dE0, dE, dN};
-  for (int i = 0; i < 6 && e == cudaSuccess; ++i)
-    if (srcs[i] != nullptr)
-      e = cudaMemcpyAsync(dsts[i], srcs[i], N * sizeof(float), cudaMemcpyHostToDevice, s);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(dT, t, B * sizeof(float), cudaMemcpyHostToDevice, s);
-  if (e != cudaSuccess) return cuda_fail(fn, e);
-
-  float* w_save = d->param == MULAN_PARAM_EPS ? dW : nullptr;
-  int r = mulan_fwd_pre(d, ws.d_x, dA, dB, dC, dT, dE0, dE, dZ, dG, w_save, dRec, dKlz, dVar, s);
-  if (r) return r;
-  if (denoiser != nullptr) {
-    if (int rc = denoiser(user, dZ, dG, dN, (void*)s))
-      return fail(MULAN_ERR_INVALID_ARG, "%s: denoiser callback returned %d", fn, rc);
-  }
-  r = mulan_fwd_post(d, ws.d_x, dA, dB, dC, dT, dE, dN, w_save, dDiff, s);
-  if (r) return r;
-  r = mulan_bpd_reduce(d, dRec, dKlz, nullptr, dDiff, dVar, dSc, nullptr, s);
-  if (r) return r;
-  if (want_grad) {
-    // d bpd / d loss_diff_b = 1 / (B * D * ln 2)   (ldm/experiment_vdm.py:62-66)
-    const float g = (float)(1.0 / ((double)B * (double)D * 0.6931471805599453));
-    for (size_t i = 0; i < B; ++i) ws.h_gl[i] = g;
-    e = cudaMemcpyAsync(dGL, ws.h_gl, B * sizeof(float), cudaMemcpyHostToDevice, s);
-    if (e != cudaSuccess) return cuda_fail(fn, e);
-    r = mulan_bwd_post(d, ws.d_x, dA, dB, dC, dT, dE, dN, w_save, dGL, dNB, s);
-    if (r) return r;
-    r = mulan_bwd_pre(d, ws.d_x, dA, dB, dC, dT, dE, dN, nullptr, nullptr, dGL, dAB, dBB, dCB, s);
-    if (r) return r;
-  }
-  // D2H: recon | klz_prior | diff are contiguous in d_row
-  e = cudaMemcpyAsync(losses, dRec, 3 * B * sizeof(float), cudaMemcpyDeviceToHost, s);
-  if (e == cudaSuccess)
-    e = cudaMemcpyAsync(scalars, dSc, 6 * sizeof(float), cudaMemcpyDeviceToHost, s);
-  if (want_grad) {
-    float* gdst[4] = {a_bar, b_bar, c_bar, n_bar};
-    float* gsrc[4] = {dAB, dBB, dCB, dNB};
-    for (int i = 0; i < 4 && e == cudaSuccess; ++i)
-      if (gdst[i] != nullptr)
-        e = cudaMemcpyAsync(gdst[i], gsrc[i], N * sizeof(float), cudaMemcpyDeviceToHost, s);
-  }
-  if (e != cudaSuccess) return cuda_fail(fn, e);
-  e = cudaStreamSynchronize(s);
-  if (e != cudaSuccess) return cuda_fail(fn, e);
-  return 0;
 }
 
 }  // extern "C"

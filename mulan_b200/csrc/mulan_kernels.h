@@ -138,6 +138,9 @@ inline int resident_ctas(const void* kernel) {
   return sms * per_sm;
 }
 
+// Publishes `msg` as this thread's mulan_last_error() (defined in mulan_abi.cu).
+void set_last_error(const char* msg);
+
 cudaError_t launch_fwd_pre(const FwdPreParams& p, cudaStream_t s);
 cudaError_t launch_fwd_post(const PostParams& p, cudaStream_t s);
 cudaError_t launch_bwd_post(const PostParams& p, cudaStream_t s);

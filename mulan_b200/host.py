@@ -54,8 +54,8 @@ def elbo_host(x, a, b, c, t, eps0, eps, net=None, *, param: int = _lib.MULAN_PAR
   arrays.  Mirrors VDM.__call__ + Experiment_VDM.loss_fn (ldm/model_mulan_epsilon.py:280-363,
   ldm/experiment_vdm.py:47-78) once (a, b, c) and the random draws exist.
 
-  denoiser(z_t_ptr, g_net_ptr, net_ptr, stream_ptr) -> int, all raw device addresses; when
-  None the supplied host `net` is used.
+  denoiser(rows, z_t_ptr, g_net_ptr, net_ptr, stream_ptr) -> int, raw device addresses of one
+  chunk of `rows` examples (called once per chunk); when None the supplied host `net` is used.
   Returns dict(loss_recon, loss_klz_prior, loss_diff, scalars[, a_bar, b_bar, c_bar, n_bar]).
   """
   B, D = a.shape
@@ -68,7 +68,7 @@ def elbo_host(x, a, b, c, t, eps0, eps, net=None, *, param: int = _lib.MULAN_PAR
   out = out or HostOutputs(B, D, want_grad)
   cb = _lib.DENOISER_FN()
   if denoiser is not None:
-    cb = _lib.DENOISER_FN(lambda user, z, g, n, s: int(denoiser(z, g, n, s) or 0))
+    cb = _lib.DENOISER_FN(lambda user, rows, z, g, n, s: int(denoiser(rows, z, g, n, s) or 0))
   d = _lib.make_desc(B, D, vocab, param, _lib.MULAN_GT_MEAN, 0, gamma_min, gamma_max)
   _lib.check(_lib.load().mulan_elbo_host(
       C.byref(d), _ptr(x), _ptr(a), _ptr(b), _ptr(c), _ptr(t), _ptr(eps0), _ptr(eps), _ptr(net),

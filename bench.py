@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- MuLAN schedule + ELBO hot path on B200 (see DESIGN.md "Measurement").
 
-A "step" is one pass of the hot path (fwd_pre -> fwd_post -> bpd_reduce -> bwd_post ->
+A "step" is one pass of the hot path (fwd_pre -> post value-and-grad -> bpd_reduce ->
 bwd_pre, i.e. ELBO loss + gradients w.r.t. the schedule coefficients and the denoiser
 output) over one batch of synthetic uint8 32x32x3 examples per GPU.  The denoiser (U-Net)
 is NOT part of the path: its output and its backward cotangents are supplied
@@ -33,9 +33,10 @@ PARAMS = {'eps': 0, 'vel': 1, 'vel_from_eps': 2}
 # algorithmic bytes per sub-pixel, kernel -> bytes (DESIGN.md "Kernels"; SURVEY.md 8d rule:
 # every declared input read once, every output written once)
 ALGO_BYTES = {
-    'eps': {'fwd_pre': 29, 'fwd_post': 12, 'bwd_post': 16, 'bwd_pre': 37},
-    'vel': {'fwd_pre': 25, 'fwd_post': 21, 'bwd_post': 25, 'bwd_pre': 37},
-    'vel_from_eps': {'fwd_pre': 25, 'fwd_post': 21, 'bwd_post': 25, 'bwd_pre': 37},
+    # post_vg = mulan_fwd_bwd_post: loss_diff and n_bar in one pass (value-and-grad)
+    'eps': {'fwd_pre': 29, 'fwd_post': 12, 'post_vg': 16, 'bwd_post': 16, 'bwd_pre': 37},
+    'vel': {'fwd_pre': 25, 'fwd_post': 21, 'post_vg': 25, 'bwd_post': 25, 'bwd_pre': 37},
+    'vel_from_eps': {'fwd_pre': 25, 'fwd_post': 21, 'post_vg': 25, 'bwd_post': 25, 'bwd_pre': 37},
 }
 
 
@@ -55,6 +56,9 @@ def parse_args():
                        'evaluation, 16 images x 128 timesteps per launch (configs[4])')
   ap.add_argument('--launch-rows', type=int, default=2048,
                   help='dense_vlb: rows per launch (16 images x 128 antithetic timesteps)')
+  ap.add_argument('--separate-post', action='store_true',
+                  help='train: run mulan_fwd_post and mulan_bwd_post as two passes instead of '
+                       'the fused value-and-grad pass')
   ap.add_argument('--no-e2e', action='store_true')
   ap.add_argument('--no-cpu-baseline', action='store_true')
   return ap.parse_args()
@@ -233,13 +237,19 @@ def run_native(args):
   kernels = {   # name -> launch closure (all write into the preallocated workspaces)
       'fwd_pre': each(lambda w_, i, g: w_.fwd_pre(i['x'], i['a'], i['b'], i['c'], i['t'],
                                                   i['eps0'], i['eps'])),
-      'fwd_post': each(lambda w_, i, g: w_.fwd_post(i['x'], i['a'], i['b'], i['c'], i['t'],
-                                                    i['eps'], i['net'])),
-      'bpd_reduce': each(lambda w_, i, g: w_.bpd_reduce(None)),
   }
+  if train and not args.separate_post:
+    # value-and-grad: the loss cotangent of a mean is known up front (jax.value_and_grad)
+    kernels['post_vg'] = each(lambda w_, i, g: w_.fwd_bwd_post(i['x'], i['a'], i['b'], i['c'],
+                                                               i['t'], i['eps'], i['net'], g))
+  else:
+    kernels['fwd_post'] = each(lambda w_, i, g: w_.fwd_post(i['x'], i['a'], i['b'], i['c'], i['t'],
+                                                            i['eps'], i['net']))
+  kernels['bpd_reduce'] = each(lambda w_, i, g: w_.bpd_reduce(None))
   if train:
-    kernels['bwd_post'] = each(lambda w_, i, g: w_.bwd_post(i['x'], i['a'], i['b'], i['c'], i['t'],
-                                                            i['eps'], i['net'], g))
+    if args.separate_post:
+      kernels['bwd_post'] = each(lambda w_, i, g: w_.bwd_post(i['x'], i['a'], i['b'], i['c'],
+                                                              i['t'], i['eps'], i['net'], g))
     kernels['bwd_pre'] = each(lambda w_, i, g: w_.bwd_pre(i['x'], i['a'], i['b'], i['c'], i['t'],
                                                           i['eps'], i['net'], i['z_bar'],
                                                           i['g_bar'], g))
@@ -350,9 +360,8 @@ def run_native(args):
     wss = ops.ElboWorkspace(desc, GROUP, dev)
     def small_step():
       wss.fwd_pre(sm['x'], sm['a'], sm['b'], sm['c'], sm['t'], sm['eps0'], sm['eps'])
-      wss.fwd_post(sm['x'], sm['a'], sm['b'], sm['c'], sm['t'], sm['eps'], sm['net'])
+      wss.fwd_bwd_post(sm['x'], sm['a'], sm['b'], sm['c'], sm['t'], sm['eps'], sm['net'], gLs)
       wss.bpd_reduce(None)
-      wss.bwd_post(sm['x'], sm['a'], sm['b'], sm['c'], sm['t'], sm['eps'], sm['net'], gLs)
       wss.bwd_pre(sm['x'], sm['a'], sm['b'], sm['c'], sm['t'], sm['eps'], sm['net'], sm['z_bar'],
                   sm['g_bar'], gLs)
     with torch.cuda.stream(stream):
@@ -372,7 +381,7 @@ def run_native(args):
       torch.cuda.synchronize()
       us = e0.elapsed_time(e1) * 1000 / 200
       lat = {'rows': GROUP, 'us_per_step': us, 'samples_per_s': GROUP / (us * 1e-6),
-             'how': 'CUDA graph of the 5 launches, 200 replays, L2-resident'}
+             'how': 'CUDA graph of the 4 launches, 200 replays, L2-resident'}
 
   # ---- cpu baseline (oracle port on host cores; rank 0, N=1 only) ----
   cpu = None

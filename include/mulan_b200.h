@@ -124,6 +124,24 @@ int mulan_bwd_post(const mulan_desc* desc,
                    const float* gL, float* n_bar, void* stream);
 
 /*
+ * mulan_fwd_bwd_post -- value-and-grad of the diffusion loss in ONE pass: loss_diff[B] and
+ * n_bar[B,D] = gL_b * d loss_diff_b / d net, for callers that know the loss cotangent gL up
+ * front (jax.value_and_grad of a mean: gL_b = 1/(B*D*ln 2), ldm/experiment_vdm.py:62-66).
+ * Reads what mulan_fwd_post reads once instead of twice (EPS: 12 B + 4 B written per
+ * sub-pixel instead of 12 + 16).  If the true cotangent turns out different,
+ * mulan_scale_rows(n_bar, true, assumed) corrects n_bar in place, touching only the rows
+ * that differ.
+ */
+int mulan_fwd_bwd_post(const mulan_desc* desc,
+                       const uint8_t* x, const float* a, const float* b, const float* c,
+                       const float* t, const float* eps, const float* net, const float* w_save,
+                       const float* gL, float* loss_diff, float* n_bar, void* stream);
+
+/* v[b, :] *= num[b] / den[b] for the rows where num[b] != den[b]; v is [rows, dim]. */
+int mulan_scale_rows(int32_t rows, int32_t dim, float* v, const float* num, const float* den,
+                     void* stream);
+
+/*
  * mulan_bwd_pre -- cotangents of the polynomial coefficients: every path from the loss to
  * (a,b,c): through z_t (z_bar, returned by the denoiser's backward), through the
  * denoiser's noise-level input (g_bar: [B] for GT_MEAN, [B,D] for GT_PIXEL), and through

@@ -46,6 +46,8 @@ SIGNATURES = {
     'mulan_fwd_pre': ([_D] + [_P] * 14, C.c_int),
     'mulan_fwd_post': ([_D] + [_P] * 10, C.c_int),
     'mulan_bwd_post': ([_D] + [_P] * 11, C.c_int),
+    'mulan_fwd_bwd_post': ([_D] + [_P] * 12, C.c_int),
+    'mulan_scale_rows': ([C.c_int32] * 2 + [_P] * 4, C.c_int),
     'mulan_bwd_pre': ([_D] + [_P] * 14, C.c_int),
     'mulan_aux_topk_fwd': ([C.c_int32] * 3 + [_P] * 5, C.c_int),
     'mulan_aux_topk_bwd': ([C.c_int32] * 3 + [_P] * 6, C.c_int),

@@ -180,6 +180,32 @@ int mulan_bwd_post(const mulan_desc* d, const uint8_t* x, const float* a, const 
   return e == cudaSuccess ? 0 : cuda_fail(fn, e);
 }
 
+int mulan_fwd_bwd_post(const mulan_desc* d, const uint8_t* x, const float* a, const float* b,
+                       const float* c, const float* t, const float* eps, const float* net,
+                       const float* w_save, const float* gL, float* loss_diff, float* n_bar,
+                       void* stream) {
+  const char* fn = "mulan_fwd_bwd_post";
+  if (int r = check_desc(d, fn)) return r;
+  if (d->rows == 0) return 0;
+  mulan::PostParams p;
+  if (int r = fill_post(fn, d, x, a, b, c, t, eps, net, w_save, &p)) return r;
+  REQ_PTR(gL, fn); REQ_PTR(loss_diff, fn); REQ_VEC(n_bar, fn);
+  p.gL = gL; p.loss_diff = loss_diff; p.n_bar = n_bar;
+  cudaError_t e = mulan::launch_fwd_bwd_post(p, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(fn, e);
+}
+
+int mulan_scale_rows(int32_t rows, int32_t dim, float* v, const float* num, const float* den,
+                     void* stream) {
+  const char* fn = "mulan_scale_rows";
+  if (rows < 0 || dim <= 0) return fail(MULAN_ERR_INVALID_ARG, "%s: bad shape", fn);
+  if (dim % 4 != 0) return fail(MULAN_ERR_ALIGNMENT, "%s: dim=%d is not a multiple of 4", fn, dim);
+  if (rows == 0) return 0;
+  REQ_VEC(v, fn); REQ_PTR(num, fn); REQ_PTR(den, fn);
+  cudaError_t e = mulan::launch_scale_rows(v, num, den, rows, dim / 4, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(fn, e);
+}
+
 int mulan_bwd_pre(const mulan_desc* d, const uint8_t* x, const float* a, const float* b,
                   const float* c, const float* t, const float* eps, const float* net,
                   const float* z_bar, const float* g_bar, const float* gL,

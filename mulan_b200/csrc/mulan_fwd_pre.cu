@@ -29,6 +29,8 @@
 // and the branch-free MUFU+Newton math of mulan_common.cuh on the hot path.  Everything
 // that decides HOW the reference rounds where it matters (z_0, u = (z_0 - x_k) e^{-g0/2},
 // 1 - sigmoid, the prior-KL summand) keeps the reference's op order.
+#include <stdlib.h>
+
 #include "mulan_kernels.h"
 
 namespace mulan {
@@ -108,6 +110,99 @@ __device__ __noinline__ float2 prior_general(float S, float gmin, float delta, f
   return make_float2((1.0f - v1) * (f * f) + v1 - logf(v1) - 1.0f, v1);
 }
 
+// One float4 column (4 sub-pixels) of one row: everything between the loads and the stores.
+// acc: logprob, klz summand, g_t, and (only off the fixed-end path) var0 / var1 corrections.
+// Launch constants of the hot path, read from the parameter bank ONCE per thread (before the
+// slab loop) so the loop body does not re-issue constant loads for every sub-pixel.
+struct PreConsts {
+  float s0, inv0, v0c, v1c, om1, lv1, gmin, delta;
+  ReconFast rc;
+  bool v1_uniform;
+};
+__device__ __forceinline__ PreConsts load_pre_consts(const FwdPreParams& p) {
+  PreConsts k;
+  k.s0 = p.k.s0; k.inv0 = p.k.inv0; k.v0c = p.k.v0; k.v1c = p.k.v1; k.om1 = p.k.om1;
+  k.lv1 = p.k.lv1; k.gmin = p.gmin; k.delta = p.delta; k.rc = p.rc;
+  k.v1_uniform = p.k.v1_uniform != 0;
+  return k;
+}
+
+template <int GT, bool SAVEW, bool FAST>
+__device__ __forceinline__ void pre_column(const FwdPreParams& p, const PreConsts& kc,
+                                           const RowT& rt, const float4 A,
+                                           const float4 Bv, const float4 C, const float4 E0,
+                                           const float4 E, const uchar4 X, size_t g4,
+                                           float (&acc)[5]) {
+  const float s0 = kc.s0, inv0 = kc.inv0, v0c = kc.v0c;
+  const float v1c = kc.v1c, om1 = kc.om1, lv1 = kc.lv1;
+  const bool v1_uniform = kc.v1_uniform;
+  const VocabInfo& vi = p.vi;
+  const ReconFast& rc = kc.rc;
+  const float gmin = kc.gmin, delta = kc.delta;
+  float4 Z, Wv, G;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float a = get(A, j), b = get(Bv, j), c = get(C, j);
+    const float e0 = get(E0, j), e = get(E, j);
+    const int xi = getx(X, j);
+    const float xf = (float)xi;
+    const float f = FAST ? fmaf(xf, rc.two_iv, rc.off)    // encode(x), exact for 2^k vocab
+                         : vi.xval(xi);
+    const Poly po = poly_eval(a, b, c, rt);
+    float gt, wt;
+    if (scale_in_range(po.S)) {                           // fixed ends are exact constants
+      const float rSd = delta * rcp_nr(po.S);
+      gt = fmaf(po.P, rSd, gmin);                         // gamma_t
+      wt = (po.q * po.q) * rSd;                           // d gamma / dt
+      const float z0 = f + s0 * e0;                       // z_0_rescaled (two roundings)
+      acc[0] += FAST ? recon_logprob_fast(xf, f, z0, rc)
+                     : recon_logprob_generic(xi, z0, inv0, p.W, vi);
+      if (v1_uniform) {
+        acc[1] += om1 * (f * f) + v1c - lv1 - 1.0f;       // reference op order
+      } else {
+        const float2 pg = prior_general(po.S, gmin, delta, f);
+        acc[1] += pg.x;
+        acc[4] += pg.y - v1c;
+      }
+    } else {
+      const SlowPix sp = slow_pixel(po, gmin, delta, xi, f, e0, vi);
+      gt = sp.gt; wt = sp.wt;
+      acc[0] += sp.lp; acc[1] += sp.kl;
+      acc[3] += sp.v0 - v0c; acc[4] += sp.v1 - v1c;
+    }
+    const float vt = sigmoid_fast(gt);
+    const float om = 1.0f - vt;
+    const float alpha = sqrt_fast0(om), sigma = sqrt_fast(vt);
+    put(Z, j, alpha * f + sigma * e);                     // z_t (two products, one add)
+    if (SAVEW) put(Wv, j, wt);
+    if (GT == MULAN_GT_PIXEL) put(G, j, gt);
+    acc[2] += gt;
+  }
+  st4(p.z_t, g4, Z);
+  if (SAVEW) st4(p.w_save, g4, Wv);
+  if (GT == MULAN_GT_PIXEL) st4(p.g_net, g4, G);
+}
+
+// Row epilogue: deterministic CTA-wide sums, per-example outputs written by thread 0.
+template <int GT>
+__device__ __forceinline__ void pre_row_end(const FwdPreParams& p, int row, float (&acc)[5],
+                                            float (*red)[5]) {
+  block_sum<5>(acc, red);
+  if (threadIdx.x == 0) {
+    const float dimf = (float)(p.dim4 * 4);
+    p.loss_recon[row] = -acc[0];
+    p.loss_klz[row] = 0.5f * acc[1];
+    if (GT == MULAN_GT_MEAN) p.g_net[row] = __fdiv_rn(acc[2], dimf);
+    // sum over the row of sigmoid(g_0), sigmoid(g_1): D * constant + corrections
+    p.var_sums[2 * row + 0] = dimf * p.k.v0 + acc[3];
+    p.var_sums[2 * row + 1] = dimf * p.k.v1 + acc[4];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Direct-load kernel: one CTA per row, operands loaded straight into registers (LDG.128).
+// Serves any dim (multiple of 4), any vocab / window, any 4-byte aligned x.
+// ---------------------------------------------------------------------------------------
 template <int GT, bool SAVEW, bool FAST>
 __global__ void __launch_bounds__(kThreads, 4)
 fwd_pre_kernel(const FwdPreParams p) {
@@ -115,89 +210,129 @@ fwd_pre_kernel(const FwdPreParams p) {
   __shared__ float red[kWarps][5];
   const int row = blockIdx.x;
   const int tid = threadIdx.x;
-
   if (tid == 0) s_rt = make_row_t(__ldg(p.t + row));
   __syncthreads();
   const RowT rt = s_rt;
-  // everything below lives in the kernel parameter (constant) bank: no registers
-  const float s0 = p.k.s0, inv0 = p.k.inv0, v0c = p.k.v0;
-  const float v1c = p.k.v1, om1 = p.k.om1;
-  const float lv1 = p.k.lv1;
-  const bool v1_uniform = p.k.v1_uniform != 0;
-  const VocabInfo& vi = p.vi;
-  const ReconFast& rc = p.rc;
-  const float gmin = p.gmin, delta = p.delta;
-
+  const PreConsts kc = load_pre_consts(p);
   const size_t base4 = (size_t)row * p.dim4;
-  // logprob, klz summand, g_t, and (only off the fixed-end path) var0 / var1 corrections
   float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-
   for (int i4 = tid; i4 < p.dim4; i4 += kThreads) {
     const size_t g4 = base4 + i4;
     const float4 A = ld4(p.a, g4), Bv = ld4(p.b, g4), C = ld4(p.c, g4);
     const float4 E0 = ld4(p.eps0, g4), E = ld4(p.eps, g4);
     const uchar4 X = ldx4(p.x, g4);
-    float4 Z, Wv, G;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float a = get(A, j), b = get(Bv, j), c = get(C, j);
-      const float e0 = get(E0, j), e = get(E, j);
-      const int xi = getx(X, j);
-      const float xf = (float)xi;
-      const float f = FAST ? fmaf(xf, rc.two_iv, rc.off)  // encode(x), exact for 2^k vocab
-                           : vi.xval(xi);
-      const Poly po = poly_eval(a, b, c, rt);
-      float gt, wt;
-      if (scale_in_range(po.S)) {                         // fixed ends are exact constants
-        const float rSd = delta * rcp_nr(po.S);
-        gt = fmaf(po.P, rSd, gmin);                       // gamma_t
-        wt = (po.q * po.q) * rSd;                         // d gamma / dt
-        const float z0 = f + s0 * e0;                     // z_0_rescaled (two roundings)
-        acc[0] += FAST ? recon_logprob_fast(xf, f, z0, rc)
-                       : recon_logprob_generic(xi, z0, inv0, p.W, vi);
-        if (v1_uniform) {
-          acc[1] += om1 * (f * f) + v1c - lv1 - 1.0f;     // reference op order
-        } else {
-          const float2 pg = prior_general(po.S, gmin, delta, f);
-          acc[1] += pg.x;
-          acc[4] += pg.y - v1c;
-        }
-      } else {
-        const SlowPix sp = slow_pixel(po, gmin, delta, xi, f, e0, vi);
-        gt = sp.gt; wt = sp.wt;
-        acc[0] += sp.lp; acc[1] += sp.kl;
-        acc[3] += sp.v0 - v0c; acc[4] += sp.v1 - v1c;
-      }
-      const float vt = sigmoid_fast(gt);
-      const float om = 1.0f - vt;
-      const float alpha = sqrt_fast0(om), sigma = sqrt_fast(vt);
-      put(Z, j, alpha * f + sigma * e);                   // z_t (two products, one add)
-      if (SAVEW) put(Wv, j, wt);
-      if (GT == MULAN_GT_PIXEL) put(G, j, gt);
-      acc[2] += gt;
-    }
-    st4(p.z_t, g4, Z);
-    if (SAVEW) st4(p.w_save, g4, Wv);
-    if (GT == MULAN_GT_PIXEL) st4(p.g_net, g4, G);
+    pre_column<GT, SAVEW, FAST>(p, kc, rt, A, Bv, C, E0, E, X, g4, acc);
   }
+  pre_row_end<GT>(p, row, acc, red);
+}
 
-  block_sum<5>(acc, red);
+// ---------------------------------------------------------------------------------------
+// TMA-pipelined kernel (the shipped configs: dim % 1024 == 0, 16-byte aligned operands).
+// Persistent CTAs walk rows blockIdx.x, += gridDim.x; a row is consumed in slabs of 256 float4
+// columns.  Thread 0 moves each slab global -> shared with six cp.async.bulk copies (4 KB per
+// float array, 1 KB of x) that complete on a `full` mbarrier; every thread then reads its own
+// 16-byte slots (conflict-free LDS.128), one lane per warp arrives on the `empty` mbarrier,
+// and the slab after next is requested as soon as its buffer is free.  DRAM latency is hidden
+// by a full slab of arithmetic with no registers held in flight and no per-thread address
+// arithmetic for the loads.
+// ---------------------------------------------------------------------------------------
+struct __align__(128) PreSlab {
+  float4 f[5][kThreads];   // a, b, c, eps0, eps
+  uchar4 x[kThreads];
+};
+constexpr unsigned kPreSlabBytes = 5 * kThreads * 16 + kThreads * 4;
+
+#ifndef MULAN_TMA_CTAS
+#define MULAN_TMA_CTAS 3
+#endif
+template <int GT, bool SAVEW>
+__global__ void __launch_bounds__(kThreads, MULAN_TMA_CTAS)
+fwd_pre_tma_kernel(const FwdPreParams p) {
+  __shared__ PreSlab slab[2];
+  __shared__ __align__(8) uint64_t full[2], empty[2];
+  __shared__ float red[2][kWarps][5];
+  const int tid = threadIdx.x;
+  const int nslab = p.dim4 / kThreads;
+  const int my_rows = (p.rows - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int total = my_rows * nslab;
+
   if (tid == 0) {
-    const float dimf = (float)(p.dim4 * 4);
-    p.loss_recon[row] = -acc[0];
-    p.loss_klz[row] = 0.5f * acc[1];
-    if (GT == MULAN_GT_MEAN) p.g_net[row] = __fdiv_rn(acc[2], dimf);
-    // sum over the row of sigmoid(g_0), sigmoid(g_1): D * constant + corrections
-    p.var_sums[2 * row + 0] = dimf * v0c + acc[3];
-    p.var_sums[2 * row + 1] = dimf * v1c + acc[4];
+    mbar_init(&full[0], 1); mbar_init(&full[1], 1);
+    mbar_init(&empty[0], kWarps); mbar_init(&empty[1], kWarps);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  // producer cursor (thread 0 only): the next slab to request
+  int prow = blockIdx.x, pslab = 0;
+  auto request = [&](int stage) {
+    const size_t g4 = (size_t)prow * p.dim4 + (size_t)pslab * kThreads;
+    mbar_expect_tx(&full[stage], kPreSlabBytes);
+    bulk_g2s(&slab[stage].f[0][0], reinterpret_cast<const float4*>(p.a) + g4, kThreads * 16, &full[stage]);
+    bulk_g2s(&slab[stage].f[1][0], reinterpret_cast<const float4*>(p.b) + g4, kThreads * 16, &full[stage]);
+    bulk_g2s(&slab[stage].f[2][0], reinterpret_cast<const float4*>(p.c) + g4, kThreads * 16, &full[stage]);
+    bulk_g2s(&slab[stage].f[3][0], reinterpret_cast<const float4*>(p.eps0) + g4, kThreads * 16, &full[stage]);
+    bulk_g2s(&slab[stage].f[4][0], reinterpret_cast<const float4*>(p.eps) + g4, kThreads * 16, &full[stage]);
+    bulk_g2s(&slab[stage].x[0], reinterpret_cast<const uchar4*>(p.x) + g4, kThreads * 4, &full[stage]);
+    if (++pslab == nslab) { pslab = 0; prow += gridDim.x; }
+  };
+  if (tid == 0 && total > 0) request(0);
+
+  const PreConsts kc = load_pre_consts(p);
+  int row = blockIdx.x, s = 0, parity = 0;
+  RowT rt;
+  float acc[5];
+  for (int it = 0; it < total; ++it) {
+    const int stage = it & 1;
+    if (tid == 0 && it + 1 < total) {
+      // the other buffer held slab it-1: wait until every warp has read it, then refill
+      if (it >= 1) mbar_wait(&empty[stage ^ 1], ((it - 1) >> 1) & 1);
+      request(stage ^ 1);
+    }
+    if (s == 0) {
+      rt = make_row_t(__ldg(p.t + row));                  // per-example t powers
+#pragma unroll
+      for (int k = 0; k < 5; ++k) acc[k] = 0.f;
+    }
+    mbar_wait(&full[stage], (it >> 1) & 1);               // slab `it` has landed
+    const float4 A = slab[stage].f[0][tid], Bv = slab[stage].f[1][tid], C = slab[stage].f[2][tid];
+    const float4 E0 = slab[stage].f[3][tid], E = slab[stage].f[4][tid];
+    const uchar4 X = slab[stage].x[tid];
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(&empty[stage]);      // this warp is done with the buffer
+    const size_t g4 = (size_t)row * p.dim4 + (size_t)s * kThreads + tid;
+    pre_column<GT, SAVEW, true>(p, kc, rt, A, Bv, C, E0, E, X, g4, acc);
+    if (++s == nslab) {
+      pre_row_end<GT>(p, row, acc, red[parity]);
+      parity ^= 1;
+      s = 0;
+      row += gridDim.x;
+    }
   }
 }
 
+static bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; }
+
 template <int GT, bool SAVEW>
 static cudaError_t launch_w(const FwdPreParams& p, cudaStream_t s) {
+  const bool fast = p.W == 1 && p.vi.pow2;
+  // The TMA-pipelined kernel is opt-in (MULAN_FWD_PRE_TMA=1): measured on B200 it hides DRAM
+  // latency (issue utilisation 71 % -> 79 %) but executes 144 instead of 120 instructions per
+  // sub-pixel, and this kernel is issue-bound: 0.260 ms vs 0.243 ms (profiles/).
+  static const int use_tma = [] {
+    const char* e = getenv("MULAN_FWD_PRE_TMA");
+    return (e != nullptr && e[0] == '1') ? 1 : 0;
+  }();
+  if (fast && use_tma && p.dim4 % kThreads == 0 && aligned16(p.x)) {
+    static int max_ctas = 0;   // resident CTAs of this variant on the current device
+    if (max_ctas == 0) max_ctas = resident_ctas((const void*)fwd_pre_tma_kernel<GT, SAVEW>);
+    const int grid = p.rows < max_ctas ? p.rows : max_ctas;
+    fwd_pre_tma_kernel<GT, SAVEW><<<grid, kThreads, 0, s>>>(p);
+    return cudaGetLastError();
+  }
   dim3 grid(p.rows), block(kThreads);
-  if (p.W == 1 && p.vi.pow2) fwd_pre_kernel<GT, SAVEW, true><<<grid, block, 0, s>>>(p);
-  else                       fwd_pre_kernel<GT, SAVEW, false><<<grid, block, 0, s>>>(p);
+  if (fast) fwd_pre_kernel<GT, SAVEW, true><<<grid, block, 0, s>>>(p);
+  else      fwd_pre_kernel<GT, SAVEW, false><<<grid, block, 0, s>>>(p);
   return cudaGetLastError();
 }
 

@@ -159,11 +159,13 @@ int mulan_elbo_host(const mulan_desc* d, const uint8_t* x, const float* a, const
         return (int)MULAN_ERR_INVALID_ARG;
       }
     }
-    r = mulan_fwd_post(&dc, ws.d_x + o, dA + o, dB + o, dC + o, dT + r0, dE + o, dN + o, w_save,
-                       dDiff + r0, sc);
-    if (!r && want_grad) {
-      r = mulan_bwd_post(&dc, ws.d_x + o, dA + o, dB + o, dC + o, dT + r0, dE + o, dN + o, w_save,
-                         dGL + r0, dNB + o, sc);
+    if (!want_grad) {
+      r = mulan_fwd_post(&dc, ws.d_x + o, dA + o, dB + o, dC + o, dT + r0, dE + o, dN + o, w_save,
+                         dDiff + r0, sc);
+    } else {
+      // value-and-grad in one pass: the cotangent of a mean is known up front
+      r = mulan_fwd_bwd_post(&dc, ws.d_x + o, dA + o, dB + o, dC + o, dT + r0, dE + o, dN + o,
+                             w_save, dGL + r0, dDiff + r0, dNB + o, sc);
       if (!r)
         r = mulan_bwd_pre(&dc, ws.d_x + o, dA + o, dB + o, dC + o, dT + r0, dE + o, dN + o, nullptr,
                           nullptr, dGL + r0, dAB + o, dBB + o, dCB + o, sc);

@@ -144,6 +144,9 @@ void set_last_error(const char* msg);
 cudaError_t launch_fwd_pre(const FwdPreParams& p, cudaStream_t s);
 cudaError_t launch_fwd_post(const PostParams& p, cudaStream_t s);
 cudaError_t launch_bwd_post(const PostParams& p, cudaStream_t s);
+cudaError_t launch_fwd_bwd_post(const PostParams& p, cudaStream_t s);
+cudaError_t launch_scale_rows(float* v, const float* num, const float* den, int rows, int dim4,
+                              cudaStream_t s);
 cudaError_t launch_bwd_pre(const BwdPreParams& p, cudaStream_t s);
 cudaError_t launch_discrete_w(const DiscreteWParams& p, cudaStream_t s);
 cudaError_t launch_aux_topk_fwd(int rows, int latent, int k, const float* logits,

@@ -161,6 +161,8 @@ class VDM(nn.Module):
                          n_timesteps=config.sm_n_timesteps, gamma_min=config.gamma_min,
                          gamma_max=config.gamma_max)
     self._generator = None
+    # fuse d loss_diff / d net into the forward pass of the post kernel when training
+    self.fused_value_and_grad = True
 
   def make_draws(self, n_batch: int, device, generator: Optional[torch.Generator] = None):
     """The four make_rng('sample') draws of __call__, in the reference's order."""
@@ -199,7 +201,15 @@ class VDM(nn.Module):
     cond = embedding if cfg.z_conditioning else conditioning[:, None]
     g_in = g_net if cfg.unet_type == 'vdm' else g_net.reshape(n_batch, 32, 32, 3)
     net = self.score_model(z_t.reshape(n_batch, 32, 32, 3), g_in, cond, deterministic)
-    loss_diff = ops.mulan_post(tape, net.reshape(n_batch, D), link)
+    net_flat = net.reshape(n_batch, D)
+    if torch.is_grad_enabled() and net_flat.requires_grad and self.fused_value_and_grad:
+      # value-and-grad in one pass: the cotangent loss_fn will send is 1/(B*D*ln 2)
+      # (ldm/experiment_vdm.py:62-66); any other upstream gradient is corrected per row
+      hint = torch.full((n_batch,), 1.0 / (n_batch * D * math.log(2.0)), dtype=torch.float32,
+                        device=dev)
+      loss_diff = ops.mulan_post_fused(tape, net_flat, link, hint)
+    else:
+      loss_diff = ops.mulan_post(tape, net_flat, link)
     n = float(n_batch * D)
     return VDMOutput(loss_recon=loss_recon, loss_klz=kl_z + klz_prior, loss_diff=loss_diff,
                      var_0=var_sums[:, 0].sum() / n, var_1=var_sums[:, 1].sum() / n)

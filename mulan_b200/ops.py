@@ -111,6 +111,30 @@ def bwd_post(desc: Desc, x, a, b, c, t, eps, net, w, gL):
   return out
 
 
+def fwd_bwd_post(desc: Desc, x, a, b, c, t, eps, net, w, gL):
+  """mulan_fwd_bwd_post -> (loss_diff[B], n_bar[B,D]) in one pass, for a known cotangent gL."""
+  B, D = eps.shape
+  _req(net, torch.float32, (B, D), 'net')
+  _req(gL, torch.float32, (B,), 'gL')
+  diff = torch.empty((B,), dtype=torch.float32, device=eps.device)
+  n_bar = torch.empty((B, D), dtype=torch.float32, device=eps.device)
+  d = desc.c(B)
+  _lib.check(_lib.load().mulan_fwd_bwd_post(
+      C.byref(d), _p(x), _p(a), _p(b), _p(c), _p(t), _p(eps), _p(net), _p(w), _p(gL), _p(diff),
+      _p(n_bar), _stream()))
+  return diff, n_bar
+
+
+def scale_rows(v, num, den):
+  """mulan_scale_rows: v[b,:] *= num[b]/den[b] in place for rows where they differ."""
+  B, D = v.shape
+  _req(v, torch.float32, (B, D), 'v')
+  _req(num, torch.float32, (B,), 'num')
+  _req(den, torch.float32, (B,), 'den')
+  _lib.check(_lib.load().mulan_scale_rows(B, D, _p(v), _p(num), _p(den), _stream()))
+  return v
+
+
 def bwd_pre(desc: Desc, x, a, b, c, t, eps, net, z_bar, g_bar, gL):
   """mulan_bwd_pre -> (a_bar, b_bar, c_bar)."""
   B, D = a.shape
@@ -192,6 +216,11 @@ class ElboWorkspace:
         C.byref(self._d), _p(x), _p(a), _p(b), _p(c), _p(t), _p(eps), _p(net), _p(self.w),
         _p(self.loss_diff), _stream()))
 
+  def fwd_bwd_post(self, x, a, b, c, t, eps, net, gL):
+    _lib.check(self._lib.mulan_fwd_bwd_post(
+        C.byref(self._d), _p(x), _p(a), _p(b), _p(c), _p(t), _p(eps), _p(net), _p(self.w), _p(gL),
+        _p(self.loss_diff), _p(self.n_bar), _stream()))
+
   def bpd_reduce(self, kl_z=None):
     _lib.check(self._lib.mulan_bpd_reduce(
         C.byref(self._d), _p(self.loss_recon), _p(self.loss_klz_prior), _p(kl_z),
@@ -263,6 +292,36 @@ class _MulanPost(torch.autograd.Function):
     gL = gL.contiguous()
     n_bar = bwd_post(tp.desc, tp.x, tp.a, tp.b, tp.c, tp.t, tp.eps, tp.net, tp.w, gL)
     return None, n_bar, gL
+
+
+class _MulanPostFused(torch.autograd.Function):
+  """loss_diff AND the denoiser cotangent in the forward pass, for the cotangent `gL_hint` the
+  caller expects (the mean-of-losses scaling of loss_fn).  backward() hands out the
+  precomputed n_bar; a row whose true cotangent differs from the hint is rescaled in place
+  by mulan_scale_rows (no host sync, no traffic for matching rows)."""
+
+  @staticmethod
+  def forward(ctx, tape: ElboTape, net, link, gL_hint):
+    net_c = net.contiguous()
+    tape.net = net_c.detach()
+    ctx.tape = tape
+    diff, n_bar = fwd_bwd_post(tape.desc, tape.x, tape.a, tape.b, tape.c, tape.t, tape.eps,
+                               net_c, tape.w, gL_hint)
+    ctx.n_bar, ctx.hint = n_bar, gL_hint
+    return diff
+
+  @staticmethod
+  def backward(ctx, gL):
+    gL = gL.contiguous()
+    n_bar = scale_rows(ctx.n_bar, gL, ctx.hint)
+    ctx.n_bar = None
+    return None, n_bar, gL, None
+
+
+def mulan_post_fused(tape: ElboTape, net, link, gL_hint):
+  """-> loss_diff[B]; the backward pass costs no extra kernel when d loss / d loss_diff_b
+  equals gL_hint[b] (single backward only)."""
+  return _MulanPostFused.apply(tape, net, link, gL_hint)
 
 
 def mulan_pre(tape: ElboTape, x, a, b, c, t, eps0, eps):

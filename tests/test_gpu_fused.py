@@ -1,0 +1,125 @@
+"""GPU tests of the fused / alternative code paths: value-and-grad post kernel, row rescale,
+and the opt-in TMA-pipelined fwd_pre; each must reproduce the plain path bit for bit (or to
+rounding where the arithmetic order legitimately differs)."""
+import math
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mulan_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+MODES = {'eps': O.MODE_EPS, 'vel': O.MODE_VEL, 'vel_from_eps': O.MODE_VEL_FROM_EPS}
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _dev(d, device):
+  return {k: v.to(device).contiguous() for k, v in d.items()}
+
+
+@pytest.mark.parametrize('mode', list(MODES))
+def test_fwd_bwd_post_equals_separate_passes(cuda_device, mode):
+  from mulan_b200 import ops
+  B = 64
+  inp = O.synth_inputs(B, 91)
+  g = _dev(inp, cuda_device)
+  desc = ops.Desc(param=MODES[mode])
+  rng = np.random.default_rng(1)
+  gL = torch.from_numpy(rng.uniform(0.5, 1.5, B).astype(np.float32)).to(cuda_device) * 1e-6
+  w = None
+  if mode == 'eps':
+    w = ops.fwd_pre(desc, g['x'], g['a'], g['b'], g['c'], g['t'], g['eps_0'], g['eps'])['w']
+  args = (g['x'], g['a'], g['b'], g['c'], g['t'], g['eps'], g['net'], w)
+  diff = ops.fwd_post(desc, *args)
+  nbar = ops.bwd_post(desc, *args, gL)
+  diff2, nbar2 = ops.fwd_bwd_post(desc, *args, gL)
+  assert torch.equal(diff, diff2)
+  assert torch.equal(nbar, nbar2)
+
+
+def test_scale_rows(cuda_device):
+  from mulan_b200 import ops
+  B = 9
+  v = torch.randn(B, 3072, device=cuda_device)
+  v0 = v.clone()
+  num = torch.rand(B, device=cuda_device) + 0.5
+  den = num.clone()
+  den[3] = num[3] * 2.0
+  den[7] = num[7] * 0.25
+  ops.scale_rows(v, num, den)
+  want = v0.clone()
+  want[3] *= 0.5
+  want[7] *= 4.0
+  assert torch.equal(v, want)          # untouched rows bit-identical, scaled rows exact (2^k)
+
+
+@pytest.mark.parametrize('scale', [1.0, 3.0])
+def test_fused_value_and_grad_in_model(cuda_device, scale):
+  """VDM with fused_value_and_grad on/off gives identical losses and gradients, also when the
+  upstream gradient is NOT the one the fused kernel assumed (loss scaled by 3)."""
+  from mulan_b200.model import VDM, VDMConfig, loss_fn
+  sys.path.insert(0, os.path.join(ROOT, 'tests', 'golden'))
+  import golden_inputs as GI
+  dev = cuda_device
+  B = 16
+  rng = np.random.default_rng(2)
+  images = torch.from_numpy(rng.integers(0, 256, (B, 32, 32, 3), dtype=np.uint8)).to(dev)
+  enc_w = torch.from_numpy(GI.encoder_weights(5)).to(dev)
+  res = []
+  for fused in (False, True):
+    w1 = torch.tensor(0.8, device=dev, requires_grad=True)
+    encoder = lambda f, det: f.reshape(f.shape[0], -1)[:, :256] @ enc_w
+    score = lambda z, g_, cond, det: w1 * z + 0.01 * g_.reshape(-1, 1, 1, 1)
+    model = VDM(VDMConfig(vdm_type='mulan_velocity', velocity_from_epsilon=True), encoder,
+                score).to(dev)
+    model.gamma.load_flax(GI.mlp_weights(6))
+    model.fused_value_and_grad = fused
+    gen = torch.Generator(device=dev).manual_seed(11)
+    draws = model.make_draws(B, dev, gen)
+    bpd, _ = loss_fn(model, {'images': images}, draws=draws)
+    (scale * bpd).backward()
+    res.append((bpd.item(), w1.grad.clone(), model.gamma.dense_out_b.bias.grad.clone()))
+  assert res[0][0] == res[1][0]
+  assert abs(res[0][1].item() - res[1][1].item()) <= 2e-6 * abs(res[0][1].item())
+  num = (res[0][2] - res[1][2]).norm().item()
+  assert num <= 2e-6 * res[0][2].norm().item()
+
+
+def test_tma_pipelined_fwd_pre_matches_direct(cuda_device):
+  """MULAN_FWD_PRE_TMA=1 selects the cp.async.bulk + mbarrier kernel; same arithmetic per
+  sub-pixel and the same reduction tree, so every output must be bit-identical."""
+  code = r'''
+import sys, torch, numpy as np
+sys.path.insert(0, %r)
+from mulan_b200 import ops
+from oracle import mulan_oracle as O
+dev = torch.device('cuda:0')
+out = {}
+for B in (3, 700, 2500):
+  inp = O.synth_inputs(B, 7, group=128)
+  g = {k: v.to(dev).contiguous() for k, v in inp.items()}
+  for gt in (0, 1):
+    r = ops.fwd_pre(ops.Desc(gt_mode=gt), g['x'], g['a'], g['b'], g['c'], g['t'], g['eps_0'],
+                    g['eps'], save_w=(gt == 0))
+    for k, v in r.items():
+      if v is not None:
+        out['%%d_%%d_%%s' %% (B, gt, k)] = v.cpu().numpy()
+np.savez(sys.argv[1], **out)
+''' % ROOT
+  import tempfile
+  outs = []
+  for flag in ('0', '1'):
+    with tempfile.NamedTemporaryFile(suffix='.npz', delete=False) as f:
+      path = f.name
+    env = dict(os.environ, MULAN_FWD_PRE_TMA=flag)
+    subprocess.run([sys.executable, '-c', code, path], check=True, env=env)
+    outs.append(np.load(path))
+    os.unlink(path)
+  assert set(outs[0].files) == set(outs[1].files)
+  for k in outs[0].files:
+    assert np.array_equal(outs[0][k], outs[1][k]), k

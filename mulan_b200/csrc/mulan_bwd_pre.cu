@@ -66,7 +66,8 @@ bwd_pre_kernel(const BwdPreParams p) {
       const float w = (p.delta * Q) * rS;
       const float v = sigmoid_fast(gt);
       const float om = 1.0f - v;
-      const float alpha = sqrt_nr(om), sigma = sqrt_nr(v);
+      const float kr = rsqrt_approx(fmaxf(om, 1e-30f));   // 1/alpha = sqrt(1 + e^gamma)
+      const float alpha = om * kr, sigma = sqrt_fast(v);
       const float dal = -0.5f * v * alpha;      // d alpha / d gamma
       const float dsg = 0.5f * sigma * om;      // d sigma / d gamma
 
@@ -87,13 +88,11 @@ bwd_pre_kernel(const BwdPreParams p) {
         wbar = 0.5f * gL * (r * r);
       } else {
         const float vtg = alpha * e - sigma * f;
-        float vhat = n, eh = 0.f, k = 1.f, zt = 0.f, eg = 0.f;
+        float vhat = n, zt = 0.f;
         if (PARAM == MULAN_PARAM_VEL_FROM_EPS) {
+          // e^g = v/(1-v): sqrt(1+e^g) = 1/alpha = kr, e^{g/2} = sigma kr, e^g/sqrt(1+e^g) = v kr
           zt = alpha * f + sigma * e;
-          eg = exp_fast(gt);
-          eh = exp_fast(0.5f * gt);
-          k = sqrt_nr(1.0f + eg);
-          vhat = -eh * zt + k * n;
+          vhat = kr * (n - sigma * zt);
         }
         const float r = vtg - vhat;
         const float r2 = r * r;
@@ -102,8 +101,8 @@ bwd_pre_kernel(const BwdPreParams p) {
         gbar += -0.5f * gL * w * r2 * (v * om);          // through (1 - var_t)
         gbar += rb * (dal * e - dsg * f);                // through v_target
         if (PARAM == MULAN_PARAM_VEL_FROM_EPS) {
-          zb += rb * eh;                                 // v_hat's direct use of z_t
-          gbar -= rb * (-0.5f * eh * zt + 0.5f * n * __fdiv_rn(eg, k));
+          zb += rb * (sigma * kr);                       // v_hat's direct use of z_t
+          gbar += 0.5f * rb * kr * (sigma * zt - n * v);  // v_hat's own gamma dependence
         }
       }
       gbar += zb * (dal * f + dsg * e);                  // through z_t = alpha f + sigma eps

@@ -46,13 +46,17 @@ __device__ __forceinline__ PostPix post_pixel(float a, float b, float c, int xi,
     const float f = vi.xval(xi);
     const float vt = sigmoid_fast(gt);
     const float om = 1.0f - vt;
-    const float alpha = sqrt_nr(om), sigma = sqrt_nr(vt);
+    // alpha = sqrt(1-v), sigma = sqrt(v) exactly as mulan_fwd_pre forms them (same z_t)
+    const float kr = rsqrt_approx(fmaxf(om, 1e-30f));
+    const float alpha = om * kr, sigma = sqrt_fast(vt);
     const float vtg = alpha * e - sigma * f;
     float vhat = n, k = 1.0f;
     if (PARAM == MULAN_PARAM_VEL_FROM_EPS) {
+      // v_hat = -e^{g/2} z_t + sqrt(1 + e^g) net with e^g = v/(1-v):
+      //   sqrt(1 + e^g) = 1/alpha,  e^{g/2} = sigma/alpha  =>  v_hat = (net - sigma z_t)/alpha
       const float zt = alpha * f + sigma * e;
-      k = sqrt_nr(1.0f + exp_fast(gt));
-      vhat = -exp_fast(0.5f * gt) * zt + k * n;
+      k = kr;
+      vhat = k * (n - sigma * zt);
     }
     const float r = vtg - vhat;
     const float omw = om * w;

@@ -42,7 +42,8 @@ KEYS = [
     ('l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum', 'L1 global load sectors'),
     ('l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum', 'L1 global load requests'),
 ]
-ALGO = {'fwd_pre': 29, 'post_kernel<0, 1, 0>': 12, 'post_kernel<0, 1, 1>': 16, 'bwd_pre': 37}
+ALGO = {'fwd_pre': 29, 'post_kernel<0, 1, 0>': 12, 'post_kernel<0, 1, 1>': 16,
+        'post_kernel<0, 1, 2>': 16, 'bwd_pre': 37}
 
 
 def ncu_csv(rep, page, extra=()):
@@ -86,7 +87,7 @@ def main():
       md.append(f'| traffic / algorithmic | {(rd + wr) / (algo * nsub):.3f} |')
     md.append(f'| thread instructions per sub-pixel | {inst * 32 / nsub:.1f} |')
     key = 'fwd_pre' if 'fwd_pre' in name else 'bwd_pre' if 'bwd_pre' in name else (
-        'fwd_post' if name.strip().endswith('0>(PostParams)') or ', 0>' in name else 'bwd_post')
+        'fwd_post' if ', 0>(' in name else 'bwd_post' if ', 1>(' in name else 'post_vg')
     traffic[key] = {'rows': rows, 'dram_bytes_per_launch': rd + wr, 'kernel': short}
     # instruction mix from the source page
     src = ncu_csv(rep, 'source', ['--kernel-name', 'regex:' + re.escape(short.split('<')[0].split('::')[-1])])

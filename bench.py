@@ -51,9 +51,16 @@ def parse_args():
   ap.add_argument('--param', choices=list(PARAMS), default='eps')
   ap.add_argument('--ref-rows', type=int, default=GROUP,
                   help='rows of the bounded CPU sample (cpu_baseline / --impl reference)')
-  ap.add_argument('--workload', choices=['train', 'dense_vlb'], default='train',
+  ap.add_argument('--workload', choices=['train', 'dense_vlb', 'train_step'], default='train',
                   help='train: ELBO loss+grad (configs[1..3]); dense_vlb: forward-only VLB '
                        'evaluation, 16 images x 128 timesteps per launch (configs[4])')
+  ap.add_argument('--net-config', choices=['cifar10', 'imagenet32'], default='cifar10',
+                  help='train_step: sm_n_embd 128 / 256 stand-in networks (mulan_b200/standin.py)')
+  ap.add_argument('--batch', type=int, default=128, help='train_step: per-GPU batch')
+  ap.add_argument('--global-batch', type=int, default=0,
+                  help='train_step: fixed global batch (strong scaling) instead of --batch')
+  ap.add_argument('--tf32', action='store_true',
+                  help='train_step: allow TF32 in the stand-in networks (reference: float32)')
   ap.add_argument('--launch-rows', type=int, default=2048,
                   help='dense_vlb: rows per launch (16 images x 128 antithetic timesteps)')
   ap.add_argument('--separate-post', action='store_true',
@@ -533,6 +540,173 @@ def emit(line: dict):
     sys.stdout.flush()
 
 
+def run_train_step(args):
+  """Whole train step around the kernels (BASELINE.json configs[1..3]): stand-in encoder and
+  U-Net on cuDNN/cuBLAS float32 (mulan_b200/standin.py -- the reference keeps them on the
+  framework path), the ELBO kernels, ONE all-reduce of the flat gradient bucket (+ scalars),
+  ONE fused AdamW+EMA launch.  Reports samples/s and the ELBO kernels' share of the step."""
+  import torch
+  import torch.distributed as dist
+  from mulan_b200 import _lib, ops
+  from mulan_b200.model import VDM, VDMConfig
+  from mulan_b200.optim import FlatTrainState, train_step
+  from mulan_b200.standin import ScoreUNet, UnetEncoder
+
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  rank = int(os.environ.get('RANK', '0'))
+  local = int(os.environ.get('LOCAL_RANK', '0'))
+  if world > 1:
+    dist.init_process_group('nccl', device_id=torch.device(f'cuda:{local}'))
+  assert world == args.gpus, f'--gpus {args.gpus} but WORLD_SIZE={world}'
+  torch.cuda.set_device(local)
+  dev = torch.device(f'cuda:{local}')
+  _lib.load()
+  torch.backends.cuda.matmul.allow_tf32 = args.tf32      # reference: matmul precision float32
+  torch.backends.cudnn.allow_tf32 = args.tf32
+  torch.backends.cudnn.benchmark = True
+  torch.manual_seed(1234)                                 # same init on every rank
+  n_embd = 128 if args.net_config == 'cifar10' else 256
+  B = args.global_batch // world if args.global_batch else args.batch
+  cfg = VDMConfig(vdm_type='mulan_epsilon' if args.param == 'eps' else 'mulan_velocity',
+                  velocity_from_epsilon=(args.param == 'vel_from_eps'))
+  model = VDM(cfg, UnetEncoder(n_embd, 4), ScoreUNet(n_embd, 32)).to(dev)
+  model.train()
+  state = FlatTrainState(model.named_parameters())
+  gen = torch.Generator(device=dev).manual_seed(100 + rank)
+  host_images = torch.randint(0, 256, (B, 32, 32, 3), dtype=torch.uint8).pin_memory()
+  K, W = args.steps, max(args.warmup, 3)
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  def one_step():
+    images = host_images.to(dev, non_blocking=True)       # H2D of the step's inputs
+    return train_step(model, state, {'images': images}, generator=gen)
+
+  for _ in range(W):
+    sc = one_step()
+  barrier()
+  try:
+    uuid = torch.cuda.get_device_properties(local).uuid
+  except Exception:
+    uuid = None
+  sampler = ClockSampler(local, uuid)
+  if rank == 0:
+    sampler.start()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  barrier()
+  mark0 = sampler.mark()
+  t0 = time.perf_counter()
+  e0.record()
+  for _ in range(K):
+    sc = one_step()
+    bpd = float(sc['bpd'])                                # D2H read of the step's result
+  e1.record()
+  barrier()
+  wall = time.perf_counter() - t0
+  clocks = sampler.stop(mark0, None) if rank == 0 else None
+  tm = torch.tensor([e0.elapsed_time(e1), wall * 1e3], device=dev, dtype=torch.float64)
+  if world > 1:
+    dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+  ms, wall_ms = tm[0].item() / K, tm[1].item() / K
+
+  # ELBO kernels alone at this batch (CUDA graph of the 4 launches)
+  elbo_us = None
+  if rank == 0:
+    desc = model.desc
+    inp = make_inputs(B, dev, seed=7)
+    ws = ops.ElboWorkspace(desc, B, dev)
+    gL = torch.full((B,), 1.0 / (B * D * math.log(2.0)), device=dev)
+    def elbo():
+      ws.fwd_pre(inp['x'], inp['a'], inp['b'], inp['c'], inp['t'], inp['eps0'], inp['eps'])
+      ws.fwd_bwd_post(inp['x'], inp['a'], inp['b'], inp['c'], inp['t'], inp['eps'], inp['net'], gL)
+      ws.bpd_reduce(None)
+      ws.bwd_pre(inp['x'], inp['a'], inp['b'], inp['c'], inp['t'], inp['eps'], inp['net'],
+                 inp['z_bar'], inp['g_bar'], gL)
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+      for _ in range(3):
+        elbo()
+      torch.cuda.synchronize()
+      g2 = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(g2, stream=st):
+        elbo()
+      a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      a0.record(st)
+      for _ in range(100):
+        g2.replay()
+      a1.record(st)
+      torch.cuda.synchronize()
+      elbo_us = a0.elapsed_time(a1) * 10.0
+  # fused AdamW+EMA alone (36 B per parameter) and, for context, torch's fused AdamW + foreach EMA
+  optim = None
+  if rank == 0:
+    o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    state.apply_gradients()
+    torch.cuda.synchronize()
+    o0.record()
+    for _ in range(20):
+      state.apply_gradients()
+    o1.record()
+    torch.cuda.synchronize()
+    us = o0.elapsed_time(o1) * 1000 / 20
+    peaks, peak_src = load_peak()
+    gbs = 36.0 * state.n / (us * 1e-6) / 1e9
+    optim = {'kernel': 'mulan_adamw_ema', 'us': us, 'algo_bytes': 36 * state.n, 'gbs': gbs,
+             'frac_of_measured': gbs / peaks}
+    try:
+      tp = [torch.nn.Parameter(torch.randn(state.n // 8, device=dev)) for _ in range(8)]
+      for q in tp:
+        q.grad = torch.randn_like(q)
+      te = [q.detach().clone() for q in tp]
+      topt = torch.optim.AdamW(tp, lr=2e-4, betas=(0.9, 0.99), weight_decay=0.01, fused=True)
+      def torch_step():
+        topt.step()
+        torch._foreach_lerp_(te, [q.detach() for q in tp], 1e-4)
+      torch_step()
+      torch.cuda.synchronize()
+      o0.record()
+      for _ in range(20):
+        torch_step()
+      o1.record()
+      torch.cuda.synchronize()
+      optim['torch_fused_adamw_plus_foreach_ema_us'] = o0.elapsed_time(o1) * 1000 / 20
+      del tp, te, topt
+    except Exception as exc:      # context figure only
+      optim['torch_fused_adamw_plus_foreach_ema_us'] = f'unavailable: {exc}'
+  if rank != 0:
+    if world > 1:
+      dist.destroy_process_group()
+    return
+  nparam = state.n
+  line = {
+      'metric': 'mulan_train_step_samples_per_s', 'value': world * B / (ms * 1e-3),
+      'unit': 'samples/s', 'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms,
+      'higher_is_better': True, 'scaling': 'strong' if args.global_batch else 'weak',
+      'vs_baseline': None, 'dtype': 'tf32' if args.tf32 else 'f32', 'data': 'synthetic',
+      'config': {'workload': f'{args.net_config} {cfg.vdm_type}'
+                             f'{"(velocity_from_epsilon)" if cfg.velocity_from_epsilon else ""} '
+                             f'train step, per-GPU batch {B}, global {B * world}; STAND-IN '
+                             f'encoder/U-Net on cuDNN/cuBLAS (mulan_b200/standin.py), ELBO in '
+                             f'libmulan_b200, flat-bucket all-reduce, fused AdamW+EMA',
+                 'sm_n_embd': n_embd, 'sm_n_layer': 32, 'parameters': nparam,
+                 'grad_allreduce_bytes': 4 * (nparam + state.extra), 'parallelism': f'dp{world}'},
+      'elbo_kernels': {'us_per_step': elbo_us, 'share_of_step': elbo_us / (ms * 1e3),
+                       'how': 'CUDA graph of fwd_pre, post value-and-grad, bpd_reduce, bwd_pre '
+                              'at this batch'},
+      'optimizer': optim,
+      'e2e': {'value': world * B / (wall_ms * 1e-3), 'unit': 'samples/s',
+              'h2d_bytes_per_step': B * D, 'd2h_bytes_per_step': 4,
+              'api': 'optim.train_step(model, state, batch) with host uint8 images'},
+      'gpu_launches': 7 * K, 'clocks': clocks, 'bpd': bpd,   # aux fwd/bwd, fwd_pre, post_vg, scale_rows, bwd_pre, adamw_ema
+  }
+  emit(line)
+  if world > 1:
+    dist.destroy_process_group()
+
+
 def main():
   global _REAL_STDOUT
   args = parse_args()
@@ -541,6 +715,8 @@ def main():
   os.dup2(2, 1)
   if args.impl == 'reference':
     run_reference(args)
+  elif args.workload == 'train_step':
+    run_train_step(args)
   else:
     run_native(args)
 

@@ -210,6 +210,32 @@ int mulan_elbo_host(const mulan_desc* desc,
                     float* losses, float* scalars,
                     float* a_bar, float* b_bar, float* c_bar, float* n_bar);
 
+/*
+ * mulan_adamw_ema -- "next" row 1 of the scope table: the AdamW + EMA update that follows the
+ * gradient all-reduce of every train step, fused over one flat float32 buffer.
+ * Replaces TrainState.apply_gradients (ldm/train_state.py:70-102) with the optax.adamw chain
+ * of ldm/experiment.py:132-182 (scale_by_adam -> add_decayed_weights(mask) -> scale(-lr)),
+ * the EMA of ldm/train_state.py:91-95, and the 1/world of pmean(grads) (ldm/experiment.py:341)
+ * via grad_scale.  Parameters are laid out decayed-first: elements [0, n_decay) receive weight
+ * decay (the reference's mask: everything but biases).  n and n_decay must be multiples of 4,
+ * pointers 16-byte aligned.  36 B per parameter.
+ */
+typedef struct mulan_adamw_desc {
+  int64_t n;            /* parameters in the flat buffer                    */
+  int64_t n_decay;      /* [0, n_decay) get weight decay                    */
+  int32_t step;         /* 1-based update count (bias correction)           */
+  int32_t reserved;
+  /* Hyper-parameters are doubles, as in the reference's Python config: each is rounded to
+   * float32 where optax would use it (e.g. (1 - b1) is formed in double first).            */
+  double lr;            /* learning rate for THIS step (schedule on the host) */
+  double b1, b2, eps, weight_decay;
+  double ema_rate;      /* 0.9999: ema += (1 - ema_rate) (p_new - ema)       */
+  double grad_scale;    /* g is multiplied by this first (1/world, clipping) */
+} mulan_adamw_desc;
+
+int mulan_adamw_ema(const mulan_adamw_desc* desc, float* params, const float* grads,
+                    float* mu, float* nu, float* ema_params, void* stream);
+
 /* Frees the calling thread's cached mulan_elbo_host workspace (device + pinned host). */
 void mulan_host_workspace_release(void);
 

@@ -27,6 +27,14 @@ class MulanDesc(C.Structure):
               ('gamma_min', C.c_double), ('gamma_max', C.c_double)]
 
 
+class MulanAdamwDesc(C.Structure):
+  """struct mulan_adamw_desc."""
+  _fields_ = [('n', C.c_int64), ('n_decay', C.c_int64), ('step', C.c_int32),
+              ('reserved', C.c_int32), ('lr', C.c_double), ('b1', C.c_double), ('b2', C.c_double),
+              ('eps', C.c_double), ('weight_decay', C.c_double), ('ema_rate', C.c_double),
+              ('grad_scale', C.c_double)]
+
+
 class MulanError(RuntimeError):
   def __init__(self, status: int, msg: str):
     super().__init__(f'libmulan_b200 status {status}: {msg}')
@@ -53,6 +61,7 @@ SIGNATURES = {
     'mulan_aux_topk_bwd': ([C.c_int32] * 3 + [_P] * 6, C.c_int),
     'mulan_bpd_reduce': ([_D] + [_P] * 8, C.c_int),
     'mulan_elbo_host': ([_D] + [_P] * 8 + [DENOISER_FN, _P, C.c_int32] + [_P] * 6, C.c_int),
+    'mulan_adamw_ema': ([C.POINTER(MulanAdamwDesc)] + [_P] * 6, C.c_int),
     'mulan_host_workspace_release': ([], None),
 }
 

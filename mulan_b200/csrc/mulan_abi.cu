@@ -277,4 +277,20 @@ int mulan_bpd_reduce(const mulan_desc* d, const float* loss_recon, const float* 
   return e == cudaSuccess ? 0 : cuda_fail(fn, e);
 }
 
+int mulan_adamw_ema(const mulan_adamw_desc* d, float* params, const float* grads, float* mu,
+                    float* nu, float* ema_params, void* stream) {
+  const char* fn = "mulan_adamw_ema";
+  if (d == nullptr) return fail(MULAN_ERR_INVALID_ARG, "%s: desc is NULL", fn);
+  if (d->n < 0 || d->n_decay < 0 || d->n_decay > d->n)
+    return fail(MULAN_ERR_INVALID_ARG, "%s: need 0 <= n_decay <= n", fn);
+  if (d->n % 4 != 0 || d->n_decay % 4 != 0)
+    return fail(MULAN_ERR_ALIGNMENT, "%s: n and n_decay must be multiples of 4", fn);
+  if (d->step < 1) return fail(MULAN_ERR_INVALID_ARG, "%s: step=%d must be >= 1", fn, d->step);
+  if (d->n == 0) return 0;
+  REQ_VEC(params, fn); REQ_VEC(grads, fn); REQ_VEC(mu, fn); REQ_VEC(nu, fn); REQ_VEC(ema_params, fn);
+  cudaError_t e = mulan::launch_adamw_ema(*d, params, grads, mu, nu, ema_params,
+                                          (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(fn, e);
+}
+
 }  // extern "C"

@@ -1,0 +1,89 @@
+// mulan_adamw_ema: the optimizer update that follows the gradient all-reduce of every train
+// step, fused over ONE flat float32 parameter buffer.
+//
+// Reference statements (what TrainState.apply_gradients runs, ldm/train_state.py:70-102, with
+// the optax chain of ldm/experiment.py:132-182 and the schedule of :106-129):
+//   optax.adamw = scale_by_adam(b1, b2, eps) -> add_decayed_weights(wd, mask) -> scale(-lr)
+//     mu  = (1-b1) g + b1 mu ;  nu = (1-b2) g^2 + b2 nu          (update_moment)
+//     u   = (mu / (1-b1^t)) / (sqrt(nu / (1-b2^t)) + eps)        (bias_correction, eps_root=0)
+//     u  += wd * p   where the decay mask holds (everything but biases, :135-141)
+//     p  += -lr * u                                               (optax.apply_updates)
+//   ema  = ema + (1 - ema_rate) (p_new - ema)                    (train_state.py:91-95)
+//   (+ the pmean of the gradients, ldm/experiment.py:341: NCCL sums, `grad_scale` = 1/world
+//    finishes the mean here instead of in a separate pass over the bucket)
+//
+// Layout: parameters are laid out decayed-first, so the mask is one boundary index instead of
+// a per-element byte.  Purely HBM-bound: p, g, mu, nu, ema read (20 B) and p, mu, nu, ema
+// written (16 B) = 36 B per parameter, float4 accesses, grid-stride over 148 x k CTAs.
+#include "mulan_kernels.h"
+
+namespace mulan {
+
+struct AdamwParams {
+  float *p, *mu, *nu, *ema;
+  const float* g;
+  long long n4;        // float4 count (n padded to 4 by the host side)
+  long long decay4;    // float4 index below which weight decay applies
+  float lr, b1, b2, om_b1, om_b2, eps, wd, one_minus_ema;
+  float bc1, bc2;      // 1 - b1^t, 1 - b2^t
+  float grad_scale;
+};
+
+__device__ __forceinline__ void adamw_one(float& p, float g, float& mu, float& nu, float& ema,
+                                          const AdamwParams& k, bool decay) {
+  g = g * k.grad_scale;
+  mu = k.om_b1 * g + k.b1 * mu;
+  nu = k.om_b2 * (g * g) + k.b2 * nu;
+  const float mu_hat = __fdiv_rn(mu, k.bc1);
+  const float nu_hat = __fdiv_rn(nu, k.bc2);
+  float u = __fdiv_rn(mu_hat, sqrtf(nu_hat) + k.eps);
+  if (decay) u = u + k.wd * p;
+  p = p + (-k.lr) * u;
+  ema = ema + k.one_minus_ema * (p - ema);
+}
+
+__global__ void __launch_bounds__(kThreads)
+adamw_ema_kernel(const AdamwParams k) {
+  const long long stride = (long long)gridDim.x * kThreads;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < k.n4; i += stride) {
+    float4 P = reinterpret_cast<float4*>(k.p)[i];
+    const float4 G = __ldg(reinterpret_cast<const float4*>(k.g) + i);
+    float4 M = reinterpret_cast<float4*>(k.mu)[i];
+    float4 V = reinterpret_cast<float4*>(k.nu)[i];
+    float4 E = reinterpret_cast<float4*>(k.ema)[i];
+    const bool decay = i < k.decay4;
+    adamw_one(P.x, G.x, M.x, V.x, E.x, k, decay);
+    adamw_one(P.y, G.y, M.y, V.y, E.y, k, decay);
+    adamw_one(P.z, G.z, M.z, V.z, E.z, k, decay);
+    adamw_one(P.w, G.w, M.w, V.w, E.w, k, decay);
+    reinterpret_cast<float4*>(k.p)[i] = P;
+    reinterpret_cast<float4*>(k.mu)[i] = M;
+    reinterpret_cast<float4*>(k.nu)[i] = V;
+    reinterpret_cast<float4*>(k.ema)[i] = E;
+  }
+}
+
+cudaError_t launch_adamw_ema(const mulan_adamw_desc& d, float* p, const float* g, float* mu,
+                             float* nu, float* ema, cudaStream_t s) {
+  if (d.n == 0) return cudaSuccess;
+  AdamwParams k;
+  k.p = p; k.g = g; k.mu = mu; k.nu = nu; k.ema = ema;
+  k.n4 = d.n / 4; k.decay4 = d.n_decay / 4;
+  // Python-double hyper-parameters become float32 where optax's weak-typed scalars would
+  k.lr = (float)d.lr; k.b1 = (float)d.b1; k.b2 = (float)d.b2; k.eps = (float)d.eps;
+  k.wd = (float)d.weight_decay;
+  k.om_b1 = (float)(1.0 - d.b1); k.om_b2 = (float)(1.0 - d.b2);
+  k.one_minus_ema = (float)(1.0 - d.ema_rate);
+  // 1 - b^t: optax raises the Python float to an int32 array -> a float32 power
+  k.bc1 = 1.0f - powf((float)d.b1, (float)d.step);
+  k.bc2 = 1.0f - powf((float)d.b2, (float)d.step);
+  k.grad_scale = (float)d.grad_scale;
+  static int max_ctas = 0;
+  if (max_ctas == 0) max_ctas = resident_ctas((const void*)adamw_ema_kernel);
+  const long long want = (k.n4 + kThreads - 1) / kThreads;
+  const int grid = (int)(want < max_ctas ? want : max_ctas);
+  adamw_ema_kernel<<<grid, kThreads, 0, s>>>(k);
+  return cudaGetLastError();
+}
+
+}  // namespace mulan

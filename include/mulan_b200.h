@@ -211,6 +211,28 @@ int mulan_elbo_host(const mulan_desc* desc,
                     float* a_bar, float* b_bar, float* c_bar, float* n_bar);
 
 /*
+ * Ancestral sampler ("next" row 3 of the scope table): the schedule math of VDM.sample /
+ * conditional_sample (ldm/model_mulan_epsilon.py:377-438, ldm/model_mulan_velocity.py:281-347)
+ * and VDM.generate_x (ldm/model_mulan_epsilon.py:440-457), run T = 1000 times per generated
+ * batch by Experiment_VDM.sample_fn (ldm/experiment_vdm.py:80-110).
+ * a, b, c are [abc_rows, D] with abc_rows == rows, or == 1 to broadcast one coefficient row
+ * over the batch (the unconditional sampler's deterministic embedding).
+ *   mulan_sample_gamma : g_net = per-row mean (GT_MEAN, [B]) or per-pixel (GT_PIXEL, [B,D])
+ *                        gamma(t) -- the denoiser's noise-level input (:397-411, :273-278)
+ *   mulan_sample_step  : z_s = sqrt(a/b)(z_t - sigma_t c eps_hat) + sqrt((1-a) c) eps with
+ *                        a = sigmoid(-g_s), b = sigmoid(-g_t), c = -expm1(g_s - g_t);
+ *                        desc->param != EPS: eps_hat = net*sqrt(b) + sigma_t z_t (velocity model)
+ *   mulan_generate_x   : x[B,D] u8 = argmax_k decode(z_0 / sqrt(1 - sigmoid(g_0)), g_0)
+ *                        (sample_softmax = False; g_0 = gamma_min, the fixed end)
+ */
+int mulan_sample_gamma(const mulan_desc* desc, int32_t abc_rows, const float* a, const float* b,
+                       const float* c, const float* t, float* g_net, void* stream);
+int mulan_sample_step(const mulan_desc* desc, int32_t abc_rows, const float* a, const float* b,
+                      const float* c, const float* t, const float* s, const float* z_t,
+                      const float* net, const float* eps, float* z_s, void* stream);
+int mulan_generate_x(const mulan_desc* desc, const float* z_0, uint8_t* x, void* stream);
+
+/*
  * mulan_adamw_ema -- "next" row 1 of the scope table: the AdamW + EMA update that follows the
  * gradient all-reduce of every train step, fused over one flat float32 buffer.
  * Replaces TrainState.apply_gradients (ldm/train_state.py:70-102) with the optax.adamw chain

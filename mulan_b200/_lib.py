@@ -61,6 +61,9 @@ SIGNATURES = {
     'mulan_aux_topk_bwd': ([C.c_int32] * 3 + [_P] * 6, C.c_int),
     'mulan_bpd_reduce': ([_D] + [_P] * 8, C.c_int),
     'mulan_elbo_host': ([_D] + [_P] * 8 + [DENOISER_FN, _P, C.c_int32] + [_P] * 6, C.c_int),
+    'mulan_sample_gamma': ([_D, C.c_int32] + [_P] * 6, C.c_int),
+    'mulan_sample_step': ([_D, C.c_int32] + [_P] * 10, C.c_int),
+    'mulan_generate_x': ([_D] + [_P] * 3, C.c_int),
     'mulan_adamw_ema': ([C.POINTER(MulanAdamwDesc)] + [_P] * 6, C.c_int),
     'mulan_host_workspace_release': ([], None),
 }

@@ -277,6 +277,70 @@ int mulan_bpd_reduce(const mulan_desc* d, const float* loss_recon, const float* 
   return e == cudaSuccess ? 0 : cuda_fail(fn, e);
 }
 
+static int fill_sampler(const char* fn, const mulan_desc* d, int32_t abc_rows, const float* a,
+                        const float* b, const float* c, mulan::SamplerParams* p) {
+  if (abc_rows != 1 && abc_rows != d->rows)
+    return fail(MULAN_ERR_INVALID_ARG, "%s: abc_rows=%d must be 1 (broadcast) or rows=%d", fn,
+                abc_rows, d->rows);
+  REQ_VEC(a, fn); REQ_VEC(b, fn); REQ_VEC(c, fn);
+  memset(p, 0, sizeof(*p));
+  p->a = a; p->b = b; p->c = c;
+  p->rows = d->rows; p->dim4 = d->dim / 4; p->abc_rows = abc_rows; p->param = d->param;
+  p->gt_mode = d->gt_mode;
+  p->gmin = f32_gmin(d); p->delta = f32_delta(d);
+  p->vi = mulan::make_vocab(d->vocab);
+  return 0;
+}
+
+int mulan_sample_gamma(const mulan_desc* d, int32_t abc_rows, const float* a, const float* b,
+                       const float* c, const float* t, float* g_net, void* stream) {
+  const char* fn = "mulan_sample_gamma";
+  if (int r = check_desc(d, fn)) return r;
+  if (d->rows == 0) return 0;
+  mulan::SamplerParams p;
+  if (int r = fill_sampler(fn, d, abc_rows, a, b, c, &p)) return r;
+  REQ_PTR(t, fn); REQ_PTR(g_net, fn);
+  if (d->gt_mode == MULAN_GT_PIXEL) REQ_VEC(g_net, fn);
+  p.t = t; p.g_net = g_net;
+  cudaError_t e = mulan::launch_sample_gamma(p, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(fn, e);
+}
+
+int mulan_sample_step(const mulan_desc* d, int32_t abc_rows, const float* a, const float* b,
+                      const float* c, const float* t, const float* s, const float* z_t,
+                      const float* net, const float* eps, float* z_s, void* stream) {
+  const char* fn = "mulan_sample_step";
+  if (int r = check_desc(d, fn)) return r;
+  if (d->rows == 0) return 0;
+  mulan::SamplerParams p;
+  if (int r = fill_sampler(fn, d, abc_rows, a, b, c, &p)) return r;
+  REQ_PTR(t, fn); REQ_PTR(s, fn); REQ_VEC(z_t, fn); REQ_VEC(net, fn); REQ_VEC(eps, fn);
+  REQ_VEC(z_s, fn);
+  p.t = t; p.s = s; p.z_t = z_t; p.net = net; p.eps = eps; p.z_s = z_s;
+  cudaError_t e = mulan::launch_sample_step(p, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(fn, e);
+}
+
+int mulan_generate_x(const mulan_desc* d, const float* z_0, uint8_t* x, void* stream) {
+  const char* fn = "mulan_generate_x";
+  if (int r = check_desc(d, fn)) return r;
+  if (d->rows == 0) return 0;
+  REQ_VEC(z_0, fn); REQ_X(x, fn);
+  if (d->vocab > 256)
+    return fail(MULAN_ERR_UNSUPPORTED, "%s: vocab=%d does not fit the uint8 output", fn, d->vocab);
+  mulan::SamplerParams p;
+  memset(&p, 0, sizeof(p));
+  p.z_t = z_0; p.x = x; p.rows = d->rows; p.dim4 = d->dim / 4;
+  p.gmin = f32_gmin(d); p.delta = f32_delta(d);
+  p.vi = mulan::make_vocab(d->vocab);
+  // gamma(0) == gamma_min exactly (fixed end): var_0 and the decoder scale are constants
+  const mulan::EndConsts k = mulan::make_end_consts(p.gmin, p.delta);
+  p.den0 = (float)sqrt((double)(1.0f - k.v0));
+  p.inv0 = k.inv0;
+  cudaError_t e = mulan::launch_generate_x(p, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(fn, e);
+}
+
 int mulan_adamw_ema(const mulan_adamw_desc* d, float* params, const float* grads, float* mu,
                     float* nu, float* ema_params, void* stream) {
   const char* fn = "mulan_adamw_ema";

@@ -126,6 +126,22 @@ struct DiscreteWParams {
   float gmin, delta, inv_T;
 };
 
+// Ancestral sampler step / decode (mulan_sampler.cu)
+struct SamplerParams {
+  const float *a, *b, *c, *t, *s;
+  const float *z_t, *net, *eps;
+  float* z_s;       // sample_step
+  float* g_net;     // sample_gamma: [B] or [B,D]
+  uint8_t* x;       // generate_x
+  int rows, dim4, abc_rows, param, gt_mode;
+  float gmin, delta;
+  float den0, inv0; // generate_x: sqrt(1 - sigmoid(g0)), exp(-g0/2)
+  VocabInfo vi;
+};
+cudaError_t launch_sample_gamma(const SamplerParams& p, cudaStream_t s);
+cudaError_t launch_sample_step(const SamplerParams& p, cudaStream_t s);
+cudaError_t launch_generate_x(const SamplerParams& p, cudaStream_t s);
+
 // Number of CTAs of `kernel` (kThreads threads, static shared memory only) that are resident
 // on the current device at once: the grid size of the persistent kernels.
 inline int resident_ctas(const void* kernel) {

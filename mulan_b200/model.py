@@ -215,6 +215,64 @@ class VDM(nn.Module):
                      var_0=var_sums[:, 0].sum() / n, var_1=var_sums[:, 1].sum() / n)
 
 
+def _deterministic_embedding(model: VDM, batch_size: int, device):
+  """_get_deterministic_embedding, latent_type='topk' (ldm/model_mulan_epsilon.py:369-374)."""
+  cfg = model.config
+  e = torch.zeros((batch_size, cfg.latent_size), dtype=torch.float32, device=device)
+  e[:, :cfg.latent_k] = 1.0
+  return e
+
+
+@torch.no_grad()
+def sample(model: VDM, i: int, T: int, z_t, conditioning=None, eps=None, generator=None,
+           coeffs=None):
+  """VDM.sample (ldm/model_mulan_epsilon.py:407-438, ldm/model_mulan_velocity.py:314-347): one
+  ancestral step t=(T-i)/T -> s=(T-i-1)/T.  `coeffs` = cached (a, b, c) of the deterministic
+  embedding ([1, D]: it is the same for every example and every step)."""
+  cfg = model.config
+  B = z_t.shape[0]
+  dev = z_t.device
+  D = 32 * 32 * 3
+  if coeffs is None:
+    coeffs = tuple(v.contiguous() for v in
+                   model.gamma._compute_coefficients(_deterministic_embedding(model, 1, dev)))
+  a, b, c = coeffs
+  t = torch.full((B,), (T - i) / T, dtype=torch.float32, device=dev)
+  s = torch.full((B,), (T - i - 1) / T, dtype=torch.float32, device=dev)
+  if eps is None:
+    eps = torch.randn((B, 32, 32, 3), generator=generator, device=dev)
+  g_net = ops.sample_gamma(model.desc, a, b, c, t)
+  embedding = _deterministic_embedding(model, B, dev)
+  cond = embedding if cfg.z_conditioning else conditioning[:, None]
+  g_in = g_net if cfg.unet_type == 'vdm' else g_net.reshape(B, 32, 32, 3)
+  net = model.score_model(z_t.reshape(B, 32, 32, 3), g_in, cond, True)
+  z_s = ops.sample_step(model.desc, a, b, c, t, s, z_t.reshape(B, D).contiguous(),
+                        net.reshape(B, D).contiguous(), eps.reshape(B, D).contiguous())
+  return z_s.reshape(B, 32, 32, 3)
+
+
+@torch.no_grad()
+def generate_x(model: VDM, z_0):
+  """VDM.generate_x (ldm/model_mulan_epsilon.py:440-457), sample_softmax=False."""
+  B = z_0.shape[0]
+  x = ops.generate_x(model.desc, z_0.reshape(B, 32 * 32 * 3).contiguous())
+  return x.reshape(B, 32, 32, 3)
+
+
+@torch.no_grad()
+def sample_fn(model: VDM, n: int, T: int = 1000, generator=None, sigma_prior: float = 1.0,
+              device=None):
+  """Experiment_VDM.sample_fn (ldm/experiment_vdm.py:80-110): z_init ~ N(0, sigma_prior^2),
+  T ancestral steps, decode."""
+  device = device or next(model.gamma.parameters()).device
+  z = sigma_prior * torch.randn((n, 32, 32, 3), generator=generator, device=device)
+  coeffs = tuple(v.contiguous() for v in
+                 model.gamma._compute_coefficients(_deterministic_embedding(model, 1, device)))
+  for i in range(T):
+    z = sample(model, i, T, z, generator=generator, coeffs=coeffs)
+  return generate_x(model, z)
+
+
 def loss_fn(model: VDM, inputs: dict, step=0, is_train: bool = True, draws=None,
             generator=None):
   """Experiment_VDM.loss_fn (ldm/experiment_vdm.py:47-78): -> (bpd, metrics)."""

@@ -185,6 +185,51 @@ def bpd_reduce(desc: Desc, loss_recon, loss_klz_prior, kl_z, loss_diff, var_sums
   return (sc, tot) if want_klz_total else sc
 
 
+def sample_gamma(desc: Desc, a, b, c, t):
+  """mulan_sample_gamma -> the denoiser's noise-level input for a sampler step ([B] or [B,D]).
+  a, b, c: [B,D] or [1,D] (one coefficient row broadcast over the batch)."""
+  B = t.shape[0]
+  D = a.shape[1]
+  rows_abc = a.shape[0]
+  for n, v in (('a', a), ('b', b), ('c', c)):
+    _req(v, torch.float32, (rows_abc, D), n)
+  _req(t, torch.float32, (B,), 't')
+  out = torch.empty((B,) if desc.gt_mode == MULAN_GT_MEAN else (B, D), dtype=torch.float32,
+                    device=a.device)
+  d = desc.c(B)
+  _lib.check(_lib.load().mulan_sample_gamma(C.byref(d), rows_abc, _p(a), _p(b), _p(c), _p(t),
+                                            _p(out), _stream()))
+  return out
+
+
+def sample_step(desc: Desc, a, b, c, t, s, z_t, net, eps, out=None):
+  """mulan_sample_step -> z_s[B,D] (one ancestral step; VDM.sample after the denoiser call)."""
+  B, D = z_t.shape
+  rows_abc = a.shape[0]
+  for n, v in (('a', a), ('b', b), ('c', c)):
+    _req(v, torch.float32, (rows_abc, D), n)
+  for n, v in (('z_t', z_t), ('net', net), ('eps', eps)):
+    _req(v, torch.float32, (B, D), n)
+  _req(t, torch.float32, (B,), 't')
+  _req(s, torch.float32, (B,), 's')
+  if out is None:
+    out = torch.empty((B, D), dtype=torch.float32, device=z_t.device)
+  d = desc.c(B)
+  _lib.check(_lib.load().mulan_sample_step(C.byref(d), rows_abc, _p(a), _p(b), _p(c), _p(t),
+                                           _p(s), _p(z_t), _p(net), _p(eps), _p(out), _stream()))
+  return out
+
+
+def generate_x(desc: Desc, z_0):
+  """mulan_generate_x -> x[B,D] uint8 (argmax decode of z_0; VDM.generate_x)."""
+  B, D = z_0.shape
+  _req(z_0, torch.float32, (B, D), 'z_0')
+  out = torch.empty((B, D), dtype=torch.uint8, device=z_0.device)
+  d = desc.c(B)
+  _lib.check(_lib.load().mulan_generate_x(C.byref(d), _p(z_0), _p(out), _stream()))
+  return out
+
+
 class ElboWorkspace:
   """Preallocated outputs of the whole path for a fixed shard size: every launch writes into
   the same buffers, so a step makes no allocation and can be captured in a CUDA graph

@@ -394,6 +394,41 @@ def eval_bpd_dense(images, n_timesteps: int, run_loss_fn: Callable):
 
 
 # ----------------------------------------------------------------------------
+# Ancestral sampler (model_mulan_epsilon.py:365-457, model_mulan_velocity.py:270-366)
+# ----------------------------------------------------------------------------
+
+def deterministic_embedding(batch_size: int, cfg: OracleConfig, dtype=torch.float32):
+  """_get_deterministic_embedding, latent_type == 'topk' (epsilon.py:369-374)."""
+  ones = torch.ones((batch_size, cfg.latent_k), dtype=dtype)
+  zeros = torch.zeros((batch_size, cfg.latent_size - cfg.latent_k), dtype=dtype)
+  return torch.cat([ones, zeros], dim=1)
+
+
+def sample_step(z_t, g_t, g_s, net, eps, mode: int):
+  """The arithmetic of VDM.sample after the denoiser call (epsilon.py:432-438;
+  velocity.py:337-345, which converts the velocity output to eps first)."""
+  a = sigmoid(-g_s)
+  b = sigmoid(-g_t)
+  c = -torch.expm1(g_s - g_t)
+  sigma_t = torch.sqrt(sigmoid(g_t))
+  if mode == MODE_EPS:
+    eps_hat = net
+  else:
+    alpha_t = torch.sqrt(sigmoid(-g_t))
+    eps_hat = net * alpha_t + sigma_t * z_t
+  z_s_mean = torch.sqrt(a / b) * (z_t - sigma_t * c * eps_hat)
+  return z_s_mean + torch.sqrt((1. - a) * c) * eps
+
+
+def generate_x(z_0, g_0, vocab_size: int):
+  """epsilon.py:440-457 with sample_softmax=False: argmax of the decoder logits."""
+  var_0 = sigmoid(g_0)
+  z_0_rescaled = z_0 / torch.sqrt(1. - var_0)
+  logits = decode(z_0_rescaled, g_0, vocab_size)
+  return torch.argmax(logits, dim=-1)
+
+
+# ----------------------------------------------------------------------------
 # Helpers for tests / bench (synthetic inputs, SURVEY.md 8d)
 # ----------------------------------------------------------------------------
 

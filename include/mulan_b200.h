@@ -233,6 +233,25 @@ int mulan_sample_step(const mulan_desc* desc, int32_t abc_rows, const float* a, 
 int mulan_generate_x(const mulan_desc* desc, const float* z_0, uint8_t* x, void* stream);
 
 /*
+ * Probability-flow ODE ("next" row 4): drift of VDM.reverse_ode
+ * (ldm/model_mulan_epsilon.py:459-478; the velocity model's version returns nothing) and the
+ * local pieces of its Hutchinson divergence (_get_value_div_fn, ldm/notebook_utils.py:204-216).
+ *   drift = 0.5 (-sigma x_t + eps_hat) sigma dgamma/dt,  sigma = sqrt(sigmoid(g_t))
+ *           (high_precision != 0: sigma = exp(g_t/2) where sigmoid(g_t) <= 1e-3)
+ *   with Hutchinson noise v (NULL: drift only), k = 0.5 sigma dgamma/dt:
+ *     net_bar[B,D]  = k v                 cotangent for the denoiser's backward
+ *     div_direct[B] = sum_d -sigma k v^2  the part of v^T J v that bypasses the denoiser
+ *   mulan_row_dot(u = J_net^T net_bar, v, add = div_direct) then completes the divergence.
+ */
+int mulan_ode_drift(const mulan_desc* desc, int32_t abc_rows, const float* a, const float* b,
+                    const float* c, const float* t, const float* x_t, const float* eps_hat,
+                    const float* v, int32_t high_precision, float* drift, float* net_bar,
+                    float* div_direct, void* stream);
+/* out[b] = sum_d u[b,d] v[b,d] (+ add[b] when add != NULL); u, v are [rows, dim]. */
+int mulan_row_dot(int32_t rows, int32_t dim, const float* u, const float* v, const float* add,
+                  float* out, void* stream);
+
+/*
  * mulan_adamw_ema -- "next" row 1 of the scope table: the AdamW + EMA update that follows the
  * gradient all-reduce of every train step, fused over one flat float32 buffer.
  * Replaces TrainState.apply_gradients (ldm/train_state.py:70-102) with the optax.adamw chain

@@ -64,6 +64,8 @@ SIGNATURES = {
     'mulan_sample_gamma': ([_D, C.c_int32] + [_P] * 6, C.c_int),
     'mulan_sample_step': ([_D, C.c_int32] + [_P] * 10, C.c_int),
     'mulan_generate_x': ([_D] + [_P] * 3, C.c_int),
+    'mulan_ode_drift': ([_D, C.c_int32] + [_P] * 7 + [C.c_int32] + [_P] * 4, C.c_int),
+    'mulan_row_dot': ([C.c_int32] * 2 + [_P] * 5, C.c_int),
     'mulan_adamw_ema': ([C.POINTER(MulanAdamwDesc)] + [_P] * 6, C.c_int),
     'mulan_host_workspace_release': ([], None),
 }

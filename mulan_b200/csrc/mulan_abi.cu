@@ -341,6 +341,37 @@ int mulan_generate_x(const mulan_desc* d, const float* z_0, uint8_t* x, void* st
   return e == cudaSuccess ? 0 : cuda_fail(fn, e);
 }
 
+int mulan_ode_drift(const mulan_desc* d, int32_t abc_rows, const float* a, const float* b,
+                    const float* c, const float* t, const float* x_t, const float* eps_hat,
+                    const float* v, int32_t high_precision, float* drift, float* net_bar,
+                    float* div_direct, void* stream) {
+  const char* fn = "mulan_ode_drift";
+  if (int r = check_desc(d, fn)) return r;
+  if (d->param != MULAN_PARAM_EPS)
+    return fail(MULAN_ERR_UNSUPPORTED, "%s: only the epsilon model has a working reverse_ode "
+                "(ldm/model_mulan_velocity.py:393-420 returns nothing)", fn);
+  if (d->rows == 0) return 0;
+  mulan::SamplerParams p;
+  if (int r = fill_sampler(fn, d, abc_rows, a, b, c, &p)) return r;
+  REQ_PTR(t, fn); REQ_VEC(x_t, fn); REQ_VEC(eps_hat, fn); REQ_VEC(drift, fn); OPT_VEC(v, fn);
+  if (v != nullptr) { REQ_VEC(net_bar, fn); REQ_PTR(div_direct, fn); }
+  p.t = t; p.z_t = x_t; p.net = eps_hat; p.eps = v; p.z_s = drift; p.g_net = net_bar;
+  p.div_direct = div_direct;
+  cudaError_t e = mulan::launch_ode_drift(p, high_precision != 0, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(fn, e);
+}
+
+int mulan_row_dot(int32_t rows, int32_t dim, const float* u, const float* v, const float* add,
+                  float* out, void* stream) {
+  const char* fn = "mulan_row_dot";
+  if (rows < 0 || dim <= 0) return fail(MULAN_ERR_INVALID_ARG, "%s: bad shape", fn);
+  if (dim % 4 != 0) return fail(MULAN_ERR_ALIGNMENT, "%s: dim=%d is not a multiple of 4", fn, dim);
+  if (rows == 0) return 0;
+  REQ_VEC(u, fn); REQ_VEC(v, fn); REQ_PTR(out, fn);
+  cudaError_t e = mulan::launch_row_dot(u, v, add, out, rows, dim / 4, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(fn, e);
+}
+
 int mulan_adamw_ema(const mulan_adamw_desc* d, float* params, const float* grads, float* mu,
                     float* nu, float* ema_params, void* stream) {
   const char* fn = "mulan_adamw_ema";

@@ -133,6 +133,9 @@ struct SamplerParams {
   float* z_s;       // sample_step
   float* g_net;     // sample_gamma: [B] or [B,D]
   uint8_t* x;       // generate_x
+  // ode_drift reuses: z_t = x_t, net = eps_hat, eps = Hutchinson noise v (or NULL),
+  //                   z_s = drift out, g_net = net_bar out, div_direct = [B] out
+  float* div_direct;
   int rows, dim4, abc_rows, param, gt_mode;
   float gmin, delta;
   float den0, inv0; // generate_x: sqrt(1 - sigmoid(g0)), exp(-g0/2)
@@ -141,6 +144,9 @@ struct SamplerParams {
 cudaError_t launch_sample_gamma(const SamplerParams& p, cudaStream_t s);
 cudaError_t launch_sample_step(const SamplerParams& p, cudaStream_t s);
 cudaError_t launch_generate_x(const SamplerParams& p, cudaStream_t s);
+cudaError_t launch_ode_drift(const SamplerParams& p, bool high_precision, cudaStream_t s);
+cudaError_t launch_row_dot(const float* u, const float* v, const float* add, float* out, int rows,
+                           int dim4, cudaStream_t s);
 
 // Number of CTAs of `kernel` (kThreads threads, static shared memory only) that are resident
 // on the current device at once: the grid size of the persistent kernels.

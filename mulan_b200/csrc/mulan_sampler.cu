@@ -131,6 +131,94 @@ generate_x_kernel(const SamplerParams p) {
   }
 }
 
+// ---- probability-flow ODE drift + the local part of its Hutchinson divergence -------------
+// VDM.reverse_ode (ldm/model_mulan_epsilon.py:459-478):
+//   sigma = sqrt(sigmoid(g_t))   (high_precision: exp(g_t/2) where sigmoid(g_t) <= 1e-3)
+//   drift = 0.5 (-sigma x + eps_hat) sigma g_t_grad
+// _get_value_div_fn (ldm/notebook_utils.py:204-216): div = sum_d v (d<drift, v>/dx).  With
+// k = 0.5 sigma g_t_grad:  d<drift,v>/dx = -sigma k v  +  J_net^T (k v), so this pass also emits
+// net_bar = k v (the cotangent the denoiser's backward needs) and the per-row direct part
+// div_direct = sum_d -sigma k v^2.  mulan_row_dot adds <J_net^T net_bar, v> afterwards.
+template <bool HP, bool HUTCH>
+__global__ void __launch_bounds__(kThreads)
+ode_drift_kernel(const SamplerParams p) {
+  __shared__ RowT s_rt;
+  __shared__ float red[kWarps][1];
+  const int row = blockIdx.x, tid = threadIdx.x;
+  if (tid == 0) s_rt = make_row_t(__ldg(p.t + row));
+  __syncthreads();
+  const RowT rt = s_rt;
+  const size_t cbase = p.abc_rows == 1 ? 0 : (size_t)row * p.dim4;
+  const size_t base4 = (size_t)row * p.dim4;
+  float acc[1] = {0.f};
+  for (int i4 = tid; i4 < p.dim4; i4 += kThreads) {
+    const float4 A = ld4(p.a, cbase + i4), Bv = ld4(p.b, cbase + i4), C = ld4(p.c, cbase + i4);
+    const float4 X = ld4(p.z_t, base4 + i4), N = ld4(p.net, base4 + i4);
+    float4 V = make_float4(0.f, 0.f, 0.f, 0.f), DR, NB;
+    if (HUTCH) V = ld4(p.eps, base4 + i4);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const Poly po = poly_eval(get(A, j), get(Bv, j), get(C, j), rt);
+      const float rS = rcp_scale(po.S);
+      const float gt = p.gmin + (p.delta * po.P) * rS;
+      const float w = (p.delta * (po.q * po.q)) * rS;
+      const float var = sigmoid_ref(gt);
+      float sigma = sqrtf(var);
+      if (HP && var <= 1e-3f) sigma = expf(gt / 2.0f);
+      const float x = get(X, j), n = get(N, j);
+      put(DR, j, 0.5f * (-sigma * x + n) * sigma * w);
+      if (HUTCH) {
+        const float v = get(V, j);
+        const float k = 0.5f * sigma * w;
+        put(NB, j, k * v);
+        acc[0] += -(sigma * k) * (v * v);
+      }
+    }
+    st4(p.z_s, base4 + i4, DR);
+    if (HUTCH) st4(p.g_net, base4 + i4, NB);
+  }
+  if (HUTCH) {
+    block_sum<1>(acc, red);
+    if (tid == 0) p.div_direct[row] = acc[0];
+  }
+}
+
+// out[b] = sum_d u[b,d] v[b,d] (+ add[b])
+__global__ void __launch_bounds__(kThreads)
+row_dot_kernel(const float* __restrict__ u, const float* __restrict__ v,
+               const float* __restrict__ add, float* __restrict__ out, int dim4) {
+  __shared__ float red[kWarps][1];
+  const int row = blockIdx.x;
+  const size_t base4 = (size_t)row * dim4;
+  float acc[1] = {0.f};
+  for (int i4 = threadIdx.x; i4 < dim4; i4 += kThreads) {
+    const float4 U = ld4(u, base4 + i4), V = ld4(v, base4 + i4);
+    acc[0] += U.x * V.x; acc[0] += U.y * V.y; acc[0] += U.z * V.z; acc[0] += U.w * V.w;
+  }
+  block_sum<1>(acc, red);
+  if (threadIdx.x == 0) out[row] = add != nullptr ? acc[0] + add[row] : acc[0];
+}
+
+cudaError_t launch_ode_drift(const SamplerParams& p, bool high_precision, cudaStream_t s) {
+  if (p.rows == 0) return cudaSuccess;
+  const bool hutch = p.eps != nullptr;
+  if (high_precision) {
+    if (hutch) ode_drift_kernel<true, true><<<p.rows, kThreads, 0, s>>>(p);
+    else       ode_drift_kernel<true, false><<<p.rows, kThreads, 0, s>>>(p);
+  } else {
+    if (hutch) ode_drift_kernel<false, true><<<p.rows, kThreads, 0, s>>>(p);
+    else       ode_drift_kernel<false, false><<<p.rows, kThreads, 0, s>>>(p);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_row_dot(const float* u, const float* v, const float* add, float* out, int rows,
+                           int dim4, cudaStream_t s) {
+  if (rows == 0) return cudaSuccess;
+  row_dot_kernel<<<rows, kThreads, 0, s>>>(u, v, add, out, dim4);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_sample_gamma(const SamplerParams& p, cudaStream_t s) {
   if (p.rows == 0) return cudaSuccess;
   if (p.gt_mode == MULAN_GT_MEAN) sample_gamma_kernel<MULAN_GT_MEAN><<<p.rows, kThreads, 0, s>>>(p);

@@ -273,6 +273,31 @@ def sample_fn(model: VDM, n: int, T: int = 1000, generator=None, sigma_prior: fl
   return generate_x(model, z)
 
 
+def value_div_fn(model: VDM, x, embeddings, t, hutchinson_noise, high_precision: bool = False):
+  """VDM.reverse_ode (ldm/model_mulan_epsilon.py:459-478) and its Hutchinson divergence
+  (_get_value_div_fn, ldm/notebook_utils.py:204-216): -> (drift[B,32,32,3], div[B]).
+  The denoiser's Jacobian-vector product comes from torch autograd through `score_model`;
+  everything else is mulan_sample_gamma / mulan_ode_drift / mulan_row_dot."""
+  cfg = model.config
+  B = x.shape[0]
+  D = 32 * 32 * 3
+  with torch.no_grad():
+    a, b, c = (q.contiguous() for q in model.gamma._compute_coefficients(embeddings))
+    tt = (t * torch.ones((B,), dtype=torch.float32, device=x.device)).contiguous()
+    g_net = ops.sample_gamma(model.desc, a, b, c, tt)
+  g_in = g_net if cfg.unet_type == 'vdm' else g_net.reshape(B, 32, 32, 3)
+  xg = x.detach().reshape(B, 32, 32, 3).requires_grad_(True)
+  with torch.enable_grad():
+    net = model.score_model(xg, g_in, embeddings, True)
+  v = hutchinson_noise.reshape(B, D).contiguous()
+  drift, net_bar, div_direct = ops.ode_drift(
+      model.desc, a, b, c, tt, xg.detach().reshape(B, D).contiguous(),
+      net.detach().reshape(B, D).contiguous(), v, high_precision)
+  (x_bar,) = torch.autograd.grad(net, xg, grad_outputs=net_bar.reshape(net.shape))
+  div = ops.row_dot(x_bar.reshape(B, D).contiguous(), v, add=div_direct)
+  return drift.reshape(B, 32, 32, 3), div
+
+
 def loss_fn(model: VDM, inputs: dict, step=0, is_train: bool = True, draws=None,
             generator=None):
   """Experiment_VDM.loss_fn (ldm/experiment_vdm.py:47-78): -> (bpd, metrics)."""

@@ -230,6 +230,37 @@ def generate_x(desc: Desc, z_0):
   return out
 
 
+def ode_drift(desc: Desc, a, b, c, t, x_t, eps_hat, v=None, high_precision: bool = False):
+  """mulan_ode_drift -> drift[B,D] (v is None) or (drift, net_bar[B,D], div_direct[B])."""
+  B, D = x_t.shape
+  rows_abc = a.shape[0]
+  for n, q in (('a', a), ('b', b), ('c', c)):
+    _req(q, torch.float32, (rows_abc, D), n)
+  for n, q in (('x_t', x_t), ('eps_hat', eps_hat)):
+    _req(q, torch.float32, (B, D), n)
+  _opt(v, torch.float32, (B, D), 'v')
+  _req(t, torch.float32, (B,), 't')
+  drift = torch.empty((B, D), dtype=torch.float32, device=x_t.device)
+  nb = torch.empty_like(drift) if v is not None else None
+  dd = torch.empty((B,), dtype=torch.float32, device=x_t.device) if v is not None else None
+  d = desc.c(B)
+  _lib.check(_lib.load().mulan_ode_drift(
+      C.byref(d), rows_abc, _p(a), _p(b), _p(c), _p(t), _p(x_t), _p(eps_hat), _p(v),
+      1 if high_precision else 0, _p(drift), _p(nb), _p(dd), _stream()))
+  return drift if v is None else (drift, nb, dd)
+
+
+def row_dot(u, v, add=None):
+  """mulan_row_dot -> out[b] = <u[b], v[b]> (+ add[b])."""
+  B, D = u.shape
+  _req(u, torch.float32, (B, D), 'u')
+  _req(v, torch.float32, (B, D), 'v')
+  _opt(add, torch.float32, (B,), 'add')
+  out = torch.empty((B,), dtype=torch.float32, device=u.device)
+  _lib.check(_lib.load().mulan_row_dot(B, D, _p(u), _p(v), _p(add), _p(out), _stream()))
+  return out
+
+
 class ElboWorkspace:
   """Preallocated outputs of the whole path for a fixed shard size: every launch writes into
   the same buffers, so a step makes no allocation and can be captured in a CUDA graph

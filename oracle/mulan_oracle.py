@@ -429,6 +429,29 @@ def generate_x(z_0, g_0, vocab_size: int):
 
 
 # ----------------------------------------------------------------------------
+# Probability-flow ODE (model_mulan_epsilon.py:459-478, notebook_utils.py:204-216)
+# ----------------------------------------------------------------------------
+
+def reverse_ode(xt, g_t, g_t_grad, eps_hat, high_precision: bool = False):
+  """epsilon.py:459-478 once g_t, d gamma/dt and the denoiser output exist."""
+  if high_precision:
+    sigma = torch.where(sigmoid(g_t) <= 1e-3, torch.exp(g_t / 2), torch.sqrt(sigmoid(g_t)))
+  else:
+    sigma = torch.sqrt(sigmoid(g_t))
+  return 0.5 * (-sigma * xt + eps_hat) * sigma * g_t_grad
+
+
+def value_div(x, g_t, g_t_grad, score_fn, hutchinson_noise, high_precision: bool = False):
+  """_get_value_div_fn (notebook_utils.py:204-216): drift and its Hutchinson divergence
+  estimate sum(grad_x <drift, v> * v) by autograd.  score_fn(x) -> eps_hat."""
+  x = x.detach().clone().requires_grad_(True)
+  f = reverse_ode(x, g_t, g_t_grad, score_fn(x), high_precision)
+  (grad_fn_eps,) = torch.autograd.grad(torch.sum(f * hutchinson_noise), x)
+  red = tuple(range(1, x.ndim))
+  return f.detach(), torch.sum(grad_fn_eps * hutchinson_noise, dim=red)
+
+
+# ----------------------------------------------------------------------------
 # Helpers for tests / bench (synthetic inputs, SURVEY.md 8d)
 # ----------------------------------------------------------------------------
 

@@ -119,6 +119,7 @@ def _make_jnp():
       lambda x: torch.ceil(_t(x)), lambda x: torch.exp(_t(x)), lambda x: torch.log(_t(x)),
       lambda x: torch.sqrt(_t(x)), lambda x: torch.square(_t(x)), lambda x: torch.expm1(_t(x)))
   m.maximum = lambda x, y: torch.maximum(_t(x), _t(y))
+  m.where = lambda c, x, y: torch.where(c, x, y)
 
   def _red(fn):
     def f(x, **k):

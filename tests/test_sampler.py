@@ -129,3 +129,71 @@ def test_sampler_per_row_coefficients_and_loop(cuda_device):
                      ops.sample_gamma(vdm.desc, a.repeat(Bn, 1), b.repeat(Bn, 1), c.repeat(Bn, 1), t))
   x = M.sample_fn(vdm, 3, T=8, generator=torch.Generator(device=dev).manual_seed(0))
   assert x.shape == (3, 32, 32, 3) and x.dtype == torch.uint8
+
+
+ODE_T = [0.03, 0.6]
+
+
+@pytest.mark.parametrize('tag', ['f32', 'f64'])
+@pytest.mark.parametrize('hp', [False, True])
+def test_oracle_reverse_ode_matches_reference_source(tag, hp):
+  dtype = torch.float32 if tag == 'f32' else torch.float64
+  cfg = O.OracleConfig()
+  inp = sampler_inputs()
+  tt = lambda v: torch.from_numpy(np.asarray(v)).to(dtype)
+  W = {k: tt(v) for k, v in GI.mlp_weights(SEED + 1000).items()}
+  a, b, c = O.compute_coefficients(W, O.deterministic_embedding(B, cfg, dtype))
+  t = tt(np.asarray(ODE_T, np.float32)).reshape(B, 1)
+  g_t = O.eval_polynomial(a, b, c, t, cfg).reshape(B, 32, 32, 3)
+  w = O.eval_polynomial_dt(a, b, c, t, cfg).reshape(B, 32, 32, 3)
+  x = tt(inp['z_t'])
+  net = 0.7 * x + 0.05 * O.score_model_gt(g_t, cfg).reshape(-1, 1, 1, 1) + tt(inp['noise'])
+  drift = O.reverse_ode(x, g_t, w, net, hp)
+  want = G[f'eps_{tag}_ode_drift_hp{int(hp)}']
+  tol = (2e-5 if tag == 'f32' else 1e-10) * np.abs(want).max()
+  assert np.abs(drift.numpy() - want).max() < tol
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('hp', [False, True])
+def test_cuda_reverse_ode_and_divergence(cuda_device, hp):
+  """Drift against the golden from the reference's reverse_ode; Hutchinson divergence
+  (drift pieces + autograd through a torch denoiser) against the oracle's autograd."""
+  from mulan_b200 import model as M
+  dev = cuda_device
+  inp = sampler_inputs()
+  tt = lambda v: torch.from_numpy(np.asarray(v)).to(dev)
+  noise = tt(inp['noise'])
+  w1 = torch.tensor(0.7, device=dev)
+  conv = torch.nn.Conv2d(3, 3, 3, padding=1).to(dev)
+
+  def score_lin(z, g, cond, det):
+    return w1 * z + 0.05 * g.reshape(-1, 1, 1, 1) + noise
+  cfg = M.VDMConfig()
+  vdm = M.VDM(cfg, lambda f, d: None, score_lin).to(dev)
+  vdm.gamma.load_flax(GI.mlp_weights(SEED + 1000))
+  emb = M._deterministic_embedding(vdm, B, dev)
+  t = tt(np.asarray(ODE_T, np.float32))
+  x = tt(inp['z_t'])
+  rng = np.random.default_rng(4)
+  v = tt((rng.integers(0, 2, (B, 32, 32, 3)) * 2 - 1).astype(np.float32))   # Rademacher
+  drift, div = M.value_div_fn(vdm, x, emb, t, v, high_precision=hp)
+  want = G[f'eps_f32_ode_drift_hp{int(hp)}']
+  assert np.abs(drift.cpu().numpy() - want).max() < 3e-5 * np.abs(want).max()
+  # divergence with a non-trivial denoiser Jacobian (a conv), against oracle autograd in f64
+  vdm.score_model = lambda z, g, cond, det: (
+      w1 * z + 0.3 * conv(z.permute(0, 3, 1, 2)).permute(0, 2, 3, 1) + noise)
+  drift, div = M.value_div_fn(vdm, x, emb, t, v, high_precision=hp)
+  ocfg = O.OracleConfig()
+  Wd = {k: torch.from_numpy(val).double() for k, val in GI.mlp_weights(SEED + 1000).items()}
+  a, b, c = O.compute_coefficients(Wd, O.deterministic_embedding(B, ocfg, torch.float64))
+  td = t.cpu().double().reshape(B, 1)
+  g_t = O.eval_polynomial(a, b, c, td, ocfg).reshape(B, 32, 32, 3)
+  wd = O.eval_polynomial_dt(a, b, c, td, ocfg).reshape(B, 32, 32, 3)
+  conv64 = torch.nn.Conv2d(3, 3, 3, padding=1).double()
+  conv64.load_state_dict({k: val.cpu().double() for k, val in conv.state_dict().items()})
+  score64 = lambda z: (0.7 * z + 0.3 * conv64(z.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
+                       + noise.cpu().double())
+  f64, div64 = O.value_div(x.cpu().double(), g_t, wd, score64, v.cpu().double(), hp)
+  assert np.abs(drift.cpu().numpy() - f64.numpy()).max() < 1e-4 * f64.abs().max().item()
+  assert np.abs(div.cpu().numpy() - div64.numpy()).max() < 1e-4 * div64.abs().max().item()

@@ -210,31 +210,6 @@ __device__ __forceinline__ void block_sum(float (&acc)[N], float (*smem)[N]) {
 }
 
 // ---------------------------------------------------------------------------------------
-// Asynchronous row pipeline (persistent CTAs).
-//
-// Each CTA walks rows blockIdx.x, blockIdx.x + gridDim.x, ...; a row is dim4 float4 columns,
-// consumed 256 columns ("a slab") at a time.  The operands of slab k+1 are copied
-// global -> shared with cp.async (LDGSTS: no registers held while the data is in flight)
-// while slab k is being computed, across row boundaries, so DRAM latency is covered by a
-// full slab of arithmetic (~110 instructions x 4 sub-pixels per thread) instead of by
-// occupancy alone.  Every thread copies and later reads ONLY its own 16-byte slots, so
-// cp.async.wait_group is the only synchronisation the pipeline needs.
-// ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
-// ---------------------------------------------------------------------------------------
 // TMA bulk copies (cp.async.bulk, SASS UBLKCP) + mbarrier: one elected thread moves a whole
 // 4 KB slab per operand array; no per-thread address arithmetic, no registers in flight.
 // ---------------------------------------------------------------------------------------
@@ -270,50 +245,6 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
       ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
-// Shared-memory slab of NF float4 operands (+ one uchar4 of x) per thread, double buffered.
-template <int NF>
-struct SlabBuf {
-  float4 f[2][NF][kThreads];
-  uchar4 x[2][kThreads];
-};
-
-// Position of a CTA in its (row, slab) walk.
-struct SlabWalk {
-  int row, slab;        // current row and slab index within the row
-  int nslab;            // slabs per row = ceil(dim4 / kThreads)
-  int dim4, rows;
-  __device__ __forceinline__ void init(int rows_, int dim4_) {
-    rows = rows_; dim4 = dim4_;
-    nslab = (dim4_ + kThreads - 1) / kThreads;
-    row = blockIdx.x; slab = 0;
-  }
-  __device__ __forceinline__ bool valid() const { return row < rows; }
-  __device__ __forceinline__ void next() {
-    if (++slab == nslab) { slab = 0; row += gridDim.x; }
-  }
-  // float4 column of this thread in the slab, and whether it exists (ragged last slab)
-  __device__ __forceinline__ int col() const { return slab * kThreads + threadIdx.x; }
-  __device__ __forceinline__ bool live() const { return col() < dim4; }
-  __device__ __forceinline__ size_t g4() const { return (size_t)row * dim4 + col(); }
-};
-
-// Issue the copies of one slab: ptr[k] are the NF float operand arrays, x the uint8 array
-// (nullptr entries are skipped).
-template <int NF>
-__device__ __forceinline__ void slab_issue(SlabBuf<NF>& sb, int stage, const SlabWalk& w,
-                                           const float* const (&ptr)[NF], const uint8_t* x) {
-  if (w.valid() && w.live()) {
-    const size_t g4 = w.g4();
-#pragma unroll
-    for (int k = 0; k < NF; ++k)
-      if (ptr[k] != nullptr)
-        cp_async16(&sb.f[stage][k][threadIdx.x], reinterpret_cast<const float4*>(ptr[k]) + g4);
-    if (x != nullptr)
-      cp_async4(&sb.x[stage][threadIdx.x], reinterpret_cast<const uchar4*>(x) + g4);
-  }
-  cp_async_commit();
 }
 
 }  // namespace mulan

@@ -164,6 +164,25 @@ class VDM(nn.Module):
     # fuse d loss_diff / d net into the forward pass of the post kernel when training
     self.fused_value_and_grad = True
 
+  def apply_encoder(self, images_int):
+    """ldm/model_mulan_epsilon.py:178-180."""
+    return self.encoder_model(self.encdec.encode(images_int), True)
+
+  @torch.no_grad()
+  def apply_gamma(self, t, embedding=None):
+    """ldm/model_mulan_epsilon.py:182-193 with the embedding supplied (None -> zeros, as the
+    reference does for x_zero=None): per-pixel gamma(embedding, t), [B, 3072]."""
+    dev = next(self.gamma.parameters()).device
+    t = torch.as_tensor(t, dtype=torch.float32, device=dev).reshape(-1)
+    B = t.shape[0]
+    if embedding is None:
+      embedding = torch.zeros((B, self.config.latent_size), dtype=torch.float32, device=dev)
+    a, b, c = (v.contiguous() for v in self.gamma._compute_coefficients(embedding))
+    pix = ops.Desc(dim=self.desc.dim, vocab=self.desc.vocab, param=self.desc.param,
+                   gt_mode=MULAN_GT_PIXEL, gamma_min=self.desc.gamma_min,
+                   gamma_max=self.desc.gamma_max)
+    return ops.sample_gamma(pix, a, b, c, t.contiguous())
+
   def make_draws(self, n_batch: int, device, generator: Optional[torch.Generator] = None):
     """The four make_rng('sample') draws of __call__, in the reference's order."""
     g = generator

@@ -258,3 +258,38 @@ def test_world_size_2_gloo():
                                           seed=3)
   assert abs(bpd0 - all_bpd) < 1e-6 * abs(all_bpd)
   assert mine0.size == 2 and mine1.size == 2
+
+
+def test_bench_reference_arm_contract():
+  """`bench.py --impl reference` prints exactly ONE JSON line with the contract's keys (the CPU
+  oracle port is the reference arm; no GPU needed)."""
+  import json
+  import subprocess
+  out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference',
+                        '--steps', '1', '--warmup', '0', '--ref-rows', '8'],
+                       capture_output=True, text=True, timeout=600)
+  assert out.returncode == 0, out.stderr[-2000:]
+  lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+  assert len(lines) == 1
+  d = json.loads(lines[0])
+  for k in ('impl', 'metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step',
+            'higher_is_better', 'scaling', 'vs_baseline', 'dtype', 'data', 'config', 'cpu_baseline',
+            'e2e'):
+    assert k in d, k
+  assert d['impl'] == 'reference' and d['vs_baseline'] is None and d['value'] > 0
+  assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
+  assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0
+  assert 'workload' in d['config']
+
+
+def test_native_bench_fails_loudly_without_gpu():
+  """No CPU fallback: without a CUDA device the native arm must exit non-zero and print no
+  JSON line."""
+  import subprocess
+  if torch.cuda.is_available():
+    pytest.skip('a GPU is present')
+  out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--steps', '1',
+                        '--no-e2e', '--no-cpu-baseline'], capture_output=True, text=True,
+                       timeout=600)
+  assert out.returncode != 0
+  assert out.stdout.strip() == ''

@@ -197,3 +197,25 @@ def test_cuda_reverse_ode_and_divergence(cuda_device, hp):
   f64, div64 = O.value_div(x.cpu().double(), g_t, wd, score64, v.cpu().double(), hp)
   assert np.abs(drift.cpu().numpy() - f64.numpy()).max() < 1e-4 * f64.abs().max().item()
   assert np.abs(div.cpu().numpy() - div64.numpy()).max() < 1e-4 * div64.abs().max().item()
+
+
+@pytest.mark.gpu
+def test_apply_gamma(cuda_device):
+  """VDM.apply_gamma (ldm/model_mulan_epsilon.py:182-193): per-pixel gamma(embedding, t);
+  fixed ends at t = 0 / 1, oracle in between."""
+  from mulan_b200 import model as M
+  dev = cuda_device
+  vdm = M.VDM(M.VDMConfig(), lambda f, d: None, lambda *a: None).to(dev)
+  W = GI.mlp_weights(12)
+  vdm.gamma.load_flax(W)
+  t = torch.tensor([0.0, 1.0, 0.37], device=dev)
+  emb = M._deterministic_embedding(vdm, 3, dev)
+  g = vdm.apply_gamma(t, emb).cpu()
+  assert g.shape == (3, 3072)
+  assert torch.all(g[0] == torch.tensor(-13.3, dtype=torch.float32))
+  assert (g[1] - 5.0).abs().max().item() < 5e-6
+  ocfg = O.OracleConfig()
+  Wd = {k: torch.from_numpy(v).double() for k, v in W.items()}
+  a, b, c = O.compute_coefficients(Wd, O.deterministic_embedding(3, ocfg, torch.float64))
+  want = O.eval_polynomial(a, b, c, t.cpu().double().reshape(3, 1), ocfg)
+  assert (g.double() - want).abs().max().item() < 1e-4

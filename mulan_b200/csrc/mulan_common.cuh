@@ -86,13 +86,6 @@ __device__ __forceinline__ bool scale_in_range(float S) {
 __device__ __forceinline__ float rcp_scale(float S) {
   return scale_in_range(S) ? rcp_nr(S) : __frcp_rn(S);
 }
-// sqrt(x), 0 <= x < 2^100: x * rsqrt(x) + one Newton step; sqrt(0) = 0.
-__device__ __forceinline__ float sqrt_nr(float x) {
-  const float y = rsqrt_approx(x);
-  float s = x * y;
-  s = fmaf(fmaf(-s, s, x), 0.5f * y, s);
-  return x > 0.0f ? s : 0.0f;
-}
 // sqrt(x) = x * rsqrt(x) straight off the MUFU (~2^-22 relative): for alpha/sigma, whose
 // rounding in the reference is itself pseudo-random per sub-pixel.  x > 0.
 __device__ __forceinline__ float sqrt_fast(float x) { return x * rsqrt_approx(x); }

@@ -30,6 +30,7 @@
 // that decides HOW the reference rounds where it matters (z_0, u = (z_0 - x_k) e^{-g0/2},
 // 1 - sigmoid, the prior-KL summand) keeps the reference's op order.
 #include <stdlib.h>
+#include <string.h>
 
 #include "mulan_kernels.h"
 
@@ -119,12 +120,48 @@ struct PreConsts {
   ReconFast rc;
   bool v1_uniform;
 };
+// The shipped configuration (gamma_min = -13.3, gamma_max = 5, vocab = 256 in both
+// ldm/configs/*.py) with every launch constant as a compile-time literal: the kernel then
+// carries them as instruction immediates instead of re-loading ~8 constants per sub-pixel
+// from the parameter bank (the kernel is instruction-issue bound).  The literals are the
+// values make_end_consts / make_recon_fast produce; launch_w() uses this specialisation only
+// when the run-time constants match them BIT FOR BIT, so a different gamma range, vocab or
+// host libm silently takes the generic kernel.
+struct Shipped {
+  static constexpr float gmin = -0x1.a9999ap+3f, delta = 0x1.24ccccp+4f;
+  static constexpr float s0 = 0x1.533858p-10f, inv0 = 0x1.826468p+9f, v0 = 0x1.c17e14p-20f;
+  static constexpr float v1 = 0x1.fc92c2p-1f, om1 = 0x1.b69fp-8f, lv1 = -0x1.b81872p-8f;
+  static constexpr float s = 0x1.826468p+2f, s2 = 0x1.16b91ap+3f, c0 = -0x1.a4b06cp+4f;
+  static constexpr float two_iv = 0x1p-7f, off = -0x1.fep-1f, half_vocab = 128.0f,
+                         vocab_m1 = 255.0f;
+};
+
+template <bool BAKED>
 __device__ __forceinline__ PreConsts load_pre_consts(const FwdPreParams& p) {
   PreConsts k;
-  k.s0 = p.k.s0; k.inv0 = p.k.inv0; k.v0c = p.k.v0; k.v1c = p.k.v1; k.om1 = p.k.om1;
-  k.lv1 = p.k.lv1; k.gmin = p.gmin; k.delta = p.delta; k.rc = p.rc;
-  k.v1_uniform = p.k.v1_uniform != 0;
+  if (BAKED) {
+    k.s0 = Shipped::s0; k.inv0 = Shipped::inv0; k.v0c = Shipped::v0; k.v1c = Shipped::v1;
+    k.om1 = Shipped::om1; k.lv1 = Shipped::lv1; k.gmin = Shipped::gmin; k.delta = Shipped::delta;
+    k.rc.inv0 = Shipped::inv0; k.rc.s = Shipped::s; k.rc.s2 = Shipped::s2; k.rc.c0 = Shipped::c0;
+    k.rc.two_iv = Shipped::two_iv; k.rc.off = Shipped::off;
+    k.rc.half_vocab = Shipped::half_vocab; k.rc.vocab_m1 = Shipped::vocab_m1;
+    k.v1_uniform = true;
+  } else {
+    k.s0 = p.k.s0; k.inv0 = p.k.inv0; k.v0c = p.k.v0; k.v1c = p.k.v1; k.om1 = p.k.om1;
+    k.lv1 = p.k.lv1; k.gmin = p.gmin; k.delta = p.delta; k.rc = p.rc;
+    k.v1_uniform = p.k.v1_uniform != 0;
+  }
   return k;
+}
+
+static bool is_shipped(const FwdPreParams& p) {
+  auto eq = [](float a, float b) { return memcmp(&a, &b, sizeof(float)) == 0; };
+  return p.k.v1_uniform != 0 && p.W == 1 && p.vi.vocab == 256 && eq(p.gmin, Shipped::gmin) &&
+         eq(p.delta, Shipped::delta) && eq(p.k.s0, Shipped::s0) && eq(p.k.inv0, Shipped::inv0) &&
+         eq(p.k.v0, Shipped::v0) && eq(p.k.v1, Shipped::v1) && eq(p.k.om1, Shipped::om1) &&
+         eq(p.k.lv1, Shipped::lv1) && eq(p.rc.s, Shipped::s) && eq(p.rc.s2, Shipped::s2) &&
+         eq(p.rc.c0, Shipped::c0) && eq(p.rc.two_iv, Shipped::two_iv) &&
+         eq(p.rc.off, Shipped::off);
 }
 
 template <int GT, bool SAVEW, bool FAST>
@@ -203,7 +240,7 @@ __device__ __forceinline__ void pre_row_end(const FwdPreParams& p, int row, floa
 // Direct-load kernel: one CTA per row, operands loaded straight into registers (LDG.128).
 // Serves any dim (multiple of 4), any vocab / window, any 4-byte aligned x.
 // ---------------------------------------------------------------------------------------
-template <int GT, bool SAVEW, bool FAST>
+template <int GT, bool SAVEW, bool FAST, bool BAKED>
 __global__ void __launch_bounds__(kThreads, 4)
 fwd_pre_kernel(const FwdPreParams p) {
   __shared__ RowT s_rt;
@@ -213,7 +250,7 @@ fwd_pre_kernel(const FwdPreParams p) {
   if (tid == 0) s_rt = make_row_t(__ldg(p.t + row));
   __syncthreads();
   const RowT rt = s_rt;
-  const PreConsts kc = load_pre_consts(p);
+  const PreConsts kc = load_pre_consts<BAKED>(p);
   const size_t base4 = (size_t)row * p.dim4;
   float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
   for (int i4 = tid; i4 < p.dim4; i4 += kThreads) {
@@ -245,7 +282,7 @@ constexpr unsigned kPreSlabBytes = 5 * kThreads * 16 + kThreads * 4;
 #ifndef MULAN_TMA_CTAS
 #define MULAN_TMA_CTAS 3
 #endif
-template <int GT, bool SAVEW>
+template <int GT, bool SAVEW, bool BAKED>
 __global__ void __launch_bounds__(kThreads, MULAN_TMA_CTAS)
 fwd_pre_tma_kernel(const FwdPreParams p) {
   __shared__ PreSlab slab[2];
@@ -278,7 +315,7 @@ fwd_pre_tma_kernel(const FwdPreParams p) {
   };
   if (tid == 0 && total > 0) request(0);
 
-  const PreConsts kc = load_pre_consts(p);
+  const PreConsts kc = load_pre_consts<BAKED>(p);
   int row = blockIdx.x, s = 0, parity = 0;
   RowT rt;
   float acc[5];
@@ -316,6 +353,12 @@ static bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 
 template <int GT, bool SAVEW>
 static cudaError_t launch_w(const FwdPreParams& p, cudaStream_t s) {
   const bool fast = p.W == 1 && p.vi.pow2;
+  // MULAN_NO_BAKED=1 forces the generic constants (A/B measurements, tests)
+  static const int no_baked = [] {
+    const char* e = getenv("MULAN_NO_BAKED");
+    return (e != nullptr && e[0] == '1') ? 1 : 0;
+  }();
+  const bool baked = fast && !no_baked && is_shipped(p);
   // The TMA-pipelined kernel is opt-in (MULAN_FWD_PRE_TMA=1): measured on B200 it hides DRAM
   // latency (issue utilisation 71 % -> 79 %) but executes 144 instead of 120 instructions per
   // sub-pixel, and this kernel is issue-bound: 0.260 ms vs 0.243 ms (profiles/).
@@ -325,14 +368,17 @@ static cudaError_t launch_w(const FwdPreParams& p, cudaStream_t s) {
   }();
   if (fast && use_tma && p.dim4 % kThreads == 0 && aligned16(p.x)) {
     static int max_ctas = 0;   // resident CTAs of this variant on the current device
-    if (max_ctas == 0) max_ctas = resident_ctas((const void*)fwd_pre_tma_kernel<GT, SAVEW>);
+    if (max_ctas == 0)
+      max_ctas = resident_ctas((const void*)fwd_pre_tma_kernel<GT, SAVEW, false>);
     const int grid = p.rows < max_ctas ? p.rows : max_ctas;
-    fwd_pre_tma_kernel<GT, SAVEW><<<grid, kThreads, 0, s>>>(p);
+    if (baked) fwd_pre_tma_kernel<GT, SAVEW, true><<<grid, kThreads, 0, s>>>(p);
+    else       fwd_pre_tma_kernel<GT, SAVEW, false><<<grid, kThreads, 0, s>>>(p);
     return cudaGetLastError();
   }
   dim3 grid(p.rows), block(kThreads);
-  if (fast) fwd_pre_kernel<GT, SAVEW, true><<<grid, block, 0, s>>>(p);
-  else      fwd_pre_kernel<GT, SAVEW, false><<<grid, block, 0, s>>>(p);
+  if (baked)     fwd_pre_kernel<GT, SAVEW, true, true><<<grid, block, 0, s>>>(p);
+  else if (fast) fwd_pre_kernel<GT, SAVEW, true, false><<<grid, block, 0, s>>>(p);
+  else           fwd_pre_kernel<GT, SAVEW, false, false><<<grid, block, 0, s>>>(p);
   return cudaGetLastError();
 }
 

@@ -90,9 +90,11 @@ def test_fused_value_and_grad_in_model(cuda_device, scale):
   assert num <= 2e-6 * res[0][2].norm().item()
 
 
-def test_tma_pipelined_fwd_pre_matches_direct(cuda_device):
-  """MULAN_FWD_PRE_TMA=1 selects the cp.async.bulk + mbarrier kernel; same arithmetic per
-  sub-pixel and the same reduction tree, so every output must be bit-identical."""
+def test_fwd_pre_variants_are_bit_identical(cuda_device):
+  """The fwd_pre variants -- generic constants (MULAN_NO_BAKED=1), constants baked as immediates
+  for the shipped configuration (default), and the opt-in cp.async.bulk + mbarrier pipeline
+  (MULAN_FWD_PRE_TMA=1) -- run the same arithmetic per sub-pixel and the same reduction tree,
+  so every output must be bit-identical."""
   code = r'''
 import sys, torch, numpy as np
 sys.path.insert(0, %r)
@@ -113,13 +115,14 @@ np.savez(sys.argv[1], **out)
 ''' % ROOT
   import tempfile
   outs = []
-  for flag in ('0', '1'):
+  for tma, nobaked in (('0', '1'), ('0', '0'), ('1', '0'), ('1', '1')):
     with tempfile.NamedTemporaryFile(suffix='.npz', delete=False) as f:
       path = f.name
-    env = dict(os.environ, MULAN_FWD_PRE_TMA=flag)
+    env = dict(os.environ, MULAN_FWD_PRE_TMA=tma, MULAN_NO_BAKED=nobaked)
     subprocess.run([sys.executable, '-c', code, path], check=True, env=env)
     outs.append(np.load(path))
     os.unlink(path)
-  assert set(outs[0].files) == set(outs[1].files)
-  for k in outs[0].files:
-    assert np.array_equal(outs[0][k], outs[1][k]), k
+  for other in outs[1:]:
+    assert set(outs[0].files) == set(other.files)
+    for k in outs[0].files:
+      assert np.array_equal(outs[0][k], other[k]), k

@@ -175,6 +175,35 @@ int mulan_aux_topk_bwd(int32_t rows, int32_t latent, int32_t k,
                        float* logits_bar, void* stream);
 
 /*
+ * The other auxiliary-latent variants of _get_embedding_and_kl_z
+ * (ldm/model_mulan_epsilon.py:257-271; neither shipped config selects them):
+ *   mulan_aux_topk_add_*  : top-k with an ADDITIVE noise [B,L] instead of the gamma draw
+ *                           (topk_noise_type == 'gumbel', :238-239)
+ *   mulan_aux_gumbel_*    : latent_type == 'gumbel' (:195-219): l = (logits + gumbel)/tau,
+ *                           emb = stop_grad(one_hot(argmax l) - softmax l) + softmax l,
+ *                           kl_z = KL(softmax(logits) || uniform);
+ *                           tau = max(.5, exp(-1e-5 step)) is computed by the caller
+ *   mulan_aux_gaussian_*  : latent_type == 'gaussian' (:264-270): emb = mu + sqrt(var) eps_z,
+ *                           kl_z = .5 sum(mu^2 + var - log var - 1); bwd -> mu_bar, var_bar
+ * All arrays are [B,L] (kl_z, klz_bar: [B]); L <= 64; noise / bar pointers may be NULL (zero).
+ */
+int mulan_aux_topk_add_fwd(int32_t rows, int32_t latent, int32_t k, const float* logits,
+                           const float* noise, float* embedding, float* kl_z, void* stream);
+int mulan_aux_topk_add_bwd(int32_t rows, int32_t latent, int32_t k, const float* logits,
+                           const float* noise, const float* emb_bar, const float* klz_bar,
+                           float* logits_bar, void* stream);
+int mulan_aux_gumbel_fwd(int32_t rows, int32_t latent, double tau, const float* logits,
+                         const float* gumbel_noise, float* embedding, float* kl_z, void* stream);
+int mulan_aux_gumbel_bwd(int32_t rows, int32_t latent, double tau, const float* logits,
+                         const float* gumbel_noise, const float* emb_bar, const float* klz_bar,
+                         float* logits_bar, void* stream);
+int mulan_aux_gaussian_fwd(int32_t rows, int32_t latent, const float* mu, const float* var,
+                           const float* eps_z, float* embedding, float* kl_z, void* stream);
+int mulan_aux_gaussian_bwd(int32_t rows, int32_t latent, const float* mu, const float* var,
+                           const float* eps_z, const float* emb_bar, const float* klz_bar,
+                           float* mu_bar, float* var_bar, void* stream);
+
+/*
  * mulan_bpd_reduce -- VDMOutput assembly + Experiment_VDM.loss_fn scalars
  * (ldm/model_mulan_epsilon.py:357-363, ldm/experiment_vdm.py:62-74).
  *   in : loss_recon[B], loss_klz_prior[B], kl_z[B] or NULL, loss_diff[B], var_sums[B,2]

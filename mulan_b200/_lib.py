@@ -59,6 +59,12 @@ SIGNATURES = {
     'mulan_bwd_pre': ([_D] + [_P] * 14, C.c_int),
     'mulan_aux_topk_fwd': ([C.c_int32] * 3 + [_P] * 5, C.c_int),
     'mulan_aux_topk_bwd': ([C.c_int32] * 3 + [_P] * 6, C.c_int),
+    'mulan_aux_topk_add_fwd': ([C.c_int32] * 3 + [_P] * 5, C.c_int),
+    'mulan_aux_topk_add_bwd': ([C.c_int32] * 3 + [_P] * 6, C.c_int),
+    'mulan_aux_gumbel_fwd': ([C.c_int32] * 2 + [C.c_double] + [_P] * 5, C.c_int),
+    'mulan_aux_gumbel_bwd': ([C.c_int32] * 2 + [C.c_double] + [_P] * 6, C.c_int),
+    'mulan_aux_gaussian_fwd': ([C.c_int32] * 2 + [_P] * 6, C.c_int),
+    'mulan_aux_gaussian_bwd': ([C.c_int32] * 2 + [_P] * 8, C.c_int),
     'mulan_bpd_reduce': ([_D] + [_P] * 8, C.c_int),
     'mulan_elbo_host': ([_D] + [_P] * 8 + [DENOISER_FN, _P, C.c_int32] + [_P] * 6, C.c_int),
     'mulan_sample_gamma': ([_D, C.c_int32] + [_P] * 6, C.c_int),

@@ -243,8 +243,8 @@ int mulan_aux_topk_fwd(int32_t rows, int32_t latent, int32_t k, const float* log
     return fail(MULAN_ERR_INVALID_ARG, "%s: k=%d outside [1,latent=%d]", fn, k, latent);
   if (rows == 0) return 0;
   REQ_PTR(logits, fn); REQ_PTR(embedding, fn); REQ_PTR(kl_z, fn);
-  cudaError_t e = mulan::launch_aux_topk_fwd(rows, latent, k, logits, gamma_draw, embedding, kl_z,
-                                             (cudaStream_t)stream);
+  cudaError_t e = mulan::launch_aux_topk_fwd(rows, latent, k, 0, logits, gamma_draw, embedding,
+                                             kl_z, (cudaStream_t)stream);
   return e == cudaSuccess ? 0 : cuda_fail(fn, e);
 }
 
@@ -259,8 +259,91 @@ int mulan_aux_topk_bwd(int32_t rows, int32_t latent, int32_t k, const float* log
     return fail(MULAN_ERR_INVALID_ARG, "%s: k=%d outside [1,latent=%d]", fn, k, latent);
   if (rows == 0) return 0;
   REQ_PTR(logits, fn); REQ_PTR(logits_bar, fn);
-  cudaError_t e = mulan::launch_aux_topk_bwd(rows, latent, k, logits, gamma_draw, emb_bar, klz_bar,
+  cudaError_t e = mulan::launch_aux_topk_bwd(rows, latent, k, 0, logits, gamma_draw, emb_bar,
+                                             klz_bar, logits_bar, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(fn, e);
+}
+
+static int check_aux(const char* fn, int32_t rows, int32_t latent) {
+  if (rows < 0) return fail(MULAN_ERR_INVALID_ARG, "%s: rows=%d < 0", fn, rows);
+  if (latent < 1 || latent > 64)
+    return fail(MULAN_ERR_INVALID_ARG, "%s: latent=%d outside [1,64]", fn, latent);
+  return 0;
+}
+
+int mulan_aux_topk_add_fwd(int32_t rows, int32_t latent, int32_t k, const float* logits,
+                           const float* noise, float* embedding, float* kl_z, void* stream) {
+  const char* fn = "mulan_aux_topk_add_fwd";
+  if (int r = check_aux(fn, rows, latent)) return r;
+  if (k < 1 || k > latent)
+    return fail(MULAN_ERR_INVALID_ARG, "%s: k=%d outside [1,latent=%d]", fn, k, latent);
+  if (rows == 0) return 0;
+  REQ_PTR(logits, fn); REQ_PTR(embedding, fn); REQ_PTR(kl_z, fn);
+  cudaError_t e = mulan::launch_aux_topk_fwd(rows, latent, k, 1, logits, noise, embedding, kl_z,
+                                             (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(fn, e);
+}
+
+int mulan_aux_topk_add_bwd(int32_t rows, int32_t latent, int32_t k, const float* logits,
+                           const float* noise, const float* emb_bar, const float* klz_bar,
+                           float* logits_bar, void* stream) {
+  const char* fn = "mulan_aux_topk_add_bwd";
+  if (int r = check_aux(fn, rows, latent)) return r;
+  if (k < 1 || k > latent)
+    return fail(MULAN_ERR_INVALID_ARG, "%s: k=%d outside [1,latent=%d]", fn, k, latent);
+  if (rows == 0) return 0;
+  REQ_PTR(logits, fn); REQ_PTR(logits_bar, fn);
+  cudaError_t e = mulan::launch_aux_topk_bwd(rows, latent, k, 1, logits, noise, emb_bar, klz_bar,
                                              logits_bar, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(fn, e);
+}
+
+int mulan_aux_gumbel_fwd(int32_t rows, int32_t latent, double tau, const float* logits,
+                         const float* gumbel_noise, float* embedding, float* kl_z, void* stream) {
+  const char* fn = "mulan_aux_gumbel_fwd";
+  if (int r = check_aux(fn, rows, latent)) return r;
+  if (!(tau > 0)) return fail(MULAN_ERR_INVALID_ARG, "%s: tau must be positive", fn);
+  if (rows == 0) return 0;
+  REQ_PTR(logits, fn); REQ_PTR(embedding, fn); REQ_PTR(kl_z, fn);
+  cudaError_t e = mulan::launch_aux_gumbel(false, rows, latent, (float)tau, logits, gumbel_noise,
+                                           nullptr, nullptr, embedding, kl_z, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(fn, e);
+}
+
+int mulan_aux_gumbel_bwd(int32_t rows, int32_t latent, double tau, const float* logits,
+                         const float* gumbel_noise, const float* emb_bar, const float* klz_bar,
+                         float* logits_bar, void* stream) {
+  const char* fn = "mulan_aux_gumbel_bwd";
+  if (int r = check_aux(fn, rows, latent)) return r;
+  if (!(tau > 0)) return fail(MULAN_ERR_INVALID_ARG, "%s: tau must be positive", fn);
+  if (rows == 0) return 0;
+  REQ_PTR(logits, fn); REQ_PTR(logits_bar, fn);
+  cudaError_t e = mulan::launch_aux_gumbel(true, rows, latent, (float)tau, logits, gumbel_noise,
+                                           emb_bar, klz_bar, logits_bar, nullptr,
+                                           (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(fn, e);
+}
+
+int mulan_aux_gaussian_fwd(int32_t rows, int32_t latent, const float* mu, const float* var,
+                           const float* eps_z, float* embedding, float* kl_z, void* stream) {
+  const char* fn = "mulan_aux_gaussian_fwd";
+  if (int r = check_aux(fn, rows, latent)) return r;
+  if (rows == 0) return 0;
+  REQ_PTR(mu, fn); REQ_PTR(var, fn); REQ_PTR(eps_z, fn); REQ_PTR(embedding, fn); REQ_PTR(kl_z, fn);
+  cudaError_t e = mulan::launch_aux_gaussian(false, rows, latent, mu, var, eps_z, nullptr, nullptr,
+                                             embedding, kl_z, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(fn, e);
+}
+
+int mulan_aux_gaussian_bwd(int32_t rows, int32_t latent, const float* mu, const float* var,
+                           const float* eps_z, const float* emb_bar, const float* klz_bar,
+                           float* mu_bar, float* var_bar, void* stream) {
+  const char* fn = "mulan_aux_gaussian_bwd";
+  if (int r = check_aux(fn, rows, latent)) return r;
+  if (rows == 0) return 0;
+  REQ_PTR(mu, fn); REQ_PTR(var, fn); REQ_PTR(eps_z, fn); REQ_PTR(mu_bar, fn); REQ_PTR(var_bar, fn);
+  cudaError_t e = mulan::launch_aux_gaussian(true, rows, latent, mu, var, eps_z, emb_bar, klz_bar,
+                                             mu_bar, var_bar, (cudaStream_t)stream);
   return e == cudaSuccess ? 0 : cuda_fail(fn, e);
 }
 

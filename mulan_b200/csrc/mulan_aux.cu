@@ -27,7 +27,9 @@ struct AuxRow {
   bool valid[2];
 };
 
-__device__ __forceinline__ AuxRow aux_forward(int row, int rows, int L, int k,
+// noise_kind 0: G is the jax.random.gamma draw [10, B, L] of _gamma_noise; 1: G is an additive
+// noise [B, L] (topk_noise_type == 'gumbel', ldm/model_mulan_epsilon.py:238-239).
+__device__ __forceinline__ AuxRow aux_forward(int row, int rows, int L, int k, int noise_kind,
                                               const float* __restrict__ logits,
                                               const float* __restrict__ G) {
   const int lane = threadIdx.x & 31;
@@ -65,7 +67,9 @@ __device__ __forceinline__ AuxRow aux_forward(int row, int rows, int L, int k,
   for (int s = 0; s < 2; ++s) {
     const int i = lane + 32 * s;
     float noise = 0.f;
-    if (G != nullptr && r.valid[s]) {
+    if (G != nullptr && r.valid[s] && noise_kind == 1) {
+      noise = __ldg(G + (size_t)row * L + i);
+    } else if (G != nullptr && r.valid[s]) {
       float acc = 0.f;
       for (int m = 1; m <= 10; ++m) {
         const float beta = __fdiv_rn((float)k, (float)m);
@@ -101,13 +105,13 @@ __device__ __forceinline__ AuxRow aux_forward(int row, int rows, int L, int k,
 }
 
 __global__ void __launch_bounds__(32 * kAuxRowsPerCta)
-aux_topk_fwd_kernel(int rows, int L, int k, const float* __restrict__ logits,
+aux_topk_fwd_kernel(int rows, int L, int k, int noise_kind, const float* __restrict__ logits,
                     const float* __restrict__ G, float* __restrict__ emb,
                     float* __restrict__ kl_z) {
   const int row = blockIdx.x * kAuxRowsPerCta + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
-  const AuxRow r = aux_forward(row, rows, L, k, logits, G);
+  const AuxRow r = aux_forward(row, rows, L, k, noise_kind, logits, G);
 #pragma unroll
   for (int s = 0; s < 2; ++s) {
     const int i = lane + 32 * s;
@@ -118,13 +122,13 @@ aux_topk_fwd_kernel(int rows, int L, int k, const float* __restrict__ logits,
 }
 
 __global__ void __launch_bounds__(32 * kAuxRowsPerCta)
-aux_topk_bwd_kernel(int rows, int L, int k, const float* __restrict__ logits,
+aux_topk_bwd_kernel(int rows, int L, int k, int noise_kind, const float* __restrict__ logits,
                     const float* __restrict__ G, const float* __restrict__ emb_bar,
                     const float* __restrict__ klz_bar, float* __restrict__ logits_bar) {
   const int row = blockIdx.x * kAuxRowsPerCta + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
-  const AuxRow r = aux_forward(row, rows, L, k, logits, G);
+  const AuxRow r = aux_forward(row, rows, L, k, noise_kind, logits, G);
   const float log_unif = logf((float)(1.0 / (double)L));
   float sb[2], dot = 0.f;
 #pragma unroll
@@ -153,23 +157,157 @@ aux_topk_bwd_kernel(int rows, int L, int k, const float* __restrict__ logits,
   }
 }
 
-cudaError_t launch_aux_topk_fwd(int rows, int latent, int k, const float* logits,
-                                const float* gamma_draw, float* embedding, float* kl_z,
+cudaError_t launch_aux_topk_fwd(int rows, int latent, int k, int noise_kind, const float* logits,
+                                const float* noise, float* embedding, float* kl_z,
                                 cudaStream_t s) {
   if (rows == 0) return cudaSuccess;
   const int grid = (rows + kAuxRowsPerCta - 1) / kAuxRowsPerCta;
-  aux_topk_fwd_kernel<<<grid, 32 * kAuxRowsPerCta, 0, s>>>(rows, latent, k, logits, gamma_draw,
-                                                          embedding, kl_z);
+  aux_topk_fwd_kernel<<<grid, 32 * kAuxRowsPerCta, 0, s>>>(rows, latent, k, noise_kind, logits,
+                                                          noise, embedding, kl_z);
   return cudaGetLastError();
 }
 
-cudaError_t launch_aux_topk_bwd(int rows, int latent, int k, const float* logits,
-                                const float* gamma_draw, const float* emb_bar,
+cudaError_t launch_aux_topk_bwd(int rows, int latent, int k, int noise_kind, const float* logits,
+                                const float* noise, const float* emb_bar,
                                 const float* klz_bar, float* logits_bar, cudaStream_t s) {
   if (rows == 0) return cudaSuccess;
   const int grid = (rows + kAuxRowsPerCta - 1) / kAuxRowsPerCta;
-  aux_topk_bwd_kernel<<<grid, 32 * kAuxRowsPerCta, 0, s>>>(rows, latent, k, logits, gamma_draw,
-                                                          emb_bar, klz_bar, logits_bar);
+  aux_topk_bwd_kernel<<<grid, 32 * kAuxRowsPerCta, 0, s>>>(rows, latent, k, noise_kind, logits,
+                                                          noise, emb_bar, klz_bar, logits_bar);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------
+// latent_type == 'gumbel' (ldm/model_mulan_epsilon.py:195-219): straight-through Gumbel-softmax.
+//   kl    = _gumbel_kl_loss(logits)                      (raw logits)
+//   l     = (logits + gumbel_noise) / tau                tau = max(.5, exp(-1e-5 step)), host
+//   soft  = softmax(l); hard = one_hot(argmax(l)); emb = stop_grad(hard - soft) + soft
+// latent_type == 'gaussian' (:264-270):
+//   emb = mu + sqrt(var) eps_z;  kl = .5 sum(mu^2 + var - log var - 1)
+// One warp per row, two slots per lane, like the top-k op.
+// ---------------------------------------------------------------------------------------
+template <bool BWD>
+__global__ void __launch_bounds__(32 * kAuxRowsPerCta)
+aux_gumbel_kernel(int rows, int L, float tau, const float* __restrict__ logits,
+                  const float* __restrict__ noise, const float* __restrict__ emb_bar,
+                  const float* __restrict__ klz_bar, float* __restrict__ out,
+                  float* __restrict__ kl_z) {
+  const int row = blockIdx.x * kAuxRowsPerCta + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  // KL and softmax of the raw logits: reuse the top-k forward with no noise and k = L
+  const AuxRow r = aux_forward(row, rows, L, L, 0, logits, nullptr);
+  float l[2], mx = -INFINITY;
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const int i = lane + 32 * s;
+    const float g = (noise != nullptr && r.valid[s]) ? __ldg(noise + (size_t)row * L + i) : 0.f;
+    l[s] = r.valid[s] ? __fdiv_rn(r.l[s] + g, tau) : -INFINITY;
+    mx = fmaxf(mx, l[s]);
+  }
+  mx = warp_max(mx);
+  float un[2], se = 0.f;
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    un[s] = r.valid[s] ? expf(l[s] - mx) : 0.f;
+    se += un[s];
+  }
+  se = warp_sum(se);
+  float soft[2];
+#pragma unroll
+  for (int s = 0; s < 2; ++s) soft[s] = __fdiv_rn(un[s], se);
+  if (!BWD) {
+    // argmax: FIRST index attaining the maximum (jnp.argmax)
+    int best = 1 << 30;
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+      if (r.valid[s] && l[s] == mx) best = min(best, lane + 32 * s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int i = lane + 32 * s;
+      const float hard = (i == best) ? 1.0f : 0.0f;
+      if (r.valid[s]) out[(size_t)row * L + i] = (hard - soft[s]) + soft[s];
+    }
+    if (lane == 0) kl_z[row] = r.kl;
+  } else {
+    const float log_unif = logf((float)(1.0 / (double)L));
+    float sb[2], dot = 0.f;
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int i = lane + 32 * s;
+      sb[s] = (emb_bar != nullptr && r.valid[s]) ? __ldg(emb_bar + (size_t)row * L + i) : 0.f;
+      dot += sb[s] * soft[s];
+    }
+    dot = warp_sum(dot);
+    const float kb = klz_bar != nullptr ? __ldg(klz_bar + row) : 0.f;
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int i = lane + 32 * s;
+      if (r.valid[s]) {
+        const float lbar = soft[s] * (sb[s] - dot);                  // softmax backward
+        const float dkl = r.q[s] * ((r.lq[s] - log_unif) - r.kl);
+        out[(size_t)row * L + i] = __fdiv_rn(lbar, tau) + kb * dkl;
+      }
+    }
+  }
+}
+
+cudaError_t launch_aux_gumbel(bool bwd, int rows, int latent, float tau, const float* logits,
+                              const float* noise, const float* emb_bar, const float* klz_bar,
+                              float* out, float* kl_z, cudaStream_t s) {
+  if (rows == 0) return cudaSuccess;
+  const int grid = (rows + kAuxRowsPerCta - 1) / kAuxRowsPerCta;
+  if (bwd) aux_gumbel_kernel<true><<<grid, 32 * kAuxRowsPerCta, 0, s>>>(
+      rows, latent, tau, logits, noise, emb_bar, klz_bar, out, kl_z);
+  else aux_gumbel_kernel<false><<<grid, 32 * kAuxRowsPerCta, 0, s>>>(
+      rows, latent, tau, logits, noise, emb_bar, klz_bar, out, kl_z);
+  return cudaGetLastError();
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(32 * kAuxRowsPerCta)
+aux_gaussian_kernel(int rows, int L, const float* __restrict__ mu, const float* __restrict__ var,
+                    const float* __restrict__ eps, const float* __restrict__ emb_bar,
+                    const float* __restrict__ klz_bar, float* __restrict__ out0,
+                    float* __restrict__ out1) {
+  const int row = blockIdx.x * kAuxRowsPerCta + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float kl = 0.f;
+  const float kb = (BWD && klz_bar != nullptr) ? __ldg(klz_bar + row) : 0.f;
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const int i = lane + 32 * s;
+    if (i >= L) continue;
+    const size_t o = (size_t)row * L + i;
+    const float m = __ldg(mu + o), v = __ldg(var + o), e = __ldg(eps + o);
+    const float sd = sqrtf(v);
+    if (!BWD) {
+      out0[o] = m + sd * e;                                          // embedding
+      kl += m * m + v - logf(v) - 1.0f;
+    } else {
+      const float eb = emb_bar != nullptr ? __ldg(emb_bar + o) : 0.f;
+      out0[o] = eb + kb * m;                                         // mu_bar
+      out1[o] = eb * __fdiv_rn(e, 2.0f * sd) + kb * 0.5f * (1.0f - __fdiv_rn(1.0f, v));  // var_bar
+    }
+  }
+  if (!BWD) {
+    kl = warp_sum(kl);
+    if (lane == 0) out1[row] = 0.5f * kl;
+  }
+}
+
+cudaError_t launch_aux_gaussian(bool bwd, int rows, int latent, const float* mu, const float* var,
+                                const float* eps, const float* emb_bar, const float* klz_bar,
+                                float* out0, float* out1, cudaStream_t s) {
+  if (rows == 0) return cudaSuccess;
+  const int grid = (rows + kAuxRowsPerCta - 1) / kAuxRowsPerCta;
+  if (bwd) aux_gaussian_kernel<true><<<grid, 32 * kAuxRowsPerCta, 0, s>>>(
+      rows, latent, mu, var, eps, emb_bar, klz_bar, out0, out1);
+  else aux_gaussian_kernel<false><<<grid, 32 * kAuxRowsPerCta, 0, s>>>(
+      rows, latent, mu, var, eps, emb_bar, klz_bar, out0, out1);
   return cudaGetLastError();
 }
 

@@ -173,12 +173,18 @@ cudaError_t launch_bwd_pre(const BwdPreParams& p, cudaStream_t s);
 cudaError_t launch_discrete_w(const DiscreteWParams& p, cudaStream_t s);
 cudaError_t launch_adamw_ema(const mulan_adamw_desc& d, float* p, const float* g, float* mu,
                              float* nu, float* ema, cudaStream_t s);
-cudaError_t launch_aux_topk_fwd(int rows, int latent, int k, const float* logits,
-                                const float* gamma_draw, float* embedding, float* kl_z,
+cudaError_t launch_aux_topk_fwd(int rows, int latent, int k, int noise_kind, const float* logits,
+                                const float* noise, float* embedding, float* kl_z,
                                 cudaStream_t s);
-cudaError_t launch_aux_topk_bwd(int rows, int latent, int k, const float* logits,
-                                const float* gamma_draw, const float* emb_bar,
+cudaError_t launch_aux_topk_bwd(int rows, int latent, int k, int noise_kind, const float* logits,
+                                const float* noise, const float* emb_bar,
                                 const float* klz_bar, float* logits_bar, cudaStream_t s);
+cudaError_t launch_aux_gumbel(bool bwd, int rows, int latent, float tau, const float* logits,
+                              const float* noise, const float* emb_bar, const float* klz_bar,
+                              float* out, float* kl_z, cudaStream_t s);
+cudaError_t launch_aux_gaussian(bool bwd, int rows, int latent, const float* mu, const float* var,
+                                const float* eps, const float* emb_bar, const float* klz_bar,
+                                float* out0, float* out1, cudaStream_t s);
 cudaError_t launch_bpd_reduce(int rows, int dim, const float* loss_recon,
                               const float* loss_klz_prior, const float* kl_z,
                               const float* loss_diff, const float* var_sums, float* scalars,

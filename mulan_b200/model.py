@@ -141,10 +141,11 @@ class VDM(nn.Module):
     if config.gamma_type != 'poly_fixedend':
       raise NotImplementedError('only gamma_type="poly_fixedend" (both shipped configs) is on '
                                 'the kernel path')
-    if config.latent_type != 'topk' or config.reparam_type != 'true':
-      raise NotImplementedError('only latent_type="topk", reparam_type="true" is on the kernel path')
-    if config.topk_noise_type != 'gamma':
-      raise NotImplementedError('only topk_noise_type="gamma" is on the kernel path')
+    if config.latent_type not in ('topk', 'gumbel', 'gaussian') or config.reparam_type != 'true':
+      raise NotImplementedError('latent_type must be topk / gumbel / gaussian with '
+                                'reparam_type="true"')
+    if config.topk_noise_type not in ('gamma', 'gumbel'):
+      raise NotImplementedError('topk_noise_type must be "gamma" or "gumbel"')
     self.config = config
     self.encdec = EncDec(config)
     self.encoder_model = encoder_model
@@ -186,12 +187,36 @@ class VDM(nn.Module):
   def make_draws(self, n_batch: int, device, generator: Optional[torch.Generator] = None):
     """The four make_rng('sample') draws of __call__, in the reference's order."""
     g = generator
-    L = self.config.latent_size
+    cfg = self.config
+    L = cfg.latent_size
+    t0 = torch.rand((), generator=g, device=device)
+    if cfg.latent_type == 'topk' and cfg.topk_noise_type == 'gamma':
+      G = gamma_draw((10, n_batch, L), cfg.latent_k, g, device)          # jax.random.gamma
+    elif cfg.latent_type == 'gaussian':
+      G = torch.randn((n_batch, L), generator=g, device=device)           # eps_z
+    else:                                                                  # jax.random.gumbel
+      u = torch.rand((n_batch, L), generator=g, device=device).clamp_min(1e-20)
+      G = -torch.log(-torch.log(u))
     return dict(
-        t0=torch.rand((), generator=g, device=device),
-        G=gamma_draw((10, n_batch, L), self.config.latent_k, g, device),
+        t0=t0, G=G,
         eps_0=torch.randn((n_batch, 32, 32, 3), generator=g, device=device),
         eps=torch.randn((n_batch, 32, 32, 3), generator=g, device=device))
+
+  def _get_embedding_and_kl_z(self, orig_f, step, deterministic, noise):
+    """ldm/model_mulan_epsilon.py:257-271; `noise` is the helper's single random draw."""
+    cfg = self.config
+    noise = noise.contiguous()
+    if cfg.latent_type == 'topk':
+      logits = self.encoder_model(orig_f, deterministic)
+      if cfg.topk_noise_type == 'gamma':
+        return ops.aux_topk(logits, noise, cfg.latent_k)
+      return ops.aux_topk_add(logits, noise, cfg.latent_k)
+    if cfg.latent_type == 'gumbel':
+      logits = self.encoder_model(orig_f, deterministic)
+      tau = max(0.5, math.exp(-0.00001 * float(step)))                   # :218
+      return ops.aux_gumbel(logits, noise, tau)
+    mu_z, var_z = self.encoder_model(orig_f, deterministic)               # gaussian
+    return ops.aux_gaussian(mu_z, var_z, noise)
 
   def forward(self, images, labels=None, conditioning=None, step=0, deterministic: bool = True,
               draws: Optional[dict] = None, generator: Optional[torch.Generator] = None):
@@ -209,8 +234,7 @@ class VDM(nn.Module):
 
     x_u8 = x.to(torch.uint8).reshape(n_batch, D).contiguous()
     orig_f = self.encdec.encode(x)
-    logits = self.encoder_model(orig_f, deterministic)
-    embedding, kl_z = ops.aux_topk(logits, draws['G'].contiguous(), cfg.latent_k)
+    embedding, kl_z = self._get_embedding_and_kl_z(orig_f, step, deterministic, draws['G'])
     a, b, c = self.gamma._compute_coefficients(embedding)
 
     tape = ops.ElboTape(self.desc)
@@ -235,10 +259,14 @@ class VDM(nn.Module):
 
 
 def _deterministic_embedding(model: VDM, batch_size: int, device):
-  """_get_deterministic_embedding, latent_type='topk' (ldm/model_mulan_epsilon.py:369-374)."""
+  """_get_deterministic_embedding (ldm/model_mulan_epsilon.py:365-376): k leading ones for
+  'topk', one_hot(1) for 'gumbel', zeros for 'gaussian'."""
   cfg = model.config
   e = torch.zeros((batch_size, cfg.latent_size), dtype=torch.float32, device=device)
-  e[:, :cfg.latent_k] = 1.0
+  if cfg.latent_type == 'topk':
+    e[:, :cfg.latent_k] = 1.0
+  elif cfg.latent_type == 'gumbel':
+    e[:, 1] = 1.0
   return e
 
 

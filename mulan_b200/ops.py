@@ -430,3 +430,105 @@ class _AuxTopK(torch.autograd.Function):
 def aux_topk(logits, gamma_draw, k: int):
   """_topk_embedding_and_loss (ldm/model_mulan_epsilon.py:233-252) -> (embedding, kl_z)."""
   return _AuxTopK.apply(logits, gamma_draw, k)
+
+
+# ------------------------------------------------------------------------------------
+# The other auxiliary-latent variants (ldm/model_mulan_epsilon.py:195-219, 238-239, 264-270)
+# ------------------------------------------------------------------------------------
+
+class _AuxTopKAdd(torch.autograd.Function):
+  """top-k with additive noise [B,L] (topk_noise_type == 'gumbel')."""
+
+  @staticmethod
+  def forward(ctx, logits, noise, k: int):
+    logits = logits.contiguous()
+    B, L = logits.shape
+    _req(logits, torch.float32, (B, L), 'logits')
+    _opt(noise, torch.float32, (B, L), 'noise')
+    emb = torch.empty_like(logits)
+    kl = torch.empty((B,), dtype=torch.float32, device=logits.device)
+    _lib.check(_lib.load().mulan_aux_topk_add_fwd(B, L, k, _p(logits), _p(noise), _p(emb), _p(kl),
+                                                  _stream()))
+    ctx.save_for_backward(logits, noise)
+    ctx.k = k
+    return emb, kl
+
+  @staticmethod
+  def backward(ctx, emb_bar, kl_bar):
+    logits, noise = ctx.saved_tensors
+    B, L = logits.shape
+    cont = lambda v: None if v is None else v.contiguous()
+    out = torch.empty_like(logits)
+    _lib.check(_lib.load().mulan_aux_topk_add_bwd(B, L, ctx.k, _p(logits), _p(noise),
+                                                  _p(cont(emb_bar)), _p(cont(kl_bar)), _p(out),
+                                                  _stream()))
+    return out, None, None
+
+
+class _AuxGumbel(torch.autograd.Function):
+  """latent_type == 'gumbel' (_gumbel_embedding_and_loss)."""
+
+  @staticmethod
+  def forward(ctx, logits, noise, tau: float):
+    logits = logits.contiguous()
+    B, L = logits.shape
+    _req(logits, torch.float32, (B, L), 'logits')
+    _opt(noise, torch.float32, (B, L), 'gumbel_noise')
+    emb = torch.empty_like(logits)
+    kl = torch.empty((B,), dtype=torch.float32, device=logits.device)
+    _lib.check(_lib.load().mulan_aux_gumbel_fwd(B, L, float(tau), _p(logits), _p(noise), _p(emb),
+                                                _p(kl), _stream()))
+    ctx.save_for_backward(logits, noise)
+    ctx.tau = float(tau)
+    return emb, kl
+
+  @staticmethod
+  def backward(ctx, emb_bar, kl_bar):
+    logits, noise = ctx.saved_tensors
+    B, L = logits.shape
+    cont = lambda v: None if v is None else v.contiguous()
+    out = torch.empty_like(logits)
+    _lib.check(_lib.load().mulan_aux_gumbel_bwd(B, L, ctx.tau, _p(logits), _p(noise),
+                                                _p(cont(emb_bar)), _p(cont(kl_bar)), _p(out),
+                                                _stream()))
+    return out, None, None
+
+
+class _AuxGaussian(torch.autograd.Function):
+  """latent_type == 'gaussian' (:264-270)."""
+
+  @staticmethod
+  def forward(ctx, mu, var, eps_z):
+    mu, var = mu.contiguous(), var.contiguous()
+    B, L = mu.shape
+    for n, v in (('mu', mu), ('var', var), ('eps_z', eps_z)):
+      _req(v, torch.float32, (B, L), n)
+    emb = torch.empty_like(mu)
+    kl = torch.empty((B,), dtype=torch.float32, device=mu.device)
+    _lib.check(_lib.load().mulan_aux_gaussian_fwd(B, L, _p(mu), _p(var), _p(eps_z), _p(emb), _p(kl),
+                                                  _stream()))
+    ctx.save_for_backward(mu, var, eps_z)
+    return emb, kl
+
+  @staticmethod
+  def backward(ctx, emb_bar, kl_bar):
+    mu, var, eps_z = ctx.saved_tensors
+    B, L = mu.shape
+    cont = lambda v: None if v is None else v.contiguous()
+    mb, vb = torch.empty_like(mu), torch.empty_like(mu)
+    _lib.check(_lib.load().mulan_aux_gaussian_bwd(B, L, _p(mu), _p(var), _p(eps_z),
+                                                  _p(cont(emb_bar)), _p(cont(kl_bar)), _p(mb),
+                                                  _p(vb), _stream()))
+    return mb, vb, None
+
+
+def aux_topk_add(logits, noise, k: int):
+  return _AuxTopKAdd.apply(logits, noise, k)
+
+
+def aux_gumbel(logits, gumbel_noise, tau: float):
+  return _AuxGumbel.apply(logits, gumbel_noise, tau)
+
+
+def aux_gaussian(mu, var, eps_z):
+  return _AuxGaussian.apply(mu, var, eps_z)

@@ -253,6 +253,33 @@ def topk_embedding_and_loss(logits, G, k: int, latent_size: int):
   return embedding, kl_loss
 
 
+def gumbel_embedding_and_loss(logits, gumbel_noise, tau, latent_size: int):
+  """epsilon.py:195-219 (latent_type == 'gumbel'); tau = max(.5, exp(-1e-5 step))."""
+  l = (logits + gumbel_noise) / tau
+  soft_argmax = softmax(l)
+  hard_argmax = torch.nn.functional.one_hot(torch.argmax(l, dim=-1), latent_size).to(l.dtype)
+  embedding = (hard_argmax - soft_argmax).detach() + soft_argmax
+  return embedding, gumbel_kl_loss(logits, latent_size)
+
+
+def topk_add_embedding_and_loss(logits, noise, k: int, latent_size: int):
+  """epsilon.py:233-252 with topk_noise_type == 'gumbel' (:238-239): additive noise."""
+  kl_loss = gumbel_kl_loss(logits, latent_size)
+  logits = logits + noise
+  logits = logits - torch.mean(logits, dim=1, keepdim=True)
+  soft_topk = logits / torch.linalg.norm(logits, dim=1, keepdim=True)
+  top_k_vals = torch.topk(logits, k, dim=1).values
+  hard_topk = (logits >= top_k_vals[:, -1][:, None]).to(logits.dtype)
+  return (hard_topk - soft_topk).detach() + soft_topk, kl_loss
+
+
+def gaussian_embedding_and_loss(mu_z, var_z, eps_z):
+  """epsilon.py:264-270 (latent_type == 'gaussian')."""
+  embedding = mu_z + torch.sqrt(var_z) * eps_z
+  kl_z = 0.5 * torch.sum(mu_z ** 2 + var_z - torch.log(var_z) - 1., dim=1)
+  return embedding, kl_z
+
+
 # ----------------------------------------------------------------------------
 # Time sampling (epsilon.py:287-297)
 # ----------------------------------------------------------------------------
@@ -342,9 +369,10 @@ def elbo_terms(x, a, b, c, t, eps_0, eps, score_fn: Callable, mode: int,
 
 def vdm_call(images, draws: dict, coeff_fn: Callable, encoder_fn: Callable,
              score_fn: Callable, mode: int, cfg: OracleConfig, dtype=torch.float32,
-             return_aux: bool = False):
+             return_aux: bool = False, latent_fn: Optional[Callable] = None):
   """Whole VDM.__call__ (epsilon.py:280-363 / velocity.py:188-268) with
-  latent_type='topk', reparam_type='true', z_conditioning=True.
+  latent_type='topk', reparam_type='true', z_conditioning=True.  For the other latent types
+  pass latent_fn(orig_f, draws['G']) -> (embedding, kl_z) (epsilon.py:257-271).
 
   draws = {'t0': scalar, 'G': [10,B,L], 'eps_0': [B,32,32,3], 'eps': [B,32,32,3]}
   in the order the reference calls make_rng('sample').
@@ -355,9 +383,12 @@ def vdm_call(images, draws: dict, coeff_fn: Callable, encoder_fn: Callable,
   n_batch = x.shape[0]
   t = sample_t(draws['t0'], n_batch, cfg, dtype)                  # :287-297
   orig_f = encode(x, cfg.vocab_size, dtype)
-  logits = encoder_fn(orig_f)
-  embedding, kl_z = topk_embedding_and_loss(
-      logits, draws['G'], cfg.latent_k, cfg.latent_size)          # :301-303
+  if latent_fn is not None:
+    embedding, kl_z = latent_fn(orig_f, draws['G'])
+  else:
+    logits = encoder_fn(orig_f)
+    embedding, kl_z = topk_embedding_and_loss(
+        logits, draws['G'], cfg.latent_k, cfg.latent_size)        # :301-303
   a, b, c = coeff_fn(embedding)
   return elbo_terms(x, a, b, c, t, draws['eps_0'], draws['eps'],
                     lambda z, g: score_fn(z, g, embedding),       # :330-337
@@ -397,8 +428,14 @@ def eval_bpd_dense(images, n_timesteps: int, run_loss_fn: Callable):
 # Ancestral sampler (model_mulan_epsilon.py:365-457, model_mulan_velocity.py:270-366)
 # ----------------------------------------------------------------------------
 
-def deterministic_embedding(batch_size: int, cfg: OracleConfig, dtype=torch.float32):
-  """_get_deterministic_embedding, latent_type == 'topk' (epsilon.py:369-374)."""
+def deterministic_embedding(batch_size: int, cfg: OracleConfig, dtype=torch.float32,
+                            latent_type: str = 'topk'):
+  """_get_deterministic_embedding (epsilon.py:365-376)."""
+  if latent_type == 'gumbel':
+    return torch.nn.functional.one_hot(torch.ones(batch_size, dtype=torch.long),
+                                       cfg.latent_size).to(dtype)
+  if latent_type == 'gaussian':
+    return torch.zeros((batch_size, cfg.latent_size), dtype=dtype)
   ones = torch.ones((batch_size, cfg.latent_k), dtype=dtype)
   zeros = torch.zeros((batch_size, cfg.latent_size - cfg.latent_k), dtype=dtype)
   return torch.cat([ones, zeros], dim=1)

@@ -109,9 +109,13 @@ def test_model_rejects_off_path_configs():
   with pytest.raises(NotImplementedError):
     VDM(VDMConfig(gamma_type='learnable_nnet'), f, f)
   with pytest.raises(NotImplementedError):
-    VDM(VDMConfig(latent_type='gaussian'), f, f)
+    VDM(VDMConfig(latent_type='vq'), f, f)
+  with pytest.raises(NotImplementedError):
+    VDM(VDMConfig(topk_noise_type='laplace'), f, f)
   with pytest.raises(NotImplementedError):
     VDM(VDMConfig(vdm_type='vdm'), f, f)
+  for lt in ('topk', 'gumbel', 'gaussian'):
+    VDM(VDMConfig(latent_type=lt), f, f)
 
 
 def test_schedule_head_matches_oracle_coefficients():

@@ -281,6 +281,29 @@ int mulan_row_dot(int32_t rows, int32_t dim, const float* u, const float* v, con
                   float* out, void* stream);
 
 /*
+ * Device-resident state of the adaptive RK45 (Dormand-Prince 5(4)) integrator that drives the
+ * probability-flow ODE: replaces the host float64 numpy state of
+ * scipy.integrate.solve_ivp(method='RK45') in likelihood_fn / sample_fn
+ * (ldm/notebook_utils.py:343-353, :417-429), whose every function evaluation ships the whole
+ * state host->device and the derivative back (_from/_to_flattened_numpy, :193-200).
+ *   y[n] float64 state, K[7][n] float32 stage derivatives (row j at K + j*k_stride), all in HBM.
+ *   mulan_rk45_stage: v = y + (sum_{j<n_k} coef[j] K_j) h;  y_stage = (float)v and/or y_out = v
+ *                     (either may be NULL; n_k = 0 is a plain float64 -> float32 cast).
+ *   mulan_rk45_norm : out[0] = sum_i (v_i / (atol + rtol max(|y_i|, |y_new_i|)))^2 with
+ *                     v = y (of_y != 0) or (sum_j coef[j] K_j) h; y_new may be NULL.
+ *                     Deterministic (fixed-order) reduction; scratch holds
+ *                     MULAN_RK45_SCRATCH doubles; out is a DEVICE pointer.
+ * coef is a HOST array of n_k <= 7 doubles, read before the call returns.
+ */
+#define MULAN_RK45_SCRATCH 2048
+int mulan_rk45_stage(int64_t n, int32_t n_k, const double* coef, double h, const double* y,
+                     const float* K, int64_t k_stride, float* y_stage, double* y_out,
+                     void* stream);
+int mulan_rk45_norm(int64_t n, int32_t n_k, const double* coef, double h, double rtol,
+                    double atol, const double* y, const double* y_new, const float* K,
+                    int64_t k_stride, int32_t of_y, double* scratch, double* out, void* stream);
+
+/*
  * mulan_adamw_ema -- "next" row 1 of the scope table: the AdamW + EMA update that follows the
  * gradient all-reduce of every train step, fused over one flat float32 buffer.
  * Replaces TrainState.apply_gradients (ldm/train_state.py:70-102) with the optax.adamw chain

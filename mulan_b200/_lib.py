@@ -15,6 +15,7 @@ MULAN_PARAM_VEL = 1
 MULAN_PARAM_VEL_FROM_EPS = 2
 MULAN_GT_MEAN = 0
 MULAN_GT_PIXEL = 1
+MULAN_RK45_SCRATCH = 2048
 
 PARAM_NAMES = {'eps': MULAN_PARAM_EPS, 'vel': MULAN_PARAM_VEL,
                'vel_from_eps': MULAN_PARAM_VEL_FROM_EPS}
@@ -72,6 +73,10 @@ SIGNATURES = {
     'mulan_generate_x': ([_D] + [_P] * 3, C.c_int),
     'mulan_ode_drift': ([_D, C.c_int32] + [_P] * 7 + [C.c_int32] + [_P] * 4, C.c_int),
     'mulan_row_dot': ([C.c_int32] * 2 + [_P] * 5, C.c_int),
+    'mulan_rk45_stage': ([C.c_int64, C.c_int32, _P, C.c_double, _P, _P, C.c_int64, _P, _P, _P],
+                         C.c_int),
+    'mulan_rk45_norm': ([C.c_int64, C.c_int32, _P, C.c_double, C.c_double, C.c_double, _P, _P, _P,
+                         C.c_int64, C.c_int32, _P, _P, _P], C.c_int),
     'mulan_adamw_ema': ([C.POINTER(MulanAdamwDesc)] + [_P] * 6, C.c_int),
     'mulan_host_workspace_release': ([], None),
 }

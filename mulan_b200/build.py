@@ -15,7 +15,8 @@ CSRC = PKG_DIR / 'csrc'
 LIB_PATH = PKG_DIR / 'libmulan_b200.so'
 
 SOURCES = ['mulan_fwd_pre.cu', 'mulan_post.cu', 'mulan_bwd_pre.cu', 'mulan_aux.cu',
-           'mulan_optim.cu', 'mulan_sampler.cu', 'mulan_abi.cu', 'mulan_host.cu']
+           'mulan_optim.cu', 'mulan_sampler.cu', 'mulan_rk45.cu', 'mulan_abi.cu',
+           'mulan_host.cu']
 
 NVCC_FLAGS = [
     '-O3', '-std=c++17',

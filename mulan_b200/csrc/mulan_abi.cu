@@ -455,6 +455,52 @@ int mulan_row_dot(int32_t rows, int32_t dim, const float* u, const float* v, con
   return e == cudaSuccess ? 0 : cuda_fail(fn, e);
 }
 
+static int rk45_fill(const char* fn, mulan::Rk45Params& p, int64_t n, int32_t n_k,
+                     const double* coef, double h, const double* y, const float* K,
+                     int64_t k_stride) {
+  if (n < 0 || n_k < 0 || n_k > 7) return fail(MULAN_ERR_INVALID_ARG, "%s: need n >= 0, 0 <= n_k <= 7", fn);
+  if (n_k > 0 && (coef == nullptr || K == nullptr))
+    return fail(MULAN_ERR_INVALID_ARG, "%s: coef / K is NULL with n_k=%d", fn, n_k);
+  if (n_k > 1 && k_stride < n) return fail(MULAN_ERR_INVALID_ARG, "%s: k_stride < n", fn);
+  if (y == nullptr) return fail(MULAN_ERR_INVALID_ARG, "%s: y is NULL", fn);
+  if ((reinterpret_cast<uintptr_t>(y) & 7u) != 0)
+    return fail(MULAN_ERR_ALIGNMENT, "%s: y is not 8-byte aligned", fn);
+  p = mulan::Rk45Params{};
+  p.n = n; p.k_stride = k_stride; p.n_k = n_k; p.h = h; p.y = y; p.K = K;
+  for (int j = 0; j < n_k; ++j) p.coef[j] = coef[j];
+  return 0;
+}
+
+int mulan_rk45_stage(int64_t n, int32_t n_k, const double* coef, double h, const double* y,
+                     const float* K, int64_t k_stride, float* y_stage, double* y_out,
+                     void* stream) {
+  const char* fn = "mulan_rk45_stage";
+  mulan::Rk45Params p;
+  if (int rc = rk45_fill(fn, p, n, n_k, coef, h, y, K, k_stride)) return rc;
+  if (y_stage == nullptr && y_out == nullptr)
+    return fail(MULAN_ERR_INVALID_ARG, "%s: both outputs are NULL", fn);
+  if (n == 0) return 0;
+  p.y_stage = y_stage; p.y_out = y_out;
+  cudaError_t e = mulan::launch_rk45_stage(p, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(fn, e);
+}
+
+int mulan_rk45_norm(int64_t n, int32_t n_k, const double* coef, double h, double rtol,
+                    double atol, const double* y, const double* y_new, const float* K,
+                    int64_t k_stride, int32_t of_y, double* scratch, double* out, void* stream) {
+  const char* fn = "mulan_rk45_norm";
+  mulan::Rk45Params p;
+  if (int rc = rk45_fill(fn, p, n, n_k, coef, h, y, K, k_stride)) return rc;
+  if (n == 0) return fail(MULAN_ERR_INVALID_ARG, "%s: n = 0", fn);
+  if (!of_y && n_k == 0) return fail(MULAN_ERR_INVALID_ARG, "%s: nothing to measure", fn);
+  if (!(rtol >= 0.0) || !(atol >= 0.0) || (rtol == 0.0 && atol == 0.0))
+    return fail(MULAN_ERR_INVALID_ARG, "%s: bad tolerances", fn);
+  REQ_PTR(scratch, fn); REQ_PTR(out, fn);
+  p.rtol = rtol; p.atol = atol; p.y_new = y_new; p.of_y = of_y; p.scratch = scratch;
+  cudaError_t e = mulan::launch_rk45_norm(p, out, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(fn, e);
+}
+
 int mulan_adamw_ema(const mulan_adamw_desc* d, float* params, const float* grads, float* mu,
                     float* nu, float* ema_params, void* stream) {
   const char* fn = "mulan_adamw_ema";

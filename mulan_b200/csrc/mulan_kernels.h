@@ -148,6 +148,20 @@ cudaError_t launch_ode_drift(const SamplerParams& p, bool high_precision, cudaSt
 cudaError_t launch_row_dot(const float* u, const float* v, const float* add, float* out, int rows,
                            int dim4, cudaStream_t s);
 
+// Adaptive RK45 integrator state (mulan_rk45.cu)
+struct Rk45Params {
+  int64_t n, k_stride;
+  int n_k, of_y;
+  double coef[7];
+  double h, rtol, atol;
+  const double *y, *y_new;
+  const float* K;
+  float* y_stage;
+  double *y_out, *scratch;
+};
+cudaError_t launch_rk45_stage(const Rk45Params& p, cudaStream_t s);
+cudaError_t launch_rk45_norm(const Rk45Params& p, double* out, cudaStream_t s);
+
 // Number of CTAs of `kernel` (kThreads threads, static shared memory only) that are resident
 // on the current device at once: the grid size of the persistent kernels.
 inline int resident_ctas(const void* kernel) {

@@ -320,28 +320,43 @@ def sample_fn(model: VDM, n: int, T: int = 1000, generator=None, sigma_prior: fl
   return generate_x(model, z)
 
 
-def value_div_fn(model: VDM, x, embeddings, t, hutchinson_noise, high_precision: bool = False):
+def value_div_fn(model: VDM, x, embeddings, t, hutchinson_noise, high_precision: bool = False,
+                 coeffs=None, out=None):
   """VDM.reverse_ode (ldm/model_mulan_epsilon.py:459-478) and its Hutchinson divergence
   (_get_value_div_fn, ldm/notebook_utils.py:204-216): -> (drift[B,32,32,3], div[B]).
   The denoiser's Jacobian-vector product comes from torch autograd through `score_model`;
-  everything else is mulan_sample_gamma / mulan_ode_drift / mulan_row_dot."""
+  everything else is mulan_sample_gamma / mulan_ode_drift / mulan_row_dot.
+
+  hutchinson_noise=None: drift only (the ODE sampler discards the divergence,
+  notebook_utils.py:419), div is None.  coeffs = cached (a, b, c) of `embeddings` (they do not
+  change along an ODE solve); out = (drift_out[B,D], div_out[B]) buffers to write into."""
   cfg = model.config
   B = x.shape[0]
   D = 32 * 32 * 3
+  drift_out, div_out = out if out is not None else (None, None)
   with torch.no_grad():
-    a, b, c = (q.contiguous() for q in model.gamma._compute_coefficients(embeddings))
-    tt = (t * torch.ones((B,), dtype=torch.float32, device=x.device)).contiguous()
+    if coeffs is None:
+      coeffs = tuple(q.contiguous() for q in model.gamma._compute_coefficients(embeddings))
+    a, b, c = coeffs
+    tt = torch.full((B,), float(t), dtype=torch.float32, device=x.device)
     g_net = ops.sample_gamma(model.desc, a, b, c, tt)
   g_in = g_net if cfg.unet_type == 'vdm' else g_net.reshape(B, 32, 32, 3)
+  if hutchinson_noise is None:
+    with torch.no_grad():
+      x4 = x.detach().reshape(B, 32, 32, 3)
+      net = model.score_model(x4, g_in, embeddings, True)
+      drift = ops.ode_drift(model.desc, a, b, c, tt, x4.reshape(B, D).contiguous(),
+                            net.reshape(B, D).contiguous(), None, high_precision, out=drift_out)
+    return drift.reshape(B, 32, 32, 3), None
   xg = x.detach().reshape(B, 32, 32, 3).requires_grad_(True)
   with torch.enable_grad():
     net = model.score_model(xg, g_in, embeddings, True)
   v = hutchinson_noise.reshape(B, D).contiguous()
   drift, net_bar, div_direct = ops.ode_drift(
       model.desc, a, b, c, tt, xg.detach().reshape(B, D).contiguous(),
-      net.detach().reshape(B, D).contiguous(), v, high_precision)
+      net.detach().reshape(B, D).contiguous(), v, high_precision, out=drift_out)
   (x_bar,) = torch.autograd.grad(net, xg, grad_outputs=net_bar.reshape(net.shape))
-  div = ops.row_dot(x_bar.reshape(B, D).contiguous(), v, add=div_direct)
+  div = ops.row_dot(x_bar.reshape(B, D).contiguous(), v, add=div_direct, out=div_out)
   return drift.reshape(B, 32, 32, 3), div
 
 

@@ -230,8 +230,10 @@ def generate_x(desc: Desc, z_0):
   return out
 
 
-def ode_drift(desc: Desc, a, b, c, t, x_t, eps_hat, v=None, high_precision: bool = False):
-  """mulan_ode_drift -> drift[B,D] (v is None) or (drift, net_bar[B,D], div_direct[B])."""
+def ode_drift(desc: Desc, a, b, c, t, x_t, eps_hat, v=None, high_precision: bool = False,
+              out=None):
+  """mulan_ode_drift -> drift[B,D] (v is None) or (drift, net_bar[B,D], div_direct[B]);
+  `out` (optional) receives the drift."""
   B, D = x_t.shape
   rows_abc = a.shape[0]
   for n, q in (('a', a), ('b', b), ('c', c)):
@@ -240,7 +242,8 @@ def ode_drift(desc: Desc, a, b, c, t, x_t, eps_hat, v=None, high_precision: bool
     _req(q, torch.float32, (B, D), n)
   _opt(v, torch.float32, (B, D), 'v')
   _req(t, torch.float32, (B,), 't')
-  drift = torch.empty((B, D), dtype=torch.float32, device=x_t.device)
+  drift = (torch.empty((B, D), dtype=torch.float32, device=x_t.device) if out is None
+           else _req(out, torch.float32, (B, D), 'out'))
   nb = torch.empty_like(drift) if v is not None else None
   dd = torch.empty((B,), dtype=torch.float32, device=x_t.device) if v is not None else None
   d = desc.c(B)
@@ -250,15 +253,53 @@ def ode_drift(desc: Desc, a, b, c, t, x_t, eps_hat, v=None, high_precision: bool
   return drift if v is None else (drift, nb, dd)
 
 
-def row_dot(u, v, add=None):
+def row_dot(u, v, add=None, out=None):
   """mulan_row_dot -> out[b] = <u[b], v[b]> (+ add[b])."""
   B, D = u.shape
   _req(u, torch.float32, (B, D), 'u')
   _req(v, torch.float32, (B, D), 'v')
   _opt(add, torch.float32, (B,), 'add')
-  out = torch.empty((B,), dtype=torch.float32, device=u.device)
+  out = (torch.empty((B,), dtype=torch.float32, device=u.device) if out is None
+         else _req(out, torch.float32, (B,), 'out'))
   _lib.check(_lib.load().mulan_row_dot(B, D, _p(u), _p(v), _p(add), _p(out), _stream()))
   return out
+
+
+def _rk45_K(K, n_k: int, n: int):
+  """K: [>= n_k, k_stride >= n] float32 stage derivatives (rows may be padded for alignment)."""
+  if K.dim() != 2 or K.shape[0] < n_k or K.shape[1] < n:
+    raise ValueError(f'K: expected [>= {n_k}, >= {n}], got {tuple(K.shape)}')
+  _req(K, torch.float32, tuple(K.shape), 'K')
+
+
+def rk45_stage(n_k: int, coef, h: float, y, K, y_stage=None, y_out=None):
+  """mulan_rk45_stage: v = y + (sum_{j<n_k} coef[j] K[j]) h -> y_stage (float32) / y_out (float64)."""
+  n = y.numel()
+  _req(y, torch.float64, (n,), 'y')
+  _rk45_K(K, n_k, n)
+  if y_stage is not None:
+    _req(y_stage, torch.float32, (n,), 'y_stage')
+  if y_out is not None:
+    _req(y_out, torch.float64, (n,), 'y_out')
+  cf = (C.c_double * 7)(*[float(v) for v in coef[:n_k]])
+  _lib.check(_lib.load().mulan_rk45_stage(n, n_k, cf, float(h), _p(y), _p(K), K.shape[1], _p(y_stage),
+                                          _p(y_out), _stream()))
+
+
+def rk45_norm(n_k: int, coef, h: float, rtol: float, atol: float, y, y_new, K, of_y: bool,
+              scratch, out):
+  """mulan_rk45_norm: out[0] = sum ((y | (sum coef K) h) / (atol + rtol max(|y|,|y_new|)))^2."""
+  n = y.numel()
+  _req(y, torch.float64, (n,), 'y')
+  if y_new is not None:
+    _req(y_new, torch.float64, (n,), 'y_new')
+  _rk45_K(K, n_k, n)
+  _req(scratch, torch.float64, (_lib.MULAN_RK45_SCRATCH,), 'scratch')
+  _req(out, torch.float64, (1,), 'out')
+  cf = (C.c_double * 7)(*[float(v) for v in coef[:n_k]])
+  _lib.check(_lib.load().mulan_rk45_norm(n, n_k, cf, float(h), float(rtol), float(atol), _p(y),
+                                         _p(y_new), _p(K), K.shape[1], 1 if of_y else 0, _p(scratch),
+                                         _p(out), _stream()))
 
 
 class ElboWorkspace:

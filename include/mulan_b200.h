@@ -323,11 +323,23 @@ typedef struct mulan_adamw_desc {
   double lr;            /* learning rate for THIS step (schedule on the host) */
   double b1, b2, eps, weight_decay;
   double ema_rate;      /* 0.9999: ema += (1 - ema_rate) (p_new - ema)       */
-  double grad_scale;    /* g is multiplied by this first (1/world, clipping) */
+  double grad_scale;    /* g is multiplied by this first (1/world of the pmean) */
+  /* optax.clip_by_global_norm(config.gradient_clip_norm), ldm/experiment.py:176-178, applied to
+   * grad_scale * g:  0 = off; else grad_sumsq (DEVICE scalar from mulan_grad_sumsq over the raw
+   * bucket) must be set and g <- (g / norm) * clip_norm whenever norm >= clip_norm.            */
+  double clip_norm;
+  const float* grad_sumsq;
 } mulan_adamw_desc;
 
 int mulan_adamw_ema(const mulan_adamw_desc* desc, float* params, const float* grads,
                     float* mu, float* nu, float* ema_params, void* stream);
+
+/* out[0] (device float) = sum_i g[i]^2 over the flat bucket: optax.global_norm(grads)^2 for
+ * clip_by_global_norm.  n % 4 == 0, g 16-byte aligned; scratch holds MULAN_SUMSQ_SCRATCH doubles.
+ * Fixed-order two-launch reduction (float64 accumulation of float32 squares): run to run
+ * identical, 4 B per parameter. */
+#define MULAN_SUMSQ_SCRATCH 2048
+int mulan_grad_sumsq(int64_t n, const float* g, double* scratch, float* out, void* stream);
 
 /* Frees the calling thread's cached mulan_elbo_host workspace (device + pinned host). */
 void mulan_host_workspace_release(void);

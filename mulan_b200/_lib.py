@@ -16,6 +16,7 @@ MULAN_PARAM_VEL_FROM_EPS = 2
 MULAN_GT_MEAN = 0
 MULAN_GT_PIXEL = 1
 MULAN_RK45_SCRATCH = 2048
+MULAN_SUMSQ_SCRATCH = 2048
 
 PARAM_NAMES = {'eps': MULAN_PARAM_EPS, 'vel': MULAN_PARAM_VEL,
                'vel_from_eps': MULAN_PARAM_VEL_FROM_EPS}
@@ -33,7 +34,8 @@ class MulanAdamwDesc(C.Structure):
   _fields_ = [('n', C.c_int64), ('n_decay', C.c_int64), ('step', C.c_int32),
               ('reserved', C.c_int32), ('lr', C.c_double), ('b1', C.c_double), ('b2', C.c_double),
               ('eps', C.c_double), ('weight_decay', C.c_double), ('ema_rate', C.c_double),
-              ('grad_scale', C.c_double)]
+              ('grad_scale', C.c_double), ('clip_norm', C.c_double),
+              ('grad_sumsq', C.c_void_p)]
 
 
 class MulanError(RuntimeError):
@@ -78,6 +80,7 @@ SIGNATURES = {
     'mulan_rk45_norm': ([C.c_int64, C.c_int32, _P, C.c_double, C.c_double, C.c_double, _P, _P, _P,
                          C.c_int64, C.c_int32, _P, _P, _P], C.c_int),
     'mulan_adamw_ema': ([C.POINTER(MulanAdamwDesc)] + [_P] * 6, C.c_int),
+    'mulan_grad_sumsq': ([C.c_int64, _P, _P, _P, _P], C.c_int),
     'mulan_host_workspace_release': ([], None),
 }
 

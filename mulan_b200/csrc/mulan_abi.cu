@@ -510,10 +510,23 @@ int mulan_adamw_ema(const mulan_adamw_desc* d, float* params, const float* grads
   if (d->n % 4 != 0 || d->n_decay % 4 != 0)
     return fail(MULAN_ERR_ALIGNMENT, "%s: n and n_decay must be multiples of 4", fn);
   if (d->step < 1) return fail(MULAN_ERR_INVALID_ARG, "%s: step=%d must be >= 1", fn, d->step);
+  if (!(d->clip_norm >= 0.0)) return fail(MULAN_ERR_INVALID_ARG, "%s: clip_norm < 0", fn);
+  if (d->clip_norm > 0.0 && d->grad_sumsq == nullptr)
+    return fail(MULAN_ERR_INVALID_ARG, "%s: clip_norm set but grad_sumsq is NULL", fn);
   if (d->n == 0) return 0;
   REQ_VEC(params, fn); REQ_VEC(grads, fn); REQ_VEC(mu, fn); REQ_VEC(nu, fn); REQ_VEC(ema_params, fn);
   cudaError_t e = mulan::launch_adamw_ema(*d, params, grads, mu, nu, ema_params,
                                           (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(fn, e);
+}
+
+int mulan_grad_sumsq(int64_t n, const float* g, double* scratch, float* out, void* stream) {
+  const char* fn = "mulan_grad_sumsq";
+  if (n < 0) return fail(MULAN_ERR_INVALID_ARG, "%s: n < 0", fn);
+  if (n % 4 != 0) return fail(MULAN_ERR_ALIGNMENT, "%s: n must be a multiple of 4", fn);
+  REQ_PTR(scratch, fn); REQ_PTR(out, fn);
+  if (n > 0) REQ_VEC(g, fn);
+  cudaError_t e = mulan::launch_grad_sumsq(g, n, scratch, out, (cudaStream_t)stream);
   return e == cudaSuccess ? 0 : cuda_fail(fn, e);
 }
 

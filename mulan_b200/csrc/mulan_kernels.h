@@ -187,6 +187,8 @@ cudaError_t launch_bwd_pre(const BwdPreParams& p, cudaStream_t s);
 cudaError_t launch_discrete_w(const DiscreteWParams& p, cudaStream_t s);
 cudaError_t launch_adamw_ema(const mulan_adamw_desc& d, float* p, const float* g, float* mu,
                              float* nu, float* ema, cudaStream_t s);
+cudaError_t launch_grad_sumsq(const float* g, long long n, double* scratch, float* out,
+                              cudaStream_t s);
 cudaError_t launch_aux_topk_fwd(int rows, int latent, int k, int noise_kind, const float* logits,
                                 const float* noise, float* embedding, float* kl_z,
                                 cudaStream_t s);

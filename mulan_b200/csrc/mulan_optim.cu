@@ -11,6 +11,11 @@
 //   ema  = ema + (1 - ema_rate) (p_new - ema)                    (train_state.py:91-95)
 //   (+ the pmean of the gradients, ldm/experiment.py:341: NCCL sums, `grad_scale` = 1/world
 //    finishes the mean here instead of in a separate pass over the bucket)
+//   optional optax.clip_by_global_norm(config.gradient_clip_norm) in front of the chain
+//   (ldm/experiment.py:176-178):  n = sqrt(sum g^2);  g = n < max ? g : (g / n) * max.
+//   mulan_grad_sumsq makes one extra 4 B/param read pass over the bucket (deterministic
+//   two-launch reduction, float64 accumulation of float32 squares); the update kernel reads the
+//   scalar from device memory, so there is no host synchronisation.
 //
 // Layout: parameters are laid out decayed-first, so the mask is one boundary index instead of
 // a per-element byte.  Purely HBM-bound: p, g, mu, nu, ema read (20 B) and p, mu, nu, ema
@@ -27,11 +32,15 @@ struct AdamwParams {
   float lr, b1, b2, om_b1, om_b2, eps, wd, one_minus_ema;
   float bc1, bc2;      // 1 - b1^t, 1 - b2^t
   float grad_scale;
+  const float* sumsq;  // device scalar: sum of squares of the RAW bucket (before grad_scale)
+  float clip;          // max global norm
 };
 
 __device__ __forceinline__ void adamw_one(float& p, float g, float& mu, float& nu, float& ema,
-                                          const AdamwParams& k, bool decay) {
+                                          const AdamwParams& k, bool decay, bool clip,
+                                          float g_norm) {
   g = g * k.grad_scale;
+  if (clip) g = __fdiv_rn(g, g_norm) * k.clip;
   mu = k.om_b1 * g + k.b1 * mu;
   nu = k.om_b2 * (g * g) + k.b2 * nu;
   const float mu_hat = __fdiv_rn(mu, k.bc1);
@@ -42,9 +51,16 @@ __device__ __forceinline__ void adamw_one(float& p, float g, float& mu, float& n
   ema = ema + k.one_minus_ema * (p - ema);
 }
 
+template <bool CLIP>
 __global__ void __launch_bounds__(kThreads)
 adamw_ema_kernel(const AdamwParams k) {
   const long long stride = (long long)gridDim.x * kThreads;
+  float g_norm = 0.f;
+  bool clip = false;
+  if (CLIP) {
+    g_norm = k.grad_scale * sqrtf(__ldg(k.sumsq));
+    clip = !(g_norm < k.clip);
+  }
   for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < k.n4; i += stride) {
     float4 P = reinterpret_cast<float4*>(k.p)[i];
     const float4 G = __ldg(reinterpret_cast<const float4*>(k.g) + i);
@@ -52,10 +68,10 @@ adamw_ema_kernel(const AdamwParams k) {
     float4 V = reinterpret_cast<float4*>(k.nu)[i];
     float4 E = reinterpret_cast<float4*>(k.ema)[i];
     const bool decay = i < k.decay4;
-    adamw_one(P.x, G.x, M.x, V.x, E.x, k, decay);
-    adamw_one(P.y, G.y, M.y, V.y, E.y, k, decay);
-    adamw_one(P.z, G.z, M.z, V.z, E.z, k, decay);
-    adamw_one(P.w, G.w, M.w, V.w, E.w, k, decay);
+    adamw_one(P.x, G.x, M.x, V.x, E.x, k, decay, clip, g_norm);
+    adamw_one(P.y, G.y, M.y, V.y, E.y, k, decay, clip, g_norm);
+    adamw_one(P.z, G.z, M.z, V.z, E.z, k, decay, clip, g_norm);
+    adamw_one(P.w, G.w, M.w, V.w, E.w, k, decay, clip, g_norm);
     reinterpret_cast<float4*>(k.p)[i] = P;
     reinterpret_cast<float4*>(k.mu)[i] = M;
     reinterpret_cast<float4*>(k.nu)[i] = V;
@@ -78,11 +94,76 @@ cudaError_t launch_adamw_ema(const mulan_adamw_desc& d, float* p, const float* g
   k.bc1 = 1.0f - powf((float)d.b1, (float)d.step);
   k.bc2 = 1.0f - powf((float)d.b2, (float)d.step);
   k.grad_scale = (float)d.grad_scale;
+  k.sumsq = d.grad_sumsq;
+  k.clip = (float)d.clip_norm;
   static int max_ctas = 0;
-  if (max_ctas == 0) max_ctas = resident_ctas((const void*)adamw_ema_kernel);
+  if (max_ctas == 0) max_ctas = resident_ctas((const void*)adamw_ema_kernel<false>);
   const long long want = (k.n4 + kThreads - 1) / kThreads;
   const int grid = (int)(want < max_ctas ? want : max_ctas);
-  adamw_ema_kernel<<<grid, kThreads, 0, s>>>(k);
+  if (d.clip_norm > 0.0)
+    adamw_ema_kernel<true><<<grid, kThreads, 0, s>>>(k);
+  else
+    adamw_ema_kernel<false><<<grid, kThreads, 0, s>>>(k);
+  return cudaGetLastError();
+}
+
+// ---- global sum of squares of the gradient bucket (optax.global_norm ** 2) ------------------
+namespace {
+
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ double cta_sum_f64(double v, double* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_sum_f64(v);
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (warp == 0) {
+    t = lane < kWarps ? red[lane] : 0.0;
+    t = warp_sum_f64(t);
+  }
+  return t;
+}
+
+__global__ void __launch_bounds__(kThreads)
+grad_sumsq_partial_kernel(const float* __restrict__ g, long long n4, double* __restrict__ part) {
+  __shared__ double red[kWarps];
+  const long long stride = (long long)gridDim.x * kThreads;
+  double acc = 0.0;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n4; i += stride) {
+    const float4 G = __ldg(reinterpret_cast<const float4*>(g) + i);
+    acc += (double)(G.x * G.x) + (double)(G.y * G.y) + (double)(G.z * G.z) + (double)(G.w * G.w);
+  }
+  const double t = cta_sum_f64(acc, red);
+  if (threadIdx.x == 0) part[blockIdx.x] = t;
+}
+
+__global__ void __launch_bounds__(kThreads)
+grad_sumsq_final_kernel(const double* __restrict__ part, int n_part, float* __restrict__ out) {
+  __shared__ double red[kWarps];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n_part; i += kThreads) acc += part[i];
+  const double t = cta_sum_f64(acc, red);
+  if (threadIdx.x == 0) out[0] = (float)t;
+}
+
+}  // namespace
+
+cudaError_t launch_grad_sumsq(const float* g, long long n, double* scratch, float* out,
+                              cudaStream_t s) {
+  static int max_ctas = 0;
+  if (max_ctas == 0) max_ctas = resident_ctas((const void*)grad_sumsq_partial_kernel);
+  const long long n4 = n / 4;
+  long long want = (n4 + kThreads - 1) / kThreads;
+  if (want < 1) want = 1;
+  int grid = (int)(want < max_ctas ? want : max_ctas);
+  if (grid > MULAN_SUMSQ_SCRATCH) grid = MULAN_SUMSQ_SCRATCH;
+  grad_sumsq_partial_kernel<<<grid, kThreads, 0, s>>>(g, n4, scratch);
+  grad_sumsq_final_kernel<<<1, kThreads, 0, s>>>(scratch, grid, out);
   return cudaGetLastError();
 }
 

@@ -22,12 +22,21 @@ import torch.distributed as dist
 from . import _lib
 
 
-def lr_schedule(step: int, learning_rate: float = 2e-4, num_steps_lr_warmup: int = 100) -> float:
-  """optax.linear_schedule(0, lr, warmup) (ldm/experiment.py:106-129, lr_decay=False);
+def lr_schedule(step: int, learning_rate: float = 2e-4, num_steps_lr_warmup: int = 100,
+                lr_decay: bool = False, num_steps_train: int = 0) -> float:
+  """get_lr_schedule (ldm/experiment.py:106-129): optax.linear_schedule(0, lr, warmup), joined
+  at `warmup` with a linear decay to 0 over num_steps_train - warmup steps when lr_decay.
   `step` is the 0-based count optax sees before the update."""
+  step = max(step, 0)
+  if lr_decay and step >= num_steps_lr_warmup:
+    span = num_steps_train - num_steps_lr_warmup
+    if span <= 0:
+      return 0.0 if step > num_steps_lr_warmup else learning_rate
+    frac = 1.0 - min(step - num_steps_lr_warmup, span) / span
+    return learning_rate * frac
   if num_steps_lr_warmup <= 0:
     return learning_rate
-  frac = min(max(step, 0), num_steps_lr_warmup) / num_steps_lr_warmup
+  frac = min(step, num_steps_lr_warmup) / num_steps_lr_warmup
   return learning_rate * frac
 
 
@@ -43,7 +52,8 @@ class FlatTrainState:
   def __init__(self, named_params: Iterable[Tuple[str, torch.nn.Parameter]], extra: int = 8,
                b1: float = 0.9, b2: float = 0.99, eps: float = 1e-8, weight_decay: float = 0.01,
                learning_rate: float = 2e-4, num_steps_lr_warmup: int = 100,
-               ema_rate: float = 0.9999):
+               ema_rate: float = 0.9999, gradient_clip_norm: Optional[float] = None,
+               lr_decay: bool = False, num_steps_train: int = 0):
     named = [(n, p) for n, p in named_params if p.requires_grad]
     if not named:
       raise ValueError('no trainable parameters')
@@ -79,6 +89,23 @@ class FlatTrainState:
     self.step = 0
     self.hp = dict(b1=b1, b2=b2, eps=eps, weight_decay=weight_decay)
     self.learning_rate, self.warmup, self.ema_rate = learning_rate, num_steps_lr_warmup, ema_rate
+    self.lr_decay, self.num_steps_train = lr_decay, num_steps_train
+    # optax.clip_by_global_norm in front of the chain when the config has gradient_clip_norm
+    # (ldm/experiment.py:176-178)
+    self.clip_norm = float(gradient_clip_norm) if gradient_clip_norm else 0.0
+    if self.clip_norm > 0.0:
+      self._sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
+      self._scratch = torch.empty(_lib.MULAN_SUMSQ_SCRATCH, dtype=torch.float64, device=dev)
+
+  def grad_global_norm(self) -> torch.Tensor:
+    """optax.global_norm of the (all-reduced, not yet averaged) gradient bucket: device scalar."""
+    ptr = lambda t: C.c_void_p(t.data_ptr())
+    if self.clip_norm <= 0.0:
+      raise RuntimeError('grad_global_norm needs gradient_clip_norm to be configured')
+    _lib.check(_lib.load().mulan_grad_sumsq(
+        self.n, ptr(self.grads), ptr(self._scratch), ptr(self._sumsq),
+        C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    return self._sumsq.sqrt()
 
   def zero_grad(self):
     self.grads.zero_()
@@ -95,11 +122,17 @@ class FlatTrainState:
     world = dist.get_world_size() if dist.is_initialized() else 1
     if grad_scale is None:
       grad_scale = 1.0 / world
-    lr = lr_schedule(self.step, self.learning_rate, self.warmup)
+    lr = lr_schedule(self.step, self.learning_rate, self.warmup, self.lr_decay,
+                     self.num_steps_train)
     self.step += 1
-    d = _lib.MulanAdamwDesc(self.n, self.n_decay, self.step, 0, lr, self.hp['b1'], self.hp['b2'],
-                            self.hp['eps'], self.hp['weight_decay'], self.ema_rate, grad_scale)
     ptr = lambda t: C.c_void_p(t.data_ptr())
+    sumsq = None
+    if self.clip_norm > 0.0:
+      self.grad_global_norm()
+      sumsq = self._sumsq.data_ptr()
+    d = _lib.MulanAdamwDesc(self.n, self.n_decay, self.step, 0, lr, self.hp['b1'], self.hp['b2'],
+                            self.hp['eps'], self.hp['weight_decay'], self.ema_rate, grad_scale,
+                            self.clip_norm, sumsq)
     _lib.check(_lib.load().mulan_adamw_ema(
         C.byref(d), ptr(self.params), ptr(self.grads), ptr(self.mu), ptr(self.nu), ptr(self.ema),
         C.c_void_p(torch.cuda.current_stream().cuda_stream)))

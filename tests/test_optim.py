@@ -1,5 +1,7 @@
 """Fused AdamW + EMA update (mulan_adamw_ema) against the CPU oracle of the optax chain, and the
 oracle against torch.optim.AdamW (independent implementation of the same published formulas)."""
+import math
+
 import numpy as np
 import pytest
 import torch
@@ -31,6 +33,63 @@ def test_lr_schedule_and_mask():
   assert lr_schedule(100) == 2e-4 and lr_schedule(10**6) == 2e-4
   assert decay_mask('score.conv_in.weight') and decay_mask('score.norm_out.weight')
   assert not decay_mask('score.conv_in.bias')
+  # lr_decay=True: join_schedules([warm-up, linear decay to 0], boundaries=[warm-up])
+  for step in (0, 1, 50, 99, 100, 101, 500, 999, 1000, 5000):
+    for decay in (False, True):
+      want = AO.lr_schedule(step, 2e-4, 100, decay, 1000)
+      got = lr_schedule(step, 2e-4, 100, decay, 1000)
+      assert abs(got - want) < 1e-18, (step, decay)
+  assert lr_schedule(550, 2e-4, 100, True, 1000) == pytest.approx(1e-4)
+  assert lr_schedule(1000, 2e-4, 100, True, 1000) == 0.0
+
+
+def test_oracle_clip_by_global_norm():
+  g = [torch.tensor([3.0, 0.0]), torch.tensor([[4.0]])]
+  out, norm = AO.clip_by_global_norm(g, 10.0)
+  assert norm.item() == 5.0 and all(torch.equal(a, b) for a, b in zip(out, g))
+  out, _ = AO.clip_by_global_norm(g, 1.0)
+  assert torch.allclose(out[0], torch.tensor([0.6, 0.0])) and torch.allclose(out[1], torch.tensor([[0.8]]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('clip', [0.5, 1e6])
+def test_adamw_ema_clip_by_global_norm(cuda_device, clip):
+  """gradient_clip_norm: mulan_grad_sumsq + the clipped update == the oracle's
+  clip_by_global_norm -> adamw -> ema on the same bucket (clip active / inactive)."""
+  import ctypes as C
+  from mulan_b200 import _lib
+  dev = cuda_device
+  rng = np.random.default_rng(1)
+  n = 1_000_004
+  p = torch.from_numpy(rng.standard_normal(n).astype(np.float32))
+  g = torch.from_numpy((rng.standard_normal(n) * 1e-2).astype(np.float32))
+  mu, nu, ema = torch.zeros(n), torch.zeros(n), p.clone()
+  gp, gg, gmu, gnu, gema = (t.clone().to(dev) for t in (p, g, mu, nu, ema))
+  ptr = lambda t: C.c_void_p(t.data_ptr())
+  sumsq = torch.zeros(1, device=dev)
+  scratch = torch.empty(_lib.MULAN_SUMSQ_SCRATCH, dtype=torch.float64, device=dev)
+  lib = _lib.load()
+  _lib.check(lib.mulan_grad_sumsq(n, ptr(gg), ptr(scratch), ptr(sumsq), None))
+  want_ss = (g.double() ** 2).sum().item()
+  assert abs(sumsq.item() - want_ss) < 1e-6 * want_ss
+  first = sumsq.item()
+  _lib.check(lib.mulan_grad_sumsq(n, ptr(gg), ptr(scratch), ptr(sumsq), None))
+  assert sumsq.item() == first                                      # deterministic
+  d = _lib.MulanAdamwDesc(n, n, 3, 0, 2e-4, 0.9, 0.99, 1e-8, 0.01, 0.9999, 0.5, clip,
+                          sumsq.data_ptr())
+  _lib.check(lib.mulan_adamw_ema(C.byref(d), ptr(gp), ptr(gg), ptr(gmu), ptr(gnu), ptr(gema), None))
+  torch.cuda.synchronize()
+  wp, wmu, wnu, wema = AO.adamw_ema_step(p, g, mu, nu, ema, 3, 2e-4, grad_scale=0.5,
+                                         clip_norm=clip)
+  clipped = 0.5 * math.sqrt(want_ss) >= clip
+  assert clipped == (clip == 0.5)
+  for got, want in ((gp, wp), (gmu, wmu), (gnu, wnu), (gema, wema)):
+    tol = 2e-6 * want.abs() + 2e-7 * want.abs().max()
+    assert torch.all((got.cpu() - want).abs() <= tol)
+  # clip_norm without the device scalar is refused
+  bad = _lib.MulanAdamwDesc(n, n, 3, 0, 2e-4, 0.9, 0.99, 1e-8, 0.01, 0.9999, 0.5, clip, None)
+  assert lib.mulan_adamw_ema(C.byref(bad), ptr(gp), ptr(gg), ptr(gmu), ptr(gnu), ptr(gema),
+                             None) == -1
 
 
 @pytest.mark.gpu
@@ -106,3 +165,31 @@ def test_flat_train_state_step(cuda_device):
     q, mu, nu, e = AO.adamw_ema_step(q, grads2[n], mu, nu, e, 2, 2e-6, decay_mask=m)
     assert torch.allclose(p.detach().cpu(), q, rtol=1e-6, atol=1e-9), n
     assert torch.allclose(ema[n].cpu().view_as(e), e, rtol=1e-6, atol=1e-9), n
+
+
+@pytest.mark.gpu
+def test_flat_train_state_gradient_clip(cuda_device):
+  """config.gradient_clip_norm: the clip uses the GLOBAL norm over every parameter tensor."""
+  from mulan_b200.optim import FlatTrainState, decay_mask
+  dev = cuda_device
+  torch.manual_seed(1)
+  net = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.Linear(5, 3)).to(dev)
+  before = {n: p.detach().clone().cpu() for n, p in net.named_parameters()}
+  state = FlatTrainState(net.named_parameters(), num_steps_lr_warmup=0, gradient_clip_norm=0.05)
+  x = torch.randn(4, 7, device=dev)
+  state.zero_grad()
+  (10 * net(x).square().mean()).backward()
+  grads = {n: p.grad.detach().clone().cpu() for n, p in net.named_parameters()}
+  names = list(grads)
+  clipped, norm = AO.clip_by_global_norm([grads[n] for n in names], 0.05)
+  assert norm.item() > 0.05
+  assert abs(state.grad_global_norm().item() - norm.item()) < 1e-6 * norm.item()
+  lr = state.apply_gradients()
+  assert lr == 2e-4
+  for n, gc in zip(names, clipped):
+    q = before[n]
+    m = torch.full_like(q, decay_mask(n), dtype=torch.bool)
+    q, _, _, _ = AO.adamw_ema_step(q, gc, torch.zeros_like(q), torch.zeros_like(q), q, 1, 2e-4,
+                                   decay_mask=m)
+    got = dict(net.named_parameters())[n].detach().cpu()
+    assert torch.allclose(got, q, rtol=1e-6, atol=1e-8), n

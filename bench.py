@@ -63,6 +63,9 @@ def parse_args():
                   help='train_step: allow TF32 in the stand-in networks (reference: float32)')
   ap.add_argument('--launch-rows', type=int, default=2048,
                   help='dense_vlb: rows per launch (16 images x 128 antithetic timesteps)')
+  ap.add_argument('--streams', type=int, default=8,
+                  help='streams the independent launches of one step are spread over '
+                       '(only matters when a step has several launches: dense_vlb)')
   ap.add_argument('--separate-post', action='store_true',
                   help='train: run mulan_fwd_post and mulan_bwd_post as two passes instead of '
                        'the fused value-and-grad pass')
@@ -236,36 +239,62 @@ def run_native(args):
                    ci, torch.full((lrows,), 1.0 / (lrows * D * math.log(2.0)), device=dev)))
   ws = chunks[0][0]
 
+  # Several launches per step (dense VLB: 2048 rows each = 3.46 waves of 592 resident CTAs) are
+  # independent, so they go round-robin over a few streams: the ragged last wave of one launch
+  # overlaps the first wave of the next.  Fork/join by events, capturable in the CUDA graph.
+  n_side = min(len(chunks), args.streams) - 1
+  side = [torch.cuda.Stream() for _ in range(max(n_side, 0))]
+
+  def fan_out(per_chunk):
+    cur = torch.cuda.current_stream()
+    if not side:
+      for ch in chunks:
+        per_chunk(*ch)
+      return
+    fork = torch.cuda.Event()
+    fork.record(cur)
+    lanes = [cur] + side
+    for s in side:
+      s.wait_event(fork)
+    for j, ch in enumerate(chunks):
+      with torch.cuda.stream(lanes[j % len(lanes)]):
+        per_chunk(*ch)
+    for s in side:
+      join = torch.cuda.Event()
+      join.record(s)
+      cur.wait_event(join)
+
   def each(fn):
-    def run():
-      for w_, i, g in chunks:
-        fn(w_, i, g)
-    return run
-  kernels = {   # name -> launch closure (all write into the preallocated workspaces)
-      'fwd_pre': each(lambda w_, i, g: w_.fwd_pre(i['x'], i['a'], i['b'], i['c'], i['t'],
-                                                  i['eps0'], i['eps'])),
+    return lambda: fan_out(fn)
+  per_chunk = {   # name -> launch on one chunk (all write into the preallocated workspaces)
+      'fwd_pre': lambda w_, i, g: w_.fwd_pre(i['x'], i['a'], i['b'], i['c'], i['t'],
+                                             i['eps0'], i['eps']),
   }
   if train and not args.separate_post:
     # value-and-grad: the loss cotangent of a mean is known up front (jax.value_and_grad)
-    kernels['post_vg'] = each(lambda w_, i, g: w_.fwd_bwd_post(i['x'], i['a'], i['b'], i['c'],
-                                                               i['t'], i['eps'], i['net'], g))
+    per_chunk['post_vg'] = lambda w_, i, g: w_.fwd_bwd_post(i['x'], i['a'], i['b'], i['c'],
+                                                            i['t'], i['eps'], i['net'], g)
   else:
-    kernels['fwd_post'] = each(lambda w_, i, g: w_.fwd_post(i['x'], i['a'], i['b'], i['c'], i['t'],
-                                                            i['eps'], i['net']))
-  kernels['bpd_reduce'] = each(lambda w_, i, g: w_.bpd_reduce(None))
+    per_chunk['fwd_post'] = lambda w_, i, g: w_.fwd_post(i['x'], i['a'], i['b'], i['c'], i['t'],
+                                                         i['eps'], i['net'])
+  per_chunk['bpd_reduce'] = lambda w_, i, g: w_.bpd_reduce(None)
   if train:
     if args.separate_post:
-      kernels['bwd_post'] = each(lambda w_, i, g: w_.bwd_post(i['x'], i['a'], i['b'], i['c'],
-                                                              i['t'], i['eps'], i['net'], g))
-    kernels['bwd_pre'] = each(lambda w_, i, g: w_.bwd_pre(i['x'], i['a'], i['b'], i['c'], i['t'],
-                                                          i['eps'], i['net'], i['z_bar'],
-                                                          i['g_bar'], g))
-  names = list(kernels)
+      per_chunk['bwd_post'] = lambda w_, i, g: w_.bwd_post(i['x'], i['a'], i['b'], i['c'],
+                                                           i['t'], i['eps'], i['net'], g)
+    per_chunk['bwd_pre'] = lambda w_, i, g: w_.bwd_pre(i['x'], i['a'], i['b'], i['c'], i['t'],
+                                                       i['eps'], i['net'], i['z_bar'],
+                                                       i['g_bar'], g)
+  names = list(per_chunk)
+  kernels = {n: each(fn) for n, fn in per_chunk.items()}   # one kernel over every chunk
   launches_per_step = len(names) * len(chunks)
 
-  def step():
+  def whole_chunk(w_, i, g):
     for n in names:
-      kernels[n]()
+      per_chunk[n](w_, i, g)
+
+  def step():
+    fan_out(whole_chunk)                  # chunk-major: a chunk's kernels stay in stream order
 
   def barrier():
     if world > 1:
@@ -435,7 +464,7 @@ def run_native(args):
                  'param': args.param, 'l2': 'inputs larger than L2 (%.2f GB of HBM traffic per '
                  'step)' % (total_algo / 1e9), 'parallelism': f'dp{world} (rows sharded)',
                  'timed_loop': 'CUDA-graph replay of one step (%d launches)' % launches_per_step,
-                 'rows_per_launch': lrows},
+                 'rows_per_launch': lrows, 'streams': 1 + len(side)},
       'roofline': {'bound': 'hbm', 'kernel': dom, 'achieved': kinfo[dom]['gbs'],
                    'peak': peaks, 'peak_source': peak_src, 'unit': 'GB/s',
                    'frac': kinfo[dom]['gbs'] / peaks, 'traffic': traffic,

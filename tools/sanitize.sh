@@ -43,12 +43,45 @@ n = 4096
 bufs = [torch.randn(n, device=dev) for _ in range(5)]
 dd = _lib.MulanAdamwDesc(n, 2048, 1, 0, 1e-4, 0.9, 0.99, 1e-8, 0.01, 0.9999, 1.0)
 _lib.check(_lib.load().mulan_adamw_ema(C.byref(dd), *[C.c_void_p(b.data_ptr()) for b in bufs], None))
+# aux-latent variants
+nz = torch.randn(B, 50, device=dev); kb = torch.randn(B, device=dev)
+lgr = lg.clone().requires_grad_(True)
+for fn, extra in ((ops.aux_topk_add, 15), (ops.aux_gumbel, 0.7)):
+  e, k = fn(lgr, nz, extra); ((e * nz).sum() + (k * kb).sum()).backward()
+mu_ = torch.randn(B, 50, device=dev, requires_grad=True)
+var_ = (torch.rand(B, 50, device=dev) + 0.1).requires_grad_(True)
+e, k = ops.aux_gaussian(mu_, var_, nz); ((e * nz).sum() + (k * kb).sum()).backward()
+# RK45 state kernels (odd n: rows not 16-byte multiples) and a short device-resident solve
+from mulan_b200 import ode
+nn_ = 3 * 3073
+y = torch.randn(nn_, dtype=torch.float64, device=dev); yn = y + 0.01
+K = torch.randn(7, (nn_ + 3) // 4 * 4, device=dev)
+y32 = torch.empty(nn_, device=dev); yo = torch.empty_like(y)
+scr = torch.empty(_lib.MULAN_RK45_SCRATCH, dtype=torch.float64, device=dev)
+out1 = torch.empty(1, dtype=torch.float64, device=dev)
+for s_ in range(7):
+  ops.rk45_stage(s_, ode.RK45_E, 0.1, y, K, y_stage=y32, y_out=yo)
+ops.rk45_norm(7, ode.RK45_E, 0.1, 1e-5, 1e-5, y, yn, K, False, scr, out1)
+ops.rk45_norm(0, (), 0.0, 1e-5, 1e-5, y, None, K, True, scr, out1)
+ode.solve_ivp_rk45(lambda t_, yy, o: torch.mul(yy, -1.0, out=o), (0.0, 1.0), y32, 1e-3, 1e-3)
+# global-norm clip
+ss = torch.zeros(1, device=dev)
+scr2 = torch.empty(_lib.MULAN_SUMSQ_SCRATCH, dtype=torch.float64, device=dev)
+_lib.check(_lib.load().mulan_grad_sumsq(n, C.c_void_p(bufs[1].data_ptr()), C.c_void_p(scr2.data_ptr()),
+                                        C.c_void_p(ss.data_ptr()), None))
+dd = _lib.MulanAdamwDesc(n, 2048, 2, 0, 1e-4, 0.9, 0.99, 1e-8, 0.01, 0.9999, 1.0, 0.5, ss.data_ptr())
+_lib.check(_lib.load().mulan_adamw_ema(C.byref(dd), *[C.c_void_p(b.data_ptr()) for b in bufs], None))
 torch.cuda.synchronize()
 print('drive ok')
 PY
-for tool in memcheck racecheck initcheck synccheck; do
-  MULAN_FWD_PRE_TMA=0 compute-sanitizer --tool $tool --kernel-regex kns=mulan --print-limit 5 python /tmp/san_drive.py > gpurun_out/sanitizer_$tool.txt 2>&1
+mkdir -p gpurun_out
+for tool in memcheck racecheck synccheck; do
+  MULAN_FWD_PRE_TMA=0 timeout 600 compute-sanitizer --tool $tool --kernel-regex kns=mulan --print-limit 5 python /tmp/san_drive.py > gpurun_out/sanitizer_$tool.txt 2>&1
   echo "== $tool: $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|drive ok' gpurun_out/sanitizer_$tool.txt | tr '\n' ' ')"
 done
+# initcheck must see torch's own initialising kernels (a kernel filter makes every torch-written
+# input look uninitialised) and needs the caching allocator off
+MULAN_FWD_PRE_TMA=0 PYTORCH_NO_CUDA_MEMORY_CACHING=1 timeout 900 compute-sanitizer --tool initcheck --print-limit 5 python /tmp/san_drive.py > gpurun_out/sanitizer_initcheck.txt 2>&1
+echo "== initcheck: $(grep -E 'ERROR SUMMARY|drive ok' gpurun_out/sanitizer_initcheck.txt | tr '\n' ' ')"
 MULAN_FWD_PRE_TMA=1 compute-sanitizer --tool racecheck --kernel-regex kns=mulan --print-limit 5 python /tmp/san_drive.py > gpurun_out/sanitizer_racecheck_tma.txt 2>&1
 echo "== racecheck (TMA fwd_pre): $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|drive ok' gpurun_out/sanitizer_racecheck_tma.txt | tr '\n' ' ')"

@@ -341,6 +341,20 @@ int mulan_adamw_ema(const mulan_adamw_desc* desc, float* params, const float* gr
 #define MULAN_SUMSQ_SCRATCH 2048
 int mulan_grad_sumsq(int64_t n, const float* g, double* scratch, float* out, void* stream);
 
+/*
+ * "Next" row 2: the random draws of VDM.__call__ generated on the device with JAX's default
+ * counter-based generator, so that a JAX binding can hand over the 2 x uint32 key of a draw
+ * instead of a materialised array: t0 = jax.random.uniform(rng, ()) and
+ * eps_0 / eps = jax.random.normal(rng, shape) (ldm/model_mulan_epsilon.py:287-292, :315, :327).
+ * out[i], i < n, equals jax.random.{bits,uniform,normal}(key, (n,)) (float32 / uint32,
+ * threefry2x32, jax_threefry_partitionable=False, jax <= 0.4.2x) - the reshape to
+ * [B,32,32,3] is free.  n < 2^32 - 1.  Flax's make_rng key folding stays with the caller.
+ */
+int mulan_rng_bits(uint32_t key0, uint32_t key1, int64_t n, uint32_t* out, void* stream);
+int mulan_rng_uniform(uint32_t key0, uint32_t key1, int64_t n, float minval, float maxval,
+                      float* out, void* stream);
+int mulan_rng_normal(uint32_t key0, uint32_t key1, int64_t n, float* out, void* stream);
+
 /* Frees the calling thread's cached mulan_elbo_host workspace (device + pinned host). */
 void mulan_host_workspace_release(void);
 

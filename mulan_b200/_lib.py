@@ -80,6 +80,10 @@ SIGNATURES = {
     'mulan_rk45_norm': ([C.c_int64, C.c_int32, _P, C.c_double, C.c_double, C.c_double, _P, _P, _P,
                          C.c_int64, C.c_int32, _P, _P, _P], C.c_int),
     'mulan_adamw_ema': ([C.POINTER(MulanAdamwDesc)] + [_P] * 6, C.c_int),
+    'mulan_rng_bits': ([C.c_uint32, C.c_uint32, C.c_int64, _P, _P], C.c_int),
+    'mulan_rng_uniform': ([C.c_uint32, C.c_uint32, C.c_int64, C.c_float, C.c_float, _P, _P],
+                          C.c_int),
+    'mulan_rng_normal': ([C.c_uint32, C.c_uint32, C.c_int64, _P, _P], C.c_int),
     'mulan_grad_sumsq': ([C.c_int64, _P, _P, _P, _P], C.c_int),
     'mulan_host_workspace_release': ([], None),
 }

@@ -520,6 +520,35 @@ int mulan_adamw_ema(const mulan_adamw_desc* d, float* params, const float* grads
   return e == cudaSuccess ? 0 : cuda_fail(fn, e);
 }
 
+static int rng_draw(const char* fn, int kind, uint32_t key0, uint32_t key1, int64_t n,
+                    float minval, float maxval, void* out, void* stream) {
+  if (n < 0 || n >= 0xFFFFFFFFLL)
+    return fail(MULAN_ERR_INVALID_ARG, "%s: n must be in [0, 2^32 - 1)", fn);
+  if (n == 0) return 0;
+  if (out == nullptr) return fail(MULAN_ERR_INVALID_ARG, "%s: out is NULL", fn);
+  if (!aligned(out, 4)) return fail(MULAN_ERR_ALIGNMENT, "%s: out is not 4-byte aligned", fn);
+  if (kind == 1 && !(maxval >= minval))
+    return fail(MULAN_ERR_INVALID_ARG, "%s: need maxval >= minval", fn);
+  cudaError_t e = mulan::launch_rng_draw(kind, key0, key1, n, minval, maxval, out,
+                                         (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(fn, e);
+}
+
+int mulan_rng_bits(uint32_t key0, uint32_t key1, int64_t n, uint32_t* out, void* stream) {
+  return rng_draw("mulan_rng_bits", 0, key0, key1, n, 0.f, 1.f, out, stream);
+}
+
+int mulan_rng_uniform(uint32_t key0, uint32_t key1, int64_t n, float minval, float maxval,
+                      float* out, void* stream) {
+  return rng_draw("mulan_rng_uniform", 1, key0, key1, n, minval, maxval, out, stream);
+}
+
+int mulan_rng_normal(uint32_t key0, uint32_t key1, int64_t n, float* out, void* stream) {
+  // uniform on [nextafter(-1, 0), 1): jax._src.random._normal_real
+  return rng_draw("mulan_rng_normal", 2, key0, key1, n, nextafterf(-1.0f, 0.0f), 1.0f, out,
+                  stream);
+}
+
 int mulan_grad_sumsq(int64_t n, const float* g, double* scratch, float* out, void* stream) {
   const char* fn = "mulan_grad_sumsq";
   if (n < 0) return fail(MULAN_ERR_INVALID_ARG, "%s: n < 0", fn);

@@ -162,6 +162,10 @@ struct Rk45Params {
 cudaError_t launch_rk45_stage(const Rk45Params& p, cudaStream_t s);
 cudaError_t launch_rk45_norm(const Rk45Params& p, double* out, cudaStream_t s);
 
+// JAX-compatible threefry draws (mulan_rng.cu): kind 0 = bits, 1 = uniform, 2 = normal
+cudaError_t launch_rng_draw(int kind, uint32_t k0, uint32_t k1, long long n, float minval,
+                            float maxval, void* out, cudaStream_t s);
+
 // Number of CTAs of `kernel` (kThreads threads, static shared memory only) that are resident
 // on the current device at once: the grid size of the persistent kernels.
 inline int resident_ctas(const void* kernel) {

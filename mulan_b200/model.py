@@ -184,12 +184,19 @@ class VDM(nn.Module):
                    gamma_max=self.desc.gamma_max)
     return ops.sample_gamma(pix, a, b, c, t.contiguous())
 
-  def make_draws(self, n_batch: int, device, generator: Optional[torch.Generator] = None):
-    """The four make_rng('sample') draws of __call__, in the reference's order."""
+  def make_draws(self, n_batch: int, device, generator: Optional[torch.Generator] = None,
+                 jax_keys: Optional[dict] = None):
+    """The four make_rng('sample') draws of __call__, in the reference's order.
+
+    jax_keys = {'t0': (k0, k1), 'eps_0': (k0, k1), 'eps': (k0, k1)}: the raw threefry keys
+    Flax's make_rng would hand to jax.random.uniform / normal for those draws; they are then
+    generated on the device exactly as JAX would (mulan_rng_uniform / mulan_rng_normal).  The
+    latent noise G stays a torch draw (jax.random.gamma is not restated)."""
     g = generator
     cfg = self.config
     L = cfg.latent_size
-    t0 = torch.rand((), generator=g, device=device)
+    if jax_keys is None:
+      t0 = torch.rand((), generator=g, device=device)
     if cfg.latent_type == 'topk' and cfg.topk_noise_type == 'gamma':
       G = gamma_draw((10, n_batch, L), cfg.latent_k, g, device)          # jax.random.gamma
     elif cfg.latent_type == 'gaussian':
@@ -197,6 +204,11 @@ class VDM(nn.Module):
     else:                                                                  # jax.random.gumbel
       u = torch.rand((n_batch, L), generator=g, device=device).clamp_min(1e-20)
       G = -torch.log(-torch.log(u))
+    if jax_keys is not None:
+      shape = (n_batch, 32, 32, 3)
+      return dict(t0=ops.rng_uniform(jax_keys['t0'], (), device=device), G=G,
+                  eps_0=ops.rng_normal(jax_keys['eps_0'], shape, device=device),
+                  eps=ops.rng_normal(jax_keys['eps'], shape, device=device))
     return dict(
         t0=t0, G=G,
         eps_0=torch.randn((n_batch, 32, 32, 3), generator=g, device=device),

@@ -15,6 +15,7 @@ through loss_diff) instead of two kernels plus an add.
 from __future__ import annotations
 
 import ctypes as C
+import math
 from typing import Optional
 
 import torch
@@ -573,3 +574,36 @@ def aux_gumbel(logits, gumbel_noise, tau: float):
 
 def aux_gaussian(mu, var, eps_z):
   return _AuxGaussian.apply(mu, var, eps_z)
+
+
+# ------------------------------------------------------------------------------------
+# JAX-compatible threefry draws ("next" row 2): key = (uint32, uint32) of ONE draw
+# ------------------------------------------------------------------------------------
+
+def _rng_out(shape, dtype, device, out):
+  n = int(math.prod(shape))
+  if out is None:
+    return torch.empty(shape, dtype=dtype, device=device), n
+  return _req(out, dtype, tuple(shape), 'out'), n
+
+
+def rng_bits(key, shape, device='cuda', out=None):
+  """jax.random.bits(key, shape) as int64-free uint32 stored in an int32 tensor's bits."""
+  out, n = _rng_out(tuple(shape), torch.int32, device, out)
+  _lib.check(_lib.load().mulan_rng_bits(int(key[0]), int(key[1]), n, _p(out), _stream()))
+  return out
+
+
+def rng_uniform(key, shape, minval: float = 0.0, maxval: float = 1.0, device='cuda', out=None):
+  """jax.random.uniform(key, shape, float32, minval, maxval)."""
+  out, n = _rng_out(tuple(shape), torch.float32, device, out)
+  _lib.check(_lib.load().mulan_rng_uniform(int(key[0]), int(key[1]), n, float(minval),
+                                           float(maxval), _p(out), _stream()))
+  return out
+
+
+def rng_normal(key, shape, device='cuda', out=None):
+  """jax.random.normal(key, shape, float32)."""
+  out, n = _rng_out(tuple(shape), torch.float32, device, out)
+  _lib.check(_lib.load().mulan_rng_normal(int(key[0]), int(key[1]), n, _p(out), _stream()))
+  return out

@@ -427,7 +427,7 @@ def run_native(args):
   # ---- cpu baseline (oracle port on host cores; rank 0, N=1 only) ----
   cpu = None
   if rank == 0 and world == 1 and not args.no_cpu_baseline:
-    cpu = cpu_reference(args, steps=2, warmup=1)
+    cpu = cpu_reference(args, steps=0, warmup=1, min_seconds=10.0)
 
   if rank != 0:
     if world > 1:
@@ -509,7 +509,7 @@ def load_traffic(kernel, rows):
 # ----------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port of the reference on the host cores
 # ----------------------------------------------------------------------------------------
-def cpu_reference(args, steps, warmup):
+def cpu_reference(args, steps, warmup, min_seconds=0.0):
   import torch
   from oracle import mulan_oracle as O   # CPU baseline leg: allowed to execute oracle/
   cores = os.cpu_count() or 1
@@ -530,8 +530,14 @@ def cpu_reference(args, steps, warmup):
   for _ in range(warmup):
     one()
   t0 = time.perf_counter()
-  for _ in range(steps):
-    one()
+  if min_seconds:        # bounded sample: whole steps until ~min_seconds of CPU work are in
+    steps = 0
+    while steps < 2 or (time.perf_counter() - t0 < min_seconds and steps < 256):
+      one()
+      steps += 1
+  else:
+    for _ in range(steps):
+      one()
   dt = time.perf_counter() - t0
   return {'value': B * steps / dt, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
           'ms_per_step': dt / steps * 1e3,

@@ -350,7 +350,10 @@ def value_div_fn(model: VDM, x, embeddings, t, hutchinson_noise, high_precision:
     if coeffs is None:
       coeffs = tuple(q.contiguous() for q in model.gamma._compute_coefficients(embeddings))
     a, b, c = coeffs
-    tt = torch.full((B,), float(t), dtype=torch.float32, device=x.device)
+    if torch.is_tensor(t) and t.numel() == B:      # per-row t (the reference passes vec_t)
+      tt = t.to(device=x.device, dtype=torch.float32).reshape(B).contiguous()
+    else:
+      tt = torch.full((B,), float(t), dtype=torch.float32, device=x.device)
     g_net = ops.sample_gamma(model.desc, a, b, c, tt)
   g_in = g_net if cfg.unet_type == 'vdm' else g_net.reshape(B, 32, 32, 3)
   if hutchinson_noise is None:

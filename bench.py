@@ -69,6 +69,9 @@ def parse_args():
   ap.add_argument('--separate-post', action='store_true',
                   help='train: run mulan_fwd_post and mulan_bwd_post as two passes instead of '
                        'the fused value-and-grad pass')
+  ap.add_argument('--no-save-w', action='store_true',
+                  help='epsilon form: recompute the loss weight in the post kernels instead of '
+                       'saving it in fwd_pre')
   ap.add_argument('--no-e2e', action='store_true')
   ap.add_argument('--no-cpu-baseline', action='store_true')
   return ap.parse_args()
@@ -231,11 +234,15 @@ def run_native(args):
   inp = make_inputs(rows, dev, seed=1234 + rank)
   train = args.workload == 'train'
   lrows = rows if train else min(args.launch_rows, rows)   # rows per launch
+  # velocity_from_epsilon evaluates the (algebraically identical) epsilon form: same kernels,
+  # same bytes as 'eps' (mulan_kernel_param; MULAN_VFE_LITERAL=1 restores the literal formula)
+  eps_form = _lib.kernel_param(param) == PARAMS['eps']
+  save_w = eps_form and not args.no_save_w   # fwd_pre +4 B, post -8 B per sub-pixel
   assert rows % lrows == 0
   chunks = []
   for s0 in range(0, rows, lrows):
     ci = {k: v[s0:s0 + lrows] for k, v in inp.items()}
-    chunks.append((ops.ElboWorkspace(desc, lrows, dev, save_w=(train and args.param == 'eps')),
+    chunks.append((ops.ElboWorkspace(desc, lrows, dev, save_w=save_w),
                    ci, torch.full((lrows,), 1.0 / (lrows * D * math.log(2.0)), device=dev)))
   ws = chunks[0][0]
 
@@ -436,11 +443,9 @@ def run_native(args):
 
   nsub = rows * D
   dom = max((n for n in names if n != 'bpd_reduce'), key=lambda n: kern_ms[n])
-  ab = dict(ALGO_BYTES[args.param])
-  if not train:
-    ab['fwd_pre'] = 25        # no saved w
-    if args.param == 'eps':
-      ab['fwd_post'] = 20     # w recomputed from a, b, c
+  ab = dict(ALGO_BYTES['eps' if eps_form else args.param])
+  if eps_form and not save_w:
+    ab.update(fwd_pre=25, fwd_post=20, post_vg=24, bwd_post=24)   # w recomputed from a, b, c
   ab = {k: v for k, v in ab.items() if k in names}
   peaks, peak_src = load_peak()
   kinfo = {}
@@ -461,7 +466,8 @@ def run_native(args):
       'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak',
       'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
       'config': {'workload': workload_name(args), 'rows_per_gpu': rows, 'dim': D,
-                 'param': args.param, 'l2': 'inputs larger than L2 (%.2f GB of HBM traffic per '
+                 'param': args.param, 'loss_form': 'eps' if eps_form else 'velocity',
+                 'saved_w': save_w, 'l2': 'inputs larger than L2 (%.2f GB of HBM traffic per '
                  'step)' % (total_algo / 1e9), 'parallelism': f'dp{world} (rows sharded)',
                  'timed_loop': 'CUDA-graph replay of one step (%d launches)' % launches_per_step,
                  'rows_per_launch': lrows, 'streams': 1 + len(side)},

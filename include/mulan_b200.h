@@ -75,6 +75,20 @@ const char* mulan_last_error(void);
 int mulan_abi_version(void);
 
 /*
+ * mulan_kernel_param -- the mulan_param whose loss formula mulan_fwd_post / mulan_bwd_post /
+ * mulan_fwd_bwd_post / mulan_bwd_pre run for a descriptor with this `param`.  Identity except
+ * MULAN_PARAM_VEL_FROM_EPS -> MULAN_PARAM_EPS: the velocity_from_epsilon loss
+ * (ldm/model_mulan_velocity.py:246-249, 256-260) is algebraically the epsilon loss
+ * (ldm/model_mulan_epsilon.py:345-347) -- (1-v) w (v_target - v_hat)^2 == w (eps - net)^2 --
+ * with identical cotangents, so those entry points evaluate the epsilon form (1.3e-7 / 3e-6
+ * relative from the reference's float32 loss / gradients on its own golden vectors, 1e-15 in
+ * float64).  A caller uses it to decide whether a w_save buffer pays (it does when the result
+ * is MULAN_PARAM_EPS) and whether x is read by the post kernels (it is not, then).
+ * MULAN_VFE_LITERAL=1 in the environment keeps the literal formula (identity mapping).
+ */
+int mulan_kernel_param(int32_t param);
+
+/*
  * mulan_fwd_pre -- everything in VDM.__call__ that precedes the denoiser call.
  * Replaces: EncDec.encode (ldm/model_vdm.py:274-280); NoiseSchedule_polynomial_fixedend.
  * _eval_polynomial at t in {0,1,t} (ldm/model_mulan_epsilon.py:514-529, call sites :307-309);

@@ -76,7 +76,7 @@ static ffi::Error FwdPostImpl(cudaStream_t stream, ffi::Buffer<ffi::U8> x, ffi::
   mulan_desc d = MakeDesc(dims[0], dims[1], vocab, param, gt_mode, 0, gamma_min, gamma_max);
   return Check(mulan_fwd_post(&d, x.typed_data(), a.typed_data(), b.typed_data(), c.typed_data(),
                               t.typed_data(), eps.typed_data(), net.typed_data(),
-                              param == MULAN_PARAM_EPS ? w.typed_data() : nullptr,
+                              mulan_kernel_param(param) == MULAN_PARAM_EPS ? w.typed_data() : nullptr,
                               loss_diff->typed_data(), stream));
 }
 XLA_FFI_DEFINE_HANDLER_SYMBOL(
@@ -101,7 +101,7 @@ static ffi::Error BwdPostImpl(cudaStream_t stream, ffi::Buffer<ffi::U8> x, ffi::
   mulan_desc d = MakeDesc(dims[0], dims[1], vocab, param, gt_mode, 0, gamma_min, gamma_max);
   return Check(mulan_bwd_post(&d, x.typed_data(), a.typed_data(), b.typed_data(), c.typed_data(),
                               t.typed_data(), eps.typed_data(), net.typed_data(),
-                              param == MULAN_PARAM_EPS ? w.typed_data() : nullptr,
+                              mulan_kernel_param(param) == MULAN_PARAM_EPS ? w.typed_data() : nullptr,
                               gL.typed_data(), n_bar->typed_data(), stream));
 }
 XLA_FFI_DEFINE_HANDLER_SYMBOL(

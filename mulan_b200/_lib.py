@@ -54,6 +54,7 @@ _D = C.POINTER(MulanDesc)
 SIGNATURES = {
     'mulan_last_error': ([], C.c_char_p),
     'mulan_abi_version': ([], C.c_int),
+    'mulan_kernel_param': ([C.c_int32], C.c_int),
     'mulan_fwd_pre': ([_D] + [_P] * 14, C.c_int),
     'mulan_fwd_post': ([_D] + [_P] * 10, C.c_int),
     'mulan_bwd_post': ([_D] + [_P] * 11, C.c_int),
@@ -117,3 +118,9 @@ def make_desc(rows: int, dim: int = 3072, vocab: int = 256, param: int = MULAN_P
               gt_mode: int = MULAN_GT_MEAN, n_timesteps: int = 0,
               gamma_min: float = -13.3, gamma_max: float = 5.0) -> MulanDesc:
   return MulanDesc(rows, dim, vocab, param, gt_mode, n_timesteps, gamma_min, gamma_max)
+
+
+def kernel_param(param: int) -> int:
+  """mulan_kernel_param: the loss formula the post / bwd_pre kernels run for `param`
+  (velocity_from_epsilon evaluates the algebraically identical epsilon form)."""
+  return int(load().mulan_kernel_param(int(param)))

@@ -2,6 +2,7 @@
 // parameter-block assembly, launches, and the host-buffer convenience entry.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "mulan_kernels.h"
@@ -87,12 +88,21 @@ int recon_window(const mulan_desc* d) {
 
 namespace mulan {
 void set_last_error(const char* msg) { snprintf(g_err, sizeof(g_err), "%s", msg); }
+
+int kernel_param(int param) {
+  static const int literal = [] {
+    const char* e = getenv("MULAN_VFE_LITERAL");
+    return (e != nullptr && e[0] == '1') ? 1 : 0;
+  }();
+  return (param == MULAN_PARAM_VEL_FROM_EPS && !literal) ? (int)MULAN_PARAM_EPS : param;
+}
 }  // namespace mulan
 
 extern "C" {
 
 const char* mulan_last_error(void) { return g_err; }
 int mulan_abi_version(void) { return MULAN_ABI_VERSION; }
+int mulan_kernel_param(int32_t param) { return mulan::kernel_param(param); }
 
 int mulan_fwd_pre(const mulan_desc* d, const uint8_t* x, const float* a, const float* b,
                   const float* c, const float* t, const float* eps0, const float* eps,
@@ -135,13 +145,14 @@ static int fill_post(const char* fn, const mulan_desc* d, const uint8_t* x, cons
                      const float* b, const float* c, const float* t, const float* eps,
                      const float* net, const float* w_save, mulan::PostParams* p) {
   REQ_VEC(eps, fn); REQ_VEC(net, fn); OPT_VEC(w_save, fn);
-  const bool need_poly = !(d->param == MULAN_PARAM_EPS && w_save != nullptr);
+  const int kparam = mulan::kernel_param(d->param);   // v-from-eps runs the epsilon form
+  const bool need_poly = !(kparam == MULAN_PARAM_EPS && w_save != nullptr);
   if (need_poly) { REQ_VEC(a, fn); REQ_VEC(b, fn); REQ_VEC(c, fn); REQ_PTR(t, fn); }
-  if (d->param != MULAN_PARAM_EPS) REQ_X(x, fn);
+  if (kparam != MULAN_PARAM_EPS) REQ_X(x, fn);
   p->x = x; p->a = a; p->b = b; p->c = c; p->t = t; p->eps = eps; p->net = net;
-  p->w_save = (d->param == MULAN_PARAM_EPS) ? w_save : nullptr;
+  p->w_save = (kparam == MULAN_PARAM_EPS) ? w_save : nullptr;
   p->gL = nullptr; p->loss_diff = nullptr; p->n_bar = nullptr;
-  p->rows = d->rows; p->dim4 = d->dim / 4; p->param = d->param;
+  p->rows = d->rows; p->dim4 = d->dim / 4; p->param = kparam;
   p->gmin = f32_gmin(d); p->delta = f32_delta(d);
   // .5 * sum(...)  |  .5 * T * sum(...)   (ldm/model_mulan_epsilon.py:345, :353)
   p->scale = d->n_timesteps > 0 ? (float)(0.5 * (double)d->n_timesteps) : 0.5f;
@@ -219,12 +230,13 @@ int mulan_bwd_pre(const mulan_desc* d, const uint8_t* x, const float* a, const f
   if (d->gt_mode == MULAN_GT_PIXEL) OPT_VEC(g_bar, fn);
   if (gL != nullptr) { REQ_VEC(net, fn); }
   if (gL != nullptr || z_bar != nullptr) { REQ_VEC(eps, fn); }
-  if (z_bar != nullptr || (gL != nullptr && d->param != MULAN_PARAM_EPS)) REQ_X(x, fn);
+  const int kparam = mulan::kernel_param(d->param);   // v-from-eps runs the epsilon form
+  if (z_bar != nullptr || (gL != nullptr && kparam != MULAN_PARAM_EPS)) REQ_X(x, fn);
   mulan::BwdPreParams p;
   p.x = x; p.a = a; p.b = b; p.c = c; p.t = t; p.eps = eps; p.net = net;
   p.z_bar = z_bar; p.g_bar = g_bar; p.gL = gL;
   p.a_bar = a_bar; p.b_bar = b_bar; p.c_bar = c_bar;
-  p.rows = d->rows; p.dim4 = d->dim / 4; p.param = d->param; p.gt_mode = d->gt_mode;
+  p.rows = d->rows; p.dim4 = d->dim / 4; p.param = kparam; p.gt_mode = d->gt_mode;
   p.gmin = f32_gmin(d); p.delta = f32_delta(d);
   p.T = d->n_timesteps;
   p.inv_T = d->n_timesteps > 0 ? (float)(1.0 / (double)d->n_timesteps) : 0.f;

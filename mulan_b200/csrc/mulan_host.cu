@@ -115,7 +115,7 @@ int mulan_elbo_host(const mulan_desc* d, const uint8_t* x, const float* a, const
   float* dT = ws.d_row; float* dG = ws.d_row + B; float* dRec = ws.d_row + 2 * B;
   float* dKlz = ws.d_row + 3 * B; float* dDiff = ws.d_row + 4 * B; float* dGL = ws.d_row + 5 * B;
   float* dVar = ws.d_row + 6 * B; float* dSc = ws.d_row + 8 * B;
-  const bool save_w = d->param == MULAN_PARAM_EPS;
+  const bool save_w = mulan::kernel_param(d->param) == MULAN_PARAM_EPS;
 
   // chunking: ~1024 rows (75 MB in, 50 MB out) per chunk, at most kMaxChunks chunks
   size_t chunk = 1024;

@@ -62,6 +62,11 @@ class Desc:
                      self.gamma_min, self.gamma_max)
 
 
+def saves_w(desc: 'Desc') -> bool:
+  """Whether mulan_fwd_pre should save the loss weight w for the post kernels of this model."""
+  return _lib.kernel_param(desc.param) == MULAN_PARAM_EPS
+
+
 # ------------------------------------------------------------------------------------
 # Raw launches (no autograd)
 # ------------------------------------------------------------------------------------
@@ -311,7 +316,7 @@ class ElboWorkspace:
 
   def __init__(self, desc: Desc, rows: int, device, save_w: Optional[bool] = None):
     self.desc, self.rows = desc, rows
-    self.save_w = (desc.param == MULAN_PARAM_EPS) if save_w is None else save_w
+    self.save_w = saves_w(desc) if save_w is None else save_w
     D = desc.dim
     f = lambda *s: torch.empty(s, dtype=torch.float32, device=device)
     self.z_t = f(rows, D)
@@ -364,9 +369,10 @@ class ElboTape:
 
   def __init__(self, desc: Desc, save_w: Optional[bool] = None):
     self.desc = desc
-    # Saving w pays for EPS (post kernels read 12 B instead of 20 B); the velocity models
-    # recompute gamma_t anyway.
-    self.save_w = (desc.param == MULAN_PARAM_EPS) if save_w is None else save_w
+    # Saving w pays for the epsilon form (post kernels read 12 B instead of 20 B) -- which
+    # velocity_from_epsilon also runs (mulan_kernel_param); the plain velocity model
+    # recomputes gamma_t anyway.
+    self.save_w = saves_w(desc) if save_w is None else save_w
     self.x = self.a = self.b = self.c = self.t = self.eps = self.w = self.net = None
 
 

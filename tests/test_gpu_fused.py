@@ -126,3 +126,69 @@ np.savez(sys.argv[1], **out)
     assert set(outs[0].files) == set(other.files)
     for k in outs[0].files:
       assert np.array_equal(outs[0][k], other[k]), k
+
+
+def test_vfe_eps_form_matches_literal_formula(cuda_device):
+  """velocity_from_epsilon runs the epsilon form by default (mulan_kernel_param); the literal
+  formula of ldm/model_mulan_velocity.py:246-260 stays reachable with MULAN_VFE_LITERAL=1.
+  Both must agree with each other and with the oracle's literal float32 evaluation."""
+  code = r'''
+import sys, math, torch, numpy as np
+sys.path.insert(0, %r)
+from mulan_b200 import ops, _lib
+from oracle import mulan_oracle as O
+dev = torch.device('cuda:0')
+B = 40
+inp = O.synth_inputs(B, 17)
+g = {k: v.to(dev).contiguous() for k, v in inp.items()}
+desc = ops.Desc(param=2)
+ws = ops.ElboWorkspace(desc, B, dev)
+gL = torch.full((B,), 1.0 / (B * 3072 * math.log(2.0)), device=dev)
+rng = np.random.default_rng(5)
+zb = torch.from_numpy(1e-4 * rng.standard_normal((B, 3072)).astype(np.float32)).to(dev)
+gb = torch.from_numpy(1e-3 * rng.standard_normal(B).astype(np.float32)).to(dev)
+args = (g['x'], g['a'], g['b'], g['c'], g['t'])
+ws.fwd_pre(*args, g['eps_0'], g['eps'])
+ws.fwd_bwd_post(*args, g['eps'], g['net'], gL)
+ws.bwd_pre(*args, g['eps'], g['net'], zb, gb, gL)
+torch.cuda.synchronize()
+np.savez(sys.argv[1], kparam=_lib.kernel_param(2), saved_w=ws.w is not None,
+         loss_diff=ws.loss_diff.cpu().numpy(), n_bar=ws.n_bar.cpu().numpy(),
+         a_bar=ws.a_bar.cpu().numpy(), b_bar=ws.b_bar.cpu().numpy(), c_bar=ws.c_bar.cpu().numpy(),
+         zb=zb.cpu().numpy(), gb=gb.cpu().numpy(), gL=gL.cpu().numpy())
+''' % ROOT
+  import tempfile
+  res = {}
+  for literal in ('0', '1'):
+    with tempfile.NamedTemporaryFile(suffix='.npz', delete=False) as f:
+      path = f.name
+    subprocess.run([sys.executable, '-c', code, path], check=True,
+                   env=dict(os.environ, MULAN_VFE_LITERAL=literal))
+    res[literal] = dict(np.load(path))
+    os.unlink(path)
+  assert int(res['0']['kparam']) == 0 and bool(res['0']['saved_w'])
+  assert int(res['1']['kparam']) == 2 and not bool(res['1']['saved_w'])
+  l2 = lambda a, b: np.linalg.norm(a.astype(np.float64) - b) / np.linalg.norm(b.astype(np.float64))
+  e, l = res['0'], res['1']
+  assert np.max(np.abs(e['loss_diff'] - l['loss_diff']) / np.abs(l['loss_diff'])) < 1e-5
+  assert l2(e['n_bar'], l['n_bar']) < 1e-5
+  for k in ('a_bar', 'b_bar', 'c_bar'):
+    assert l2(e[k], l[k]) < 1e-4, k
+  # the oracle's literal formula, float64, for L = sum gL loss_diff + <zb, z_t> + <gb, g_net>
+  B = 40
+  inp = O.synth_inputs(B, 17)
+  cfg = O.OracleConfig()
+  i = {k: (v.double() if v.is_floating_point() else v) for k, v in inp.items()}
+  a, b, c, net = (i[k].clone().requires_grad_(True) for k in ('a', 'b', 'c', 'net'))
+  out, aux = O.elbo_terms(i['x'], a, b, c, i['t'], i['eps_0'], i['eps'], lambda z, g: net,
+                          O.MODE_VEL_FROM_EPS, cfg, dtype=torch.float64, return_aux=True)
+  L = (torch.from_numpy(e['gL']).double() * out.loss_diff).sum()
+  L = L + (torch.from_numpy(e['zb']).double() * aux['z_t'].reshape(B, -1)).sum()
+  L = L + (torch.from_numpy(e['gb']).double() * O.score_model_gt(aux['g_t'], cfg).reshape(B)).sum()
+  ga, gb_, gc, gn = torch.autograd.grad(L, [a, b, c, net])
+  for r in (e, l):
+    assert np.max(np.abs(r['loss_diff'] - out.loss_diff.detach().numpy())
+                  / out.loss_diff.detach().numpy()) < 1e-5
+    assert l2(r['n_bar'], gn.reshape(B, -1).numpy()) < 1e-4
+    for k, want in (('a_bar', ga), ('b_bar', gb_), ('c_bar', gc)):
+      assert l2(r[k], want.reshape(B, -1).numpy()) < 1e-4, k

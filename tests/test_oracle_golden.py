@@ -139,3 +139,27 @@ def test_f32_golden_close_to_f64_golden():
     for k in ('loss_klz', 'loss_diff'):
       _close(g['f32_' + k], g['f64_' + k], 2e-5)
     _close(g['f32_loss_recon'], g['f64_loss_recon'], 1e-4)   # z_0 rounding amplified by e^{-g0/2}
+
+
+@pytest.mark.parametrize('name,full', [('glue_vfe', False), ('full_vfe', True)])
+@pytest.mark.parametrize('tag', ['f32', 'f64'])
+def test_vfe_is_eps(name, full, tag, monkeypatch):
+  """velocity_from_epsilon == the epsilon loss, values AND gradients: the oracle run in
+  MODE_EPS reproduces the goldens the reference's own velocity_from_epsilon source produced
+  (ldm/model_mulan_velocity.py:246-260).  This is what lets the kernels evaluate the epsilon
+  form for MULAN_PARAM_VEL_FROM_EPS (include/mulan_b200.h: mulan_kernel_param)."""
+  g = load(name)
+  seed, B = int(g['seed']), int(g['B'])
+  monkeypatch.setitem(MODES, 'vfe', O.MODE_EPS)
+  dtype = torch.float32 if tag == 'f32' else torch.float64
+  r = run_oracle('vfe', seed, B, dtype, full)
+  _close(r['loss_diff'], g[f'{tag}_loss_diff'], 1e-6 if tag == 'f32' else 1e-12)
+  _close(r['bpd'], g[f'{tag}_bpd'], 1e-6 if tag == 'f32' else 1e-12)
+  for k in [k for k in g.files if k.startswith(f'{tag}_grad_')]:
+    want, got = g[k], r[k[len(tag) + 1:]]
+    if np.linalg.norm(want) == 0:
+      assert np.linalg.norm(got) == 0
+    else:
+      # 1e-4 is the north_star gradient tolerance; measured 3e-6 (a,b,c), 6e-5 (logits, whose
+      # float32 golden is itself that far from the float64 one)
+      assert _rel_l2(got, want) < (1e-4 if tag == 'f32' else 1e-12), (k, _rel_l2(got, want))

@@ -89,6 +89,25 @@ SIGNATURES = {
     'mulan_host_workspace_release': ([], None),
 }
 
+# XLA legacy custom-call targets (include/mulan_b200_xla.h):
+#   void target(stream, void** buffers, const char* opaque, size_t opaque_len, status)
+_XLA_TARGET = ([_P, C.POINTER(_P), C.c_char_p, C.c_size_t, _P], None)
+XLA_SIGNATURES = {name: _XLA_TARGET for name in (
+    'mulan_xla_fwd_pre', 'mulan_xla_fwd_post', 'mulan_xla_bwd_post', 'mulan_xla_fwd_bwd_post',
+    'mulan_xla_bwd_pre', 'mulan_xla_bpd_reduce', 'mulan_xla_aux_topk_fwd',
+    'mulan_xla_aux_topk_bwd')}
+
+
+class MulanXlaOpaque(C.Structure):
+  """mulan_xla_opaque: the custom call's backend_config bytes."""
+  _fields_ = [('desc', MulanDesc), ('absent_mask', C.c_uint32), ('reserved', C.c_uint32)]
+
+
+class MulanXlaAuxOpaque(C.Structure):
+  _fields_ = [('rows', C.c_int32), ('latent', C.c_int32), ('k', C.c_int32),
+              ('absent_mask', C.c_uint32)]
+
+
 _lib = None
 
 
@@ -101,7 +120,7 @@ def load() -> C.CDLL:
           f'{LIB_PATH} is missing: build it with `python -m mulan_b200.build` '
           '(or __graft_entry__.build()). There is no CPU / PyTorch fallback.')
     lib = C.CDLL(str(LIB_PATH))
-    for name, (argtypes, restype) in SIGNATURES.items():
+    for name, (argtypes, restype) in {**SIGNATURES, **XLA_SIGNATURES}.items():
       fn = getattr(lib, name)
       fn.argtypes = argtypes
       fn.restype = restype

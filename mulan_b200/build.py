@@ -16,7 +16,7 @@ LIB_PATH = PKG_DIR / 'libmulan_b200.so'
 
 SOURCES = ['mulan_fwd_pre.cu', 'mulan_post.cu', 'mulan_bwd_pre.cu', 'mulan_aux.cu',
            'mulan_optim.cu', 'mulan_sampler.cu', 'mulan_rk45.cu', 'mulan_rng.cu', 'mulan_abi.cu',
-           'mulan_host.cu']
+           'mulan_host.cu', 'mulan_xla_legacy.cu']
 
 NVCC_FLAGS = [
     '-O3', '-std=c++17',
@@ -42,6 +42,7 @@ def _stale() -> bool:
   built = LIB_PATH.stat().st_mtime
   deps = list(CSRC.glob('*.cu')) + list(CSRC.glob('*.cuh')) + list(CSRC.glob('*.h'))
   deps.append(PKG_DIR.parent / 'include' / 'mulan_b200.h')
+  deps.append(PKG_DIR.parent / 'include' / 'mulan_b200_xla.h')
   deps.append(Path(__file__))
   return any(d.stat().st_mtime > built for d in deps)
 

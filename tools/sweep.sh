@@ -1,12 +1,25 @@
 #!/bin/bash
 # Kernel sweep of SURVEY.md 8d: rows in {128, 2048, 16384, 65536} x {eps, vel, vel_from_eps},
-# plus the dense-VLB forward (configs[4]).  One JSON line per point -> gpurun_out/sweep.jsonl
+# the dense-VLB forward (configs[4]), and the A/B variants kept behind environment switches.
+# One JSON line per point -> gpurun_out/sweep.jsonl ; render with profiles/sweep_table.py
 out=gpurun_out/sweep.jsonl; : > $out
+run() {  # note, env assignments..., -- bench args
+  note=$1; shift
+  envs=(); while [ "$1" != "--" ]; do envs+=("$1"); shift; done; shift
+  env "${envs[@]}" python bench.py "$@" --steps 30 --warmup 3 --no-cpu-baseline 2>> gpurun_out/sweep.err \
+    | python -c "import json,sys; d=json.loads(sys.stdin.read()); d['note']='$note'; print(json.dumps(d))" >> $out
+}
 for p in eps vel vel_from_eps; do
   for r in 128 2048 16384 65536; do
-    python bench.py --param $p --rows $r --steps 30 --warmup 3 --no-e2e --no-cpu-baseline >> $out 2>> gpurun_out/sweep.err
+    run "" -- --param $p --rows $r --no-e2e
   done
 done
-python bench.py --workload dense_vlb --param vel_from_eps --rows 16384 --launch-rows 2048 --steps 30 --no-cpu-baseline >> $out 2>> gpurun_out/sweep.err
-python bench.py --workload dense_vlb --param eps --rows 16384 --launch-rows 2048 --steps 30 --no-cpu-baseline >> $out 2>> gpurun_out/sweep.err
+run "" -- --workload dense_vlb --param vel_from_eps --rows 16384 --launch-rows 2048
+run "" -- --workload dense_vlb --param eps --rows 16384 --launch-rows 2048
+run "w recomputed" -- --workload dense_vlb --param eps --rows 16384 --launch-rows 2048 --no-save-w
+run "literal v-from-eps formula" MULAN_VFE_LITERAL=1 -- --param vel_from_eps --rows 16384 --no-e2e
+run "literal v-from-eps formula" MULAN_VFE_LITERAL=1 -- --workload dense_vlb --param vel_from_eps --rows 16384 --launch-rows 2048
+run "fwd_pre generic constants" MULAN_NO_BAKED=1 -- --param eps --rows 16384 --no-e2e
+run "fwd_pre TMA pipeline" MULAN_FWD_PRE_TMA=1 -- --param eps --rows 16384 --no-e2e
+run "fwd_pre TMA pipeline, generic constants" MULAN_FWD_PRE_TMA=1 MULAN_NO_BAKED=1 -- --param eps --rows 16384 --no-e2e
 wc -l $out; tail -3 gpurun_out/sweep.err

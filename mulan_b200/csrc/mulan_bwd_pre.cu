@@ -15,12 +15,19 @@
 
 namespace mulan {
 
-template <int PARAM, int GT, bool DISC>
-__global__ void __launch_bounds__(kThreads)
+// Arithmetic notes.  The backward pass has no reference rounding order to reproduce (what
+// jax.value_and_grad emits is XLA's business; the tolerance is 1e-4 on gradients), so products
+// and sums are contracted into fmaf() freely here, and the factors 1/2 of d alpha/d gamma =
+// -v alpha/2, d sigma/d gamma = sigma (1-v)/2 and of w_bar are folded into per-row constants
+// (gLh = gL/2) -- the kernel is instruction-issue bound in the velocity modes.  gamma_t and
+// d gamma/dt are formed exactly as mulan_fwd_pre forms them (fma(P, Delta/S, gmin), Q Delta/S),
+// so alpha and sigma here are the ones z_t was built with.
+template <int PARAM, int GT, bool DISC, bool POW2>
+__global__ void __launch_bounds__(kThreads, 5)   // <= 51 registers: 5 CTAs (40 warps) per SM
 bwd_pre_kernel(const BwdPreParams p) {
   __shared__ RowT s_rt;
   __shared__ RowD s_rd;
-  __shared__ float s_gL, s_gbar;
+  __shared__ float s_gLh, s_gbar;
   const int row = blockIdx.x, tid = threadIdx.x;
   const bool has_gL = p.gL != nullptr;
   const bool has_zb = p.z_bar != nullptr;
@@ -28,7 +35,7 @@ bwd_pre_kernel(const BwdPreParams p) {
   if (tid == 0) {
     s_rt = make_row_t(__ldg(p.t + row));
     if (DISC) s_rd = make_row_d(__ldg(p.t + row), __ldg(p.t + row) - p.inv_T);   // s = t - 1/T
-    s_gL = has_gL ? __ldg(p.gL + row) : 0.f;
+    s_gLh = has_gL ? 0.5f * __ldg(p.gL + row) : 0.f;
     // jnp.mean backward: cotangent / D broadcast to every sub-pixel
     s_gbar = (GT == MULAN_GT_MEAN && has_gb)
                  ? __fdiv_rn(__ldg(p.g_bar + row), (float)(p.dim4 * 4)) : 0.f;
@@ -37,8 +44,13 @@ bwd_pre_kernel(const BwdPreParams p) {
   const RowT rt = s_rt;
   RowD rd;
   if (DISC) rd = s_rd;
-  const float gL = s_gL, gbar_row = s_gbar;
+  const float gLh = s_gLh, gbar_row = s_gbar;
   const VocabInfo vi = p.vi;
+  const float two_iv = vi.inv_vocab + vi.inv_vocab, off = vi.inv_vocab - 1.0f;
+  // t-dependent coefficients of P_a, P_b, P_c with the factors 2 folded in (exact scalings)
+  const float t = rt.t, t2 = rt.t2, t3_3 = rt.t3_3, t4_2 = rt.t4_2, t5_5 = rt.t5_5;
+  const float t5_5x2 = t5_5 + t5_5, t3_3x2 = t3_3 + t3_3, tx2 = t + t;
+  constexpr float kTwoFifths = 2.0f * kFifth, kTwoThirds = 2.0f * kThird;
   const size_t base4 = (size_t)row * p.dim4;
   const bool need_x = has_zb || (has_gL && PARAM != MULAN_PARAM_EPS);
 
@@ -57,19 +69,21 @@ bwd_pre_kernel(const BwdPreParams p) {
     for (int j = 0; j < 4; ++j) {
       const float a = get(A, j), b = get(Bv, j), c = get(C, j);
       const float e = get(E, j), n = get(N, j);
-      const float f = vi.xval(getx(X, j));
+      // encode(x): exact in one fma for a power-of-two vocab (as mulan_fwd_pre)
+      const float f = POW2 ? fmaf((float)getx(X, j), two_iv, off) : vi.xval(getx(X, j));
       const Poly po = poly_eval(a, b, c, rt);
       const float rS = rcp_scale(po.S);
+      const float dr = p.delta * rS;                   // Delta / S
       const float Q = po.q * po.q;
       const float u = po.P * rS, y = Q * rS;
-      const float gt = p.gmin + (p.delta * po.P) * rS;
-      const float w = (p.delta * Q) * rS;
+      const float gt = fmaf(po.P, dr, p.gmin);         // gamma_t
+      const float w = Q * dr;                          // d gamma / dt
       const float v = sigmoid_fast(gt);
       const float om = 1.0f - v;
       const float kr = rsqrt_approx(fmaxf(om, 1e-30f));   // 1/alpha = sqrt(1 + e^gamma)
       const float alpha = om * kr, sigma = sqrt_fast(v);
-      const float dal = -0.5f * v * alpha;      // d alpha / d gamma
-      const float dsg = 0.5f * sigma * om;      // d sigma / d gamma
+      const float ha = v * alpha;       // -2 d alpha / d gamma
+      const float hs = sigma * om;      //  2 d sigma / d gamma
 
       float gbar = (GT == MULAN_GT_MEAN) ? gbar_row : get(GB, j);
       float zb = get(ZB, j);
@@ -82,41 +96,39 @@ bwd_pre_kernel(const BwdPreParams p) {
                          fmaf(po.bc, rd.d2, po.c2 * rd.d1))));
         du = dP * rS;
         const float dexp = expf(p.delta * du);
-        gD = p.delta * rS * (0.5f * (float)p.T * gL * (r * r) * dexp);
+        gD = dr * ((float)p.T * gLh * (r * r) * dexp);
       } else if (PARAM == MULAN_PARAM_EPS) {
         const float r = e - n;
-        wbar = 0.5f * gL * (r * r);
+        wbar = gLh * (r * r);
       } else {
-        const float vtg = alpha * e - sigma * f;
+        const float vtg = fmaf(alpha, e, -(sigma * f));
         float vhat = n, zt = 0.f;
         if (PARAM == MULAN_PARAM_VEL_FROM_EPS) {
           // e^g = v/(1-v): sqrt(1+e^g) = 1/alpha = kr, e^{g/2} = sigma kr, e^g/sqrt(1+e^g) = v kr
-          zt = alpha * f + sigma * e;
-          vhat = kr * (n - sigma * zt);
+          zt = fmaf(alpha, f, sigma * e);
+          vhat = kr * fmaf(-sigma, zt, n);
         }
         const float r = vtg - vhat;
-        const float r2 = r * r;
-        const float rb = gL * om * w * r;                // d L / d r
-        wbar = 0.5f * gL * om * r2;
-        gbar += -0.5f * gL * w * r2 * (v * om);          // through (1 - var_t)
-        gbar += rb * (dal * e - dsg * f);                // through v_target
+        wbar = (gLh * (r * r)) * om;                     // .5 gL (1-v) r^2
+        const float rbh = (gLh * r) * (om * w);          // .5 dL/dr
+        gbar = fmaf(-(wbar * w), v, gbar);               // through (1 - var_t)
+        gbar = fmaf(-rbh, fmaf(ha, e, hs * f), gbar);    // through v_target
         if (PARAM == MULAN_PARAM_VEL_FROM_EPS) {
-          zb += rb * (sigma * kr);                       // v_hat's direct use of z_t
-          gbar += 0.5f * rb * kr * (sigma * zt - n * v);  // v_hat's own gamma dependence
+          zb = fmaf(rbh + rbh, sigma * kr, zb);          // v_hat's direct use of z_t
+          gbar = fmaf(rbh * kr, fmaf(sigma, zt, -(n * v)), gbar);  // v_hat's own gamma dependence
         }
       }
-      gbar += zb * (dal * f + dsg * e);                  // through z_t = alpha f + sigma eps
+      gbar = fmaf(0.5f * zb, fmaf(hs, e, -(ha * f)), gbar);  // through z_t = alpha f + sigma eps
 
-      const float gG = p.delta * rS * gbar, gW = p.delta * rS * wbar;
-      const float t = rt.t, t2 = rt.t2, t3_3 = rt.t3_3, t4_2 = rt.t4_2, t5_5 = rt.t5_5;
+      const float gG = dr * gbar, gW = dr * wbar;
       const float two_q = po.q + po.q;
       // partials of P, S, Q
-      const float Pa = fmaf(a + a, t5_5, fmaf(c + c, t3_3, b * t4_2));
-      const float Sa = fmaf(a + a, kFifth, fmaf(c + c, kThird, 0.5f * b));
-      const float Pb = fmaf(b + b, t3_3, fmaf(a, t4_2, c * t2));
-      const float Sb = fmaf(b + b, kThird, fmaf(a, 0.5f, c));
-      const float Pc = fmaf(a + a, t3_3, fmaf(b, t2, (c + c) * t));
-      const float Sc = fmaf(a + a, kThird, b + (c + c));
+      const float Pa = fmaf(a, t5_5x2, fmaf(c, t3_3x2, b * t4_2));
+      const float Sa = fmaf(a, kTwoFifths, fmaf(c, kTwoThirds, 0.5f * b));
+      const float Pb = fmaf(b, t3_3x2, fmaf(a, t4_2, c * t2));
+      const float Sb = fmaf(b, kTwoThirds, fmaf(a, 0.5f, c));
+      const float Pc = fmaf(a, t3_3x2, fmaf(b, t2, c * tx2));
+      const float Sc = fmaf(a, kTwoThirds, fmaf(c, 2.0f, b));
       const float Qa = two_q * t2, Qb = two_q * t, Qc = two_q;
       float ab_ = fmaf(gG, fmaf(-u, Sa, Pa), gW * fmaf(-y, Sa, Qa));
       float bb_ = fmaf(gG, fmaf(-u, Sb, Pb), gW * fmaf(-y, Sb, Qb));
@@ -139,18 +151,18 @@ bwd_pre_kernel(const BwdPreParams p) {
   }
 }
 
-template <int PARAM>
+template <int PARAM, bool POW2>
 static cudaError_t launch_gt(const BwdPreParams& p, cudaStream_t s) {
   dim3 grid(p.rows), block(kThreads);
   if (PARAM == MULAN_PARAM_EPS && p.T > 0) {
     if (p.gt_mode == MULAN_GT_MEAN)
-      bwd_pre_kernel<MULAN_PARAM_EPS, MULAN_GT_MEAN, true><<<grid, block, 0, s>>>(p);
+      bwd_pre_kernel<MULAN_PARAM_EPS, MULAN_GT_MEAN, true, POW2><<<grid, block, 0, s>>>(p);
     else
-      bwd_pre_kernel<MULAN_PARAM_EPS, MULAN_GT_PIXEL, true><<<grid, block, 0, s>>>(p);
+      bwd_pre_kernel<MULAN_PARAM_EPS, MULAN_GT_PIXEL, true, POW2><<<grid, block, 0, s>>>(p);
   } else if (p.gt_mode == MULAN_GT_MEAN) {
-    bwd_pre_kernel<PARAM, MULAN_GT_MEAN, false><<<grid, block, 0, s>>>(p);
+    bwd_pre_kernel<PARAM, MULAN_GT_MEAN, false, POW2><<<grid, block, 0, s>>>(p);
   } else {
-    bwd_pre_kernel<PARAM, MULAN_GT_PIXEL, false><<<grid, block, 0, s>>>(p);
+    bwd_pre_kernel<PARAM, MULAN_GT_PIXEL, false, POW2><<<grid, block, 0, s>>>(p);
   }
   return cudaGetLastError();
 }
@@ -195,10 +207,15 @@ cudaError_t launch_discrete_w(const DiscreteWParams& p, cudaStream_t s) {
 
 cudaError_t launch_bwd_pre(const BwdPreParams& p, cudaStream_t s) {
   if (p.rows == 0) return cudaSuccess;
+  const bool pow2 = p.vi.pow2 != 0;
   switch (p.param) {
-    case MULAN_PARAM_EPS: return launch_gt<MULAN_PARAM_EPS>(p, s);
-    case MULAN_PARAM_VEL: return launch_gt<MULAN_PARAM_VEL>(p, s);
-    default:              return launch_gt<MULAN_PARAM_VEL_FROM_EPS>(p, s);
+    case MULAN_PARAM_EPS:
+      return pow2 ? launch_gt<MULAN_PARAM_EPS, true>(p, s) : launch_gt<MULAN_PARAM_EPS, false>(p, s);
+    case MULAN_PARAM_VEL:
+      return pow2 ? launch_gt<MULAN_PARAM_VEL, true>(p, s) : launch_gt<MULAN_PARAM_VEL, false>(p, s);
+    default:
+      return pow2 ? launch_gt<MULAN_PARAM_VEL_FROM_EPS, true>(p, s)
+                  : launch_gt<MULAN_PARAM_VEL_FROM_EPS, false>(p, s);
   }
 }
 

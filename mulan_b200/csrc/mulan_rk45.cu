@@ -43,9 +43,53 @@ __device__ __forceinline__ double stage_sum(const Rk45Params& p, int64_t i) {
   return acc * p.h;
 }
 
+// Four consecutive elements per thread: one LDG.128 per stage row, two per float64 vector
+// (the scalar form issues 4-byte loads and runs at 64 % of the HBM roofline).  Per element the
+// arithmetic and its order are those of stage_sum, so results are bit-identical to it.
+struct Quad { double v[4]; };
+__device__ __forceinline__ Quad stage_sum4(const Rk45Params& p, int64_t i4) {
+  Quad a = {{0.0, 0.0, 0.0, 0.0}};
+#pragma unroll
+  for (int j = 0; j < 7; ++j)
+    if (j < p.n_k) {
+      const float4 k = __ldg(reinterpret_cast<const float4*>(p.K + (size_t)j * p.k_stride) + i4);
+      const double c = p.coef[j];
+      a.v[0] += c * (double)k.x; a.v[1] += c * (double)k.y;
+      a.v[2] += c * (double)k.z; a.v[3] += c * (double)k.w;
+    }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) a.v[e] *= p.h;
+  return a;
+}
+__device__ __forceinline__ Quad load4d(const double* q, int64_t i4) {
+  const double2 lo = reinterpret_cast<const double2*>(q)[2 * i4];
+  const double2 hi = reinterpret_cast<const double2*>(q)[2 * i4 + 1];
+  return Quad{{lo.x, lo.y, hi.x, hi.y}};
+}
+
+template <bool VEC>
 __global__ void __launch_bounds__(kRkThreads) rk45_stage_kernel(const Rk45Params p) {
   const int64_t step = (int64_t)gridDim.x * kRkThreads;
-  for (int64_t i = (int64_t)blockIdx.x * kRkThreads + threadIdx.x; i < p.n; i += step) {
+  const int64_t first = (int64_t)blockIdx.x * kRkThreads + threadIdx.x;
+  int64_t tail0 = 0;
+  if (VEC) {
+    const int64_t n4 = p.n >> 2;
+    tail0 = n4 << 2;
+    for (int64_t i4 = first; i4 < n4; i4 += step) {
+      const Quad y = load4d(p.y, i4), s = stage_sum4(p, i4);
+      double v[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[e] = y.v[e] + s.v[e];
+      if (p.y_stage != nullptr)
+        reinterpret_cast<float4*>(p.y_stage)[i4] =
+            make_float4((float)v[0], (float)v[1], (float)v[2], (float)v[3]);
+      if (p.y_out != nullptr) {
+        reinterpret_cast<double2*>(p.y_out)[2 * i4] = make_double2(v[0], v[1]);
+        reinterpret_cast<double2*>(p.y_out)[2 * i4 + 1] = make_double2(v[2], v[3]);
+      }
+    }
+  }
+  for (int64_t i = tail0 + first; i < p.n; i += step) {      // everything, or the <= 3 leftovers
     const double v = p.y[i] + stage_sum(p, i);
     if (p.y_stage != nullptr) p.y_stage[i] = (float)v;
     if (p.y_out != nullptr) p.y_out[i] = v;
@@ -71,11 +115,31 @@ __device__ __forceinline__ double block_sum_d(double v, double* red) {
   return t;   // valid in thread 0
 }
 
+template <bool VEC>
 __global__ void __launch_bounds__(kRkThreads) rk45_norm_partial_kernel(const Rk45Params p) {
   __shared__ double red[kRkThreads / 32];
   const int64_t step = (int64_t)gridDim.x * kRkThreads;
+  const int64_t first = (int64_t)blockIdx.x * kRkThreads + threadIdx.x;
   double acc = 0.0;
-  for (int64_t i = (int64_t)blockIdx.x * kRkThreads + threadIdx.x; i < p.n; i += step) {
+  int64_t tail0 = 0;
+  if (VEC) {
+    const int64_t n4 = p.n >> 2;
+    tail0 = n4 << 2;
+    for (int64_t i4 = first; i4 < n4; i4 += step) {
+      const Quad y = load4d(p.y, i4);
+      Quad yn = y;
+      if (p.y_new != nullptr) yn = load4d(p.y_new, i4);
+      Quad v = y;
+      if (!p.of_y) v = stage_sum4(p, i4);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const double mag = fmax(fabs(y.v[e]), fabs(yn.v[e]));
+        const double q = v.v[e] / (p.atol + mag * p.rtol);
+        acc += q * q;
+      }
+    }
+  }
+  for (int64_t i = tail0 + first; i < p.n; i += step) {
     const double yi = p.y[i];
     double mag = fabs(yi);
     if (p.y_new != nullptr) mag = fmax(mag, fabs(p.y_new[i]));
@@ -97,9 +161,17 @@ __global__ void __launch_bounds__(kRkThreads) rk45_norm_final_kernel(const doubl
   if (threadIdx.x == 0) out[0] = t;
 }
 
+// 16-byte alignment of everything a launch touches: the float64 vectors, the float32 stage
+// vector, and every row of K (base and row stride).
+bool vec_ok(const Rk45Params& p) {
+  auto a16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  return a16(p.y) && a16(p.y_new) && a16(p.y_out) && a16(p.y_stage) && a16(p.K) &&
+         (p.k_stride & 3) == 0 && p.n >= 4;
+}
+
 int rk_blocks(int64_t n) {
-  const int64_t want = (n + kRkThreads - 1) / kRkThreads;
-  static const int64_t cap = resident_ctas((const void*)rk45_norm_partial_kernel);
+  const int64_t want = ((n + 3) / 4 + kRkThreads - 1) / kRkThreads;
+  static const int64_t cap = resident_ctas((const void*)rk45_norm_partial_kernel<true>);
   int64_t b = want < cap ? want : cap;
   if (b > MULAN_RK45_SCRATCH) b = MULAN_RK45_SCRATCH;
   return (int)(b < 1 ? 1 : b);
@@ -108,13 +180,15 @@ int rk_blocks(int64_t n) {
 }  // namespace
 
 cudaError_t launch_rk45_stage(const Rk45Params& p, cudaStream_t stream) {
-  rk45_stage_kernel<<<rk_blocks(p.n), kRkThreads, 0, stream>>>(p);
+  if (vec_ok(p)) rk45_stage_kernel<true><<<rk_blocks(p.n), kRkThreads, 0, stream>>>(p);
+  else           rk45_stage_kernel<false><<<rk_blocks(p.n), kRkThreads, 0, stream>>>(p);
   return cudaGetLastError();
 }
 
 cudaError_t launch_rk45_norm(const Rk45Params& p, double* out, cudaStream_t stream) {
   const int blocks = rk_blocks(p.n);
-  rk45_norm_partial_kernel<<<blocks, kRkThreads, 0, stream>>>(p);
+  if (vec_ok(p)) rk45_norm_partial_kernel<true><<<blocks, kRkThreads, 0, stream>>>(p);
+  else           rk45_norm_partial_kernel<false><<<blocks, kRkThreads, 0, stream>>>(p);
   rk45_norm_final_kernel<<<1, kRkThreads, 0, stream>>>(p.scratch, blocks, out);
   return cudaGetLastError();
 }

@@ -18,9 +18,10 @@
 // unconditional sampler uses the same deterministic embedding for every example
 // (_get_deterministic_embedding), so a, b, c stay L2-resident for all 1000 steps.
 //
-// Numerics: sigmoid(-g) and 1 - a are formed exactly as the reference does (IEEE division;
-// at g_s -> gamma_min, 1 - a is 1.7e-6 quantised in units of 6e-8, which the reference's noise
-// scale inherits).  g_s - g_t uses the factored power differences (full float32 precision).
+// Numerics: g_s - g_t uses the factored power differences (full float32 precision); the step
+// itself has a fast default form and the reference's op-for-op form (see sample_step_kernel).
+#include <stdlib.h>
+
 #include "mulan_kernels.h"
 
 namespace mulan {
@@ -57,7 +58,27 @@ sample_gamma_kernel(const SamplerParams p) {
 }
 
 // ---- one ancestral step -------------------------------------------------------------------
-template <int PARAM>
+// 1 - e^{-x}, x >= 0 (= -expm1(-x)): alternating series below 1/2 (truncation x^8/8! < 1e-7
+// relative), MUFU.EX2 above (absolute error 2e-7 e^{-x} on a value >= 0.39).
+__device__ __forceinline__ float one_minus_exp_neg(float x) {
+  const float ser = x * fmaf(x, fmaf(x, fmaf(x, fmaf(x, fmaf(x, fmaf(x, 1.0f / 5040.0f,
+                    -1.0f / 720.0f), 1.0f / 120.0f), -1.0f / 24.0f), 1.0f / 6.0f), -0.5f), 1.0f);
+  const float big = 1.0f - ex2_approx(-x * kLog2e);
+  return x < 0.5f ? ser : big;
+}
+
+// IEEE = true: the reference's statements op for op (IEEE division, sqrtf, expf, expm1f) -- the
+// first version of this kernel, kept for A/B (MULAN_SAMPLER_IEEE=1); it is instruction-bound at
+// 39 % of the HBM roofline.
+// IEEE = false (default): the same quantities from e^{gamma/2} and MUFU reciprocal square roots,
+//   a = 1/(1+e^{g_s}),  b = 1/(1+e^{g_t}),  sqrt(a/b) = sqrt(1+e^{g_t}) rsqrt(1+e^{g_s}),
+//   1 - a = e^{g_s}/(1+e^{g_s})  (NOT formed as 1 - fl(a): near gamma_min that difference is
+//   1.7e-6 quantised in units of 6e-8 in the reference's float32, a 3.5 % error in its own noise
+//   scale -- this form is the value exact arithmetic gives, and tests/test_sampler.py bounds the
+//   kernel by the reference's own float32-to-float64 distance there),
+//   sigma_t = e^{g_t/2} rsqrt(1+e^{g_t}),  alpha_t = rsqrt(1+e^{g_t}),  c = 1 - e^{-(g_t-g_s)}.
+// Each factor is within ~3e-7 relative of exact.
+template <int PARAM, bool IEEE>
 __global__ void __launch_bounds__(kThreads)
 sample_step_kernel(const SamplerParams p) {
   __shared__ RowT s_rt, s_rs;
@@ -86,20 +107,37 @@ sample_step_kernel(const SamplerParams p) {
                        fmaf(po.bc, rs.t2, po.c2 * rs.t))));
       const float dP = fmaf(po.a2, rd.d5_5, fmaf(po.b2c, rd.d3_3, fmaf(po.ab, rd.d4_2,
                        fmaf(po.bc, rd.d2, po.c2 * rd.d1))));
-      const float gt = p.gmin + (p.delta * po.P) * rS;
-      const float gs = p.gmin + (p.delta * Ps) * rS;
-      const float av = sigmoid_ref(-gs);                 // a
-      const float bv = sigmoid_ref(-gt);                 // b
-      // c = -expm1(g_s - g_t) >= 0 since gamma is monotone.  The reference's float32 evaluation
-      // subtracts two rounded gammas and gets c <= 0 -> NaN in pixels where gamma is locally
-      // flat (tests/test_sampler.py); here the difference keeps full precision and is clamped.
-      const float cv = fmaxf(-expm1f(-(p.delta * dP) * rS), 0.0f);
-      const float sig = sqrtf(sigmoid_ref(gt));          // sigma_t
       const float z = get(Z, j);
       float eh = get(N, j);
-      if (PARAM != MULAN_PARAM_EPS) eh = eh * sqrtf(bv) + sig * z;   // v -> eps
-      const float mean = sqrtf(__fdiv_rn(av, bv)) * (z - sig * cv * eh);
-      put(O, j, mean + sqrtf((1.0f - av) * cv) * get(E, j));
+      if (IEEE) {
+        const float gt = p.gmin + (p.delta * po.P) * rS;
+        const float gs = p.gmin + (p.delta * Ps) * rS;
+        const float av = sigmoid_ref(-gs);                 // a
+        const float bv = sigmoid_ref(-gt);                 // b
+        // c = -expm1(g_s - g_t) >= 0 since gamma is monotone.  The reference's float32
+        // evaluation subtracts two rounded gammas and gets c <= 0 -> NaN in pixels where gamma
+        // is locally flat (tests/test_sampler.py); here the difference keeps full precision and
+        // is clamped.
+        const float cv = fmaxf(-expm1f(-(p.delta * dP) * rS), 0.0f);
+        const float sig = sqrtf(sigmoid_ref(gt));          // sigma_t
+        if (PARAM != MULAN_PARAM_EPS) eh = eh * sqrtf(bv) + sig * z;   // v -> eps
+        const float mean = sqrtf(__fdiv_rn(av, bv)) * (z - sig * cv * eh);
+        put(O, j, mean + sqrtf((1.0f - av) * cv) * get(E, j));
+      } else {
+        const float dr = p.delta * rS;                     // Delta / S
+        const float gt = fmaf(po.P, dr, p.gmin), gs = fmaf(Ps, dr, p.gmin);
+        // e^{gamma/2}; the clamp keeps 1 + e^gamma finite (gamma > 80 is sigma = 1 anyway)
+        const float ht = ex2_approx(fminf(gt, 80.0f) * (0.5f * kLog2e));
+        const float hs = ex2_approx(fminf(gs, 80.0f) * (0.5f * kLog2e));
+        const float pt = fmaf(ht, ht, 1.0f), ps = fmaf(hs, hs, 1.0f);   // 1/b, 1/a
+        const float rpt = rsqrt_approx(pt), rps = rsqrt_approx(ps);    // alpha_t, sqrt(a)
+        const float sig = ht * rpt;                                     // sigma_t
+        const float cv = fmaxf(one_minus_exp_neg(fmaxf(dr * dP, 0.0f)), 0.0f);   // c
+        if (PARAM != MULAN_PARAM_EPS) eh = fmaf(eh, rpt, sig * z);      // v -> eps
+        const float mean = ((pt * rpt) * rps) * fmaf(-(sig * cv), eh, z);
+        const float ns = (hs * rps) * sqrt_fast0(cv);                   // sqrt((1-a) c)
+        put(O, j, fmaf(ns, get(E, j), mean));
+      }
     }
     st4(p.z_s, base4 + i4, O);
   }
@@ -228,8 +266,18 @@ cudaError_t launch_sample_gamma(const SamplerParams& p, cudaStream_t s) {
 
 cudaError_t launch_sample_step(const SamplerParams& p, cudaStream_t s) {
   if (p.rows == 0) return cudaSuccess;
-  if (p.param == MULAN_PARAM_EPS) sample_step_kernel<MULAN_PARAM_EPS><<<p.rows, kThreads, 0, s>>>(p);
-  else                            sample_step_kernel<MULAN_PARAM_VEL><<<p.rows, kThreads, 0, s>>>(p);
+  static const int ieee = [] {
+    const char* e = getenv("MULAN_SAMPLER_IEEE");
+    return (e != nullptr && e[0] == '1') ? 1 : 0;
+  }();
+  const bool eps = p.param == MULAN_PARAM_EPS;
+  if (ieee) {
+    if (eps) sample_step_kernel<MULAN_PARAM_EPS, true><<<p.rows, kThreads, 0, s>>>(p);
+    else     sample_step_kernel<MULAN_PARAM_VEL, true><<<p.rows, kThreads, 0, s>>>(p);
+  } else {
+    if (eps) sample_step_kernel<MULAN_PARAM_EPS, false><<<p.rows, kThreads, 0, s>>>(p);
+    else     sample_step_kernel<MULAN_PARAM_VEL, false><<<p.rows, kThreads, 0, s>>>(p);
+  }
   return cudaGetLastError();
 }
 

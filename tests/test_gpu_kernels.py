@@ -481,3 +481,101 @@ def test_host_entry_denoiser_callback(cuda_device):
   ref = host.elbo_host(npy['x'], npy['a'], npy['b'], npy['c'], npy['t'], npy['eps_0'], npy['eps'],
                        npy['net'], want_grad=False)
   assert np.array_equal(r['loss_diff'], ref['loss_diff'])
+
+
+# ------------------------------------------------------------------------------------------
+# Paths the shipped configuration never takes: other gamma ranges (wider reconstruction window,
+# prior-KL constants that are NOT uniform over the three roundings of gamma_1), a vocabulary that
+# is not a power of two, and sub-pixels whose scale S is outside the fast reciprocal's range.
+# ------------------------------------------------------------------------------------------
+def _generic_case(cuda_device, cfg, inp, modes=('eps', 'vel', 'vel_from_eps'), gtol=GRAD_RTOL):
+  ops = _ops()
+  B = inp['a'].shape[0]
+  g = _dev(inp, cuda_device)
+  rng = np.random.default_rng(7)
+  gL = torch.from_numpy(rng.uniform(0.5, 1.5, B).astype(np.float32)) / (B * 3072 * math.log(2))
+  zbar = torch.from_numpy(rng.standard_normal((B, 3072)).astype(np.float32)) * 1e-4
+  gbar = torch.from_numpy(rng.standard_normal(B).astype(np.float32)) * 1e-3
+  for mode in modes:
+    out, aux = _oracle(inp, MODES[mode], cfg=cfg)
+    desc = ops.Desc(param=MODES[mode], vocab=cfg.vocab_size, gamma_min=cfg.gamma_min,
+                    gamma_max=cfg.gamma_max)
+    r = ops.fwd_pre(desc, g['x'], g['a'], g['b'], g['c'], g['t'], g['eps_0'], g['eps'])
+    assert _rel(r['loss_recon'], out.loss_recon) < LOSS_RTOL, mode
+    assert _rel(r['loss_klz_prior'], aux['loss_klz_prior']) < LOSS_RTOL, mode
+    assert _rel_l2_rows(r['z_t'], aux['z_t'].reshape(B, -1)) < 1e-5
+    var0 = r['var_sums'][:, 0].sum().item() / (B * 3072)
+    var1 = r['var_sums'][:, 1].sum().item() / (B * 3072)
+    assert abs(var0 - out.var_0.item()) < 2e-6 * out.var_0.item() + 1e-12
+    assert abs(var1 - out.var_1.item()) < 2e-6
+    got = ops.fwd_post(desc, g['x'], g['a'], g['b'], g['c'], g['t'], g['eps'], g['net'], None)
+    assert _rel(got, out.loss_diff) < LOSS_RTOL, mode
+    # backward against float64 autograd of the oracle under the same config
+    cast = lambda v: v.double() if v.is_floating_point() else v
+    i = {k: cast(v) for k, v in inp.items()}
+    a, b, c, net = (i[k].clone().requires_grad_(True) for k in ('a', 'b', 'c', 'net'))
+    o64, aux64 = O.elbo_terms(i['x'], a, b, c, i['t'], i['eps_0'], i['eps'], lambda z, gg: net,
+                              MODES[mode], cfg, dtype=torch.float64, return_aux=True)
+    L = (gL.double() * o64.loss_diff).sum() + (zbar.double() * aux64['z_t'].reshape(B, -1)).sum()
+    L = L + (gbar.double() * O.score_model_gt(aux64['g_t'], cfg).reshape(B)).sum()
+    want = torch.autograd.grad(L, [a, b, c, net])
+    n_bar = ops.bwd_post(desc, g['x'], g['a'], g['b'], g['c'], g['t'], g['eps'], g['net'], None,
+                         gL.to(cuda_device))
+    ab, bb, cb = ops.bwd_pre(desc, g['x'], g['a'], g['b'], g['c'], g['t'], g['eps'], g['net'],
+                             zbar.to(cuda_device), gbar.to(cuda_device), gL.to(cuda_device))
+    for got_, w_, name in ((ab, want[0], 'a'), (bb, want[1], 'b'), (cb, want[2], 'c'),
+                           (n_bar, want[3], 'n')):
+      assert _rel_l2_rows(got_, w_.reshape(B, -1)) < gtol, (mode, name)
+
+
+@pytest.mark.parametrize('gmin,gmax', [(-6.0, 3.0), (-2.0, 0.3), (-9.5, 7.25)])
+def test_other_gamma_ranges(cuda_device, gmin, gmax):
+  """gamma_0 = -6: bins are 0.16 decoder-sigmas apart -> the windowed generic log-softmax;
+  (-2, 0.3): sigmoid(gamma_1) depends on how (Delta S)/S rounds -> per-pixel prior KL / var_1."""
+  cfg = O.OracleConfig(gamma_min=gmin, gamma_max=gmax)
+  _generic_case(cuda_device, cfg, O.synth_inputs(6, 51))
+
+
+def test_vocab_not_a_power_of_two(cuda_device):
+  # gamma_0 = -8 puts the 100 bins 1.09 decoder-sigmas apart: a non-trivial reconstruction term
+  cfg = O.OracleConfig(vocab_size=100, gamma_min=-8.0)
+  inp = O.synth_inputs(5, 52)
+  inp['x'] = (inp['x'].to(torch.int32) % 100).to(torch.uint8)
+  _generic_case(cuda_device, cfg, inp)
+
+
+def test_scale_outside_fast_range(cuda_device):
+  """S = c^2 = 1e-32 (a = b = 0, c = 1e-16) is below the fast reciprocal's range: those
+  sub-pixels take the IEEE per-pixel path and must still match the reference; S == 0 (all
+  coefficients zero) is NaN in the reference and must be NaN here, in that row only."""
+  ops = _ops()
+  B = 4
+  inp = O.synth_inputs(B, 53)
+  for k in ('a', 'b'):
+    inp[k][1] = 0.0
+    inp[k][2, ::3] = 0.0
+  inp['c'][1] = 1e-16
+  inp['c'][2, ::3] = 1e-16
+  out, aux = _oracle(inp, O.MODE_EPS)
+  g = _dev(inp, cuda_device)
+  desc = ops.Desc()
+  r = ops.fwd_pre(desc, g['x'], g['a'], g['b'], g['c'], g['t'], g['eps_0'], g['eps'])
+  assert torch.isfinite(out.loss_recon).all()
+  assert _rel(r['loss_recon'], out.loss_recon) < LOSS_RTOL
+  assert _rel(r['loss_klz_prior'], aux['loss_klz_prior']) < LOSS_RTOL
+  assert _rel_l2_rows(r['z_t'], aux['z_t'].reshape(B, -1)) < 1e-5
+  assert _rel_l2_rows(r['w'], aux['g_t_grad'].reshape(B, -1)) < 1e-5
+  var1 = r['var_sums'][:, 1].sum().item() / (B * 3072)
+  assert abs(var1 - out.var_1.item()) < 2e-6
+  got = ops.fwd_post(desc, g['x'], g['a'], g['b'], g['c'], g['t'], g['eps'], g['net'], None)
+  assert _rel(got, out.loss_diff) < LOSS_RTOL
+  # S == 0
+  for k in ('a', 'b', 'c'):
+    inp[k][3, 5] = 0.0
+  out, aux = _oracle(inp, O.MODE_EPS)
+  assert torch.isnan(out.loss_klz[3]) and torch.isfinite(out.loss_klz[:3]).all()
+  g = _dev(inp, cuda_device)
+  r = ops.fwd_pre(desc, g['x'], g['a'], g['b'], g['c'], g['t'], g['eps_0'], g['eps'])
+  assert torch.isnan(r['loss_klz_prior'][3]) and torch.isnan(r['var_sums'][3]).all()
+  assert torch.isfinite(r['loss_klz_prior'][:3]).all() and torch.isfinite(r['var_sums'][:3]).all()
+  assert _rel(r['loss_klz_prior'][:3], aux['loss_klz_prior'][:3]) < LOSS_RTOL

@@ -393,3 +393,29 @@ def test_cuda_eval_bpd_ode_runs(cuda_device):
     bpd = ode.eval_bpd_ode(vdm, [data.to(cuda_device)], True, 'Rademacher', 'tn', num_is=num_is,
                            rtol=1e-3, atol=1e-3, generator=gen)
     assert math.isfinite(bpd)
+
+
+@pytest.mark.gpu
+def test_cuda_rk45_unaligned_vectors_take_the_scalar_path(cuda_device):
+  """The 4-wide kernels need 16-byte aligned vectors; an 8-byte offset view must give the same
+  numbers through the scalar kernels."""
+  from mulan_b200 import _lib, ops
+  n = 1001
+  rng = np.random.default_rng(5)
+  dev = cuda_device
+  base = torch.from_numpy(rng.standard_normal(n + 1)).to(dev)
+  K = torch.from_numpy(rng.standard_normal((7, 1004)).astype(np.float32)).to(dev)
+  coef = rng.standard_normal(7)
+  outs = []
+  for y in (base[1:], base[1:].clone()):        # 8-byte offset view, then an aligned copy
+    yo = torch.empty(n + 1, dtype=torch.float64, device=dev)[1:] if y.data_ptr() % 16 else \
+        torch.empty(n, dtype=torch.float64, device=dev)
+    y32 = torch.empty(n, dtype=torch.float32, device=dev)
+    ops.rk45_stage(6, coef, 0.02, y, K, y_stage=y32, y_out=yo)
+    scratch = torch.empty(_lib.MULAN_RK45_SCRATCH, dtype=torch.float64, device=dev)
+    out = torch.empty(1, dtype=torch.float64, device=dev)
+    ops.rk45_norm(7, R.E, 0.02, 1e-5, 1e-6, y, yo, K, False, scratch, out)
+    outs.append((yo.cpu().numpy().copy(), y32.cpu().numpy().copy(), out.item()))
+  assert base[1:].data_ptr() % 16 == 8
+  assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+  assert abs(outs[0][2] - outs[1][2]) < 1e-13 * abs(outs[1][2])

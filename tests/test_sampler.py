@@ -219,3 +219,18 @@ def test_apply_gamma(cuda_device):
   a, b, c = O.compute_coefficients(Wd, O.deterministic_embedding(3, ocfg, torch.float64))
   want = O.eval_polynomial(a, b, c, t.cpu().double().reshape(3, 1), ocfg)
   assert (g.double() - want).abs().max().item() < 1e-4
+
+
+@pytest.mark.gpu
+def test_cuda_sampler_ieee_variant(cuda_device):
+  """MULAN_SAMPLER_IEEE=1 selects the op-for-op form of the ancestral step (IEEE division /
+  sqrt / expm1); it must pass the same golden test as the default fast form.  The switch is
+  read once per process, hence the child process."""
+  import subprocess
+  root = os.path.dirname(HERE)
+  out = subprocess.run(
+      [sys.executable, '-m', 'pytest', os.path.join(HERE, 'test_sampler.py'), '-q', '-m', 'gpu',
+       '-k', 'test_cuda_sampler_matches_reference_source or per_row_coefficients'],
+      cwd=root, env=dict(os.environ, MULAN_SAMPLER_IEEE='1'), capture_output=True, text=True,
+      timeout=900)
+  assert out.returncode == 0 and '3 passed' in out.stdout, out.stdout[-3000:] + out.stderr[-2000:]

@@ -67,17 +67,62 @@ __device__ __forceinline__ float one_minus_exp_neg(float x) {
   return x < 0.5f ? ser : big;
 }
 
-// IEEE = true: the reference's statements op for op (IEEE division, sqrtf, expf, expm1f) -- the
-// first version of this kernel, kept for A/B (MULAN_SAMPLER_IEEE=1); it is instruction-bound at
-// 39 % of the HBM roofline.
-// IEEE = false (default): the same quantities from e^{gamma/2} and MUFU reciprocal square roots,
+// The step is linear in (z_t, net, eps) with per-sub-pixel factors that depend on the row only
+// through (t, s):   z_s = m1 z_t + m2 net + m3 eps
+//   eps model:  m1 = sqrt(a/b)                      m2 = -sqrt(a/b) sigma_t c
+//   v model:    m1 = sqrt(a/b) (1 - sigma_t^2 c)    m2 = -sqrt(a/b) sigma_t c alpha_t
+//               (eps_hat = v_hat alpha_t + sigma_t z_t substituted)
+//   both:       m3 = sqrt((1-a) c)
+// Fast form of the factors, from e^{gamma/2} and MUFU reciprocal square roots:
 //   a = 1/(1+e^{g_s}),  b = 1/(1+e^{g_t}),  sqrt(a/b) = sqrt(1+e^{g_t}) rsqrt(1+e^{g_s}),
 //   1 - a = e^{g_s}/(1+e^{g_s})  (NOT formed as 1 - fl(a): near gamma_min that difference is
 //   1.7e-6 quantised in units of 6e-8 in the reference's float32, a 3.5 % error in its own noise
 //   scale -- this form is the value exact arithmetic gives, and tests/test_sampler.py bounds the
 //   kernel by the reference's own float32-to-float64 distance there),
-//   sigma_t = e^{g_t/2} rsqrt(1+e^{g_t}),  alpha_t = rsqrt(1+e^{g_t}),  c = 1 - e^{-(g_t-g_s)}.
+//   sigma_t = e^{g_t/2} rsqrt(1+e^{g_t}),  alpha_t = rsqrt(1+e^{g_t}),  c = 1 - e^{-(g_t-g_s)}
+//   with g_t - g_s from the factored power differences (full float32 precision; the reference's
+//   own float32 subtracts two rounded gammas and gets c <= 0 -> NaN where gamma is locally flat).
 // Each factor is within ~3e-7 relative of exact.
+struct StepF { float m1, m2, m3; };
+template <int PARAM>
+__device__ __forceinline__ StepF step_factors(float a, float b, float c, const RowT& rt,
+                                              const RowT& rs, const RowD& rd, float gmin,
+                                              float delta) {
+  const Poly po = poly_eval(a, b, c, rt);
+  const float rS = rcp_scale(po.S);
+  const float Ps = fmaf(po.a2, rs.t5_5, fmaf(po.b2c, rs.t3_3, fmaf(po.ab, rs.t4_2,
+                   fmaf(po.bc, rs.t2, po.c2 * rs.t))));
+  const float dP = fmaf(po.a2, rd.d5_5, fmaf(po.b2c, rd.d3_3, fmaf(po.ab, rd.d4_2,
+                   fmaf(po.bc, rd.d2, po.c2 * rd.d1))));
+  const float dr = delta * rS;                       // Delta / S
+  const float gt = fmaf(po.P, dr, gmin), gs = fmaf(Ps, dr, gmin);
+  // e^{gamma/2}; the clamp keeps 1 + e^gamma finite (gamma > 80 is sigma = 1 anyway)
+  const float ht = ex2_approx(fminf(gt, 80.0f) * (0.5f * kLog2e));
+  const float hs = ex2_approx(fminf(gs, 80.0f) * (0.5f * kLog2e));
+  const float pt = fmaf(ht, ht, 1.0f), ps = fmaf(hs, hs, 1.0f);   // 1/b, 1/a
+  const float rpt = rsqrt_approx(pt), rps = rsqrt_approx(ps);    // alpha_t, sqrt(a)
+  const float sig = ht * rpt;                                     // sigma_t
+  const float cv = fmaxf(one_minus_exp_neg(fmaxf(dr * dP, 0.0f)), 0.0f);   // c
+  const float fm = (pt * rpt) * rps;                              // sqrt(a/b)
+  const float sc = sig * cv;                                      // sigma_t c
+  StepF f;
+  if (PARAM == MULAN_PARAM_EPS) {
+    f.m1 = fm;
+    f.m2 = -(fm * sc);
+  } else {
+    f.m1 = fm * fmaf(-sc, sig, 1.0f);
+    f.m2 = -(fm * sc) * rpt;
+  }
+  f.m3 = (hs * rps) * sqrt_fast0(cv);                             // sqrt((1-a) c)
+  return f;
+}
+__device__ __forceinline__ float step_apply(const StepF& f, float z, float n, float e) {
+  return fmaf(f.m3, e, fmaf(f.m2, n, f.m1 * z));
+}
+
+// IEEE = true: the reference's statements op for op (IEEE division, sqrtf, expf, expm1f) -- the
+// first version of this kernel, kept for A/B (MULAN_SAMPLER_IEEE=1); it is instruction-bound at
+// 39 % of the HBM roofline.  IEEE = false (default): step_factors / step_apply.
 template <int PARAM, bool IEEE>
 __global__ void __launch_bounds__(kThreads)
 sample_step_kernel(const SamplerParams p) {
@@ -101,45 +146,97 @@ sample_step_kernel(const SamplerParams p) {
     float4 O;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const Poly po = poly_eval(get(A, j), get(Bv, j), get(C, j), rt);
-      const float rS = rcp_scale(po.S);
-      const float Ps = fmaf(po.a2, rs.t5_5, fmaf(po.b2c, rs.t3_3, fmaf(po.ab, rs.t4_2,
-                       fmaf(po.bc, rs.t2, po.c2 * rs.t))));
-      const float dP = fmaf(po.a2, rd.d5_5, fmaf(po.b2c, rd.d3_3, fmaf(po.ab, rd.d4_2,
-                       fmaf(po.bc, rd.d2, po.c2 * rd.d1))));
       const float z = get(Z, j);
       float eh = get(N, j);
       if (IEEE) {
+        const Poly po = poly_eval(get(A, j), get(Bv, j), get(C, j), rt);
+        const float rS = rcp_scale(po.S);
+        const float Ps = fmaf(po.a2, rs.t5_5, fmaf(po.b2c, rs.t3_3, fmaf(po.ab, rs.t4_2,
+                         fmaf(po.bc, rs.t2, po.c2 * rs.t))));
+        const float dP = fmaf(po.a2, rd.d5_5, fmaf(po.b2c, rd.d3_3, fmaf(po.ab, rd.d4_2,
+                         fmaf(po.bc, rd.d2, po.c2 * rd.d1))));
         const float gt = p.gmin + (p.delta * po.P) * rS;
         const float gs = p.gmin + (p.delta * Ps) * rS;
         const float av = sigmoid_ref(-gs);                 // a
         const float bv = sigmoid_ref(-gt);                 // b
-        // c = -expm1(g_s - g_t) >= 0 since gamma is monotone.  The reference's float32
-        // evaluation subtracts two rounded gammas and gets c <= 0 -> NaN in pixels where gamma
-        // is locally flat (tests/test_sampler.py); here the difference keeps full precision and
-        // is clamped.
-        const float cv = fmaxf(-expm1f(-(p.delta * dP) * rS), 0.0f);
+        const float cv = fmaxf(-expm1f(-(p.delta * dP) * rS), 0.0f);   // c, clamped (see above)
         const float sig = sqrtf(sigmoid_ref(gt));          // sigma_t
         if (PARAM != MULAN_PARAM_EPS) eh = eh * sqrtf(bv) + sig * z;   // v -> eps
         const float mean = sqrtf(__fdiv_rn(av, bv)) * (z - sig * cv * eh);
         put(O, j, mean + sqrtf((1.0f - av) * cv) * get(E, j));
       } else {
-        const float dr = p.delta * rS;                     // Delta / S
-        const float gt = fmaf(po.P, dr, p.gmin), gs = fmaf(Ps, dr, p.gmin);
-        // e^{gamma/2}; the clamp keeps 1 + e^gamma finite (gamma > 80 is sigma = 1 anyway)
-        const float ht = ex2_approx(fminf(gt, 80.0f) * (0.5f * kLog2e));
-        const float hs = ex2_approx(fminf(gs, 80.0f) * (0.5f * kLog2e));
-        const float pt = fmaf(ht, ht, 1.0f), ps = fmaf(hs, hs, 1.0f);   // 1/b, 1/a
-        const float rpt = rsqrt_approx(pt), rps = rsqrt_approx(ps);    // alpha_t, sqrt(a)
-        const float sig = ht * rpt;                                     // sigma_t
-        const float cv = fmaxf(one_minus_exp_neg(fmaxf(dr * dP, 0.0f)), 0.0f);   // c
-        if (PARAM != MULAN_PARAM_EPS) eh = fmaf(eh, rpt, sig * z);      // v -> eps
-        const float mean = ((pt * rpt) * rps) * fmaf(-(sig * cv), eh, z);
-        const float ns = (hs * rps) * sqrt_fast0(cv);                   // sqrt((1-a) c)
-        put(O, j, fmaf(ns, get(E, j), mean));
+        const StepF f = step_factors<PARAM>(get(A, j), get(Bv, j), get(C, j), rt, rs, rd, p.gmin,
+                                            p.delta);
+        put(O, j, step_apply(f, z, eh, get(E, j)));
       }
     }
     st4(p.z_s, base4 + i4, O);
+  }
+}
+
+// One coefficient row broadcast over the batch (abc_rows == 1: the unconditional sampler, where
+// every example also shares t and s): the factors are identical for every row with the same
+// (t, s), so a persistent CTA keeps them in shared memory -- 3 x dim floats, each thread reading
+// back only the slots it wrote itself, hence no barrier around the table -- filled while the
+// first row of a run of equal (t, s) is processed.  Every further row of the run is three FMAs
+// per sub-pixel on 16 B of traffic: HBM-bound instead of issue-bound.  Same step_factors /
+// step_apply as the direct kernel: bit-identical results.
+template <int PARAM>
+__global__ void __launch_bounds__(kThreads, 5)
+sample_step_bcast_kernel(const SamplerParams p) {
+  extern __shared__ float4 s_tab[];          // [3][dim4]
+  __shared__ RowT s_rt, s_rs;
+  __shared__ RowD s_rd;
+  const int tid = threadIdx.x;
+  float4* const T1 = s_tab, * const T2 = s_tab + p.dim4, * const T3 = s_tab + 2 * p.dim4;
+  float ct = __int_as_float(0x7fc00000), cs = ct;    // cached (t, s): NaN = nothing cached
+  for (int row = blockIdx.x; row < p.rows; row += gridDim.x) {
+    const float t = __ldg(p.t + row), s = __ldg(p.s + row);
+    const size_t base4 = (size_t)row * p.dim4;
+    if (t == ct && s == cs) {                          // uniform over the CTA: table hit
+      for (int i4 = tid; i4 < p.dim4; i4 += kThreads) {
+        const float4 Z = ld4(p.z_t, base4 + i4), N = ld4(p.net, base4 + i4),
+                     E = ld4(p.eps, base4 + i4);
+        const float4 M1 = T1[i4], M2 = T2[i4], M3 = T3[i4];
+        float4 O;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const StepF f = {get(M1, j), get(M2, j), get(M3, j)};
+          put(O, j, step_apply(f, get(Z, j), get(N, j), get(E, j)));
+        }
+        st4(p.z_s, base4 + i4, O);
+      }
+      continue;
+    }
+    // Miss: compute this row directly; keep its factors only if the next row this CTA will
+    // process shares (t, s) -- rows with individual times never pay for a table they cannot reuse.
+    const int nxt = row + (int)gridDim.x;
+    const bool keep = nxt < p.rows && __ldg(p.t + nxt) == t && __ldg(p.s + nxt) == s;
+    __syncthreads();                                   // the previous row structs are no longer read
+    if (tid == 0) {
+      s_rt = make_row_t(t);
+      s_rs = make_row_t(s);
+      s_rd = make_row_d(t, s);
+    }
+    __syncthreads();
+    const RowT rt = s_rt, rs = s_rs;
+    const RowD rd = s_rd;
+    for (int i4 = tid; i4 < p.dim4; i4 += kThreads) {
+      const float4 A = ld4(p.a, i4), Bv = ld4(p.b, i4), C = ld4(p.c, i4);
+      const float4 Z = ld4(p.z_t, base4 + i4), N = ld4(p.net, base4 + i4),
+                   E = ld4(p.eps, base4 + i4);
+      float4 M1, M2, M3, O;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const StepF f = step_factors<PARAM>(get(A, j), get(Bv, j), get(C, j), rt, rs, rd, p.gmin,
+                                            p.delta);
+        put(M1, j, f.m1); put(M2, j, f.m2); put(M3, j, f.m3);
+        put(O, j, step_apply(f, get(Z, j), get(N, j), get(E, j)));
+      }
+      if (keep) { T1[i4] = M1; T2[i4] = M2; T3[i4] = M3; }
+      st4(p.z_s, base4 + i4, O);
+    }
+    if (keep) { ct = t; cs = s; }
   }
 }
 
@@ -274,10 +371,25 @@ cudaError_t launch_sample_step(const SamplerParams& p, cudaStream_t s) {
   if (ieee) {
     if (eps) sample_step_kernel<MULAN_PARAM_EPS, true><<<p.rows, kThreads, 0, s>>>(p);
     else     sample_step_kernel<MULAN_PARAM_VEL, true><<<p.rows, kThreads, 0, s>>>(p);
-  } else {
-    if (eps) sample_step_kernel<MULAN_PARAM_EPS, false><<<p.rows, kThreads, 0, s>>>(p);
-    else     sample_step_kernel<MULAN_PARAM_VEL, false><<<p.rows, kThreads, 0, s>>>(p);
+    return cudaGetLastError();
   }
+  const size_t tab_bytes = (size_t)3 * p.dim4 * sizeof(float4);
+  if (p.abc_rows == 1 && tab_bytes <= 48 * 1024) {      // factor table in shared memory
+    const void* k = eps ? (const void*)sample_step_bcast_kernel<MULAN_PARAM_EPS>
+                        : (const void*)sample_step_bcast_kernel<MULAN_PARAM_VEL>;
+    int dev = 0, sms = 148, per_sm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kThreads, tab_bytes) !=
+            cudaSuccess || per_sm < 1)
+      per_sm = 1;
+    const int grid = p.rows < sms * per_sm ? p.rows : sms * per_sm;
+    if (eps) sample_step_bcast_kernel<MULAN_PARAM_EPS><<<grid, kThreads, tab_bytes, s>>>(p);
+    else     sample_step_bcast_kernel<MULAN_PARAM_VEL><<<grid, kThreads, tab_bytes, s>>>(p);
+    return cudaGetLastError();
+  }
+  if (eps) sample_step_kernel<MULAN_PARAM_EPS, false><<<p.rows, kThreads, 0, s>>>(p);
+  else     sample_step_kernel<MULAN_PARAM_VEL, false><<<p.rows, kThreads, 0, s>>>(p);
   return cudaGetLastError();
 }
 

@@ -234,3 +234,32 @@ def test_cuda_sampler_ieee_variant(cuda_device):
       cwd=root, env=dict(os.environ, MULAN_SAMPLER_IEEE='1'), capture_output=True, text=True,
       timeout=900)
   assert out.returncode == 0 and '3 passed' in out.stdout, out.stdout[-3000:] + out.stderr[-2000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('kind', ['eps', 'vel'])
+def test_sampler_broadcast_factor_table(cuda_device, kind):
+  """abc_rows == 1 runs a persistent kernel that caches the step's factors per CTA while
+  consecutive rows share (t, s).  With more rows than resident CTAs every path is taken (fill on
+  the first row of a run, table hits, rows whose times differ); each must be bit-identical to
+  the per-example-coefficient kernel."""
+  from mulan_b200 import model as M, ops
+  dev = cuda_device
+  cfg = M.VDMConfig(vdm_type='mulan_epsilon' if kind == 'eps' else 'mulan_velocity')
+  vdm = M.VDM(cfg, lambda f, d: None, lambda z, g, c, d: z).to(dev)
+  vdm.gamma.load_flax(GI.mlp_weights(9))
+  a, b, c = (v.contiguous() for v in
+             vdm.gamma._compute_coefficients(M._deterministic_embedding(vdm, 1, dev)))
+  Bn = 3001
+  gen = torch.Generator(device=dev).manual_seed(1)
+  z, net, eps = (torch.randn(Bn, 3072, device=dev, generator=gen) for _ in range(3))
+  A, Bc, Cc = a.repeat(Bn, 1), b.repeat(Bn, 1), c.repeat(Bn, 1)
+  uniform = torch.full((Bn,), 0.4, device=dev)
+  halves = torch.where(torch.arange(Bn, device=dev) < 1700, 0.4, 0.7).float()
+  random_t = torch.rand(Bn, device=dev, generator=gen) * 0.9 + 0.05
+  for t in (uniform, halves, random_t):
+    s = t - 1.0 / 1000
+    one = ops.sample_step(vdm.desc, a, b, c, t, s, z, net, eps)
+    rep = ops.sample_step(vdm.desc, A, Bc, Cc, t, s, z, net, eps)
+    assert torch.equal(one, rep)
+    assert torch.isfinite(one).all()

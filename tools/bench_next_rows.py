@@ -71,9 +71,13 @@ def main():
                  'frac_of_measured': gbs / pk, 'note': note})
 
   # ---- row 3: ancestral sampler (ldm/model_mulan_epsilon.py:377-457) ----
-  rec('mulan_sample_step (one coefficient row broadcast)', 16 * N,
+  tu, su = torch.full((B,), 0.4, device=dev), torch.full((B,), 0.399, device=dev)
+  rec('mulan_sample_step (one coefficient row broadcast, one t: VDM.sample)', 16 * N,
+      lambda: ops.sample_step(desc, a1, b1, c1, tu, su, z, net, eps, out=out),
+      'z_t4 + net4 + eps4 -> z_s4; a,b,c L2-resident, factors cached per CTA (unconditional sampler)')
+  rec('mulan_sample_step (one coefficient row broadcast, per-row t)', 16 * N,
       lambda: ops.sample_step(desc, a1, b1, c1, t, s, z, net, eps, out=out),
-      'z_t4 + net4 + eps4 -> z_s4; a,b,c are L2-resident (unconditional sampler)')
+      'same traffic; factors recomputed per row: issue-bound')
   rec('mulan_sample_step (per-example coefficients)', 28 * N,
       lambda: ops.sample_step(desc, a, b, c, t, s, z, net, eps, out=out),
       '+ a,b,c 12 (conditional sampler)')

@@ -33,6 +33,20 @@ t = torch.full((B,), 0.5, device=dev); s = torch.full((B,), 0.499, device=dev)
 ops.sample_gamma(d, g['a'][:1], g['b'][:1], g['c'][:1], t)
 zs = ops.sample_step(d, g['a'], g['b'], g['c'], t, s, g['eps'], g['net'], g['eps_0'])
 ops.generate_x(d, zs)
+# broadcast coefficients: persistent factor-table kernel, more rows than resident CTAs, a run of
+# equal (t, s), a change of t mid-batch, and per-row times; eps and velocity models
+Bs = 1600
+zb_, nb_, eb_ = (torch.randn(Bs, 3072, device=dev) for _ in range(3))
+for tt_ in (torch.full((Bs,), 0.5, device=dev),
+            torch.where(torch.arange(Bs, device=dev) < 900, 0.5, 0.8).float(),
+            torch.rand(Bs, device=dev) * 0.9 + 0.05):
+  for mode in (0, 1):
+    ops.sample_step(ops.Desc(param=mode), g['a'][:1], g['b'][:1], g['c'][:1], tt_, tt_ - 0.001,
+                    zb_, nb_, eb_)
+# JAX-compatible draws
+for shp in ((7,), (4096,), (3, 1001)):
+  ops.rng_bits((1, 2), shp, device=dev); ops.rng_uniform((3, 4), shp, device=dev)
+  ops.rng_normal((5, 6), shp, device=dev)
 ops.ode_drift(d, g['a'], g['b'], g['c'], t, g['eps'], g['net'], g['eps_0'], True)
 ops.row_dot(g['eps'], g['net'], gL)
 npy = {k: v.numpy() for k, v in inp.items()}
@@ -63,6 +77,11 @@ for s_ in range(7):
   ops.rk45_stage(s_, ode.RK45_E, 0.1, y, K, y_stage=y32, y_out=yo)
 ops.rk45_norm(7, ode.RK45_E, 0.1, 1e-5, 1e-5, y, yn, K, False, scr, out1)
 ops.rk45_norm(0, (), 0.0, 1e-5, 1e-5, y, None, K, True, scr, out1)
+# 8-byte offset views: the scalar (non-vectorised) RK45 kernels
+yb = torch.randn(1002, dtype=torch.float64, device=dev)
+ops.rk45_stage(6, ode.RK45_E, 0.1, yb[1:], K, y_stage=torch.empty(1001, device=dev),
+               y_out=torch.empty(1002, dtype=torch.float64, device=dev)[1:])
+ops.rk45_norm(7, ode.RK45_E, 0.1, 1e-5, 1e-5, yb[1:], None, K, False, scr, out1)
 ode.solve_ivp_rk45(lambda t_, yy, o: torch.mul(yy, -1.0, out=o), (0.0, 1.0), y32, 1e-3, 1e-3)
 # global-norm clip
 ss = torch.zeros(1, device=dev)
@@ -83,5 +102,5 @@ done
 # input look uninitialised) and needs the caching allocator off
 MULAN_FWD_PRE_TMA=0 PYTORCH_NO_CUDA_MEMORY_CACHING=1 timeout 900 compute-sanitizer --tool initcheck --print-limit 5 python /tmp/san_drive.py > gpurun_out/sanitizer_initcheck.txt 2>&1
 echo "== initcheck: $(grep -E 'ERROR SUMMARY|drive ok' gpurun_out/sanitizer_initcheck.txt | tr '\n' ' ')"
-MULAN_FWD_PRE_TMA=1 compute-sanitizer --tool racecheck --kernel-regex kns=mulan --print-limit 5 python /tmp/san_drive.py > gpurun_out/sanitizer_racecheck_tma.txt 2>&1
-echo "== racecheck (TMA fwd_pre): $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|drive ok' gpurun_out/sanitizer_racecheck_tma.txt | tr '\n' ' ')"
+# (the opt-in TMA fwd_pre under racecheck: see profiles/r1_sanitizer.md; rerun with
+#  MULAN_FWD_PRE_TMA=1 compute-sanitizer --tool racecheck --kernel-regex kns=mulan python /tmp/san_drive.py)

@@ -169,11 +169,11 @@ bool vec_ok(const Rk45Params& p) {
          (p.k_stride & 3) == 0 && p.n >= 4;
 }
 
+// Grid-stride kernels over as many CTAs as the norm's scratch holds partials for (more than are
+// resident at once, so the tail of the sweep stays balanced); the fold order is fixed for a given n.
 int rk_blocks(int64_t n) {
   const int64_t want = ((n + 3) / 4 + kRkThreads - 1) / kRkThreads;
-  static const int64_t cap = resident_ctas((const void*)rk45_norm_partial_kernel<true>);
-  int64_t b = want < cap ? want : cap;
-  if (b > MULAN_RK45_SCRATCH) b = MULAN_RK45_SCRATCH;
+  const int64_t b = want < MULAN_RK45_SCRATCH ? want : MULAN_RK45_SCRATCH;
   return (int)(b < 1 ? 1 : b);
 }
 

@@ -311,6 +311,33 @@ def sample(model: VDM, i: int, T: int, z_t, conditioning=None, eps=None, generat
 
 
 @torch.no_grad()
+def conditional_sample(model: VDM, i: int, T: int, z_t, embedding, conditioning=None, eps=None,
+                       generator=None, coeffs=None):
+  """VDM.conditional_sample (ldm/model_mulan_epsilon.py:377-406,
+  ldm/model_mulan_velocity.py:281-312): one ancestral step with a GIVEN per-example embedding
+  (the schedule, and with z_conditioning the denoiser, are conditioned on it).  `coeffs` =
+  cached (a, b, c) of `embedding` ([B, D]; they do not change along the T steps)."""
+  cfg = model.config
+  B = z_t.shape[0]
+  dev = z_t.device
+  D = 32 * 32 * 3
+  if coeffs is None:
+    coeffs = tuple(v.contiguous() for v in model.gamma._compute_coefficients(embedding))
+  a, b, c = coeffs
+  t = torch.full((B,), (T - i) / T, dtype=torch.float32, device=dev)
+  s = torch.full((B,), (T - i - 1) / T, dtype=torch.float32, device=dev)
+  if eps is None:
+    eps = torch.randn((B, 32, 32, 3), generator=generator, device=dev)
+  g_net = ops.sample_gamma(model.desc, a, b, c, t)
+  cond = embedding if cfg.z_conditioning else conditioning[:, None]
+  g_in = g_net if cfg.unet_type == 'vdm' else g_net.reshape(B, 32, 32, 3)
+  net = model.score_model(z_t.reshape(B, 32, 32, 3), g_in, cond, True)
+  z_s = ops.sample_step(model.desc, a, b, c, t, s, z_t.reshape(B, D).contiguous(),
+                        net.reshape(B, D).contiguous(), eps.reshape(B, D).contiguous())
+  return z_s.reshape(B, 32, 32, 3)
+
+
+@torch.no_grad()
 def generate_x(model: VDM, z_0):
   """VDM.generate_x (ldm/model_mulan_epsilon.py:440-457), sample_softmax=False."""
   B = z_0.shape[0]

@@ -156,4 +156,5 @@ def train_step(model, state: FlatTrainState, batch: dict, generator=None, draws=
                                           for k in keys])
   state.all_reduce()
   state.apply_gradients()
-  return {k: state.tail[i] for i, k in enumerate(keys)}
+  out = state.tail[:len(keys)].clone()       # the bucket is zeroed by the next step
+  return {k: out[i] for i, k in enumerate(keys)}

@@ -263,3 +263,29 @@ def test_sampler_broadcast_factor_table(cuda_device, kind):
     rep = ops.sample_step(vdm.desc, A, Bc, Cc, t, s, z, net, eps)
     assert torch.equal(one, rep)
     assert torch.isfinite(one).all()
+
+
+@pytest.mark.gpu
+def test_conditional_sample_equals_sample_for_the_deterministic_embedding(cuda_device):
+  """VDM.conditional_sample with every example's embedding set to the deterministic one is
+  VDM.sample (ldm/model_mulan_epsilon.py:377-438): per-example coefficients vs one broadcast row."""
+  from mulan_b200 import model as M
+  dev = cuda_device
+  for kind in ('mulan_epsilon', 'mulan_velocity'):
+    cfg = M.VDMConfig(vdm_type=kind)
+    vdm = M.VDM(cfg, lambda f, d: None,
+                lambda z, g, c, d: 0.8 * z + 0.01 * g.reshape(-1, 1, 1, 1) + 0.001 * c.sum(1).reshape(-1, 1, 1, 1)).to(dev)
+    vdm.gamma.load_flax(GI.mlp_weights(12))
+    Bn = 7
+    gen = torch.Generator(device=dev).manual_seed(3)
+    z = torch.randn(Bn, 32, 32, 3, device=dev, generator=gen)
+    eps = torch.randn(Bn, 32, 32, 3, device=dev, generator=gen)
+    emb = M._deterministic_embedding(vdm, Bn, dev)
+    one = M.sample(vdm, 400, 1000, z, eps=eps)
+    two = M.conditional_sample(vdm, 400, 1000, z, emb, eps=eps)
+    # (the Dense layers run as a batch-7 vs a batch-1 GEMM: equal up to cuBLAS's summation order)
+    assert torch.allclose(one, two, rtol=1e-5, atol=1e-6)
+    # a different embedding changes the schedule, hence the step
+    emb2 = emb.clone()
+    emb2[:, :5] = 0.0
+    assert not torch.allclose(M.conditional_sample(vdm, 400, 1000, z, emb2, eps=eps), one, rtol=1e-3)

@@ -18,3 +18,6 @@ ncu --set full --clock-control none --import-source on \
     -k regex:'fwd_pre_kernel|post_kernel|bwd_pre_kernel' -s 3 -c 3 -o gpurun_out/prof_$tag -f \
     python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/ncu_full_$tag.log 2>&1
 ls -la gpurun_out/prof_$tag.ncu-rep gpurun_out/launches_$tag.csv
+# kernel sweep and the "next" rows' per-kernel rooflines
+bash tools/sweep.sh
+python tools/bench_next_rows.py > gpurun_out/next_rows.jsonl 2> gpurun_out/next_rows.err; tail -2 gpurun_out/next_rows.err

@@ -398,6 +398,25 @@ def run_native(args):
            'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
            'api': 'mulan_elbo_host (C ABI, pinned host buffers)',
            'bpd': float(r['scalars'][0])}
+    # the same call with eps_0 / eps drawn on the device from their threefry keys (what
+    # VDM.__call__ itself does with its rng): 8 of the 25 H2D bytes per sub-pixel stay home
+    callk = lambda: host.elbo_host(h['x'], h['a'], h['b'], h['c'], h['t'], None, None, h['net'],
+                                   param=param, want_grad=True, out=out,
+                                   jax_keys=((1234, rank), (5678, rank)))
+    callk(); callk()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(ke):
+      rk = callk()
+    t1 = time.perf_counter()
+    tk = torch.tensor([t1 - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+      dist.all_reduce(tk, op=dist.ReduceOp.MAX)
+    e2e['device_draws'] = {
+        'value': world * rows * ke / tk.item(), 'unit': 'samples/s',
+        'h2d_bytes_per_step': rows * D * (1 + 4 * 4) + rows * 4 + 16,
+        'd2h_bytes_per_step': d2h, 'api': 'mulan_elbo_host_keyed (eps_0, eps from JAX keys)',
+        'bpd': float(rk['scalars'][0])}
     _lib.load().mulan_host_workspace_release()
 
   # ---- latency of configs[1]'s literal size (one batch of 128 rows, CUDA graph) ----

@@ -254,6 +254,21 @@ int mulan_elbo_host(const mulan_desc* desc,
                     float* a_bar, float* b_bar, float* c_bar, float* n_bar);
 
 /*
+ * mulan_elbo_host_keyed -- mulan_elbo_host with eps_0 and eps DRAWN ON THE DEVICE from the raw
+ * 2 x uint32 threefry keys that the reference's make_rng('sample') hands to
+ * jax.random.normal(rng, shape=f.shape) (ldm/model_mulan_epsilon.py:315, :327): which is what
+ * VDM.__call__ itself does -- it receives images and an rng, not noise arrays.  The draws equal
+ * mulan_rng_normal(key, B*D) reshaped to [B,D]; 8 of the 25 host-to-device bytes per sub-pixel
+ * of mulan_elbo_host never cross PCIe.  rows * dim < 2^32 - 1.
+ */
+int mulan_elbo_host_keyed(const mulan_desc* desc,
+                          const uint8_t* x, const float* a, const float* b, const float* c,
+                          const float* t, const uint32_t* key_eps0, const uint32_t* key_eps,
+                          const float* net, mulan_denoiser_fn denoiser, void* user,
+                          int32_t want_grad, float* losses, float* scalars,
+                          float* a_bar, float* b_bar, float* c_bar, float* n_bar);
+
+/*
  * Ancestral sampler ("next" row 3 of the scope table): the schedule math of VDM.sample /
  * conditional_sample (ldm/model_mulan_epsilon.py:377-438, ldm/model_mulan_velocity.py:281-347)
  * and VDM.generate_x (ldm/model_mulan_epsilon.py:440-457), run T = 1000 times per generated

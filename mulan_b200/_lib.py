@@ -71,6 +71,7 @@ SIGNATURES = {
     'mulan_aux_gaussian_bwd': ([C.c_int32] * 2 + [_P] * 8, C.c_int),
     'mulan_bpd_reduce': ([_D] + [_P] * 8, C.c_int),
     'mulan_elbo_host': ([_D] + [_P] * 8 + [DENOISER_FN, _P, C.c_int32] + [_P] * 6, C.c_int),
+    'mulan_elbo_host_keyed': ([_D] + [_P] * 8 + [DENOISER_FN, _P, C.c_int32] + [_P] * 6, C.c_int),
     'mulan_sample_gamma': ([_D, C.c_int32] + [_P] * 6, C.c_int),
     'mulan_sample_step': ([_D, C.c_int32] + [_P] * 10, C.c_int),
     'mulan_generate_x': ([_D] + [_P] * 3, C.c_int),

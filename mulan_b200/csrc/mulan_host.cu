@@ -84,11 +84,19 @@ extern "C" {
 
 void mulan_host_workspace_release(void) { g_ws.release(); }
 
-int mulan_elbo_host(const mulan_desc* d, const uint8_t* x, const float* a, const float* b,
-                    const float* c, const float* t, const float* eps0, const float* eps,
-                    const float* net, mulan_denoiser_fn denoiser, void* user, int32_t want_grad,
-                    float* losses, float* scalars, float* a_bar, float* b_bar, float* c_bar,
-                    float* n_bar) {
+}  // extern "C"
+
+// The pipeline behind both host entries.  eps0 / eps are host arrays, or NULL with key_eps0 /
+// key_eps set: then the two draws are generated on the device (threefry2x32 + erfinv, exactly
+// jax.random.normal(key, [B, 32, 32, 3]) -- mulan_rng.cu) on the compute stream before the first
+// chunk's kernels, while the first chunk's operands are still crossing PCIe.
+static int elbo_host_impl(const mulan_desc* d, const uint8_t* x, const float* a, const float* b,
+                          const float* c, const float* t, const float* eps0, const float* eps,
+                          const uint32_t* key_eps0, const uint32_t* key_eps,
+                          const float* net, mulan_denoiser_fn denoiser, void* user,
+                          int32_t want_grad, float* losses, float* scalars, float* a_bar,
+                          float* b_bar, float* c_bar, float* n_bar) {
+  const bool keyed = key_eps0 != nullptr && key_eps != nullptr;
   auto bad = [](const char* msg) {
     snprintf(g_host_err, sizeof(g_host_err), "mulan_elbo_host: %s", msg);
     mulan::set_last_error(g_host_err);
@@ -97,8 +105,9 @@ int mulan_elbo_host(const mulan_desc* d, const uint8_t* x, const float* a, const
   if (d == nullptr) return bad("desc is NULL");
   if (d->rows <= 0) return bad("rows must be positive");
   if (d->dim <= 0 || d->dim % 4 != 0) return bad("dim must be a positive multiple of 4");
-  if (!x || !a || !b || !c || !t || !eps0 || !eps || !losses || !scalars)
+  if (!x || !a || !b || !c || !t || !losses || !scalars)
     return bad("a required host pointer is NULL");
+  if (!keyed && (!eps0 || !eps)) return bad("eps0 / eps are NULL and no keys were given");
   if (denoiser == nullptr && net == nullptr) return bad("net is NULL and no denoiser was given");
   if (d->gt_mode == MULAN_GT_PIXEL) {
     mulan::set_last_error("mulan_elbo_host: gt_mode=PIXEL is served by the device-pointer API");
@@ -131,12 +140,26 @@ int mulan_elbo_host(const mulan_desc* d, const uint8_t* x, const float* a, const
     CU(cudaMemcpyAsync(dGL, ws.h_gl, B * sizeof(float), cudaMemcpyHostToDevice, ws.s_in));
   }
 
+  if (keyed) {
+    // whole-batch draws (JAX's counter layout pairs element i with element i + N/2, so a draw
+    // cannot be generated chunk by chunk without doing every block twice)
+    if (N >= 0xffffffffULL) return bad("keyed draws need rows * dim < 2^32 - 1");
+    // jax.random.normal: sqrt(2) erf_inv(uniform on [nextafter(-1, 0), 1)), as mulan_rng_normal
+    const float lo = nextafterf(-1.0f, 0.0f);
+    cudaError_t e = mulan::launch_rng_draw(2, key_eps0[0], key_eps0[1], (long long)N, lo, 1.0f,
+                                           dE0, ws.s_cmp);
+    if (e == cudaSuccess)
+      e = mulan::launch_rng_draw(2, key_eps[0], key_eps[1], (long long)N, lo, 1.0f, dE, ws.s_cmp);
+    CU(e);
+  }
+
   for (int ci = 0; ci < nchunk; ++ci) {
     const size_t r0 = (size_t)ci * chunk, nr = (r0 + chunk <= B) ? chunk : B - r0;
     const size_t o = r0 * D, n = nr * D;
     // ---- copy-in stream: straight from the caller's buffers (true DMA when page-locked)
     CU(cudaMemcpyAsync(ws.d_x + o, x + o, n, cudaMemcpyHostToDevice, ws.s_in));
-    const float* srcs[6] = {a, b, c, eps0, eps, denoiser == nullptr ? net : nullptr};
+    const float* srcs[6] = {a, b, c, keyed ? nullptr : eps0, keyed ? nullptr : eps,
+                            denoiser == nullptr ? net : nullptr};
     float* dsts[6] = {dA, dB, dC, dE0, dE, dN};
     for (int k = 0; k < 6; ++k)
       if (srcs[k] != nullptr)
@@ -192,6 +215,34 @@ int mulan_elbo_host(const mulan_desc* d, const uint8_t* x, const float* a, const
   CU(cudaStreamSynchronize(ws.s_out));
   CU(cudaStreamSynchronize(ws.s_in));
   return 0;
+}
+
+extern "C" {
+
+int mulan_elbo_host(const mulan_desc* d, const uint8_t* x, const float* a, const float* b,
+                    const float* c, const float* t, const float* eps0, const float* eps,
+                    const float* net, mulan_denoiser_fn denoiser, void* user, int32_t want_grad,
+                    float* losses, float* scalars, float* a_bar, float* b_bar, float* c_bar,
+                    float* n_bar) {
+  if (eps0 == nullptr || eps == nullptr) {
+    mulan::set_last_error("mulan_elbo_host: eps0 / eps is NULL");
+    return (int)MULAN_ERR_INVALID_ARG;
+  }
+  return elbo_host_impl(d, x, a, b, c, t, eps0, eps, nullptr, nullptr, net, denoiser, user,
+                        want_grad, losses, scalars, a_bar, b_bar, c_bar, n_bar);
+}
+
+int mulan_elbo_host_keyed(const mulan_desc* d, const uint8_t* x, const float* a, const float* b,
+                          const float* c, const float* t, const uint32_t* key_eps0,
+                          const uint32_t* key_eps, const float* net, mulan_denoiser_fn denoiser,
+                          void* user, int32_t want_grad, float* losses, float* scalars,
+                          float* a_bar, float* b_bar, float* c_bar, float* n_bar) {
+  if (key_eps0 == nullptr || key_eps == nullptr) {
+    mulan::set_last_error("mulan_elbo_host_keyed: a key is NULL");
+    return (int)MULAN_ERR_INVALID_ARG;
+  }
+  return elbo_host_impl(d, x, a, b, c, t, nullptr, nullptr, key_eps0, key_eps, net, denoiser,
+                        user, want_grad, losses, scalars, a_bar, b_bar, c_bar, n_bar);
 }
 
 }  // extern "C"

@@ -75,6 +75,17 @@ def test_argument_validation_without_gpu(lib):
   assert h.mulan_aux_topk_fwd(0, 50, 15, None, None, None, None, None) == 0
 
 
+def test_keyed_host_entry_validates_without_gpu(lib):
+  h = lib.load()
+  d = lib.make_desc(rows=2)
+  assert h.mulan_elbo_host_keyed(C.byref(d), *([None] * 8), lib.DENOISER_FN(), None, 0,
+                                 *([None] * 6)) == -1
+  assert b'key is NULL' in h.mulan_last_error()
+  assert h.mulan_elbo_host(C.byref(d), *([None] * 8), lib.DENOISER_FN(), None, 0,
+                           *([None] * 6)) == -1
+  assert b'eps0 / eps is NULL' in h.mulan_last_error()
+
+
 def test_ops_refuse_cpu_tensors(lib):
   from mulan_b200 import ops
   z = torch.zeros(2, 3072)

@@ -579,3 +579,28 @@ def test_scale_outside_fast_range(cuda_device):
   assert torch.isnan(r['loss_klz_prior'][3]) and torch.isnan(r['var_sums'][3]).all()
   assert torch.isfinite(r['loss_klz_prior'][:3]).all() and torch.isfinite(r['var_sums'][:3]).all()
   assert _rel(r['loss_klz_prior'][:3], aux['loss_klz_prior'][:3]) < LOSS_RTOL
+
+
+def test_host_entry_keyed_draws(cuda_device):
+  """mulan_elbo_host_keyed draws eps_0 / eps on the device from raw threefry keys; it must equal
+  mulan_elbo_host fed with the same draws materialised by mulan_rng_normal (bit for bit), over a
+  batch that spans several chunks."""
+  ops = _ops()
+  from mulan_b200 import host
+  B = 2100
+  inp = O.synth_inputs(B, 83, group=128)
+  k0, k1 = (11, 22), (0xdeadbeef, 7)
+  e0 = ops.rng_normal(k0, (B, 3072), device=cuda_device).cpu().numpy()
+  e1 = ops.rng_normal(k1, (B, 3072), device=cuda_device).cpu().numpy()
+  npy = {k: v.numpy() for k, v in inp.items()}
+  for param in (0, 1):
+    want = host.elbo_host(npy['x'], npy['a'], npy['b'], npy['c'], npy['t'], e0, e1, npy['net'],
+                          param=param, want_grad=True)
+    want = {k: np.array(v, copy=True) for k, v in want.items()}
+    got = host.elbo_host(npy['x'], npy['a'], npy['b'], npy['c'], npy['t'], None, None, npy['net'],
+                         param=param, want_grad=True, jax_keys=(k0, k1))
+    for k in want:
+      assert np.array_equal(got[k], want[k]), (param, k)
+  with pytest.raises(ValueError):
+    host.elbo_host(npy['x'], npy['a'], npy['b'], npy['c'], npy['t'], e0, None, npy['net'],
+                   jax_keys=(k0, k1))

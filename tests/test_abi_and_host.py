@@ -308,3 +308,43 @@ def test_native_bench_fails_loudly_without_gpu():
                        timeout=600)
   assert out.returncode != 0
   assert out.stdout.strip() == ''
+
+
+def test_headers_are_plain_c_and_link_from_c(lib, tmp_path):
+  """The boundary is a C ABI: both public headers compile as strict C99 (and C++11), and a C
+  program linked against libmulan_b200.so reaches the entry points (argument validation only:
+  no device needed)."""
+  import shutil
+  import subprocess
+  if shutil.which('gcc') is None:
+    pytest.skip('no gcc')
+  src = tmp_path / 'abi.c'
+  src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "mulan_b200.h"
+#include "mulan_b200_xla.h"
+int main(void) {
+  mulan_desc d;
+  memset(&d, 0, sizeof d);
+  d.rows = 2; d.dim = 3070; d.vocab = 256; d.gamma_min = -13.3; d.gamma_max = 5.0;
+  int st = mulan_fwd_pre(&d, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0);
+  printf("%d %d %d %d|%s\n", mulan_abi_version(), (int)sizeof(mulan_desc),
+         (int)sizeof(mulan_xla_opaque), st, mulan_last_error());
+  printf("%d %d\n", mulan_kernel_param(MULAN_PARAM_VEL_FROM_EPS), mulan_kernel_param(MULAN_PARAM_VEL));
+  return 0;
+}
+''')
+  inc = os.path.join(ROOT, 'include')
+  libdir = os.path.join(ROOT, 'mulan_b200')
+  exe = tmp_path / 'abi'
+  subprocess.run(['gcc', '-std=c99', '-Wall', '-Wextra', '-Werror', '-pedantic', '-I', inc,
+                  str(src), '-o', str(exe), '-L', libdir, '-lmulan_b200',
+                  '-Wl,-rpath,' + libdir], check=True, capture_output=True)
+  env = {k: v for k, v in os.environ.items() if k != 'MULAN_VFE_LITERAL'}
+  out = subprocess.run([str(exe)], check=True, capture_output=True, text=True, env=env).stdout
+  first, second = out.strip().split('\n')
+  assert first.startswith('1 40 48 -2|') and 'not a multiple of 4' in first
+  assert second == '0 1'
+  subprocess.run(['g++', '-std=c++11', '-Wall', '-Wextra', '-Werror', '-fsyntax-only', '-I', inc,
+                  '-x', 'c++', str(src)], check=True, capture_output=True)

@@ -127,7 +127,7 @@ def main():
           continue   # keep the fixtures small
         out[f'{tag}_{k}'] = v
     out['seed'], out['B'] = np.int64(seed), np.int64(B)
-    path = os.path.join(HERE, name + '.npz')
+    path = os.path.join(os.environ.get('MULAN_GOLDEN_OUT', HERE), name + '.npz')
     np.savez_compressed(path, **out)
     print(f'{name}: bpd f32 {out["f32_bpd"]:.7f} f64 {out["f64_bpd"]:.7f}  -> '
           f'{os.path.getsize(path) / 1024:.0f} KiB')

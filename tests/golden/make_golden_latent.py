@@ -78,7 +78,7 @@ def main():
       for k, v in run(case, dtype).items():
         res[f'{case}_{tag}_{k}'] = v
   torch.set_default_dtype(torch.float32)
-  path = os.path.join(HERE, 'latent.npz')
+  path = os.path.join(os.environ.get('MULAN_GOLDEN_OUT', HERE), 'latent.npz')
   np.savez_compressed(path, **res)
   print(f'latent.npz: {os.path.getsize(path) / 1024:.0f} KiB, {len(res)} arrays')
 

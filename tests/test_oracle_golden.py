@@ -163,3 +163,34 @@ def test_vfe_is_eps(name, full, tag, monkeypatch):
       # 1e-4 is the north_star gradient tolerance; measured 3e-6 (a,b,c), 6e-5 (logits, whose
       # float32 golden is itself that far from the float64 one)
       assert _rel_l2(got, want) < (1e-4 if tag == 'f32' else 1e-12), (k, _rel_l2(got, want))
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/ldm'),
+                    reason='the reference source only exists in the build container')
+@pytest.mark.parametrize('script,files', [
+    ('make_golden.py', ['glue_eps', 'glue_vel', 'glue_vfe', 'full_eps', 'full_vfe',
+                        'glue_eps_T1000']),
+    ('make_golden_sampler.py', ['sampler']),
+    ('make_golden_latent.py', ['latent'])])
+def test_committed_goldens_are_what_the_reference_source_produces(script, files, tmp_path):
+  """Re-run the generator (it imports and executes /root/reference/ldm/*.py in place) into a
+  scratch directory and compare with the committed fixtures: the pin is reproducible and the
+  committed vectors really are the reference source's outputs."""
+  import subprocess
+  env = dict(os.environ, MULAN_GOLDEN_OUT=str(tmp_path))
+  subprocess.run([sys.executable, os.path.join(HERE, 'golden', script)], check=True, env=env,
+                 capture_output=True, timeout=900)
+  for name in files:
+    new, old = np.load(tmp_path / (name + '.npz')), load(name)
+    assert set(new.files) == set(old.files)
+    for k in old.files:
+      a, b = np.asarray(new[k]), np.asarray(old[k])
+      assert a.shape == b.shape and a.dtype == b.dtype, k
+      if a.dtype.kind != 'f':
+        assert np.array_equal(a, b), k
+        continue
+      # identical up to the BLAS thread count of the Dense layers in the full_* fixtures
+      tol = 2e-6 if a.dtype == np.float32 else 1e-12
+      scale = max(float(np.nanmax(np.abs(b))) if b.size else 0.0, 1e-30)
+      assert np.array_equal(np.isnan(a), np.isnan(b)), k
+      assert np.nanmax(np.abs(a - b), initial=0.0) <= tol * scale, (k, np.nanmax(np.abs(a - b)))

@@ -13,6 +13,7 @@ Two fixture families, float32 and float64 each:
   full_{eps,vfe}         the same call with the reference's own _compute_coefficients running
                          its five Dense layers on seeded weights.
   glue_eps_T1000         the epsilon model's discrete-time branch (sm_n_timesteps=1000).
+  glue_vel_ldm           the velocity model with unet_type='ldm' (per-pixel gamma_t to the denoiser).
 """
 from __future__ import annotations
 
@@ -64,7 +65,8 @@ def run(kind, seed, B, dtype, full, **overrides):
 
   def score_model(z, g_t, conditioning, deterministic, time=False):
     captured['z_t'], captured['g_net'], captured['cond'] = z, g_t, conditioning
-    return (w1 * z + w2 * g_t.reshape(-1, 1, 1, 1)
+    g = g_t.reshape(-1, 1, 1, 1) if g_t.ndim == 1 else g_t     # unet_type 'vdm' | 'ldm'
+    return (w1 * z + w2 * g
             + w3 * conditioning.sum(dim=1).reshape(-1, 1, 1, 1) + noise)
   vdm.score_model = score_model
 
@@ -117,7 +119,9 @@ def main():
   jobs = [('glue_eps', 'eps', 101, False, {}), ('glue_vel', 'vel', 102, False, {}),
           ('glue_vfe', 'vfe', 103, False, {}), ('full_eps', 'eps', 201, True, {}),
           ('full_vfe', 'vfe', 203, True, {}),
-          ('glue_eps_T1000', 'eps', 104, False, {'sm_n_timesteps': 1000})]
+          ('glue_eps_T1000', 'eps', 104, False, {'sm_n_timesteps': 1000}),
+          # unet_type='ldm': the denoiser receives the per-pixel gamma_t (epsilon.py:277-278)
+          ('glue_vel_ldm', 'vel', 105, False, {'unet_type': 'ldm'})]
   for name, kind, seed, full, ov in jobs:
     out = {}
     for dtype, tag in ((torch.float32, 'f32'), (torch.float64, 'f64')):

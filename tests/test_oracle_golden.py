@@ -25,9 +25,9 @@ def load(name):
   return np.load(os.path.join(HERE, 'golden', name + '.npz'))
 
 
-def run_oracle(kind, seed, B, dtype, full, T=0):
+def run_oracle(kind, seed, B, dtype, full, T=0, unet_type='vdm'):
   inp = GI.glue_inputs(seed, B)
-  cfg = O.OracleConfig(sm_n_timesteps=T)
+  cfg = O.OracleConfig(sm_n_timesteps=T, unet_type=unet_type)
   tt = lambda v: torch.from_numpy(np.asarray(v)).to(dtype)
   leaf = lambda v: tt(v).requires_grad_(True)
   w1, w2, w3 = leaf(inp['w1']), leaf(inp['w2']), leaf(inp['w3'])
@@ -36,7 +36,8 @@ def run_oracle(kind, seed, B, dtype, full, T=0):
 
   def score_fn(z, g, cond):
     cap['z_t'], cap['g_net'], cap['cond'] = z, g, cond
-    return (w1 * z + w2 * g.reshape(-1, 1, 1, 1)
+    gg = g.reshape(-1, 1, 1, 1) if g.ndim == 1 else g
+    return (w1 * z + w2 * gg
             + w3 * cond.sum(dim=1).reshape(-1, 1, 1, 1) + noise)
 
   leaves = {'w1': w1, 'w2': w2, 'w3': w3}
@@ -169,7 +170,7 @@ def test_vfe_is_eps(name, full, tag, monkeypatch):
                     reason='the reference source only exists in the build container')
 @pytest.mark.parametrize('script,files', [
     ('make_golden.py', ['glue_eps', 'glue_vel', 'glue_vfe', 'full_eps', 'full_vfe',
-                        'glue_eps_T1000']),
+                        'glue_eps_T1000', 'glue_vel_ldm']),
     ('make_golden_sampler.py', ['sampler']),
     ('make_golden_latent.py', ['latent'])])
 def test_committed_goldens_are_what_the_reference_source_produces(script, files, tmp_path):
@@ -194,3 +195,24 @@ def test_committed_goldens_are_what_the_reference_source_produces(script, files,
       scale = max(float(np.nanmax(np.abs(b))) if b.size else 0.0, 1e-30)
       assert np.array_equal(np.isnan(a), np.isnan(b)), k
       assert np.nanmax(np.abs(a - b), initial=0.0) <= tol * scale, (k, np.nanmax(np.abs(a - b)))
+
+
+@pytest.mark.parametrize('tag', ['f32', 'f64'])
+def test_oracle_matches_reference_source_ldm(tag):
+  """unet_type='ldm' (ldm/model_mulan_epsilon.py:277-278): the denoiser receives the per-pixel
+  gamma_t, so its cotangent reaches (a, b, c) per pixel instead of through a row mean."""
+  g = load('glue_vel_ldm')
+  seed, B = int(g['seed']), int(g['B'])
+  dtype = torch.float32 if tag == 'f32' else torch.float64
+  r = run_oracle('vel', seed, B, dtype, False, unet_type='ldm')
+  rt = 2e-6 if tag == 'f32' else 1e-11
+  for k in ('loss_recon', 'loss_klz', 'loss_diff', 'bpd', 'var_0', 'var_1'):
+    _close(r[k], g[f'{tag}_{k}'], rt)
+  assert r['g_net'].shape == (B, 32, 32, 3)
+  _close(r['g_net'], g[f'{tag}_g_net'], rt, atol=2e-5 if tag == 'f32' else 1e-11)
+  for k in [k for k in g.files if k.startswith(f'{tag}_grad_')]:
+    want, got = g[k], r[k[len(tag) + 1:]]
+    if np.linalg.norm(want) == 0:
+      assert np.linalg.norm(got) == 0
+    else:
+      assert _rel_l2(got, want) < (1e-4 if tag == 'f32' else 1e-9), (k, _rel_l2(got, want))

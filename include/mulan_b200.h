@@ -112,6 +112,13 @@ int mulan_fwd_pre(const mulan_desc* desc,
                   float* z_t, float* g_net, float* w_save,
                   float* loss_recon, float* loss_klz_prior, float* var_sums,
                   void* stream);
+/* Host-only query: which mulan_fwd_pre kernel this descriptor selects on this host --
+ * 0 generic (windowed log-softmax over the vocab bins), 1 closed-form 3-bin reconstruction term
+ * with the launch constants in the parameter bank, 2 the same with the constants of the shipped
+ * configuration (gamma in [-13.3, 5], vocab 256: both files under ldm/configs) as instruction
+ * immediates (selected only when the host-computed constants match them bit for bit).  All three
+ * produce the same outputs; negative = invalid descriptor. */
+int mulan_fwd_pre_variant(const mulan_desc* desc);
 
 /*
  * mulan_fwd_post -- the diffusion loss after the denoiser returned `net`.

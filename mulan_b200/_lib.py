@@ -56,6 +56,7 @@ SIGNATURES = {
     'mulan_abi_version': ([], C.c_int),
     'mulan_kernel_param': ([C.c_int32], C.c_int),
     'mulan_fwd_pre': ([_D] + [_P] * 14, C.c_int),
+    'mulan_fwd_pre_variant': ([_D], C.c_int),
     'mulan_fwd_post': ([_D] + [_P] * 10, C.c_int),
     'mulan_bwd_post': ([_D] + [_P] * 11, C.c_int),
     'mulan_fwd_bwd_post': ([_D] + [_P] * 12, C.c_int),

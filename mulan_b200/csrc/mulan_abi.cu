@@ -141,6 +141,19 @@ int mulan_fwd_pre(const mulan_desc* d, const uint8_t* x, const float* a, const f
   return e == cudaSuccess ? 0 : cuda_fail(fn, e);
 }
 
+int mulan_fwd_pre_variant(const mulan_desc* d) {
+  const char* fn = "mulan_fwd_pre_variant";
+  if (int r = check_desc(d, fn)) return r;
+  mulan::FwdPreParams p;
+  memset(&p, 0, sizeof(p));
+  p.W = recon_window(d);
+  p.gmin = f32_gmin(d); p.delta = f32_delta(d);
+  p.k = mulan::make_end_consts(p.gmin, p.delta);
+  p.vi = mulan::make_vocab(d->vocab);
+  p.rc = mulan::make_recon_fast(p.k, p.vi);
+  return mulan::fwd_pre_variant(p);
+}
+
 static int fill_post(const char* fn, const mulan_desc* d, const uint8_t* x, const float* a,
                      const float* b, const float* c, const float* t, const float* eps,
                      const float* net, const float* w_save, mulan::PostParams* p) {

@@ -382,6 +382,15 @@ static cudaError_t launch_w(const FwdPreParams& p, cudaStream_t s) {
   return cudaGetLastError();
 }
 
+// Which fwd_pre kernel launch_w() would pick for these launch constants (host-only query):
+// 0 generic (windowed log-softmax), 1 closed-form 3-bin reconstruction with the constants in the
+// parameter bank, 2 the same with the shipped configuration's constants as immediates.
+int fwd_pre_variant(const FwdPreParams& p) {
+  const bool fast = p.W == 1 && p.vi.pow2;
+  if (!fast) return 0;
+  return is_shipped(p) ? 2 : 1;
+}
+
 cudaError_t launch_fwd_pre(const FwdPreParams& p, cudaStream_t s) {
   if (p.rows == 0) return cudaSuccess;
   const bool savew = p.w_save != nullptr;

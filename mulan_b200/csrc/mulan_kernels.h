@@ -198,6 +198,7 @@ int kernel_param(int param);
 void set_last_error(const char* msg);
 
 cudaError_t launch_fwd_pre(const FwdPreParams& p, cudaStream_t s);
+int fwd_pre_variant(const FwdPreParams& p);
 cudaError_t launch_fwd_post(const PostParams& p, cudaStream_t s);
 cudaError_t launch_bwd_post(const PostParams& p, cudaStream_t s);
 cudaError_t launch_fwd_bwd_post(const PostParams& p, cudaStream_t s);

@@ -86,6 +86,18 @@ def test_keyed_host_entry_validates_without_gpu(lib):
   assert b'eps0 / eps is NULL' in h.mulan_last_error()
 
 
+def test_shipped_configuration_selects_the_specialised_fwd_pre(lib):
+  """The immediates baked into the specialised fwd_pre kernel are compared bit for bit with the
+  constants THIS host's libm produces; a mismatch would silently fall back to the generic-
+  constant kernel (same results, 4 % slower).  Other configurations take the other variants."""
+  h = lib.load()
+  assert h.mulan_fwd_pre_variant(C.byref(lib.make_desc(rows=1))) == 2
+  assert h.mulan_fwd_pre_variant(C.byref(lib.make_desc(rows=1, gamma_max=4.0))) == 1
+  assert h.mulan_fwd_pre_variant(C.byref(lib.make_desc(rows=1, gamma_min=-6.0))) == 0   # W > 1
+  assert h.mulan_fwd_pre_variant(C.byref(lib.make_desc(rows=1, vocab=100))) == 0
+  assert h.mulan_fwd_pre_variant(C.byref(lib.make_desc(rows=1, vocab=1))) == -1
+
+
 def test_ops_refuse_cpu_tensors(lib):
   from mulan_b200 import ops
   z = torch.zeros(2, 3072)

@@ -112,6 +112,37 @@ int mulan_fwd_pre(const mulan_desc* desc,
                   float* z_t, float* g_net, float* w_save,
                   float* loss_recon, float* loss_klz_prior, float* var_sums,
                   void* stream);
+/*
+ * mulan_fwd_pre_consts -- mulan_fwd_pre with the five transcendental constants of the fixed
+ * schedule ends SUPPLIED by the caller, as the caller's framework evaluates them in float32,
+ * instead of computed on the host (double, rounded once = correctly rounded).  The reference's
+ * own loss_recon depends on how its platform rounds exp(-g_0/2): the exact value lies 0.40 ulp
+ * from the correctly rounded float and one ulp moves a row's loss_recon by up to 1.8e-5 relative
+ * (DESIGN.md section 2), so a binding that wants to match ITS platform bit for rounding passes
+ *   exp_half_g0 = exp(.5 g_0), exp_neg_half_g0 = exp(-.5 g_0), sigmoid_g0, sigmoid_g1 =
+ *   sigmoid(g_min + (g_max - g_min)), log_sigmoid_g1 = log(sigmoid_g1)     with g_0 = f32(g_min)
+ * evaluated once by its own exp / log (ldm/model_mulan_epsilon.py:311-325; model_vdm.py:286).
+ * consts == NULL is exactly mulan_fwd_pre.  The kernels read these values from their parameter
+ * block either way (the immediates-specialised kernel is selected only when they equal the
+ * shipped configuration's host-computed values bit for bit).
+ * STATUS: added at the end of round 1 after the GPU budget was spent -- the plumbing is covered
+ * by CPU tests (mulan_fwd_pre_variant_consts), the numerics run through the same, GPU-tested,
+ * parameter-bank kernels, but the override itself has not yet been exercised on a GPU.
+ */
+typedef struct mulan_end_consts {
+  float exp_half_g0, exp_neg_half_g0, sigmoid_g0, sigmoid_g1, log_sigmoid_g1;
+} mulan_end_consts;
+int mulan_fwd_pre_consts(const mulan_desc* desc, const mulan_end_consts* consts,
+                         const uint8_t* x, const float* a, const float* b, const float* c,
+                         const float* t, const float* eps0, const float* eps,
+                         float* z_t, float* g_net, float* w_save,
+                         float* loss_recon, float* loss_klz_prior, float* var_sums,
+                         void* stream);
+/* Host-only: what mulan_end_consts the library itself would use for this descriptor (out), and
+ * which kernel variant (see mulan_fwd_pre_variant) a call with `consts` (NULL = own) selects. */
+int mulan_host_end_consts(const mulan_desc* desc, mulan_end_consts* out);
+int mulan_fwd_pre_variant_consts(const mulan_desc* desc, const mulan_end_consts* consts);
+
 /* Host-only query: which mulan_fwd_pre kernel this descriptor selects on this host --
  * 0 generic (windowed log-softmax over the vocab bins), 1 closed-form 3-bin reconstruction term
  * with the launch constants in the parameter bank, 2 the same with the constants of the shipped

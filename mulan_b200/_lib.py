@@ -29,6 +29,14 @@ class MulanDesc(C.Structure):
               ('gamma_min', C.c_double), ('gamma_max', C.c_double)]
 
 
+class MulanEndConsts(C.Structure):
+  """struct mulan_end_consts: the fixed-end transcendental constants as the caller's framework
+  evaluates them in float32 (mulan_fwd_pre_consts)."""
+  _fields_ = [('exp_half_g0', C.c_float), ('exp_neg_half_g0', C.c_float),
+              ('sigmoid_g0', C.c_float), ('sigmoid_g1', C.c_float),
+              ('log_sigmoid_g1', C.c_float)]
+
+
 class MulanAdamwDesc(C.Structure):
   """struct mulan_adamw_desc."""
   _fields_ = [('n', C.c_int64), ('n_decay', C.c_int64), ('step', C.c_int32),
@@ -57,6 +65,9 @@ SIGNATURES = {
     'mulan_kernel_param': ([C.c_int32], C.c_int),
     'mulan_fwd_pre': ([_D] + [_P] * 14, C.c_int),
     'mulan_fwd_pre_variant': ([_D], C.c_int),
+    'mulan_fwd_pre_consts': ([_D, _P] + [_P] * 14, C.c_int),
+    'mulan_host_end_consts': ([_D, _P], C.c_int),
+    'mulan_fwd_pre_variant_consts': ([_D, _P], C.c_int),
     'mulan_fwd_post': ([_D] + [_P] * 10, C.c_int),
     'mulan_bwd_post': ([_D] + [_P] * 11, C.c_int),
     'mulan_fwd_bwd_post': ([_D] + [_P] * 12, C.c_int),

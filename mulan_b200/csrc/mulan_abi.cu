@@ -141,6 +141,71 @@ int mulan_fwd_pre(const mulan_desc* d, const uint8_t* x, const float* a, const f
   return e == cudaSuccess ? 0 : cuda_fail(fn, e);
 }
 
+// Launch constants of fwd_pre for a descriptor, optionally with caller-supplied end constants.
+static void fill_pre_consts(const mulan_desc* d, const mulan_end_consts* kc, mulan::FwdPreParams* p) {
+  p->W = recon_window(d);
+  p->gmin = f32_gmin(d); p->delta = f32_delta(d);
+  p->k = mulan::make_end_consts(p->gmin, p->delta);
+  if (kc != nullptr) {
+    p->k.s0 = kc->exp_half_g0; p->k.inv0 = kc->exp_neg_half_g0; p->k.v0 = kc->sigmoid_g0;
+    p->k.v1 = kc->sigmoid_g1; p->k.om1 = 1.0f - kc->sigmoid_g1; p->k.lv1 = kc->log_sigmoid_g1;
+  }
+  p->vi = mulan::make_vocab(d->vocab);
+  p->rc = mulan::make_recon_fast(p->k, p->vi);
+}
+
+int mulan_host_end_consts(const mulan_desc* d, mulan_end_consts* out) {
+  const char* fn = "mulan_host_end_consts";
+  if (int r = check_desc(d, fn)) return r;
+  REQ_PTR(out, fn);
+  const mulan::EndConsts k = mulan::make_end_consts(f32_gmin(d), f32_delta(d));
+  out->exp_half_g0 = k.s0; out->exp_neg_half_g0 = k.inv0; out->sigmoid_g0 = k.v0;
+  out->sigmoid_g1 = k.v1; out->log_sigmoid_g1 = k.lv1;
+  return 0;
+}
+
+int mulan_fwd_pre_variant_consts(const mulan_desc* d, const mulan_end_consts* kc) {
+  const char* fn = "mulan_fwd_pre_variant_consts";
+  if (int r = check_desc(d, fn)) return r;
+  mulan::FwdPreParams p;
+  memset(&p, 0, sizeof(p));
+  fill_pre_consts(d, kc, &p);
+  return mulan::fwd_pre_variant(p);
+}
+
+int mulan_fwd_pre_consts(const mulan_desc* d, const mulan_end_consts* kc, const uint8_t* x,
+                         const float* a, const float* b, const float* c, const float* t,
+                         const float* eps0, const float* eps, float* z_t, float* g_net,
+                         float* w_save, float* loss_recon, float* loss_klz_prior, float* var_sums,
+                         void* stream) {
+  const char* fn = "mulan_fwd_pre_consts";
+  if (kc == nullptr)
+    return mulan_fwd_pre(d, x, a, b, c, t, eps0, eps, z_t, g_net, w_save, loss_recon,
+                         loss_klz_prior, var_sums, stream);
+  if (int r = check_desc(d, fn)) return r;
+  if (d->n_timesteps > 0)
+    return fail(MULAN_ERR_UNSUPPORTED, "%s: use mulan_fwd_pre for sm_n_timesteps > 0", fn);
+  if (!(kc->exp_half_g0 > 0.f) || !(kc->exp_neg_half_g0 > 0.f) || !(kc->sigmoid_g0 > 0.f) ||
+      !(kc->sigmoid_g1 > 0.f) || !(kc->sigmoid_g1 <= 1.f) || !(kc->log_sigmoid_g1 <= 0.f))
+    return fail(MULAN_ERR_INVALID_ARG, "%s: end constants out of range", fn);
+  if (d->rows == 0) return 0;
+  REQ_X(x, fn);
+  REQ_VEC(a, fn); REQ_VEC(b, fn); REQ_VEC(c, fn); REQ_PTR(t, fn);
+  REQ_VEC(eps0, fn); REQ_VEC(eps, fn); REQ_VEC(z_t, fn);
+  REQ_PTR(g_net, fn); OPT_VEC(w_save, fn);
+  if (d->gt_mode == MULAN_GT_PIXEL) REQ_VEC(g_net, fn);
+  REQ_PTR(loss_recon, fn); REQ_PTR(loss_klz_prior, fn); REQ_PTR(var_sums, fn);
+  mulan::FwdPreParams p;
+  memset(&p, 0, sizeof(p));
+  p.x = x; p.a = a; p.b = b; p.c = c; p.t = t; p.eps0 = eps0; p.eps = eps;
+  p.z_t = z_t; p.g_net = g_net; p.w_save = w_save;
+  p.loss_recon = loss_recon; p.loss_klz = loss_klz_prior; p.var_sums = var_sums;
+  p.rows = d->rows; p.dim4 = d->dim / 4; p.gt_mode = d->gt_mode;
+  fill_pre_consts(d, kc, &p);
+  cudaError_t e = mulan::launch_fwd_pre(p, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(fn, e);
+}
+
 int mulan_fwd_pre_variant(const mulan_desc* d) {
   const char* fn = "mulan_fwd_pre_variant";
   if (int r = check_desc(d, fn)) return r;

@@ -71,8 +71,10 @@ def saves_w(desc: 'Desc') -> bool:
 # Raw launches (no autograd)
 # ------------------------------------------------------------------------------------
 
-def fwd_pre(desc: Desc, x, a, b, c, t, eps0, eps, save_w: bool = True):
-  """mulan_fwd_pre. Returns dict(z_t, g_net, w, loss_recon, loss_klz_prior, var_sums)."""
+def fwd_pre(desc: Desc, x, a, b, c, t, eps0, eps, save_w: bool = True, end_consts=None):
+  """mulan_fwd_pre. Returns dict(z_t, g_net, w, loss_recon, loss_klz_prior, var_sums).
+  end_consts (_lib.MulanEndConsts, optional): the fixed-end constants as the caller's framework
+  rounds them (mulan_fwd_pre_consts) instead of the host-computed, correctly rounded ones."""
   B, D = a.shape
   _req(x, torch.uint8, (B, D), 'x')
   for n, v in (('a', a), ('b', b), ('c', c), ('eps0', eps0), ('eps', eps)):
@@ -87,9 +89,12 @@ def fwd_pre(desc: Desc, x, a, b, c, t, eps0, eps, save_w: bool = True):
   klz = torch.empty((B,), dtype=torch.float32, device=dev)
   vs = torch.empty((B, 2), dtype=torch.float32, device=dev)
   d = desc.c(B)
-  _lib.check(_lib.load().mulan_fwd_pre(
-      C.byref(d), _p(x), _p(a), _p(b), _p(c), _p(t), _p(eps0), _p(eps),
-      _p(z_t), _p(g_net), _p(w), _p(rec), _p(klz), _p(vs), _stream()))
+  args = (_p(x), _p(a), _p(b), _p(c), _p(t), _p(eps0), _p(eps),
+          _p(z_t), _p(g_net), _p(w), _p(rec), _p(klz), _p(vs), _stream())
+  if end_consts is None:
+    _lib.check(_lib.load().mulan_fwd_pre(C.byref(d), *args))
+  else:
+    _lib.check(_lib.load().mulan_fwd_pre_consts(C.byref(d), C.byref(end_consts), *args))
   return dict(z_t=z_t, g_net=g_net, w=w, loss_recon=rec, loss_klz_prior=klz, var_sums=vs)
 
 

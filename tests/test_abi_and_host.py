@@ -98,6 +98,38 @@ def test_shipped_configuration_selects_the_specialised_fwd_pre(lib):
   assert h.mulan_fwd_pre_variant(C.byref(lib.make_desc(rows=1, vocab=1))) == -1
 
 
+def test_end_constants_can_be_supplied_by_the_caller(lib):
+  """mulan_fwd_pre_consts: host-side plumbing (no device needed).  The library's own constants
+  are the correctly rounded ones quoted in DESIGN.md section 2; supplying them back selects the
+  same (immediates) kernel, a one-ulp different exp(-g_0/2) -- what numpy's float32 exp returns --
+  selects the parameter-bank kernel."""
+  h = lib.load()
+  d = lib.make_desc(rows=1)
+  k = lib.MulanEndConsts()
+  assert h.mulan_host_end_consts(C.byref(d), C.byref(k)) == 0
+  assert float(k.exp_neg_half_g0).hex() == '0x1.8264680000000p+9'
+  assert float(k.exp_half_g0).hex() == '0x1.5338580000000p-10'
+  assert abs(k.sigmoid_g1 - 1 / (1 + np.exp(-5.0))) < 1e-7
+  assert abs(k.log_sigmoid_g1 - np.log(k.sigmoid_g1)) < 1e-9
+  assert h.mulan_fwd_pre_variant_consts(C.byref(d), None) == 2
+  assert h.mulan_fwd_pre_variant_consts(C.byref(d), C.byref(k)) == 2
+  k2 = lib.MulanEndConsts.from_buffer_copy(k)
+  k2.exp_neg_half_g0 = float(np.nextafter(np.float32(k.exp_neg_half_g0), np.float32(0)))
+  assert float(k2.exp_neg_half_g0).hex() == '0x1.8264660000000p+9'
+  assert h.mulan_fwd_pre_variant_consts(C.byref(d), C.byref(k2)) == 1
+  # validation
+  bad = lib.MulanEndConsts.from_buffer_copy(k)
+  bad.sigmoid_g1 = 1.5
+  assert h.mulan_fwd_pre_consts(C.byref(d), C.byref(bad), *([None] * 14)) == -1
+  assert b'end constants out of range' in h.mulan_last_error()
+  assert h.mulan_fwd_pre_consts(C.byref(d), C.byref(k), *([None] * 14)) == -1
+  assert b'x is NULL' in h.mulan_last_error()
+  assert h.mulan_fwd_pre_consts(C.byref(d), None, *([None] * 14)) == -1      # == mulan_fwd_pre
+  assert b'mulan_fwd_pre: x is NULL' in h.mulan_last_error()
+  dT = lib.make_desc(rows=1, n_timesteps=10)
+  assert h.mulan_fwd_pre_consts(C.byref(dT), C.byref(k), *([None] * 14)) == -3
+
+
 def test_ops_refuse_cpu_tensors(lib):
   from mulan_b200 import ops
   z = torch.zeros(2, 3072)

@@ -116,9 +116,10 @@ int mulan_fwd_pre(const mulan_desc* desc,
  * mulan_fwd_pre_consts -- mulan_fwd_pre with the five transcendental constants of the fixed
  * schedule ends SUPPLIED by the caller, as the caller's framework evaluates them in float32,
  * instead of computed on the host (double, rounded once = correctly rounded).  The reference's
- * own loss_recon depends on how its platform rounds exp(-g_0/2): the exact value lies 0.40 ulp
- * from the correctly rounded float and one ulp moves a row's loss_recon by up to 1.8e-5 relative
- * (DESIGN.md section 2), so a binding that wants to match ITS platform bit for rounding passes
+ * own loss_recon depends on how its platform rounds them: one ulp of exp(g_0/2) moves a row's
+ * loss_recon by up to 1.8e-5 relative, and for exp(-g_0/2) the exact value lies 0.40 ulp from the
+ * correctly rounded float, where float32 exp implementations already disagree (DESIGN.md
+ * section 2).  A binding that wants to match ITS platform bit for rounding passes
  *   exp_half_g0 = exp(.5 g_0), exp_neg_half_g0 = exp(-.5 g_0), sigmoid_g0, sigmoid_g1 =
  *   sigmoid(g_min + (g_max - g_min)), log_sigmoid_g1 = log(sigmoid_g1)     with g_0 = f32(g_min)
  * evaluated once by its own exp / log (ldm/model_mulan_epsilon.py:311-325; model_vdm.py:286).

@@ -26,6 +26,7 @@ for _name in ('MulanFwdPre', 'MulanFwdPost', 'MulanBwdPost', 'MulanBwdPre'):
 def _attrs(cfg, param):
   return dict(vocab=np.int32(cfg.vocab_size), param=np.int32(param),
               gt_mode=np.int32(0 if cfg.unet_type == 'vdm' else 1),
+              n_timesteps=np.int32(cfg.sm_n_timesteps),     # every handler: T scales the loss
               gamma_min=np.float64(cfg.gamma_min), gamma_max=np.float64(cfg.gamma_max))
 
 
@@ -40,7 +41,7 @@ def _pre_fwd(cfg, param, x, a, b, c, t, eps0, eps):
   g_shape = (B,) if cfg.unet_type == 'vdm' else (B, D)
   z_t, g_net, w, rec, klz, var_sums = jax.ffi.ffi_call(
       'MulanFwdPre', (f32(B, D), f32(*g_shape), f32(B, D), f32(B), f32(B), f32(B, 2)))(
-          x, a, b, c, t, eps0, eps, n_timesteps=np.int32(cfg.sm_n_timesteps), **_attrs(cfg, param))
+          x, a, b, c, t, eps0, eps, **_attrs(cfg, param))
   return (z_t, g_net, rec, klz, var_sums, w), (x, a, b, c, t, eps)
 
 

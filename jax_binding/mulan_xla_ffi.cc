@@ -71,9 +71,12 @@ static ffi::Error FwdPostImpl(cudaStream_t stream, ffi::Buffer<ffi::U8> x, ffi::
                               ffi::Buffer<ffi::F32> t, ffi::Buffer<ffi::F32> eps,
                               ffi::Buffer<ffi::F32> net, ffi::Buffer<ffi::F32> w,
                               ffi::ResultBuffer<ffi::F32> loss_diff, int32_t vocab, int32_t param,
-                              int32_t gt_mode, double gamma_min, double gamma_max) {
+                              int32_t gt_mode, int32_t n_timesteps, double gamma_min,
+                              double gamma_max) {
   auto dims = a.dimensions();
-  mulan_desc d = MakeDesc(dims[0], dims[1], vocab, param, gt_mode, 0, gamma_min, gamma_max);
+  // n_timesteps > 0: the loss is .5 * T * sum(w ...) with the discrete weight fwd_pre saved
+  // (ldm/model_mulan_epsilon.py:348-355)
+  mulan_desc d = MakeDesc(dims[0], dims[1], vocab, param, gt_mode, n_timesteps, gamma_min, gamma_max);
   return Check(mulan_fwd_post(&d, x.typed_data(), a.typed_data(), b.typed_data(), c.typed_data(),
                               t.typed_data(), eps.typed_data(), net.typed_data(),
                               mulan_kernel_param(param) == MULAN_PARAM_EPS ? w.typed_data() : nullptr,
@@ -88,17 +91,17 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(
         .Arg<ffi::Buffer<ffi::F32>>().Arg<ffi::Buffer<ffi::F32>>()
         .Ret<ffi::Buffer<ffi::F32>>()
         .Attr<int32_t>("vocab").Attr<int32_t>("param").Attr<int32_t>("gt_mode")
-        .Attr<double>("gamma_min").Attr<double>("gamma_max"));
+        .Attr<int32_t>("n_timesteps").Attr<double>("gamma_min").Attr<double>("gamma_max"));
 
 static ffi::Error BwdPostImpl(cudaStream_t stream, ffi::Buffer<ffi::U8> x, ffi::Buffer<ffi::F32> a,
                               ffi::Buffer<ffi::F32> b, ffi::Buffer<ffi::F32> c,
                               ffi::Buffer<ffi::F32> t, ffi::Buffer<ffi::F32> eps,
                               ffi::Buffer<ffi::F32> net, ffi::Buffer<ffi::F32> w,
                               ffi::Buffer<ffi::F32> gL, ffi::ResultBuffer<ffi::F32> n_bar,
-                              int32_t vocab, int32_t param, int32_t gt_mode, double gamma_min,
-                              double gamma_max) {
+                              int32_t vocab, int32_t param, int32_t gt_mode, int32_t n_timesteps,
+                              double gamma_min, double gamma_max) {
   auto dims = a.dimensions();
-  mulan_desc d = MakeDesc(dims[0], dims[1], vocab, param, gt_mode, 0, gamma_min, gamma_max);
+  mulan_desc d = MakeDesc(dims[0], dims[1], vocab, param, gt_mode, n_timesteps, gamma_min, gamma_max);
   return Check(mulan_bwd_post(&d, x.typed_data(), a.typed_data(), b.typed_data(), c.typed_data(),
                               t.typed_data(), eps.typed_data(), net.typed_data(),
                               mulan_kernel_param(param) == MULAN_PARAM_EPS ? w.typed_data() : nullptr,
@@ -113,7 +116,7 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(
         .Arg<ffi::Buffer<ffi::F32>>().Arg<ffi::Buffer<ffi::F32>>().Arg<ffi::Buffer<ffi::F32>>()
         .Ret<ffi::Buffer<ffi::F32>>()
         .Attr<int32_t>("vocab").Attr<int32_t>("param").Attr<int32_t>("gt_mode")
-        .Attr<double>("gamma_min").Attr<double>("gamma_max"));
+        .Attr<int32_t>("n_timesteps").Attr<double>("gamma_min").Attr<double>("gamma_max"));
 
 // ---- bwd_pre: cotangents of (a, b, c) ----------------------------------------------------------
 static ffi::Error BwdPreImpl(cudaStream_t stream, ffi::Buffer<ffi::U8> x, ffi::Buffer<ffi::F32> a,
@@ -123,9 +126,11 @@ static ffi::Error BwdPreImpl(cudaStream_t stream, ffi::Buffer<ffi::U8> x, ffi::B
                              ffi::Buffer<ffi::F32> g_bar, ffi::Buffer<ffi::F32> gL,
                              ffi::ResultBuffer<ffi::F32> a_bar, ffi::ResultBuffer<ffi::F32> b_bar,
                              ffi::ResultBuffer<ffi::F32> c_bar, int32_t vocab, int32_t param,
-                             int32_t gt_mode, double gamma_min, double gamma_max) {
+                             int32_t gt_mode, int32_t n_timesteps, double gamma_min,
+                             double gamma_max) {
   auto dims = a.dimensions();
-  mulan_desc d = MakeDesc(dims[0], dims[1], vocab, param, gt_mode, 0, gamma_min, gamma_max);
+  // n_timesteps > 0 selects the discrete-time branch of the backward (expm1 weight)
+  mulan_desc d = MakeDesc(dims[0], dims[1], vocab, param, gt_mode, n_timesteps, gamma_min, gamma_max);
   return Check(mulan_bwd_pre(&d, x.typed_data(), a.typed_data(), b.typed_data(), c.typed_data(),
                              t.typed_data(), eps.typed_data(), net.typed_data(),
                              z_bar.typed_data(), g_bar.typed_data(), gL.typed_data(),
@@ -141,4 +146,4 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(
         .Arg<ffi::Buffer<ffi::F32>>()
         .Ret<ffi::Buffer<ffi::F32>>().Ret<ffi::Buffer<ffi::F32>>().Ret<ffi::Buffer<ffi::F32>>()
         .Attr<int32_t>("vocab").Attr<int32_t>("param").Attr<int32_t>("gt_mode")
-        .Attr<double>("gamma_min").Attr<double>("gamma_max"));
+        .Attr<int32_t>("n_timesteps").Attr<double>("gamma_min").Attr<double>("gamma_max"));

@@ -56,12 +56,7 @@ thread_local char g_host_err[256] = "";   // scratch; published via mulan::set_l
     }                                                                   \
   } while (0)
 
-int ensure_ws(HostWs& ws, size_t B, int dim) {
-  int dev = 0;
-  CU(cudaGetDevice(&dev));
-  if (ws.device == dev && ws.cap_rows >= B && ws.dim == dim) return 0;
-  ws.release();
-  ws.device = dev; ws.cap_rows = B; ws.dim = dim;
+int alloc_ws(HostWs& ws, size_t B, int dim) {
   const size_t N = B * (size_t)dim;
   CU(cudaStreamCreateWithFlags(&ws.s_in, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&ws.s_cmp, cudaStreamNonBlocking));
@@ -76,6 +71,32 @@ int ensure_ws(HostWs& ws, size_t B, int dim) {
   CU(cudaMalloc(&ws.d_row, (8 * B + 8) * sizeof(float)));
   CU(cudaMallocHost(&ws.h_gl, B * sizeof(float)));
   return 0;
+}
+
+// The workspace is marked valid (device / cap_rows / dim) only after EVERY allocation has
+// succeeded; a failure midway (e.g. cudaMalloc out of memory) releases the partial state, so the
+// next call starts from scratch instead of finding NULL pointers behind a matching shape.
+int ensure_ws(HostWs& ws, size_t B, int dim) {
+  int dev = 0;
+  CU(cudaGetDevice(&dev));
+  if (ws.device == dev && ws.cap_rows >= B && ws.dim == dim) return 0;
+  ws.release();
+  if (int r = alloc_ws(ws, B, dim)) {
+    ws.release();
+    cudaGetLastError();   // clear the sticky-free error state of the failed allocation
+    return r;
+  }
+  ws.device = dev; ws.cap_rows = B; ws.dim = dim;
+  return 0;
+}
+
+// Error exit of the pipeline: copies already enqueued still read / write the CALLER's host
+// buffers, so drain the three streams before handing control (and those buffers) back.
+int drain(HostWs& ws, int status) {
+  if (ws.s_in) cudaStreamSynchronize(ws.s_in);
+  if (ws.s_cmp) cudaStreamSynchronize(ws.s_cmp);
+  if (ws.s_out) cudaStreamSynchronize(ws.s_out);
+  return status;
 }
 
 }  // namespace
@@ -116,6 +137,16 @@ static int elbo_host_impl(const mulan_desc* d, const uint8_t* x, const float* a,
   const size_t B = (size_t)d->rows, D = (size_t)d->dim, N = B * D;
   HostWs& ws = g_ws;
   if (int r = ensure_ws(ws, B, d->dim)) return r;
+#undef CU
+#define CU(call)                                                        \
+  do {                                                                  \
+    cudaError_t e_ = (call);                                            \
+    if (e_ != cudaSuccess) {                                            \
+      snprintf(g_host_err, sizeof(g_host_err), "mulan_elbo_host: %s", cudaGetErrorString(e_)); \
+      mulan::set_last_error(g_host_err);                                \
+      return drain(ws, (int)MULAN_ERR_CUDA);                            \
+    }                                                                   \
+  } while (0)
 
   float* dA = ws.d_f + 0 * N; float* dB = ws.d_f + 1 * N; float* dC = ws.d_f + 2 * N;
   float* dE0 = ws.d_f + 3 * N; float* dE = ws.d_f + 4 * N; float* dN = ws.d_f + 5 * N;
@@ -143,7 +174,7 @@ static int elbo_host_impl(const mulan_desc* d, const uint8_t* x, const float* a,
   if (keyed) {
     // whole-batch draws (JAX's counter layout pairs element i with element i + N/2, so a draw
     // cannot be generated chunk by chunk without doing every block twice)
-    if (N >= 0xffffffffULL) return bad("keyed draws need rows * dim < 2^32 - 1");
+    if (N >= 0xffffffffULL) return drain(ws, bad("keyed draws need rows * dim < 2^32 - 1"));
     // jax.random.normal: sqrt(2) erf_inv(uniform on [nextafter(-1, 0), 1)), as mulan_rng_normal
     const float lo = nextafterf(-1.0f, 0.0f);
     cudaError_t e = mulan::launch_rng_draw(2, key_eps0[0], key_eps0[1], (long long)N, lo, 1.0f,
@@ -174,12 +205,12 @@ static int elbo_host_impl(const mulan_desc* d, const uint8_t* x, const float* a,
     float* w_save = save_w ? dW + o : nullptr;
     int r = mulan_fwd_pre(&dc, ws.d_x + o, dA + o, dB + o, dC + o, dT + r0, dE0 + o, dE + o, dZ + o,
                           dG + r0, w_save, dRec + r0, dKlz + r0, dVar + 2 * r0, sc);
-    if (r) return r;   // mulan_last_error() already holds the entry point's message
+    if (r) return drain(ws, r);   // mulan_last_error() already holds the entry point's message
     if (denoiser != nullptr) {
       if (int rc = denoiser(user, (int32_t)nr, dZ + o, dG + r0, dN + o, sc)) {
         snprintf(g_host_err, sizeof(g_host_err), "mulan_elbo_host: denoiser callback returned %d", rc);
         mulan::set_last_error(g_host_err);
-        return (int)MULAN_ERR_INVALID_ARG;
+        return drain(ws, (int)MULAN_ERR_INVALID_ARG);
       }
     }
     if (!want_grad) {
@@ -193,7 +224,7 @@ static int elbo_host_impl(const mulan_desc* d, const uint8_t* x, const float* a,
         r = mulan_bwd_pre(&dc, ws.d_x + o, dA + o, dB + o, dC + o, dT + r0, dE + o, dN + o, nullptr,
                           nullptr, dGL + r0, dAB + o, dBB + o, dCB + o, sc);
     }
-    if (r) return r;   // mulan_last_error() already holds the entry point's message
+    if (r) return drain(ws, r);   // mulan_last_error() already holds the entry point's message
     CU(cudaEventRecord(ws.ev_cmp[ci], ws.s_cmp));
     // ---- copy-out stream
     if (want_grad) {
@@ -208,7 +239,7 @@ static int elbo_host_impl(const mulan_desc* d, const uint8_t* x, const float* a,
   }
   // ---- tail: the six scalars over ALL rows, then losses + scalars back
   int r = mulan_bpd_reduce(d, dRec, dKlz, nullptr, dDiff, dVar, dSc, nullptr, (void*)ws.s_cmp);
-  if (r) return r;
+  if (r) return drain(ws, r);
   CU(cudaMemcpyAsync(losses, dRec, 3 * B * sizeof(float), cudaMemcpyDeviceToHost, ws.s_cmp));
   CU(cudaMemcpyAsync(scalars, dSc, 6 * sizeof(float), cudaMemcpyDeviceToHost, ws.s_cmp));
   CU(cudaStreamSynchronize(ws.s_cmp));

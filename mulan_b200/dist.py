@@ -134,15 +134,13 @@ def eval_bpd_dense_sampling(model, images: torch.Tensor, n_timesteps: int = 128,
     chunk = mine[s:s + images_per_launch]
     m = chunk.shape[0]
     tiled = chunk.repeat_interleave(n_timesteps, dim=0)   # image-major: rows of one image adjacent
-    draws = dict(t0=t_img.repeat(m), G=base['G'].repeat(1, m, 1),
+    G = base['G']
+    # latent noise: [10, n, L] for the gamma draw (tile axis 1), [n, L] for the gumbel /
+    # gaussian / additive-noise variants (tile axis 0)
+    G = G.repeat(1, m, 1) if G.dim() == 3 else G.repeat(m, 1)
+    draws = dict(t=t_img.repeat(m), G=G,
                  eps_0=base['eps_0'].repeat(m, 1, 1, 1), eps=base['eps'].repeat(m, 1, 1, 1))
-    was = cfg.antithetic_time_sampling
-    cfg.antithetic_time_sampling = False                  # t supplied per row
-    try:
-      out = model(tiled, labels=None, conditioning=None, step=0, deterministic=True,
-                  draws=draws)
-    finally:
-      cfg.antithetic_time_sampling = was
+    out = model(tiled, labels=None, conditioning=None, step=0, deterministic=True, draws=draws)
     per_row = out.loss_recon + out.loss_klz + out.loss_diff
     # per image: mean over its rows of each term, summed (ldm/experiment_vdm.py:62-66)
     bpds.append(per_row.reshape(m, n_timesteps).mean(dim=1) * rescale)

@@ -110,10 +110,15 @@ class NoiseSchedule_polynomial_fixedend(nn.Module):
 
 
 def sample_t(t0: torch.Tensor, n_batch: int, config: VDMConfig) -> torch.Tensor:
-  """ldm/model_mulan_epsilon.py:287-297: antithetic t from the scalar draw t0
-  (jnp.arange with float arguments is np.arange in double, cast to float32)."""
-  ar = torch.from_numpy(np.arange(0., 1., step=1. / n_batch).astype(np.float32)).to(t0.device)
-  t = torch.remainder(t0.to(torch.float32) + ar, 1.)
+  """ldm/model_mulan_epsilon.py:287-297.  antithetic_time_sampling: t from the SCALAR draw t0
+  (jnp.arange with float arguments is np.arange in double, cast to float32); otherwise t0 is
+  the [n_batch] uniform draw itself.  Both branches are discretised when sm_n_timesteps > 0
+  (:294-297)."""
+  if config.antithetic_time_sampling:
+    ar = torch.from_numpy(np.arange(0., 1., step=1. / n_batch).astype(np.float32)).to(t0.device)
+    t = torch.remainder(t0.to(torch.float32).reshape(()) + ar, 1.)
+  else:
+    t = t0.to(torch.float32).reshape(n_batch)
   T = config.sm_n_timesteps
   if T > 0:
     t = torch.ceil(t * T) / T
@@ -195,8 +200,10 @@ class VDM(nn.Module):
     g = generator
     cfg = self.config
     L = cfg.latent_size
+    # :287-292: a scalar draw for antithetic sampling, one uniform per example otherwise
+    t_shape = () if cfg.antithetic_time_sampling else (n_batch,)
     if jax_keys is None:
-      t0 = torch.rand((), generator=g, device=device)
+      t0 = torch.rand(t_shape, generator=g, device=device)
     if cfg.latent_type == 'topk' and cfg.topk_noise_type == 'gamma':
       G = gamma_draw((10, n_batch, L), cfg.latent_k, g, device)          # jax.random.gamma
     elif cfg.latent_type == 'gaussian':
@@ -206,7 +213,7 @@ class VDM(nn.Module):
       G = -torch.log(-torch.log(u))
     if jax_keys is not None:
       shape = (n_batch, 32, 32, 3)
-      return dict(t0=ops.rng_uniform(jax_keys['t0'], (), device=device), G=G,
+      return dict(t0=ops.rng_uniform(jax_keys['t0'], t_shape, device=device), G=G,
                   eps_0=ops.rng_normal(jax_keys['eps_0'], shape, device=device),
                   eps=ops.rng_normal(jax_keys['eps'], shape, device=device))
     return dict(
@@ -239,10 +246,12 @@ class VDM(nn.Module):
     if draws is None:
       draws = self.make_draws(n_batch, dev, generator)
     D = 32 * 32 * 3
-    if cfg.antithetic_time_sampling:
-      t = sample_t(draws['t0'], n_batch, cfg)
+    if 't' in draws:
+      # per-row times supplied ready-made (the batched dense-VLB driver tiles one image's
+      # antithetic t over several images, dist.eval_bpd_dense_sampling)
+      t = draws['t'].to(torch.float32).reshape(n_batch).contiguous()
     else:
-      t = draws['t0'].to(torch.float32).reshape(n_batch).contiguous()
+      t = sample_t(draws['t0'], n_batch, cfg)
 
     x_u8 = x.to(torch.uint8).reshape(n_batch, D).contiguous()
     orig_f = self.encdec.encode(x)

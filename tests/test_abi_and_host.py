@@ -158,6 +158,25 @@ def test_sample_t_matches_oracle():
   assert torch.equal(got, O.sample_t(0.37, 8, O.OracleConfig(sm_n_timesteps=10)))
 
 
+def test_non_antithetic_time_sampling():
+  """ldm/model_mulan_epsilon.py:291-297: without antithetic sampling t is one uniform draw PER
+  EXAMPLE, and it is discretised like the antithetic branch when sm_n_timesteps > 0."""
+  from mulan_b200.model import VDM, VDMConfig, sample_t
+  cfg = VDMConfig(antithetic_time_sampling=False, sm_n_timesteps=10)
+  f = lambda *a, **k: None
+  model = VDM(cfg, f, f)
+  draws = model.make_draws(5, 'cpu', torch.Generator().manual_seed(0))
+  assert tuple(draws['t0'].shape) == (5,)
+  t = sample_t(draws['t0'], 5, cfg)
+  assert tuple(t.shape) == (5,)
+  assert torch.equal(t, torch.ceil(draws['t0'] * 10) / 10)
+  assert len(set(t.tolist())) > 1
+  cfg0 = VDMConfig(antithetic_time_sampling=False)
+  assert torch.equal(sample_t(draws['t0'], 5, cfg0), draws['t0'])
+  # antithetic: still the scalar draw
+  assert tuple(VDM(VDMConfig(), f, f).make_draws(5, 'cpu')['t0'].shape) == ()
+
+
 def test_model_rejects_off_path_configs():
   from mulan_b200.model import VDM, VDMConfig
   f = lambda *a, **k: None
@@ -233,8 +252,7 @@ class _CpuStubVDM(torch.nn.Module):
     B = images.shape[0]
     if draws is None:
       draws = self.make_draws(B, images.device, generator)
-    t = (sample_t(draws['t0'], B, self.config) if self.config.antithetic_time_sampling
-         else draws['t0'].reshape(B))
+    t = draws['t'].reshape(B) if 't' in draws else sample_t(draws['t0'], B, self.config)
     pix = images.reshape(B, -1).float() / 255.0
     a = pix * self.head.weight[0, 0] + 0.3
     b = pix * self.head.weight[1, 1] - 0.2

@@ -109,7 +109,7 @@ def cuda_fns():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize('case', CASES)
-def test_cuda_latent_variants_match_reference_golden(case):
+def test_cuda_latent_variants_match_reference_golden(case, cuda_device):
   got = run_case(case, cuda_fns(), torch.float32, 'cuda')
   for k, v in got.items():
     want64 = GOLD[f'{case}_f64_{k}']
@@ -121,7 +121,7 @@ def test_cuda_latent_variants_match_reference_golden(case):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize('rows', [1, 37, 1024])
-def test_cuda_latent_variants_match_oracle_autograd(rows):
+def test_cuda_latent_variants_match_oracle_autograd(rows, cuda_device):
   g = torch.Generator().manual_seed(7 + rows)
   logits = 3.0 * torch.randn(rows, L, generator=g)
   noise = -torch.log(-torch.log(torch.rand(rows, L, generator=g).clamp_min(1e-20)))
@@ -161,7 +161,7 @@ def test_cuda_latent_variants_match_oracle_autograd(rows):
 
 
 @pytest.mark.gpu
-def test_cuda_latent_variants_none_cotangents():
+def test_cuda_latent_variants_none_cotangents(cuda_device):
   """Only one of (embedding, kl_z) reaching the loss must still give the right gradient."""
   topk_add, gumbel, gaussian = cuda_fns()
   g = torch.Generator().manual_seed(3)
@@ -179,7 +179,7 @@ def test_cuda_latent_variants_none_cotangents():
 @pytest.mark.gpu
 @pytest.mark.parametrize('latent_type,noise_type', [('gumbel', 'gamma'), ('gaussian', 'gamma'),
                                                     ('topk', 'gumbel')])
-def test_vdm_call_other_latent_types(latent_type, noise_type):
+def test_vdm_call_other_latent_types(latent_type, noise_type, cuda_device):
   """VDM.__call__ with the other latent types == the oracle's vdm_call (f64) with the matching
   latent_fn; encoder / denoiser are small closed-form stand-ins shared by both sides."""
   from mulan_b200.model import VDM, VDMConfig, loss_fn

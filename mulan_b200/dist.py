@@ -109,7 +109,8 @@ def train_step(model, optimizer, bucket: FlatGradBucket, batch: dict, step: int,
 
 @torch.no_grad()
 def eval_bpd_dense_sampling(model, images: torch.Tensor, n_timesteps: int = 128,
-                            images_per_launch: int = 16, seed: int = 0):
+                            images_per_launch: int = 16, seed: int = 0,
+                            base_draws: Optional[dict] = None):
   """eval_bpd_dense_sampling (ldm/notebook_utils.py:176-191), example-sharded.
 
   For every test image: tile it n_timesteps times (antithetic t gives a stratified
@@ -117,6 +118,8 @@ def eval_bpd_dense_sampling(model, images: torch.Tensor, n_timesteps: int = 128,
   and THE SAME key for every image (:178,:185), collect bpd; return the mean.
   `images` is this process's view of the whole test set [N,32,32,3] uint8; each rank takes
   images[rank::world], `images_per_launch` images (x n_timesteps rows) per kernel launch.
+  base_draws: the four draws of ONE loss_fn call over n_timesteps rows (model.make_draws);
+  default: drawn here from `seed` -- the reference uses PRNGKey(0) for every image.
   Returns (mean_bpd over all ranks' images, this rank's per-image bpds).
   """
   from .model import sample_t
@@ -126,8 +129,9 @@ def eval_bpd_dense_sampling(model, images: torch.Tensor, n_timesteps: int = 128,
   dev = mine.device
   cfg = model.config
   gen = torch.Generator(device=dev).manual_seed(seed)
-  base = model.make_draws(n_timesteps, dev, gen)          # one key for every image
-  t_img = sample_t(base['t0'], n_timesteps, cfg)
+  base = base_draws if base_draws is not None else model.make_draws(n_timesteps, dev, gen)
+  t_img = (base['t'].to(torch.float32).reshape(n_timesteps) if 't' in base
+           else sample_t(base['t0'], n_timesteps, cfg))   # one key for every image
   rescale = 1. / (np.prod(images.shape[1:]) * np.log(2.))
   bpds = []
   for s in range(0, mine.shape[0], images_per_launch):

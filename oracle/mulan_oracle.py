@@ -129,16 +129,18 @@ def encode(x, vocab_size: int, dtype=torch.float32):
   return 2 * ((xf + .5) / vocab_size) - 1
 
 
-def decode(z, g_0, vocab_size: int):
-  """model_vdm.py:282-294: 256-bin Gaussian-kernel logits -> log_softmax. [..., vocab]."""
+def decode(z, g_0, vocab_size: int, inv_stdev=None):
+  """model_vdm.py:282-294: 256-bin Gaussian-kernel logits -> log_softmax. [..., vocab].
+  inv_stdev: the platform's value of exp(-0.5 g_0) (see elbo_terms' end_consts)."""
   g_0 = g_0[..., None]
   x_vals = encode(torch.arange(0, vocab_size), vocab_size, z.dtype)  # same for all 3 channels
-  inv_stdev = torch.exp(-0.5 * g_0)
+  if inv_stdev is None:
+    inv_stdev = torch.exp(-0.5 * g_0)
   logits = -0.5 * torch.square((z[..., None] - x_vals) * inv_stdev)
   return log_softmax(logits, axis=-1)
 
 
-def logprob(x, z, g_0, vocab_size: int, chunk: int = 32):
+def logprob(x, z, g_0, vocab_size: int, chunk: int = 32, inv_stdev=None):
   """model_vdm.py:296-303: sum over all non-batch axes of onehot(x) * logprobs.
 
   Chunked over the batch so the [B, D, 256] intermediates stay small; each row's
@@ -150,7 +152,7 @@ def logprob(x, z, g_0, vocab_size: int, chunk: int = 32):
   gf = g_0.reshape(B, -1)
   outs = []
   for s in range(0, B, chunk):
-    lp = decode(zf[s:s + chunk], gf[s:s + chunk], vocab_size)
+    lp = decode(zf[s:s + chunk], gf[s:s + chunk], vocab_size, inv_stdev)
     onehot = torch.nn.functional.one_hot(xi[s:s + chunk], vocab_size).to(lp.dtype)
     outs.append(torch.sum(onehot * lp, dim=(1, 2)))
   return torch.cat(outs)
@@ -308,13 +310,21 @@ def score_model_gt(g_t, cfg: OracleConfig):
 
 def elbo_terms(x, a, b, c, t, eps_0, eps, score_fn: Callable, mode: int,
                cfg: OracleConfig, kl_z=None, dtype=torch.float32,
-               return_aux: bool = False):
+               return_aux: bool = False, end_consts: Optional[dict] = None):
   """The glue of VDM.__call__ once (a, b, c) and kl_z exist.
 
   x uint8 [B, ...]; a,b,c [B, D]; t [B]; eps_0, eps [B, ...];
   score_fn(z_t, g_for_net) -> network output shaped like z_t.
   Follows epsilon.py:300-363 (mode EPS) / velocity.py:208-268 (VEL*).
+
+  end_consts: how ANOTHER platform rounds the five transcendental constants of the fixed ends
+  (g_0 == gamma_min, g_1 == gamma_max +- 1 ulp for every sub-pixel): any of exp_half_g0,
+  exp_neg_half_g0, sigmoid_g0, sigmoid_g1, log_sigmoid_g1 replaces torch's value of that
+  expression -- the statements and their order stay the reference's.  Used to check
+  mulan_fwd_pre_consts (a binding handing over ITS framework's roundings).
   """
+  ec = end_consts or {}
+  kc = lambda name, like: torch.full_like(like, ec[name])
   shape = x.shape
   B = shape[0]
   orig_f = encode(x, cfg.vocab_size, dtype)                       # epsilon.py:300
@@ -324,15 +334,19 @@ def elbo_terms(x, a, b, c, t, eps_0, eps, score_fn: Callable, mode: int,
   g_1 = eval_polynomial(a, b, c, ones, cfg).reshape(shape)        # :308
   g_t = eval_polynomial(a, b, c, tt, cfg).reshape(shape)          # :309
   var_t = sigmoid(g_t)                                            # :311
-  var_0 = sigmoid(g_0)
-  var_1 = sigmoid(g_1)
+  var_0 = kc('sigmoid_g0', g_0) if 'sigmoid_g0' in ec else sigmoid(g_0)
+  var_1 = kc('sigmoid_g1', g_1) if 'sigmoid_g1' in ec else sigmoid(g_1)
   # 1. reconstruction loss                                        # :315-318
-  z_0_rescaled = orig_f + torch.exp(0.5 * g_0) * eps_0
-  loss_recon = -logprob(x, z_0_rescaled, g_0, cfg.vocab_size)
+  exp_half_g0 = kc('exp_half_g0', g_0) if 'exp_half_g0' in ec else torch.exp(0.5 * g_0)
+  z_0_rescaled = orig_f + exp_half_g0 * eps_0
+  inv_stdev = (kc('exp_neg_half_g0', g_0).reshape(shape[0], -1)[..., None]
+               if 'exp_neg_half_g0' in ec else None)
+  loss_recon = -logprob(x, z_0_rescaled, g_0, cfg.vocab_size, inv_stdev=inv_stdev)
   # 2. latent loss                                                # :322-325
   red = tuple(range(1, len(shape)))
   mean1_sqr = (1. - var_1) * torch.square(orig_f)
-  loss_klz = 0.5 * torch.sum(mean1_sqr + var_1 - torch.log(var_1) - 1., dim=red)
+  log_var_1 = kc('log_sigmoid_g1', g_1) if 'log_sigmoid_g1' in ec else torch.log(var_1)
+  loss_klz = 0.5 * torch.sum(mean1_sqr + var_1 - log_var_1 - 1., dim=red)
   # 3. diffusion loss                                             # :327-355
   z_t = torch.sqrt(1. - var_t) * orig_f + torch.sqrt(var_t) * eps
   net = score_fn(z_t, score_model_gt(g_t, cfg))
@@ -375,13 +389,20 @@ def vdm_call(images, draws: dict, coeff_fn: Callable, encoder_fn: Callable,
   pass latent_fn(orig_f, draws['G']) -> (embedding, kl_z) (epsilon.py:257-271).
 
   draws = {'t0': scalar, 'G': [10,B,L], 'eps_0': [B,32,32,3], 'eps': [B,32,32,3]}
-  in the order the reference calls make_rng('sample').
+  in the order the reference calls make_rng('sample').  With antithetic_time_sampling=False the
+  first draw is jax.random.uniform(rng1, shape=(n_batch,)) (epsilon.py:291-292): pass it as
+  draws['t'] ([B]); it is discretised like the antithetic one (:294-297).
   coeff_fn(embedding) -> (a, b, c);  encoder_fn(orig_f) -> logits [B, L];
   score_fn(z_t, g_for_net, conditioning) -> net output.
   """
   x = images.reshape(-1, 32, 32, 3)                               # :282
   n_batch = x.shape[0]
-  t = sample_t(draws['t0'], n_batch, cfg, dtype)                  # :287-297
+  if 't' in draws:                                                # :291-292
+    t = torch.as_tensor(draws['t']).to(dtype).reshape(n_batch)
+    if cfg.sm_n_timesteps > 0:
+      t = torch.ceil(t * cfg.sm_n_timesteps) / cfg.sm_n_timesteps
+  else:
+    t = sample_t(draws['t0'], n_batch, cfg, dtype)                # :287-297
   orig_f = encode(x, cfg.vocab_size, dtype)
   if latent_fn is not None:
     embedding, kl_z = latent_fn(orig_f, draws['G'])

@@ -10,9 +10,6 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
   config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
-  config.addinivalue_line(
-      'markers', 'gpu_pending: GPU tests written after a round\'s GPU budget was spent -- not part '
-      'of `-m gpu` until they have been run once on a B200 (run with `-m gpu_pending`)')
 
 
 @pytest.fixture(scope='session')

@@ -604,3 +604,77 @@ def test_host_entry_keyed_draws(cuda_device):
   with pytest.raises(ValueError):
     host.elbo_host(npy['x'], npy['a'], npy['b'], npy['c'], npy['t'], e0, None, npy['net'],
                    jax_keys=(k0, k1))
+
+
+# ----------------------------------------------------------------------------------------
+# mulan_fwd_pre_consts: the five fixed-end constants as ANOTHER platform rounds them
+# ----------------------------------------------------------------------------------------
+_CONST_FIELDS = ('exp_half_g0', 'exp_neg_half_g0', 'sigmoid_g0', 'sigmoid_g1', 'log_sigmoid_g1')
+# which outputs a constant may move (everything else must stay bit-identical)
+_CONST_MOVES = {'exp_half_g0': {'loss_recon'}, 'exp_neg_half_g0': {'loss_recon'},
+                'sigmoid_g0': {'var_sums'}, 'sigmoid_g1': {'loss_klz_prior', 'var_sums'},
+                'log_sigmoid_g1': {'loss_klz_prior'}}
+
+
+def _own_consts(desc, B):
+  import ctypes as C
+  from mulan_b200 import _lib
+  k = _lib.MulanEndConsts()
+  d = desc.c(B)
+  assert _lib.load().mulan_host_end_consts(C.byref(d), C.byref(k)) == 0
+  return k
+
+
+def test_caller_supplied_end_constants_are_the_librarys_own(cuda_device):
+  """Handing the library's own constants back selects the same kernel and the same bits."""
+  from mulan_b200 import ops
+  B = 6
+  inp = O.synth_inputs(B, 71)
+  g = {k: v.to(cuda_device).contiguous() for k, v in inp.items()}
+  desc = ops.Desc()
+  args = (g['x'], g['a'], g['b'], g['c'], g['t'], g['eps_0'], g['eps'])
+  base = ops.fwd_pre(desc, *args)
+  same = ops.fwd_pre(desc, *args, end_consts=_own_consts(desc, B))
+  for key in base:
+    assert torch.equal(base[key], same[key]), key
+
+
+@pytest.mark.parametrize('field', _CONST_FIELDS)
+@pytest.mark.parametrize('ulps', [-1, 1])
+def test_caller_supplied_end_constants_track_the_oracle(cuda_device, field, ulps):
+  """One ulp of each constant, as a framework with a different exp / log would supply it
+  (ldm/model_mulan_epsilon.py:311-325, model_vdm.py:286): the CUDA result follows the oracle
+  evaluated with THE SAME constant to 1e-5, and only the outputs that constant feeds move."""
+  from mulan_b200 import _lib, ops
+  B = 6
+  inp = O.synth_inputs(B, 71)
+  g = {k: v.to(cuda_device).contiguous() for k, v in inp.items()}
+  desc = ops.Desc()
+  args = (g['x'], g['a'], g['b'], g['c'], g['t'], g['eps_0'], g['eps'])
+  base = ops.fwd_pre(desc, *args)
+  own = _own_consts(desc, B)
+  k2 = _lib.MulanEndConsts.from_buffer_copy(own)
+  v = np.float32(getattr(own, field))
+  moved_v = np.nextafter(v, np.float32(np.inf if ulps > 0 else -np.inf))
+  if field == 'sigmoid_g1' and moved_v > 1:
+    pytest.skip('sigmoid(g_1) + 1 ulp exceeds 1')
+  setattr(k2, field, float(moved_v))
+  got = ops.fwd_pre(desc, *args, end_consts=k2)
+  for key in base:
+    if key in _CONST_MOVES[field] or base[key] is None:
+      continue
+    assert torch.equal(base[key], got[key]), (field, key)
+  out, aux = O.elbo_terms(inp['x'], inp['a'], inp['b'], inp['c'], inp['t'], inp['eps_0'],
+                          inp['eps'], lambda z, gg: inp['net'], O.MODE_EPS, O.OracleConfig(),
+                          return_aux=True,
+                          end_consts={f: float(np.float32(getattr(k2, f))) for f in _CONST_FIELDS})
+  rel = lambda a_, b_: float(((a_.double().cpu() - b_.double()).abs() / b_.double().abs()).max())
+  assert rel(got['loss_recon'], out.loss_recon) < 1e-5
+  assert rel(got['loss_klz_prior'], aux['loss_klz_prior']) < 1e-5
+  D = inp['a'].shape[1]
+  assert abs(got['var_sums'][:, 0].sum().item() / (B * D) - out.var_0.item()) < 1e-6 * out.var_0.item()
+  assert abs(got['var_sums'][:, 1].sum().item() / (B * D) - out.var_1.item()) < 1e-6
+  # and the constant really is live: the output it feeds moved (or the move is below float32
+  # resolution of the row sum, which only exp(-g_0/2) can be)
+  moved = any(not torch.equal(base[key], got[key]) for key in _CONST_MOVES[field])
+  assert moved or field == 'exp_neg_half_g0', field

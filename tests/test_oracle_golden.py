@@ -171,6 +171,8 @@ def test_vfe_is_eps(name, full, tag, monkeypatch):
 @pytest.mark.parametrize('script,files', [
     ('make_golden.py', ['glue_eps', 'glue_vel', 'glue_vfe', 'full_eps', 'full_vfe',
                         'glue_eps_T1000', 'glue_vel_ldm']),
+    ('make_golden_configs.py', ['cfg1_eps_B8', 'cfg2_eps_B128', 'cfg3_vel_B128', 'cfg4_vfe_B256',
+                                'edge_eps', 'edge_vel', 'edge_vfe', 'dense_vel', 'dense_vfe']),
     ('make_golden_sampler.py', ['sampler']),
     ('make_golden_latent.py', ['latent'])])
 def test_committed_goldens_are_what_the_reference_source_produces(script, files, tmp_path):
@@ -216,3 +218,115 @@ def test_oracle_matches_reference_source_ldm(tag):
       assert np.linalg.norm(got) == 0
     else:
       assert _rel_l2(got, want) < (1e-4 if tag == 'f32' else 1e-9), (k, _rel_l2(got, want))
+
+
+# ----------------------------------------------------------------------------------------
+# Reference-source fixtures at BASELINE.json's batch sizes, on edge inputs and for the dense-VLB
+# tile (tests/golden/make_golden_configs.py)
+# ----------------------------------------------------------------------------------------
+
+def run_oracle_inputs(kind, inp, dtype, antithetic=True):
+  """The oracle on an explicit input dict (a, b, c, logits injected)."""
+  cfg = O.OracleConfig(antithetic_time_sampling=antithetic)
+  tt = lambda v: torch.from_numpy(np.asarray(v)).to(dtype)
+  leaf = lambda v: tt(v).requires_grad_(True)
+  w1, w2, w3, noise = tt(inp['w1']), tt(inp['w2']), tt(inp['w3']), tt(inp['noise'])
+  cap = {}
+
+  def score_fn(z, g, cond):
+    cap['z_t'], cap['g_net'] = z, g
+    return w1 * z + w2 * g.reshape(-1, 1, 1, 1) + w3 * cond.sum(dim=1).reshape(-1, 1, 1, 1) + noise
+  logits = leaf(inp['logits'])
+  a, b, c = leaf(inp['a']), leaf(inp['b']), leaf(inp['c'])
+  draws = dict(G=tt(inp['G']), eps_0=tt(inp['eps_0']), eps=tt(inp['eps']))
+  if 't' in inp:
+    draws['t'] = tt(inp['t'])
+  else:
+    draws['t0'] = tt(inp['t0'])
+  out = O.vdm_call(torch.from_numpy(np.asarray(inp['images'])), draws, lambda emb: (a, b, c),
+                   lambda f: logits, score_fn, MODES[kind], cfg, dtype=dtype)
+  bpd, _ = O.loss_fn_bpd(out)
+  ga, gb, gc, gl = torch.autograd.grad(bpd, [a, b, c, logits])
+  n = lambda v: v.detach().numpy()
+  return dict(loss_recon=n(out.loss_recon), loss_klz=n(out.loss_klz), loss_diff=n(out.loss_diff),
+              var_0=n(out.var_0), var_1=n(out.var_1), bpd=n(bpd), z_t=n(cap['z_t']),
+              g_net=n(cap['g_net']), grad_a=n(ga), grad_b=n(gb), grad_c=n(gc), grad_logits=n(gl))
+
+
+def check_compact(got, g, tag, key, rtol, row_scale=None):
+  """got [B, ...] against the compact statistics of a [B, D] golden tensor: per row, the error
+  seen through the K seeded projections (an unbiased estimate of |got - want|) stays below
+  rtol * max(|want|, row_scale)."""
+  c = GI.compact(np.asarray(got, np.float64))
+  want_n, want_p = g[f'{tag}_{key}_norm'], g[f'{tag}_{key}_proj']
+  err = np.sqrt(np.mean((c['proj'] - want_p) ** 2, axis=1))
+  scale = want_n if row_scale is None else np.maximum(want_n, row_scale)
+  assert np.all(err <= rtol * scale + 1e-300), (key, float(np.max(err / np.maximum(scale, 1e-300))))
+  return err / np.maximum(scale, 1e-300)
+
+
+def grad_row_scale(g, tag):
+  """Common scale of a row's coefficient gradients (a row where one of them vanishes
+  mathematically -- a = b = 0 makes gamma independent of c -- carries only rounding noise)."""
+  return np.max(np.stack([g[f'{tag}_grad_{k}_norm'] for k in 'abc']), axis=0)
+
+
+@pytest.mark.parametrize('name', list(GI.SIZE_CASES))
+def test_oracle_matches_reference_source_at_baseline_sizes(name):
+  kind, seed, B = GI.SIZE_CASES[name]
+  g = load(name)
+  tags = ('f32', 'f64') if B <= 8 else ('f32',)     # keep the CPU suite short
+  for tag in tags:
+    r = run_oracle_inputs(kind, GI.glue_inputs(seed, B), torch.float32 if tag == 'f32'
+                          else torch.float64)
+    rt = 2e-6 if tag == 'f32' else 1e-11
+    for k in ('loss_recon', 'loss_klz', 'loss_diff', 'bpd', 'var_0', 'var_1'):
+      _close(r[k], g[f'{tag}_{k}'], rt)
+    _close(r['g_net'], g[f'{tag}_g_net'], rt, atol=1e-6 if tag == 'f32' else 1e-12)
+    # rows whose t**n differs by an ulp (torch pow vs XLA's multiply chain) move z_t by ~1e-6
+    check_compact(r['z_t'], g, tag, 'z_t', 5e-6)
+    scale = grad_row_scale(g, tag)
+    for k in 'abc':
+      check_compact(r['grad_' + k], g, tag, 'grad_' + k, 1e-4 if tag == 'f32' else 1e-9, scale)
+    assert _rel_l2(r['grad_logits'], g[f'{tag}_grad_logits']) < (1e-4 if tag == 'f32' else 1e-9)
+
+
+@pytest.mark.parametrize('name', list(GI.EDGE_CASES))
+@pytest.mark.parametrize('tag', ['f32', 'f64'])
+def test_oracle_matches_reference_source_on_edge_inputs(name, tag):
+  kind, seed = GI.EDGE_CASES[name]
+  g = load(name)
+  r = run_oracle_inputs(kind, GI.edge_inputs(seed), torch.float32 if tag == 'f32'
+                        else torch.float64, antithetic=False)
+  rt = 2e-6 if tag == 'f32' else 1e-11
+  for k in ('loss_recon', 'loss_klz', 'loss_diff', 'bpd', 'var_0', 'var_1'):
+    assert np.all(np.isfinite(r[k]))
+    _close(r[k], g[f'{tag}_{k}'], rt)
+  _close(r['g_net'], g[f'{tag}_g_net'], rt, atol=1e-6 if tag == 'f32' else 1e-12)
+  scale = grad_row_scale(g, tag)
+  for k in 'abc':
+    check_compact(r['grad_' + k], g, tag, 'grad_' + k, 1e-4 if tag == 'f32' else 1e-9, scale)
+  if tag == 'f32':
+    assert _rel_l2(r['z_t'], g['f32_z_t']) < 1e-6
+
+
+@pytest.mark.parametrize('name', list(GI.DENSE_CASES))
+def test_oracle_dense_vlb_tile_matches_reference_source(name):
+  """O.eval_bpd_dense (ldm/notebook_utils.py:176-191) on the reference-source dense fixture."""
+  kind, seed = GI.DENSE_CASES[name]
+  g = load(name)
+  base, per_image = GI.dense_inputs(seed)
+  images = torch.from_numpy(np.concatenate([im['image'] for im in per_image]))
+  state = {'i': 0, 'rows': []}
+
+  def run_loss_fn(tiled):
+    im = per_image[state['i']]
+    state['i'] += 1
+    r = run_oracle_inputs(kind, dict(base, images=tiled.numpy(), a=im['a'], b=im['b'], c=im['c'],
+                                     logits=im['logits']), torch.float32)
+    state['rows'].append(np.stack([r['loss_recon'], r['loss_klz'], r['loss_diff']], axis=1))
+    return r['bpd']
+  mean_bpd, bpds = O.eval_bpd_dense(images, GI.DENSE_T, run_loss_fn)
+  _close(np.asarray(bpds), g['f32_bpd'], 2e-6)
+  _close(np.stack(state['rows']), g['f32_rows'], 2e-6)
+  assert abs(mean_bpd - float(np.mean(g['f64_bpd']))) < 1e-4

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MULAN_ABI_VERSION 1
+#define MULAN_ABI_VERSION 2   /* 2: mulan_desc gained flags + noise_rows; mulan_bpd_reduce a workspace */
 
 typedef enum mulan_status {
   MULAN_OK = 0,
@@ -55,6 +55,23 @@ typedef enum mulan_gt_mode {
   MULAN_GT_PIXEL = 1            /* unet_type='ldm': per-pixel gamma_t, [B,D]           */
 } mulan_gt_mode;
 
+/* mulan_desc.flags */
+typedef enum mulan_flags {
+  /* The `c` argument of mulan_fwd_pre / mulan_fwd_post / mulan_bwd_post / mulan_fwd_bwd_post /
+   * mulan_post_bpd / mulan_bwd_pre is the PRE-ACTIVATION r of dense_out_c: the kernels apply the
+   * epilogue of _compute_coefficients, c = 1e-3 + softplus(r) (ldm/model_mulan_epsilon.py:537),
+   * themselves, and mulan_bwd_pre returns c_bar as the cotangent of r (c_bar * sigmoid(r)) --
+   * the framework's softplus forward (8 B/sub-pixel) and backward (12 B/sub-pixel) disappear.
+   * Power-of-two vocabularies only. */
+  MULAN_FLAG_C_RAW = 1,
+  /* Launch with programmatic stream serialization (cudaLaunchAttributeProgrammaticStream-
+   * Serialization): the kernel's CTAs may become resident while the previous kernel on the
+   * stream drains; every kernel of the path waits (griddepcontrol.wait) for that kernel to
+   * complete before its first global-memory access, so results are unchanged.  Worth ~1-2 us per
+   * launch boundary: the literal per-GPU batch of 128 rows is launch-latency bound. */
+  MULAN_FLAG_PDL = 2
+} mulan_flags;
+
 /* POD descriptor shared by all entry points (the subset of VDMConfig,
  * ldm/model_vdm.py:33-82, the path reads). gamma_min/max are doubles because the
  * reference forms gamma_max-gamma_min in Python double before the float32 cast
@@ -68,6 +85,13 @@ typedef struct mulan_desc {
   int32_t n_timesteps;  /* sm_n_timesteps T; 0 = continuous time                 */
   double gamma_min;     /* -13.3                                                 */
   double gamma_max;     /*  5.0                                                  */
+  uint32_t flags;       /* mulan_flags, OR-ed; 0 = the plain v1 behaviour        */
+  /* 0: eps0 / eps are [rows, dim].  N > 0: they are [N, dim] and row b reads row b % N -- the
+   * dense-VLB evaluation tiles ONE key's draws over every image of a launch
+   * (ldm/notebook_utils.py:178, :185: the same PRNGKey(0) for each image), so 16 images x 128
+   * timesteps read 128 noise rows, not 2048.  Applies to mulan_fwd_pre (eps0, eps) and to eps
+   * in the post / bwd_pre entry points. */
+  int32_t noise_rows;
 } mulan_desc;
 
 /* Thread-local message describing the last non-zero status returned on this thread. */
@@ -262,11 +286,36 @@ int mulan_aux_gaussian_bwd(int32_t rows, int32_t latent, const float* mu, const 
  *   in : loss_recon[B], loss_klz_prior[B], kl_z[B] or NULL, loss_diff[B], var_sums[B,2]
  *   out: scalars[6] = {bpd, bpd_latent, bpd_recon, bpd_diff, var0, var1};
  *        loss_klz_total[B] or NULL = kl_z + loss_klz_prior
+ * The sums run in a FIXED order (groups of 128 rows, then the group partials; csrc/
+ * mulan_reduce.cuh), so the result is deterministic and identical for the three ways of
+ * obtaining it: this entry with reduce_ws (one CTA per group, last CTA finalises), this entry
+ * with reduce_ws == NULL (one CTA walks the groups: slow, for callers that cannot supply
+ * zeroed scratch) and mulan_post_bpd (fused into the post kernel).
+ *   reduce_ws: mulan_reduce_ws_bytes(rows) bytes of device memory, 16-byte aligned, ZERO before
+ *   its first use; every call leaves it zero again, so consecutive calls on one stream can share
+ *   it.  Not shareable between calls that may run concurrently.
  */
+size_t mulan_reduce_ws_bytes(int32_t rows);
 int mulan_bpd_reduce(const mulan_desc* desc,
                      const float* loss_recon, const float* loss_klz_prior, const float* kl_z,
                      const float* loss_diff, const float* var_sums,
-                     float* scalars, float* loss_klz_total, void* stream);
+                     float* scalars, float* loss_klz_total, void* reduce_ws, void* stream);
+
+/*
+ * mulan_post_bpd -- mulan_fwd_post (gL == NULL: loss_diff only) or mulan_fwd_bwd_post (gL given:
+ * loss_diff and n_bar) AND mulan_bpd_reduce in ONE launch: the CTA that completes a group of 128
+ * rows folds the group's loss terms, the CTA that completes the last group writes the six
+ * scalars.  Same bits as the separate calls; one launch and a single-CTA tail less per step
+ * (ldm/experiment_vdm.py:62-74 follows ldm/model_mulan_epsilon.py:345-363 directly).
+ * loss_recon, loss_klz_prior, var_sums are the outputs of mulan_fwd_pre for the same rows.
+ */
+int mulan_post_bpd(const mulan_desc* desc,
+                   const uint8_t* x, const float* a, const float* b, const float* c,
+                   const float* t, const float* eps, const float* net, const float* w_save,
+                   const float* gL, const float* loss_recon, const float* loss_klz_prior,
+                   const float* kl_z, const float* var_sums,
+                   float* loss_diff, float* n_bar, float* scalars, float* loss_klz_total,
+                   void* reduce_ws, void* stream);
 
 /*
  * mulan_elbo_host -- HOST-buffer convenience entry: one call = H2D of the inputs, fwd_pre,

@@ -24,7 +24,7 @@
  *            treats as optional is marked absent in the opaque's mask instead.
  *   opaque   the bytes of one mulan_xla_opaque (little-endian, as the struct lies in memory);
  *            `desc.rows` is filled by the binding from the operand shape.  opaque_len must be
- *            sizeof(mulan_xla_opaque) (48) or sizeof(mulan_desc) (40: no operand absent).
+ *            sizeof(mulan_xla_opaque) (56) or sizeof(mulan_desc) (48: no operand absent).
  *   status   on failure the message of mulan_last_error() is handed to
  *            XlaCustomCallStatusSetFailure(status, msg, len), looked up at run time in the
  *            hosting process (jaxlib's xla_extension provides it); without that symbol, or
@@ -46,7 +46,7 @@ extern "C" {
 #endif
 
 typedef struct mulan_xla_opaque {
-  mulan_desc desc;        /* 40 bytes */
+  mulan_desc desc;        /* 48 bytes (ABI v2: + flags, noise_rows) */
   uint32_t absent_mask;   /* bit i set: buffers[i] is to be read as NULL (optional operand) */
   uint32_t reserved;      /* 0 */
 } mulan_xla_opaque;
@@ -74,7 +74,9 @@ void mulan_xla_fwd_bwd_post(void* stream, void** buffers, const char* opaque, si
  *                  (net, z_bar, g_bar, gL may be marked absent) */
 void mulan_xla_bwd_pre(void* stream, void** buffers, const char* opaque, size_t opaque_len,
                        void* status);
-/* mulan_bpd_reduce.  buffers: loss_recon, loss_klz_prior, kl_z, loss_diff, var_sums |
+/* mulan_bpd_reduce (reduce_ws == NULL: XLA result buffers are not zero-initialised, so the
+ *                   single-CTA form runs; same bits as the parallel one).
+ *                   buffers: loss_recon, loss_klz_prior, kl_z, loss_diff, var_sums |
  *                             scalars[6], loss_klz_total[B]      (kl_z may be marked absent) */
 void mulan_xla_bpd_reduce(void* stream, void** buffers, const char* opaque, size_t opaque_len,
                           void* status);

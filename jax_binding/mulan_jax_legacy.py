@@ -38,11 +38,12 @@ for _name in TARGETS:
       _name.encode(), _capsule_new(_addr, b'xla._CUSTOM_CALL_TARGET', None), platform='CUDA')
 
 
-def _opaque(cfg, param, rows, dim, absent_mask=0):
-  """bytes of mulan_xla_opaque {mulan_desc; uint32 absent_mask; uint32 reserved}."""
-  return struct.pack('<6i2d2I', rows, dim, cfg.vocab_size, param,
+def _opaque(cfg, param, rows, dim, absent_mask=0, flags=0):
+  """bytes of mulan_xla_opaque {mulan_desc (ABI v2: ..., uint32 flags, int32 noise_rows);
+  uint32 absent_mask; uint32 reserved}."""
+  return struct.pack('<6i2dIi2I', rows, dim, cfg.vocab_size, param,
                      0 if cfg.unet_type == 'vdm' else 1, cfg.sm_n_timesteps,
-                     cfg.gamma_min, cfg.gamma_max, absent_mask, 0)
+                     cfg.gamma_min, cfg.gamma_max, flags, 0, absent_mask, 0)
 
 
 def _row_major(aval):

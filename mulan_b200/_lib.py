@@ -15,6 +15,9 @@ MULAN_PARAM_VEL = 1
 MULAN_PARAM_VEL_FROM_EPS = 2
 MULAN_GT_MEAN = 0
 MULAN_GT_PIXEL = 1
+MULAN_FLAG_C_RAW = 1     # c is the pre-activation of dense_out_c (kernels apply 1e-3 + softplus)
+MULAN_FLAG_PDL = 2       # programmatic dependent launch
+MULAN_ABI_VERSION = 2
 MULAN_RK45_SCRATCH = 2048
 MULAN_SUMSQ_SCRATCH = 2048
 
@@ -26,7 +29,8 @@ class MulanDesc(C.Structure):
   """struct mulan_desc."""
   _fields_ = [('rows', C.c_int32), ('dim', C.c_int32), ('vocab', C.c_int32),
               ('param', C.c_int32), ('gt_mode', C.c_int32), ('n_timesteps', C.c_int32),
-              ('gamma_min', C.c_double), ('gamma_max', C.c_double)]
+              ('gamma_min', C.c_double), ('gamma_max', C.c_double),
+              ('flags', C.c_uint32), ('noise_rows', C.c_int32)]
 
 
 class MulanEndConsts(C.Structure):
@@ -81,7 +85,9 @@ SIGNATURES = {
     'mulan_aux_gumbel_bwd': ([C.c_int32] * 2 + [C.c_double] + [_P] * 6, C.c_int),
     'mulan_aux_gaussian_fwd': ([C.c_int32] * 2 + [_P] * 6, C.c_int),
     'mulan_aux_gaussian_bwd': ([C.c_int32] * 2 + [_P] * 8, C.c_int),
-    'mulan_bpd_reduce': ([_D] + [_P] * 8, C.c_int),
+    'mulan_bpd_reduce': ([_D] + [_P] * 9, C.c_int),
+    'mulan_reduce_ws_bytes': ([C.c_int32], C.c_size_t),
+    'mulan_post_bpd': ([_D] + [_P] * 19, C.c_int),
     'mulan_elbo_host': ([_D] + [_P] * 8 + [DENOISER_FN, _P, C.c_int32] + [_P] * 6, C.c_int),
     'mulan_elbo_host_keyed': ([_D] + [_P] * 8 + [DENOISER_FN, _P, C.c_int32] + [_P] * 6, C.c_int),
     'mulan_sample_gamma': ([_D, C.c_int32] + [_P] * 6, C.c_int),
@@ -148,8 +154,10 @@ def check(status: int) -> None:
 
 def make_desc(rows: int, dim: int = 3072, vocab: int = 256, param: int = MULAN_PARAM_EPS,
               gt_mode: int = MULAN_GT_MEAN, n_timesteps: int = 0,
-              gamma_min: float = -13.3, gamma_max: float = 5.0) -> MulanDesc:
-  return MulanDesc(rows, dim, vocab, param, gt_mode, n_timesteps, gamma_min, gamma_max)
+              gamma_min: float = -13.3, gamma_max: float = 5.0, flags: int = 0,
+              noise_rows: int = 0) -> MulanDesc:
+  return MulanDesc(rows, dim, vocab, param, gt_mode, n_timesteps, gamma_min, gamma_max, flags,
+                   noise_rows)
 
 
 def kernel_param(param: int) -> int:

@@ -19,7 +19,7 @@ SOURCES = ['mulan_fwd_pre.cu', 'mulan_post.cu', 'mulan_bwd_pre.cu', 'mulan_aux.c
            'mulan_host.cu', 'mulan_xla_legacy.cu']
 
 NVCC_FLAGS = [
-    '-O3', '-std=c++17',
+    '-O3', '-std=c++17', '--threads', '0',
     '-gencode', 'arch=compute_100a,code=sm_100a',
     '-lineinfo',
     # Plain a*b+c rounds twice like the reference's op-by-op float32; FMAs only where the

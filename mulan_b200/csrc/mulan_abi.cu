@@ -41,6 +41,12 @@ int check_desc(const mulan_desc* d, const char* fn) {
     return fail(MULAN_ERR_INVALID_ARG, "%s: n_timesteps=%d < 0", fn, d->n_timesteps);
   if (!(d->gamma_max > d->gamma_min))
     return fail(MULAN_ERR_INVALID_ARG, "%s: gamma_max must exceed gamma_min", fn);
+  if (d->flags & ~(uint32_t)(MULAN_FLAG_C_RAW | MULAN_FLAG_PDL))
+    return fail(MULAN_ERR_INVALID_ARG, "%s: flags=0x%x has unknown bits", fn, d->flags);
+  if (d->noise_rows < 0)
+    return fail(MULAN_ERR_INVALID_ARG, "%s: noise_rows=%d < 0", fn, d->noise_rows);
+  if ((d->flags & MULAN_FLAG_C_RAW) && (d->vocab & (d->vocab - 1)) != 0)
+    return fail(MULAN_ERR_UNSUPPORTED, "%s: MULAN_FLAG_C_RAW needs a power-of-two vocab", fn);
   if (d->n_timesteps > 0 && d->param != MULAN_PARAM_EPS)
     return fail(MULAN_ERR_UNSUPPORTED,
                 "%s: discrete time (sm_n_timesteps=%d > 0) exists only for the epsilon model; the "
@@ -71,6 +77,7 @@ int check_desc(const mulan_desc* d, const char* fn) {
       return fail(MULAN_ERR_ALIGNMENT, "%s: %s is not 4-byte aligned", fn, #p);  \
   } while (0)
 
+int flag(const mulan_desc* d, uint32_t f) { return (d->flags & f) ? 1 : 0; }
 float f32_gmin(const mulan_desc* d) { return (float)d->gamma_min; }
 float f32_delta(const mulan_desc* d) { return (float)(d->gamma_max - d->gamma_min); }
 
@@ -122,6 +129,8 @@ int mulan_fwd_pre(const mulan_desc* d, const uint8_t* x, const float* a, const f
   p.z_t = z_t; p.g_net = g_net; p.w_save = w_save;
   p.loss_recon = loss_recon; p.loss_klz = loss_klz_prior; p.var_sums = var_sums;
   p.rows = d->rows; p.dim4 = d->dim / 4; p.gt_mode = d->gt_mode;
+  p.c_raw = flag(d, MULAN_FLAG_C_RAW); p.pdl = flag(d, MULAN_FLAG_PDL);
+  p.noise_rows = d->noise_rows;
   p.W = recon_window(d);
   p.gmin = f32_gmin(d); p.delta = f32_delta(d);
   p.k = mulan::make_end_consts(p.gmin, p.delta);
@@ -135,6 +144,7 @@ int mulan_fwd_pre(const mulan_desc* d, const uint8_t* x, const float* a, const f
     mulan::DiscreteWParams q;
     q.a = a; q.b = b; q.c = c; q.t = t; q.w = w_save;
     q.rows = d->rows; q.dim4 = d->dim / 4; q.gmin = p.gmin; q.delta = p.delta;
+    q.c_raw = p.c_raw;
     q.inv_T = (float)(1.0 / (double)d->n_timesteps);
     e = mulan::launch_discrete_w(q, (cudaStream_t)stream);
   }
@@ -201,6 +211,8 @@ int mulan_fwd_pre_consts(const mulan_desc* d, const mulan_end_consts* kc, const 
   p.z_t = z_t; p.g_net = g_net; p.w_save = w_save;
   p.loss_recon = loss_recon; p.loss_klz = loss_klz_prior; p.var_sums = var_sums;
   p.rows = d->rows; p.dim4 = d->dim / 4; p.gt_mode = d->gt_mode;
+  p.c_raw = flag(d, MULAN_FLAG_C_RAW); p.pdl = flag(d, MULAN_FLAG_PDL);
+  p.noise_rows = d->noise_rows;
   fill_pre_consts(d, kc, &p);
   cudaError_t e = mulan::launch_fwd_pre(p, (cudaStream_t)stream);
   return e == cudaSuccess ? 0 : cuda_fail(fn, e);
@@ -231,6 +243,9 @@ static int fill_post(const char* fn, const mulan_desc* d, const uint8_t* x, cons
   p->w_save = (kparam == MULAN_PARAM_EPS) ? w_save : nullptr;
   p->gL = nullptr; p->loss_diff = nullptr; p->n_bar = nullptr;
   p->rows = d->rows; p->dim4 = d->dim / 4; p->param = kparam;
+  p->c_raw = flag(d, MULAN_FLAG_C_RAW); p->pdl = flag(d, MULAN_FLAG_PDL);
+  p->noise_rows = d->noise_rows;
+  memset(&p->red, 0, sizeof(p->red));
   p->gmin = f32_gmin(d); p->delta = f32_delta(d);
   // .5 * sum(...)  |  .5 * T * sum(...)   (ldm/model_mulan_epsilon.py:345, :353)
   p->scale = d->n_timesteps > 0 ? (float)(0.5 * (double)d->n_timesteps) : 0.5f;
@@ -315,6 +330,8 @@ int mulan_bwd_pre(const mulan_desc* d, const uint8_t* x, const float* a, const f
   p.z_bar = z_bar; p.g_bar = g_bar; p.gL = gL;
   p.a_bar = a_bar; p.b_bar = b_bar; p.c_bar = c_bar;
   p.rows = d->rows; p.dim4 = d->dim / 4; p.param = kparam; p.gt_mode = d->gt_mode;
+  p.c_raw = flag(d, MULAN_FLAG_C_RAW); p.pdl = flag(d, MULAN_FLAG_PDL);
+  p.noise_rows = d->noise_rows;
   p.gmin = f32_gmin(d); p.delta = f32_delta(d);
   p.T = d->n_timesteps;
   p.inv_T = d->n_timesteps > 0 ? (float)(1.0 / (double)d->n_timesteps) : 0.f;
@@ -437,16 +454,53 @@ int mulan_aux_gaussian_bwd(int32_t rows, int32_t latent, const float* mu, const 
   return e == cudaSuccess ? 0 : cuda_fail(fn, e);
 }
 
+static int fill_reduce(const char* fn, const mulan_desc* d, const float* loss_recon,
+                       const float* loss_klz_prior, const float* kl_z, const float* loss_diff,
+                       const float* var_sums, float* scalars, float* loss_klz_total,
+                       void* reduce_ws, mulan::BpdReduceParams* r) {
+  REQ_PTR(loss_recon, fn); REQ_PTR(loss_klz_prior, fn); REQ_PTR(var_sums, fn); REQ_PTR(scalars, fn);
+  OPT_VEC(reduce_ws, fn);
+  r->loss_recon = loss_recon; r->loss_klz_prior = loss_klz_prior; r->kl_z = kl_z;
+  r->loss_diff = loss_diff; r->var_sums = var_sums; r->scalars = scalars;
+  r->loss_klz_total = loss_klz_total; r->ws = static_cast<unsigned*>(reduce_ws);
+  r->rows = d->rows; r->dim = d->dim;
+  return 0;
+}
+
+size_t mulan_reduce_ws_bytes(int32_t rows) { return mulan::reduce_ws_bytes(rows); }
+
 int mulan_bpd_reduce(const mulan_desc* d, const float* loss_recon, const float* loss_klz_prior,
                      const float* kl_z, const float* loss_diff, const float* var_sums,
-                     float* scalars, float* loss_klz_total, void* stream) {
+                     float* scalars, float* loss_klz_total, void* reduce_ws, void* stream) {
   const char* fn = "mulan_bpd_reduce";
   if (int r = check_desc(d, fn)) return r;
   if (d->rows == 0) return fail(MULAN_ERR_INVALID_ARG, "%s: rows=0 has no mean", fn);
-  REQ_PTR(loss_recon, fn); REQ_PTR(loss_klz_prior, fn); REQ_PTR(var_sums, fn); REQ_PTR(scalars, fn);
-  cudaError_t e = mulan::launch_bpd_reduce(d->rows, d->dim, loss_recon, loss_klz_prior, kl_z,
-                                           loss_diff, var_sums, scalars, loss_klz_total,
-                                           (cudaStream_t)stream);
+  mulan::BpdReduceParams q;
+  if (int r = fill_reduce(fn, d, loss_recon, loss_klz_prior, kl_z, loss_diff, var_sums, scalars,
+                          loss_klz_total, reduce_ws, &q)) return r;
+  cudaError_t e = mulan::launch_bpd_reduce(q, flag(d, MULAN_FLAG_PDL) != 0, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(fn, e);
+}
+
+int mulan_post_bpd(const mulan_desc* d, const uint8_t* x, const float* a, const float* b,
+                   const float* c, const float* t, const float* eps, const float* net,
+                   const float* w_save, const float* gL, const float* loss_recon,
+                   const float* loss_klz_prior, const float* kl_z, const float* var_sums,
+                   float* loss_diff, float* n_bar, float* scalars, float* loss_klz_total,
+                   void* reduce_ws, void* stream) {
+  const char* fn = "mulan_post_bpd";
+  if (int r = check_desc(d, fn)) return r;
+  if (d->rows == 0) return fail(MULAN_ERR_INVALID_ARG, "%s: rows=0 has no mean", fn);
+  mulan::PostParams p;
+  if (int r = fill_post(fn, d, x, a, b, c, t, eps, net, w_save, &p)) return r;
+  REQ_PTR(loss_diff, fn);
+  REQ_PTR(reduce_ws, fn);
+  if (gL != nullptr) REQ_VEC(n_bar, fn);
+  p.gL = gL; p.loss_diff = loss_diff; p.n_bar = gL != nullptr ? n_bar : nullptr;
+  if (int r = fill_reduce(fn, d, loss_recon, loss_klz_prior, kl_z, loss_diff, var_sums, scalars,
+                          loss_klz_total, reduce_ws, &p.red)) return r;
+  cudaError_t e = gL != nullptr ? mulan::launch_fwd_bwd_post(p, (cudaStream_t)stream)
+                                : mulan::launch_fwd_post(p, (cudaStream_t)stream);
   return e == cudaSuccess ? 0 : cuda_fail(fn, e);
 }
 

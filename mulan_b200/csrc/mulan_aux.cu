@@ -10,6 +10,7 @@
 //
 // aux: one warp per row, two slots per lane (L <= 64); all reductions are warp shuffles.
 #include "mulan_kernels.h"
+#include "mulan_reduce.cuh"
 
 namespace mulan {
 
@@ -312,49 +313,54 @@ cudaError_t launch_aux_gaussian(bool bwd, int rows, int latent, const float* mu,
 }
 
 // ---------------------------------------------------------------------------------------
-// VDMOutput + loss_fn scalars.  Single CTA, fixed-order sums (deterministic).
+// VDMOutput + loss_fn scalars (mulan_bpd_reduce): the fixed-order reduction of mulan_reduce.cuh.
+// With a workspace: one CTA per group of 128 rows, "last CTA done" finalisation (one launch, a
+// few microseconds at 16384 rows; the single-CTA loop of round 1 took 16-22).  Without: one CTA
+// walks the groups and reproduces the same summation order bit for bit.
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
-bpd_reduce_kernel(int rows, int dim, const float* __restrict__ loss_recon,
-                  const float* __restrict__ loss_klz_prior, const float* __restrict__ kl_z,
-                  const float* __restrict__ loss_diff, const float* __restrict__ var_sums,
-                  float* __restrict__ scalars, float* __restrict__ loss_klz_total) {
+bpd_reduce_parallel_kernel(const BpdReduceParams p) {
   __shared__ float red[kWarps][5];
-  float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int i = threadIdx.x; i < rows; i += kThreads) {
-    // loss_klz = kl_z + loss_klz (ldm/model_mulan_epsilon.py:359)
-    const float klz = kl_z != nullptr ? kl_z[i] + loss_klz_prior[i] : loss_klz_prior[i];
-    if (loss_klz_total != nullptr) loss_klz_total[i] = klz;
-    acc[0] += loss_recon[i];
-    acc[1] += klz;
-    acc[2] += loss_diff != nullptr ? loss_diff[i] : 0.f;
-    acc[3] += var_sums[2 * i];
-    acc[4] += var_sums[2 * i + 1];
-  }
-  block_sum<5>(acc, red);
-  if (threadIdx.x == 0) {
-    const float n = (float)rows;
-    const float rescale = (float)(1.0 / ((double)dim * 0.6931471805599453));
-    const float bpd_recon = __fdiv_rn(acc[0], n) * rescale;
-    const float bpd_latent = __fdiv_rn(acc[1], n) * rescale;
-    const float bpd_diff = __fdiv_rn(acc[2], n) * rescale;
-    scalars[0] = bpd_recon + bpd_latent + bpd_diff;
-    scalars[1] = bpd_latent;
-    scalars[2] = bpd_recon;
-    scalars[3] = bpd_diff;
-    const float nd = (float)((double)rows * (double)dim);
-    scalars[4] = __fdiv_rn(acc[3], nd);
-    scalars[5] = __fdiv_rn(acc[4], nd);
-  }
+  __shared__ int s_flag;
+  pdl_release_dependents();
+  pdl_wait_for_primary();
+  const int g = blockIdx.x;
+  red_rows_done(p, g, min(kRedGroup, p.rows - g * kRedGroup), red, &s_flag);
 }
 
-cudaError_t launch_bpd_reduce(int rows, int dim, const float* loss_recon,
-                              const float* loss_klz_prior, const float* kl_z,
-                              const float* loss_diff, const float* var_sums, float* scalars,
-                              float* loss_klz_total, cudaStream_t s) {
-  bpd_reduce_kernel<<<1, kThreads, 0, s>>>(rows, dim, loss_recon, loss_klz_prior, kl_z, loss_diff,
-                                           var_sums, scalars, loss_klz_total);
-  return cudaGetLastError();
+__global__ void __launch_bounds__(kThreads)
+bpd_reduce_single_kernel(const BpdReduceParams p) {
+  __shared__ float red[kWarps][5];
+  __shared__ float vacc[kThreads][5];   // the final step's per-thread accumulators
+  pdl_release_dependents();
+  pdl_wait_for_primary();
+#pragma unroll
+  for (int k = 0; k < 5; ++k) vacc[threadIdx.x][k] = 0.f;
+  const int G = red_groups(p.rows);
+  float acc[5];
+  for (int g = 0; g < G; ++g) {
+    red_group_sum(p, g, acc, red);
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) vacc[g % kThreads][k] += acc[k];
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 5; ++k) acc[k] = vacc[threadIdx.x][k];
+  block_sum<5>(acc, red);
+  if (threadIdx.x == 0) red_write_scalars(p, acc);
+}
+
+size_t reduce_ws_bytes(int rows) {
+  const int G = red_groups(rows < 1 ? 1 : rows);
+  return sizeof(unsigned) * (size_t)(red_partials_offset(G) + 8 * G);
+}
+
+cudaError_t launch_bpd_reduce(const BpdReduceParams& p, bool pdl, cudaStream_t s) {
+  if (p.ws != nullptr)
+    return launch_kernel(bpd_reduce_parallel_kernel, red_groups(p.rows), kThreads, s, pdl, p);
+  return launch_kernel(bpd_reduce_single_kernel, 1, kThreads, s, pdl, p);
 }
 
 }  // namespace mulan

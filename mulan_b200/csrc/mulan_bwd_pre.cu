@@ -22,7 +22,10 @@ namespace mulan {
 // (gLh = gL/2) -- the kernel is instruction-issue bound in the velocity modes.  gamma_t and
 // d gamma/dt are formed exactly as mulan_fwd_pre forms them (fma(P, Delta/S, gmin), Q Delta/S),
 // so alpha and sigma here are the ones z_t was built with.
-template <int PARAM, int GT, bool DISC, bool POW2>
+// CRAW (MULAN_FLAG_C_RAW): p.c is the pre-activation r of dense_out_c; c = 1e-3 + softplus(r) is
+// formed here and c_bar is returned as the cotangent of r (c_bar * sigmoid(r)), so the
+// framework's softplus backward (12 B/sub-pixel) disappears (ldm/model_mulan_epsilon.py:537).
+template <int PARAM, int GT, bool DISC, bool POW2, bool CRAW>
 __global__ void __launch_bounds__(kThreads, 5)   // <= 51 registers: 5 CTAs (40 warps) per SM
 bwd_pre_kernel(const BwdPreParams p) {
   __shared__ RowT s_rt;
@@ -32,6 +35,8 @@ bwd_pre_kernel(const BwdPreParams p) {
   const bool has_gL = p.gL != nullptr;
   const bool has_zb = p.z_bar != nullptr;
   const bool has_gb = p.g_bar != nullptr;
+  pdl_release_dependents();
+  pdl_wait_for_primary();
   if (tid == 0) {
     s_rt = make_row_t(__ldg(p.t + row));
     if (DISC) s_rd = make_row_d(__ldg(p.t + row), __ldg(p.t + row) - p.inv_T);   // s = t - 1/T
@@ -52,6 +57,7 @@ bwd_pre_kernel(const BwdPreParams p) {
   const float t5_5x2 = t5_5 + t5_5, t3_3x2 = t3_3 + t3_3, tx2 = t + t;
   constexpr float kTwoFifths = 2.0f * kFifth, kTwoThirds = 2.0f * kThird;
   const size_t base4 = (size_t)row * p.dim4;
+  const size_t nbase4 = (size_t)(p.noise_rows > 0 ? row % p.noise_rows : row) * p.dim4;
   const bool need_x = has_zb || (has_gL && PARAM != MULAN_PARAM_EPS);
 
   for (int i4 = tid; i4 < p.dim4; i4 += kThreads) {
@@ -59,7 +65,7 @@ bwd_pre_kernel(const BwdPreParams p) {
     const float4 A = ld4(p.a, g4), Bv = ld4(p.b, g4), C = ld4(p.c, g4);
     float4 E = make_float4(0.f, 0.f, 0.f, 0.f), N = E, ZB = E, GB = E;
     uchar4 X = make_uchar4(0, 0, 0, 0);
-    if (has_gL || has_zb) E = ld4(p.eps, g4);
+    if (has_gL || has_zb) E = ld4(p.eps, nbase4 + i4);
     if (has_gL) N = ld4(p.net, g4);
     if (has_zb) ZB = ld4(p.z_bar, g4);
     if (GT == MULAN_GT_PIXEL && has_gb) GB = ld4(p.g_bar, g4);
@@ -67,7 +73,9 @@ bwd_pre_kernel(const BwdPreParams p) {
     float4 AB, BB, CB;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float a = get(A, j), b = get(Bv, j), c = get(C, j);
+      const float a = get(A, j), b = get(Bv, j);
+      float dcdr = 1.0f;
+      const float c = CRAW ? c_from_raw_grad(get(C, j), &dcdr) : get(C, j);
       const float e = get(E, j), n = get(N, j);
       // encode(x): exact in one fma for a power-of-two vocab (as mulan_fwd_pre)
       const float f = POW2 ? fmaf((float)getx(X, j), two_iv, off) : vi.xval(getx(X, j));
@@ -143,7 +151,7 @@ bwd_pre_kernel(const BwdPreParams p) {
       }
       put(AB, j, ab_);
       put(BB, j, bb_);
-      put(CB, j, cb_);
+      put(CB, j, CRAW ? cb_ * dcdr : cb_);
     }
     st4(p.a_bar, g4, AB);
     st4(p.b_bar, g4, BB);
@@ -151,20 +159,29 @@ bwd_pre_kernel(const BwdPreParams p) {
   }
 }
 
-template <int PARAM, bool POW2>
+template <int PARAM, bool POW2, bool CRAW>
 static cudaError_t launch_gt(const BwdPreParams& p, cudaStream_t s) {
-  dim3 grid(p.rows), block(kThreads);
+  const bool pdl = p.pdl != 0;
   if (PARAM == MULAN_PARAM_EPS && p.T > 0) {
     if (p.gt_mode == MULAN_GT_MEAN)
-      bwd_pre_kernel<MULAN_PARAM_EPS, MULAN_GT_MEAN, true, POW2><<<grid, block, 0, s>>>(p);
-    else
-      bwd_pre_kernel<MULAN_PARAM_EPS, MULAN_GT_PIXEL, true, POW2><<<grid, block, 0, s>>>(p);
-  } else if (p.gt_mode == MULAN_GT_MEAN) {
-    bwd_pre_kernel<PARAM, MULAN_GT_MEAN, false, POW2><<<grid, block, 0, s>>>(p);
-  } else {
-    bwd_pre_kernel<PARAM, MULAN_GT_PIXEL, false, POW2><<<grid, block, 0, s>>>(p);
+      return launch_kernel(bwd_pre_kernel<MULAN_PARAM_EPS, MULAN_GT_MEAN, true, POW2, CRAW>,
+                           p.rows, kThreads, s, pdl, p);
+    return launch_kernel(bwd_pre_kernel<MULAN_PARAM_EPS, MULAN_GT_PIXEL, true, POW2, CRAW>,
+                         p.rows, kThreads, s, pdl, p);
   }
-  return cudaGetLastError();
+  if (p.gt_mode == MULAN_GT_MEAN)
+    return launch_kernel(bwd_pre_kernel<PARAM, MULAN_GT_MEAN, false, POW2, CRAW>, p.rows,
+                         kThreads, s, pdl, p);
+  return launch_kernel(bwd_pre_kernel<PARAM, MULAN_GT_PIXEL, false, POW2, CRAW>, p.rows, kThreads,
+                       s, pdl, p);
+}
+
+template <int PARAM>
+static cudaError_t launch_param(const BwdPreParams& p, cudaStream_t s) {
+  const bool pow2 = p.vi.pow2 != 0;
+  // the pre-activation form is built for power-of-two vocabularies (both shipped configs)
+  if (p.c_raw) return pow2 ? launch_gt<PARAM, true, true>(p, s) : cudaErrorNotSupported;
+  return pow2 ? launch_gt<PARAM, true, false>(p, s) : launch_gt<PARAM, false, false>(p, s);
 }
 
 // w = expm1(gamma(t) - gamma(t - 1/T)): the discrete-time weight of the epsilon loss
@@ -189,7 +206,8 @@ discrete_w_kernel(const DiscreteWParams p) {
     float4 Wv;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const Poly po = poly_eval(get(A, j), get(Bv, j), get(C, j), rt);
+      const float c = p.c_raw ? c_from_raw(get(C, j)) : get(C, j);
+      const Poly po = poly_eval(get(A, j), get(Bv, j), c, rt);
       const float rS = rcp_scale(po.S);
       const float dP = fmaf(po.a2, rd.d5_5, fmaf(po.b2c, rd.d3_3, fmaf(po.ab, rd.d4_2,
                        fmaf(po.bc, rd.d2, po.c2 * rd.d1))));
@@ -207,15 +225,10 @@ cudaError_t launch_discrete_w(const DiscreteWParams& p, cudaStream_t s) {
 
 cudaError_t launch_bwd_pre(const BwdPreParams& p, cudaStream_t s) {
   if (p.rows == 0) return cudaSuccess;
-  const bool pow2 = p.vi.pow2 != 0;
   switch (p.param) {
-    case MULAN_PARAM_EPS:
-      return pow2 ? launch_gt<MULAN_PARAM_EPS, true>(p, s) : launch_gt<MULAN_PARAM_EPS, false>(p, s);
-    case MULAN_PARAM_VEL:
-      return pow2 ? launch_gt<MULAN_PARAM_VEL, true>(p, s) : launch_gt<MULAN_PARAM_VEL, false>(p, s);
-    default:
-      return pow2 ? launch_gt<MULAN_PARAM_VEL_FROM_EPS, true>(p, s)
-                  : launch_gt<MULAN_PARAM_VEL_FROM_EPS, false>(p, s);
+    case MULAN_PARAM_EPS: return launch_param<MULAN_PARAM_EPS>(p, s);
+    case MULAN_PARAM_VEL: return launch_param<MULAN_PARAM_VEL>(p, s);
+    default: return launch_param<MULAN_PARAM_VEL_FROM_EPS>(p, s);
   }
 }
 

@@ -109,6 +109,49 @@ __device__ __forceinline__ float log_1p_sum(float s) {
   return d < 0.0078125f ? small : big;
 }
 
+// ---------------------------------------------------------------------------------------
+// The epilogue of _compute_coefficients (ldm/model_mulan_epsilon.py:537) for callers that hand
+// over the PRE-ACTIVATION of dense_out_c (MULAN_FLAG_C_RAW):
+//   c = 1e-3 + softplus(r),  softplus(r) = logaddexp(r, 0) = max(r, 0) + log1p(exp(-|r|)).
+// log1p(d), d = exp(-|r|) in (0, 1]: five-term series below 1/16 (truncation < 2e-7 relative),
+// MUFU.LG2 above (absolute error <= 2^-22 against a result >= 0.06: < 4e-6 relative); the
+// residual is pseudo-random per sub-pixel like every other fast-math rounding here.
+// dc/dr = sigmoid(r) for the backward pass.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float log1p_unit(float d) {
+  const float ser = d * fmaf(d, fmaf(d, fmaf(d, fmaf(d, kFifth, -0.25f), kThird), -0.5f), 1.0f);
+  const float big = lg2_approx(1.0f + d) * kLn2;
+  return d < 0.0625f ? ser : big;
+}
+__device__ __forceinline__ float c_from_raw(float r) {
+  const float d = ex2_approx(-fabsf(r) * kLog2e);
+  return 1e-3f + (fmaxf(r, 0.0f) + log1p_unit(d));
+}
+// c and dc/dr = sigmoid(r) from one exponential (backward pass)
+__device__ __forceinline__ float c_from_raw_grad(float r, float* dcdr) {
+  const float d = ex2_approx(-fabsf(r) * kLog2e);
+  const float inv = rcp_nr(1.0f + d);
+  *dcdr = r >= 0.0f ? inv : d * inv;
+  return 1e-3f + (fmaxf(r, 0.0f) + log1p_unit(d));
+}
+__device__ __forceinline__ float4 c_from_raw4(float4 r) {
+  return make_float4(c_from_raw(r.x), c_from_raw(r.y), c_from_raw(r.z), c_from_raw(r.w));
+}
+
+// ---------------------------------------------------------------------------------------
+// Programmatic dependent launch (sm_90+).  Every kernel of the path releases its dependents as
+// soon as it starts and, before touching global memory, waits for the grid it depends on to
+// have completed and flushed.  Both are no-ops for a plain launch; with MULAN_FLAG_PDL the host
+// sets cudaLaunchAttributeProgrammaticStreamSerialization, so the next kernel's CTAs are
+// already resident (prologue done) when the previous one drains.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_release_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait_for_primary() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // Per-example time powers, staged once per row in shared memory.  Integer powers follow
 // XLA's integer_pow lowering (binary exponentiation), see oracle.integer_pow.
 struct RowT {
@@ -181,8 +224,8 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// Sum N per-thread accumulators over the CTA; result valid in thread 0.
-template <int N>
+// Sum N per-thread accumulators over a CTA of NW warps; result valid in thread 0.
+template <int N, int NW = kWarps>
 __device__ __forceinline__ void block_sum(float (&acc)[N], float (*smem)[N]) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -196,7 +239,8 @@ __device__ __forceinline__ void block_sum(float (&acc)[N], float (*smem)[N]) {
 #pragma unroll
     for (int k = 0; k < N; ++k) {
       float s = smem[0][k];
-      for (int w = 1; w < kWarps; ++w) s += smem[w][k];
+#pragma unroll
+      for (int w = 1; w < NW; ++w) s += smem[w][k];
       acc[k] = s;
     }
   }

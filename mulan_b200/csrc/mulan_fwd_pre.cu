@@ -164,12 +164,14 @@ static bool is_shipped(const FwdPreParams& p) {
          eq(p.rc.off, Shipped::off);
 }
 
-template <int GT, bool SAVEW, bool FAST>
+template <int GT, bool SAVEW, bool FAST, bool CRAW = false>
 __device__ __forceinline__ void pre_column(const FwdPreParams& p, const PreConsts& kc,
                                            const RowT& rt, const float4 A,
-                                           const float4 Bv, const float4 C, const float4 E0,
+                                           const float4 Bv, const float4 Cin, const float4 E0,
                                            const float4 E, const uchar4 X, size_t g4,
                                            float (&acc)[5]) {
+  // MULAN_FLAG_C_RAW: c = 1e-3 + softplus(pre-activation), ldm/model_mulan_epsilon.py:537
+  const float4 C = CRAW ? c_from_raw4(Cin) : Cin;
   const float s0 = kc.s0, inv0 = kc.inv0, v0c = kc.v0c;
   const float v1c = kc.v1c, om1 = kc.om1, lv1 = kc.lv1;
   const bool v1_uniform = kc.v1_uniform;
@@ -221,10 +223,10 @@ __device__ __forceinline__ void pre_column(const FwdPreParams& p, const PreConst
 }
 
 // Row epilogue: deterministic CTA-wide sums, per-example outputs written by thread 0.
-template <int GT>
+template <int GT, int NW = kWarps>
 __device__ __forceinline__ void pre_row_end(const FwdPreParams& p, int row, float (&acc)[5],
                                             float (*red)[5]) {
-  block_sum<5>(acc, red);
+  block_sum<5, NW>(acc, red);
   if (threadIdx.x == 0) {
     const float dimf = (float)(p.dim4 * 4);
     p.loss_recon[row] = -acc[0];
@@ -237,30 +239,69 @@ __device__ __forceinline__ void pre_row_end(const FwdPreParams& p, int row, floa
 }
 
 // ---------------------------------------------------------------------------------------
-// Direct-load kernel: one CTA per row, operands loaded straight into registers (LDG.128).
-// Serves any dim (multiple of 4), any vocab / window, any 4-byte aligned x.
+// Direct-load kernel: one CTA (NT threads) per row, operands loaded straight into registers
+// (LDG.128).  Serves any dim (multiple of 4), any vocab / window, any 4-byte aligned x.
+//
+// DBUF: register double-buffering -- the six loads of column k+1 are issued BEFORE the ~460
+// arithmetic instructions of column k, so every warp keeps 84 B per lane in flight while it
+// computes.  Memory-level parallelism then no longer depends on how many warps happen to sit in
+// their load phase (the plain loop: 4 CTAs/SM, 47 % occupancy, DRAM at 75 % of peak with the
+// issue slots 70 % busy -- co-limited by latency, profiles/r1_ncu_summary.md), at the price of
+// ~21 more live registers.  KIND: 0 generic window, 1 closed-form 3-bin term with the launch
+// constants in the parameter bank, 2 the same with the shipped configuration's constants as
+// immediates.
 // ---------------------------------------------------------------------------------------
-template <int GT, bool SAVEW, bool FAST, bool BAKED>
-__global__ void __launch_bounds__(kThreads, 4)
+struct PreCol {
+  float4 A, B, C, E0, E;
+  uchar4 X;
+};
+__device__ __forceinline__ PreCol load_pre_col(const FwdPreParams& p, size_t g4, size_t n4) {
+  PreCol c;
+  c.A = ld4(p.a, g4); c.B = ld4(p.b, g4); c.C = ld4(p.c, g4);
+  c.E0 = ld4(p.eps0, n4); c.E = ld4(p.eps, n4);
+  c.X = ldx4(p.x, g4);
+  return c;
+}
+
+template <int GT, bool SAVEW, int KIND, bool CRAW, int NT, int MINB, bool DBUF>
+__global__ void __launch_bounds__(NT, MINB)
 fwd_pre_kernel(const FwdPreParams p) {
+  constexpr bool FAST = KIND != 0, BAKED = KIND == 2;
+  constexpr int NW = NT / 32;
   __shared__ RowT s_rt;
-  __shared__ float red[kWarps][5];
+  __shared__ float red[NW][5];
   const int row = blockIdx.x;
   const int tid = threadIdx.x;
+  pdl_release_dependents();
+  pdl_wait_for_primary();
   if (tid == 0) s_rt = make_row_t(__ldg(p.t + row));
-  __syncthreads();
-  const RowT rt = s_rt;
   const PreConsts kc = load_pre_consts<BAKED>(p);
   const size_t base4 = (size_t)row * p.dim4;
+  // eps_0 / eps broadcast over the batch (dense-VLB evaluation: every image shares one key)
+  const size_t nbase4 = (size_t)(p.noise_rows > 0 ? row % p.noise_rows : row) * p.dim4;
   float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int i4 = tid; i4 < p.dim4; i4 += kThreads) {
-    const size_t g4 = base4 + i4;
-    const float4 A = ld4(p.a, g4), Bv = ld4(p.b, g4), C = ld4(p.c, g4);
-    const float4 E0 = ld4(p.eps0, g4), E = ld4(p.eps, g4);
-    const uchar4 X = ldx4(p.x, g4);
-    pre_column<GT, SAVEW, FAST>(p, kc, rt, A, Bv, C, E0, E, X, g4, acc);
+  if (DBUF) {
+    PreCol cur;
+    if (tid < p.dim4) cur = load_pre_col(p, base4 + tid, nbase4 + tid);
+    __syncthreads();
+    const RowT rt = s_rt;
+    for (int i4 = tid; i4 < p.dim4; i4 += NT) {
+      PreCol nxt;
+      const int n4 = i4 + NT;
+      if (n4 < p.dim4) nxt = load_pre_col(p, base4 + n4, nbase4 + n4);
+      pre_column<GT, SAVEW, FAST, CRAW>(p, kc, rt, cur.A, cur.B, cur.C, cur.E0, cur.E, cur.X,
+                                        base4 + i4, acc);
+      cur = nxt;
+    }
+  } else {
+    __syncthreads();
+    const RowT rt = s_rt;
+    for (int i4 = tid; i4 < p.dim4; i4 += NT) {
+      const PreCol c = load_pre_col(p, base4 + i4, nbase4 + i4);
+      pre_column<GT, SAVEW, FAST, CRAW>(p, kc, rt, c.A, c.B, c.C, c.E0, c.E, c.X, base4 + i4, acc);
+    }
   }
-  pre_row_end<GT>(p, row, acc, red);
+  pre_row_end<GT, NW>(p, row, acc, red);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -292,6 +333,8 @@ fwd_pre_tma_kernel(const FwdPreParams p) {
   const int nslab = p.dim4 / kThreads;
   const int my_rows = (p.rows - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int total = my_rows * nslab;
+  pdl_release_dependents();
+  pdl_wait_for_primary();
 
   if (tid == 0) {
     mbar_init(&full[0], 1); mbar_init(&full[1], 1);
@@ -350,6 +393,48 @@ fwd_pre_tma_kernel(const FwdPreParams p) {
 
 static bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; }
 
+// Shape of the default direct-load kernel (threads per CTA, minimum resident CTAs per SM,
+// register double-buffering), chosen by measurement on B200 (profiles/r2_fwd_pre_variants.md).
+#ifndef MULAN_PRE_NT
+#define MULAN_PRE_NT 256
+#define MULAN_PRE_MINB 4
+#define MULAN_PRE_DBUF false
+#endif
+
+// MULAN_FWD_PRE_V=<n> (read per launch; A/B measurements only) selects one of the alternative
+// shapes below for the shipped configuration's kernel; every shape is bit-identical in its
+// per-pixel outputs (same arithmetic, same per-thread accumulation order only when NT matches:
+// the per-row sums of a 128-thread shape differ from the 256-thread ones by float32 rounding).
+static int experimental_shape() {
+  const char* e = getenv("MULAN_FWD_PRE_V");
+  return (e == nullptr || e[0] == '\0') ? -1 : atoi(e);
+}
+
+template <int GT, bool SAVEW, int KIND, bool CRAW>
+static cudaError_t launch_shape(const FwdPreParams& p, cudaStream_t s) {
+  if constexpr (GT == MULAN_GT_MEAN && KIND == 2 && !CRAW) {
+#define MULAN_SHAPE(NT, MINB, DBUF) \
+    return launch_kernel(fwd_pre_kernel<GT, SAVEW, KIND, CRAW, NT, MINB, DBUF>, p.rows, NT, s, \
+                         p.pdl != 0, p)
+    switch (experimental_shape()) {
+      case 0: MULAN_SHAPE(256, 4, false);
+      case 1: MULAN_SHAPE(256, 5, false);
+      case 2: MULAN_SHAPE(256, 3, true);
+      case 3: MULAN_SHAPE(256, 4, true);
+      case 4: MULAN_SHAPE(128, 6, true);
+      case 5: MULAN_SHAPE(128, 8, false);
+      case 6: MULAN_SHAPE(128, 5, true);
+      case 7: MULAN_SHAPE(384, 2, true);
+      case 8: MULAN_SHAPE(128, 10, false);
+      default: break;
+    }
+#undef MULAN_SHAPE
+  }
+  return launch_kernel(
+      fwd_pre_kernel<GT, SAVEW, KIND, CRAW, MULAN_PRE_NT, MULAN_PRE_MINB, MULAN_PRE_DBUF>, p.rows,
+      MULAN_PRE_NT, s, p.pdl != 0, p);
+}
+
 template <int GT, bool SAVEW>
 static cudaError_t launch_w(const FwdPreParams& p, cudaStream_t s) {
   const bool fast = p.W == 1 && p.vi.pow2;
@@ -366,20 +451,29 @@ static cudaError_t launch_w(const FwdPreParams& p, cudaStream_t s) {
     const char* e = getenv("MULAN_FWD_PRE_TMA");
     return (e != nullptr && e[0] == '1') ? 1 : 0;
   }();
-  if (fast && use_tma && p.dim4 % kThreads == 0 && aligned16(p.x)) {
-    static int max_ctas = 0;   // resident CTAs of this variant on the current device
-    if (max_ctas == 0)
-      max_ctas = resident_ctas((const void*)fwd_pre_tma_kernel<GT, SAVEW, false>);
+  if (fast && use_tma && p.dim4 % kThreads == 0 && aligned16(p.x) && !p.c_raw &&
+      p.noise_rows == 0) {
+    // resident CTAs of this variant on the CURRENT device (queried per launch: no process-wide
+    // cache, an XLA-style host calls in from one thread per device)
+    const int max_ctas = resident_ctas((const void*)fwd_pre_tma_kernel<GT, SAVEW, false>);
     const int grid = p.rows < max_ctas ? p.rows : max_ctas;
     if (baked) fwd_pre_tma_kernel<GT, SAVEW, true><<<grid, kThreads, 0, s>>>(p);
     else       fwd_pre_tma_kernel<GT, SAVEW, false><<<grid, kThreads, 0, s>>>(p);
     return cudaGetLastError();
   }
-  dim3 grid(p.rows), block(kThreads);
-  if (baked)     fwd_pre_kernel<GT, SAVEW, true, true><<<grid, block, 0, s>>>(p);
-  else if (fast) fwd_pre_kernel<GT, SAVEW, true, false><<<grid, block, 0, s>>>(p);
-  else           fwd_pre_kernel<GT, SAVEW, false, false><<<grid, block, 0, s>>>(p);
-  return cudaGetLastError();
+  const int kind = baked ? 2 : (fast ? 1 : 0);
+  if (p.c_raw) {
+    switch (kind) {
+      case 2: return launch_shape<GT, SAVEW, 2, true>(p, s);
+      case 1: return launch_shape<GT, SAVEW, 1, true>(p, s);
+      default: return launch_shape<GT, SAVEW, 0, true>(p, s);
+    }
+  }
+  switch (kind) {
+    case 2: return launch_shape<GT, SAVEW, 2, false>(p, s);
+    case 1: return launch_shape<GT, SAVEW, 1, false>(p, s);
+    default: return launch_shape<GT, SAVEW, 0, false>(p, s);
+  }
 }
 
 // Which fwd_pre kernel launch_w() would pick for these launch constants (host-only query):

@@ -238,7 +238,8 @@ static int elbo_host_impl(const mulan_desc* d, const uint8_t* x, const float* a,
     }
   }
   // ---- tail: the six scalars over ALL rows, then losses + scalars back
-  int r = mulan_bpd_reduce(d, dRec, dKlz, nullptr, dDiff, dVar, dSc, nullptr, (void*)ws.s_cmp);
+  int r = mulan_bpd_reduce(d, dRec, dKlz, nullptr, dDiff, dVar, dSc, nullptr, nullptr,
+                           (void*)ws.s_cmp);
   if (r) return drain(ws, r);
   CU(cudaMemcpyAsync(losses, dRec, 3 * B * sizeof(float), cudaMemcpyDeviceToHost, ws.s_cmp));
   CU(cudaMemcpyAsync(scalars, dSc, 6 * sizeof(float), cudaMemcpyDeviceToHost, ws.s_cmp));

@@ -89,11 +89,23 @@ struct FwdPreParams {
   const float *a, *b, *c, *t, *eps0, *eps;
   float *z_t, *g_net, *w_save, *loss_recon, *loss_klz, *var_sums;
   int rows, dim4, gt_mode;
+  int c_raw;          // MULAN_FLAG_C_RAW: c holds the pre-activation of dense_out_c
+  int pdl;            // MULAN_FLAG_PDL: launch with programmatic stream serialization
+  int noise_rows;     // eps0 / eps are [noise_rows, D], row b reads b % noise_rows (0: [rows, D])
   int W;              // reconstruction window half-width for gamma_0 = gamma_min
   float gmin, delta;  // f32(gamma_min), f32(gamma_max - gamma_min)
   EndConsts k;
   ReconFast rc;
   VocabInfo vi;
+};
+
+// VDMOutput assembly + loss_fn scalars (ldm/model_mulan_epsilon.py:357-363,
+// ldm/experiment_vdm.py:62-74), stand-alone or fused into the post kernel's epilogue.
+struct BpdReduceParams {
+  const float *loss_recon, *loss_klz_prior, *kl_z, *loss_diff, *var_sums;
+  float *scalars, *loss_klz_total;
+  unsigned* ws;       // mulan_reduce_ws_bytes(rows) bytes, zero before first use (self-resetting)
+  int rows, dim;
 };
 
 struct PostParams {
@@ -102,9 +114,11 @@ struct PostParams {
   float* loss_diff;   // fwd
   float* n_bar;       // bwd
   int rows, dim4, param;
+  int c_raw, pdl, noise_rows;   // as FwdPreParams (eps is the broadcast operand here)
   float gmin, delta;
   float scale;        // 0.5 (continuous) or 0.5*T (discrete)
   VocabInfo vi;
+  BpdReduceParams red;   // fused loss-scalar reduction (red.ws != nullptr), see mulan_reduce.cuh
 };
 
 struct BwdPreParams {
@@ -112,6 +126,7 @@ struct BwdPreParams {
   const float *a, *b, *c, *t, *eps, *net, *z_bar, *g_bar, *gL;
   float *a_bar, *b_bar, *c_bar;
   int rows, dim4, param, gt_mode;
+  int c_raw, pdl, noise_rows;   // c_raw: c_bar is the cotangent of the pre-activation
   float gmin, delta;
   int T;              // sm_n_timesteps (0 = continuous)
   float inv_T;        // f32(1/T): s = t - 1/T  (ldm/model_mulan_epsilon.py:350)
@@ -122,7 +137,7 @@ struct BwdPreParams {
 struct DiscreteWParams {
   const float *a, *b, *c, *t;
   float* w;
-  int rows, dim4;
+  int rows, dim4, c_raw;
   float gmin, delta, inv_T;
 };
 
@@ -166,13 +181,34 @@ cudaError_t launch_rk45_norm(const Rk45Params& p, double* out, cudaStream_t s);
 cudaError_t launch_rng_draw(int kind, uint32_t k0, uint32_t k1, long long n, float minval,
                             float maxval, void* out, cudaStream_t s);
 
+// <<<grid, block, 0, s>>> with, optionally, the programmatic-stream-serialization attribute
+// (MULAN_FLAG_PDL): the kernel may start while its predecessor on the stream drains; every
+// kernel of the path executes griddepcontrol.wait before its first global access.
+template <typename P>
+inline cudaError_t launch_kernel(void (*kernel)(const P), int grid, int block, cudaStream_t s,
+                                 bool pdl, const P& p) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, p);
+}
+
 // Number of CTAs of `kernel` (kThreads threads, static shared memory only) that are resident
 // on the current device at once: the grid size of the persistent kernels.
-inline int resident_ctas(const void* kernel) {
+// Queried per call (two driver look-ups, no caching): the answer belongs to the CURRENT device,
+// and an XLA-style host calls in from one thread per device.
+inline int resident_ctas(const void* kernel, int threads = kThreads) {
   int dev = 0, sms = 148, per_sm = 1;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0) != cudaSuccess ||
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess ||
       per_sm < 1)
     per_sm = 1;
   return sms * per_sm;
@@ -222,9 +258,7 @@ cudaError_t launch_aux_gumbel(bool bwd, int rows, int latent, float tau, const f
 cudaError_t launch_aux_gaussian(bool bwd, int rows, int latent, const float* mu, const float* var,
                                 const float* eps, const float* emb_bar, const float* klz_bar,
                                 float* out0, float* out1, cudaStream_t s);
-cudaError_t launch_bpd_reduce(int rows, int dim, const float* loss_recon,
-                              const float* loss_klz_prior, const float* kl_z,
-                              const float* loss_diff, const float* var_sums, float* scalars,
-                              float* loss_klz_total, cudaStream_t s);
+cudaError_t launch_bpd_reduce(const BpdReduceParams& p, bool pdl, cudaStream_t s);
+size_t reduce_ws_bytes(int rows);
 
 }  // namespace mulan

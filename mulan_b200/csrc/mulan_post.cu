@@ -16,6 +16,7 @@
 // EPS recompute: eps4+net4+a,b,c 12 = 20; VEL*: x1+eps4+net4+a,b,c 12 = 21 (+4 n_bar).
 // One CTA per row, float4 columns, fixed-order shuffle-tree row sum.
 #include "mulan_kernels.h"
+#include "mulan_reduce.cuh"
 
 namespace mulan {
 
@@ -69,7 +70,11 @@ __device__ __forceinline__ PostPix post_pixel(float a, float b, float c, int xi,
 // MODE 0: loss_diff only; 1: n_bar only; 2: both in one pass (value-and-grad: the caller knows
 // the loss cotangent up front, as jax.value_and_grad does -- 12 B read + 4 B written instead
 // of 12 + 16 for the two separate passes).
-template <int PARAM, bool HAVEW, int MODE>
+// CRAW: c holds the pre-activation of dense_out_c (MULAN_FLAG_C_RAW).
+// REDUCE (mulan_post_bpd): the CTA that makes the last row of a 128-row group final folds the
+// group's loss terms, the CTA that completes the last group writes the six loss_fn scalars
+// (mulan_reduce.cuh) -- VDMOutput + bpd without a separate single-CTA launch.
+template <int PARAM, bool HAVEW, int MODE, bool CRAW, bool REDUCE>
 __global__ void __launch_bounds__(kThreads)
 post_kernel(const PostParams p) {
   constexpr bool BWD = MODE != 0;
@@ -80,6 +85,8 @@ post_kernel(const PostParams p) {
   const int row = blockIdx.x, tid = threadIdx.x;
   constexpr bool kNeedPoly = !(PARAM == MULAN_PARAM_EPS && HAVEW);
   constexpr bool kNeedX = PARAM != MULAN_PARAM_EPS;
+  pdl_release_dependents();
+  pdl_wait_for_primary();
   if (tid == 0) {
     if (kNeedPoly) s_rt = make_row_t(__ldg(p.t + row));
     if (BWD) s_g = __ldg(p.gL + row) * p.scale;
@@ -90,15 +97,20 @@ post_kernel(const PostParams p) {
   const float gs = BWD ? s_g : 0.f;
   const VocabInfo vi = p.vi;
   const size_t base4 = (size_t)row * p.dim4;
+  const size_t nbase4 = (size_t)(p.noise_rows > 0 ? row % p.noise_rows : row) * p.dim4;
   float acc[1] = {0.f};
   for (int i4 = tid; i4 < p.dim4; i4 += kThreads) {
     const size_t g4 = base4 + i4;
     float4 A, Bv, C, Wv;
     uchar4 X;
-    if (kNeedPoly) { A = ld4(p.a, g4); Bv = ld4(p.b, g4); C = ld4(p.c, g4); }
-    else Wv = ld4(p.w_save, g4);
+    if (kNeedPoly) {
+      A = ld4(p.a, g4); Bv = ld4(p.b, g4); C = ld4(p.c, g4);
+      if (CRAW) C = c_from_raw4(C);
+    } else {
+      Wv = ld4(p.w_save, g4);
+    }
     if (kNeedX) X = ldx4(p.x, g4);
-    const float4 E = ld4(p.eps, g4), N = ld4(p.net, g4);
+    const float4 E = ld4(p.eps, nbase4 + i4), N = ld4(p.net, g4);
     float4 NB;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -114,27 +126,41 @@ post_kernel(const PostParams p) {
   if (FWD) {
     block_sum<1>(acc, red);
     if (tid == 0) p.loss_diff[row] = p.scale * acc[0];
+    if (REDUCE) {
+      __shared__ float red5[kWarps][5];
+      __shared__ int s_flag;
+      red_rows_done(p.red, row / kRedGroup, 1, red5, &s_flag);
+    }
   }
+}
+
+template <int PARAM, bool HAVEW, int MODE, bool CRAW>
+static cudaError_t launch_post_r(const PostParams& p, cudaStream_t s) {
+  const bool pdl = p.pdl != 0;
+  if constexpr (MODE != 1) {
+    if (p.red.ws != nullptr)
+      return launch_kernel(post_kernel<PARAM, HAVEW, MODE, CRAW, true>, p.rows, kThreads, s, pdl, p);
+  }
+  return launch_kernel(post_kernel<PARAM, HAVEW, MODE, CRAW, false>, p.rows, kThreads, s, pdl, p);
 }
 
 template <int MODE>
 static cudaError_t launch_post(const PostParams& p, cudaStream_t s) {
   if (p.rows == 0) return cudaSuccess;
-  dim3 grid(p.rows), block(kThreads);
   const bool havew = p.w_save != nullptr;
+  const bool craw = p.c_raw != 0;
   switch (p.param) {
     case MULAN_PARAM_EPS:
-      if (havew) post_kernel<MULAN_PARAM_EPS, true, MODE><<<grid, block, 0, s>>>(p);
-      else       post_kernel<MULAN_PARAM_EPS, false, MODE><<<grid, block, 0, s>>>(p);
-      break;
+      if (havew) return launch_post_r<MULAN_PARAM_EPS, true, MODE, false>(p, s);
+      return craw ? launch_post_r<MULAN_PARAM_EPS, false, MODE, true>(p, s)
+                  : launch_post_r<MULAN_PARAM_EPS, false, MODE, false>(p, s);
     case MULAN_PARAM_VEL:
-      post_kernel<MULAN_PARAM_VEL, false, MODE><<<grid, block, 0, s>>>(p);
-      break;
+      return craw ? launch_post_r<MULAN_PARAM_VEL, false, MODE, true>(p, s)
+                  : launch_post_r<MULAN_PARAM_VEL, false, MODE, false>(p, s);
     default:
-      post_kernel<MULAN_PARAM_VEL_FROM_EPS, false, MODE><<<grid, block, 0, s>>>(p);
-      break;
+      return craw ? launch_post_r<MULAN_PARAM_VEL_FROM_EPS, false, MODE, true>(p, s)
+                  : launch_post_r<MULAN_PARAM_VEL_FROM_EPS, false, MODE, false>(p, s);
   }
-  return cudaGetLastError();
 }
 
 cudaError_t launch_fwd_post(const PostParams& p, cudaStream_t s) { return launch_post<0>(p, s); }
@@ -147,6 +173,8 @@ __global__ void __launch_bounds__(kThreads)
 scale_rows_kernel(float* __restrict__ v, const float* __restrict__ num,
                   const float* __restrict__ den, int dim4) {
   const int row = blockIdx.x;
+  pdl_release_dependents();
+  pdl_wait_for_primary();
   const float n = __ldg(num + row), d = __ldg(den + row);
   // "equal" up to 4 ulp: the framework's mean-backward may round 1/(B*D*ln 2) differently
   // from the hint; a 5e-7 relative difference in a gradient is far inside its 1e-4 tolerance

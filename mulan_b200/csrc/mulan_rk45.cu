@@ -181,7 +181,8 @@ int stage_blocks(int64_t n) {
 }
 int norm_blocks(int64_t n) {
   const int64_t want = ((n + 3) / 4 + kRkThreads - 1) / kRkThreads;
-  static const int64_t cap = resident_ctas((const void*)rk45_norm_partial_kernel<true>);
+  // per call, for the CURRENT device (no process-wide cache: one host thread per device)
+  const int64_t cap = resident_ctas((const void*)rk45_norm_partial_kernel<true>, kRkThreads);
   int64_t b = want < cap ? want : cap;
   if (b > MULAN_RK45_SCRATCH) b = MULAN_RK45_SCRATCH;
   return (int)(b < 1 ? 1 : b);

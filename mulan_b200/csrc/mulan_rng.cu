@@ -102,8 +102,8 @@ __global__ void __launch_bounds__(kThreads) rng_kernel(const RngParams p) {
 
 template <int KIND>
 cudaError_t launch_rng(RngParams p, cudaStream_t s) {
-  static int max_ctas = 0;
-  if (max_ctas == 0) max_ctas = resident_ctas((const void*)rng_kernel<KIND>);
+  // per call, for the CURRENT device (no process-wide cache: one host thread per device)
+  const int max_ctas = resident_ctas((const void*)rng_kernel<KIND>);
   const long long want = (p.half + kThreads - 1) / kThreads;
   const int grid = (int)(want < max_ctas ? want : max_ctas);
   rng_kernel<KIND><<<grid < 1 ? 1 : grid, kThreads, 0, s>>>(p);

@@ -124,7 +124,7 @@ void mulan_xla_bpd_reduce(void* stream, void** buffers, const char* opaque, size
                           void* status) {
   Unpacked u;
   if (!unpack("mulan_xla_bpd_reduce", opaque, opaque_len, &u, status)) return;
-  if (mulan_bpd_reduce(&u.desc, CF(0), CF(1), CF(2), CF(3), CF(4), F(5), F(6), stream))
+  if (mulan_bpd_reduce(&u.desc, CF(0), CF(1), CF(2), CF(3), CF(4), F(5), F(6), nullptr, stream))
     report(status, "mulan_xla_bpd_reduce");
 }
 

@@ -21,8 +21,8 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import (MULAN_GT_MEAN, MULAN_GT_PIXEL, MULAN_PARAM_EPS, MULAN_PARAM_VEL,
-                   MULAN_PARAM_VEL_FROM_EPS, make_desc)
+from ._lib import (MULAN_FLAG_C_RAW, MULAN_FLAG_PDL, MULAN_GT_MEAN, MULAN_GT_PIXEL,
+                   MULAN_PARAM_EPS, MULAN_PARAM_VEL, MULAN_PARAM_VEL_FROM_EPS, make_desc)
 
 
 def _p(t: Optional[torch.Tensor]):
@@ -50,16 +50,43 @@ def _opt(t, dtype, shape, name):
 
 
 class Desc:
-  """Python view of mulan_desc (per launch; rows filled from the tensors)."""
+  """Python view of mulan_desc (per launch; rows filled from the tensors).
+
+  c_raw: the `c` tensors are the PRE-ACTIVATION of dense_out_c; the kernels apply
+  1e-3 + softplus (ldm/model_mulan_epsilon.py:537) and bwd_pre returns its cotangent.
+  pdl: programmatic dependent launch.  noise_rows: eps0 / eps are [noise_rows, D], broadcast
+  over the batch by row % noise_rows (dense-VLB evaluation)."""
 
   def __init__(self, dim=3072, vocab=256, param=MULAN_PARAM_EPS, gt_mode=MULAN_GT_MEAN,
-               n_timesteps=0, gamma_min=-13.3, gamma_max=5.0):
+               n_timesteps=0, gamma_min=-13.3, gamma_max=5.0, c_raw=False, pdl=False,
+               noise_rows=0):
     self.dim, self.vocab, self.param, self.gt_mode = dim, vocab, param, gt_mode
     self.n_timesteps, self.gamma_min, self.gamma_max = n_timesteps, gamma_min, gamma_max
+    self.c_raw, self.pdl, self.noise_rows = bool(c_raw), bool(pdl), int(noise_rows)
+
+  @property
+  def flags(self) -> int:
+    return (MULAN_FLAG_C_RAW if self.c_raw else 0) | (MULAN_FLAG_PDL if self.pdl else 0)
+
+  def replace(self, **kw) -> 'Desc':
+    d = Desc.__new__(Desc)
+    d.__dict__.update(self.__dict__)
+    d.__dict__.update(kw)
+    return d
 
   def c(self, rows: int):
     return make_desc(rows, self.dim, self.vocab, self.param, self.gt_mode, self.n_timesteps,
-                     self.gamma_min, self.gamma_max)
+                     self.gamma_min, self.gamma_max, self.flags, self.noise_rows)
+
+  def noise_shape(self, rows: int):
+    return (self.noise_rows if self.noise_rows > 0 else rows, self.dim)
+
+
+def reduce_workspace(rows: int, device) -> torch.Tensor:
+  """Zeroed scratch of the fixed-order loss-scalar reduction (mulan_reduce_ws_bytes); every
+  call leaves it zero, so one buffer serves consecutive calls on a stream."""
+  n = int(_lib.load().mulan_reduce_ws_bytes(int(rows)))
+  return torch.zeros((n + 3) // 4, dtype=torch.int32, device=device)
 
 
 def saves_w(desc: 'Desc') -> bool:
@@ -77,8 +104,10 @@ def fwd_pre(desc: Desc, x, a, b, c, t, eps0, eps, save_w: bool = True, end_const
   rounds them (mulan_fwd_pre_consts) instead of the host-computed, correctly rounded ones."""
   B, D = a.shape
   _req(x, torch.uint8, (B, D), 'x')
-  for n, v in (('a', a), ('b', b), ('c', c), ('eps0', eps0), ('eps', eps)):
+  for n, v in (('a', a), ('b', b), ('c', c)):
     _req(v, torch.float32, (B, D), n)
+  for n, v in (('eps0', eps0), ('eps', eps)):
+    _req(v, torch.float32, desc.noise_shape(B), n)
   _req(t, torch.float32, (B,), 't')
   dev = a.device
   z_t = torch.empty((B, D), dtype=torch.float32, device=dev)
@@ -100,8 +129,9 @@ def fwd_pre(desc: Desc, x, a, b, c, t, eps0, eps, save_w: bool = True, end_const
 
 def fwd_post(desc: Desc, x, a, b, c, t, eps, net, w=None):
   """mulan_fwd_post -> loss_diff[B]."""
-  B, D = eps.shape
+  B, D = net.shape
   _req(net, torch.float32, (B, D), 'net')
+  _req(eps, torch.float32, desc.noise_shape(B), 'eps')
   out = torch.empty((B,), dtype=torch.float32, device=eps.device)
   d = desc.c(B)
   _lib.check(_lib.load().mulan_fwd_post(
@@ -112,7 +142,7 @@ def fwd_post(desc: Desc, x, a, b, c, t, eps, net, w=None):
 
 def bwd_post(desc: Desc, x, a, b, c, t, eps, net, w, gL):
   """mulan_bwd_post -> n_bar[B,D]."""
-  B, D = eps.shape
+  B, D = net.shape
   _req(gL, torch.float32, (B,), 'gL')
   out = torch.empty((B, D), dtype=torch.float32, device=eps.device)
   d = desc.c(B)
@@ -124,8 +154,9 @@ def bwd_post(desc: Desc, x, a, b, c, t, eps, net, w, gL):
 
 def fwd_bwd_post(desc: Desc, x, a, b, c, t, eps, net, w, gL):
   """mulan_fwd_bwd_post -> (loss_diff[B], n_bar[B,D]) in one pass, for a known cotangent gL."""
-  B, D = eps.shape
+  B, D = net.shape
   _req(net, torch.float32, (B, D), 'net')
+  _req(eps, torch.float32, desc.noise_shape(B), 'eps')
   _req(gL, torch.float32, (B,), 'gL')
   diff = torch.empty((B,), dtype=torch.float32, device=eps.device)
   n_bar = torch.empty((B, D), dtype=torch.float32, device=eps.device)
@@ -184,16 +215,43 @@ def aux_topk_bwd(logits, gamma_draw, k: int, emb_bar, klz_bar):
 
 
 def bpd_reduce(desc: Desc, loss_recon, loss_klz_prior, kl_z, loss_diff, var_sums,
-               want_klz_total: bool = False):
-  """mulan_bpd_reduce -> scalars[6] = bpd, bpd_latent, bpd_recon, bpd_diff, var0, var1."""
+               want_klz_total: bool = False, ws='auto'):
+  """mulan_bpd_reduce -> scalars[6] = bpd, bpd_latent, bpd_recon, bpd_diff, var0, var1.
+  ws: reduce_workspace(rows) tensor, 'auto' (allocate one) or None (single-CTA form)."""
   B = loss_recon.shape[0]
   sc = torch.empty((6,), dtype=torch.float32, device=loss_recon.device)
   tot = torch.empty((B,), dtype=torch.float32, device=loss_recon.device) if want_klz_total else None
+  if isinstance(ws, str):
+    ws = reduce_workspace(B, loss_recon.device)
   d = desc.c(B)
   _lib.check(_lib.load().mulan_bpd_reduce(
       C.byref(d), _p(loss_recon), _p(loss_klz_prior), _p(kl_z), _p(loss_diff), _p(var_sums),
-      _p(sc), _p(tot), _stream()))
+      _p(sc), _p(tot), _p(ws), _stream()))
   return (sc, tot) if want_klz_total else sc
+
+
+def post_bpd(desc: Desc, x, a, b, c, t, eps, net, w, gL, loss_recon, loss_klz_prior, kl_z,
+             var_sums, want_klz_total: bool = False, ws=None):
+  """mulan_post_bpd: the post kernel (value only when gL is None, value-and-grad otherwise) with
+  the loss-scalar reduction fused into its epilogue.
+  -> dict(loss_diff[B], n_bar[B,D] | None, scalars[6], loss_klz_total[B] | None)."""
+  B, D = net.shape
+  _req(net, torch.float32, (B, D), 'net')
+  _req(eps, torch.float32, desc.noise_shape(B), 'eps')
+  _opt(gL, torch.float32, (B,), 'gL')
+  dev = net.device
+  diff = torch.empty((B,), dtype=torch.float32, device=dev)
+  n_bar = torch.empty((B, D), dtype=torch.float32, device=dev) if gL is not None else None
+  sc = torch.empty((6,), dtype=torch.float32, device=dev)
+  tot = torch.empty((B,), dtype=torch.float32, device=dev) if want_klz_total else None
+  if ws is None:
+    ws = reduce_workspace(B, dev)
+  d = desc.c(B)
+  _lib.check(_lib.load().mulan_post_bpd(
+      C.byref(d), _p(x), _p(a), _p(b), _p(c), _p(t), _p(eps), _p(net), _p(w), _p(gL),
+      _p(loss_recon), _p(loss_klz_prior), _p(kl_z), _p(var_sums), _p(diff), _p(n_bar), _p(sc),
+      _p(tot), _p(ws), _stream()))
+  return dict(loss_diff=diff, n_bar=n_bar, scalars=sc, loss_klz_total=tot)
 
 
 def sample_gamma(desc: Desc, a, b, c, t):
@@ -330,6 +388,7 @@ class ElboWorkspace:
     self.loss_recon, self.loss_klz_prior, self.loss_diff = f(rows), f(rows), f(rows)
     self.var_sums, self.scalars, self.loss_klz = f(rows, 2), f(6), f(rows)
     self.n_bar, self.a_bar, self.b_bar, self.c_bar = f(rows, D), f(rows, D), f(rows, D), f(rows, D)
+    self.reduce_ws = reduce_workspace(rows, device)
     self._d = desc.c(rows)
     self._lib = _lib.load()
 
@@ -349,10 +408,19 @@ class ElboWorkspace:
         C.byref(self._d), _p(x), _p(a), _p(b), _p(c), _p(t), _p(eps), _p(net), _p(self.w), _p(gL),
         _p(self.loss_diff), _p(self.n_bar), _stream()))
 
-  def bpd_reduce(self, kl_z=None):
+  def bpd_reduce(self, kl_z=None, parallel: bool = True):
     _lib.check(self._lib.mulan_bpd_reduce(
         C.byref(self._d), _p(self.loss_recon), _p(self.loss_klz_prior), _p(kl_z),
-        _p(self.loss_diff), _p(self.var_sums), _p(self.scalars), _p(self.loss_klz), _stream()))
+        _p(self.loss_diff), _p(self.var_sums), _p(self.scalars), _p(self.loss_klz),
+        _p(self.reduce_ws if parallel else None), _stream()))
+
+  def post_bpd(self, x, a, b, c, t, eps, net, gL=None, kl_z=None):
+    """post kernel (value-and-grad when gL is given) + the six scalars, one launch."""
+    _lib.check(self._lib.mulan_post_bpd(
+        C.byref(self._d), _p(x), _p(a), _p(b), _p(c), _p(t), _p(eps), _p(net), _p(self.w), _p(gL),
+        _p(self.loss_recon), _p(self.loss_klz_prior), _p(kl_z), _p(self.var_sums),
+        _p(self.loss_diff), _p(self.n_bar if gL is not None else None), _p(self.scalars),
+        _p(self.loss_klz), _p(self.reduce_ws), _stream()))
 
   def bwd_post(self, x, a, b, c, t, eps, net, gL):
     _lib.check(self._lib.mulan_bwd_post(

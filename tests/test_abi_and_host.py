@@ -29,7 +29,7 @@ def lib():
 def header_symbols():
   src = open(HEADER).read()
   src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
-  return sorted(set(re.findall(r'^\s*(?:const\s+char\s*\*|int|void)\s+(mulan_\w+)\s*\(', src,
+  return sorted(set(re.findall(r'^\s*(?:const\s+char\s*\*|int|void|size_t)\s+(mulan_\w+)\s*\(', src,
                                flags=re.M)))
 
 
@@ -40,13 +40,14 @@ def test_library_exports_every_declared_symbol(lib):
   for s in syms:
     assert hasattr(handle, s), f'libmulan_b200.so does not export {s}'
   assert set(syms) == set(lib.SIGNATURES), (set(syms) ^ set(lib.SIGNATURES))
-  assert handle.mulan_abi_version() == 1
+  assert handle.mulan_abi_version() == lib.MULAN_ABI_VERSION == 2
 
 
 def test_desc_layout_matches_header(lib):
   # 6 x int32 + 2 x double, no padding surprises
-  assert C.sizeof(lib.MulanDesc) == 40
+  assert C.sizeof(lib.MulanDesc) == 48
   assert lib.MulanDesc.gamma_min.offset == 24 and lib.MulanDesc.gamma_max.offset == 32
+  assert lib.MulanDesc.flags.offset == 40 and lib.MulanDesc.noise_rows.offset == 44
 
 
 def test_argument_validation_without_gpu(lib):
@@ -406,7 +407,7 @@ int main(void) {
   env = {k: v for k, v in os.environ.items() if k != 'MULAN_VFE_LITERAL'}
   out = subprocess.run([str(exe)], check=True, capture_output=True, text=True, env=env).stdout
   first, second = out.strip().split('\n')
-  assert first.startswith('1 40 48 -2|') and 'not a multiple of 4' in first
+  assert first.startswith('2 48 56 -2|') and 'not a multiple of 4' in first
   assert second == '0 1'
   subprocess.run(['g++', '-std=c++11', '-Wall', '-Wextra', '-Werror', '-fsyntax-only', '-I', inc,
                   '-x', 'c++', str(src)], check=True, capture_output=True)

@@ -674,7 +674,8 @@ def test_caller_supplied_end_constants_track_the_oracle(cuda_device, field, ulps
   D = inp['a'].shape[1]
   assert abs(got['var_sums'][:, 0].sum().item() / (B * D) - out.var_0.item()) < 1e-6 * out.var_0.item()
   assert abs(got['var_sums'][:, 1].sum().item() / (B * D) - out.var_1.item()) < 1e-6
-  # and the constant really is live: the output it feeds moved (or the move is below float32
-  # resolution of the row sum, which only exp(-g_0/2) can be)
-  moved = any(not torch.equal(base[key], got[key]) for key in _CONST_MOVES[field])
-  assert moved or field == 'exp_neg_half_g0', field
+  # and the constant really is live where one ulp of it is above the float32 resolution of the
+  # row sum it feeds (log sigmoid(g_1) ~ -7e-3 is absorbed by v_1 - log v_1 ~ 1; one ulp of
+  # exp(-g_0/2) or sigmoid(g_0) can round away in the products)
+  if field in ('exp_half_g0', 'sigmoid_g1'):
+    assert any(not torch.equal(base[key], got[key]) for key in _CONST_MOVES[field]), field

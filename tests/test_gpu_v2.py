@@ -1,0 +1,287 @@
+"""GPU tests of the ABI v2 additions: the dense_out_c pre-activation taken by the kernels
+(MULAN_FLAG_C_RAW), broadcast noise rows, programmatic dependent launch, the fused / parallel
+loss-scalar reduction (mulan_post_bpd, mulan_bpd_reduce with a workspace), the alternative
+fwd_pre kernel shapes, and concurrent host threads (one per stream / device, as jax.pmap's
+executor threads call the custom-call targets, ldm/experiment.py:89-91)."""
+import ctypes as C
+import math
+import os
+import threading
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mulan_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+PARAMS = [O.MODE_EPS, O.MODE_VEL, O.MODE_VEL_FROM_EPS]
+
+
+def dev_inputs(B, seed, dev, raw=False):
+  inp = O.synth_inputs(B, seed)
+  g = {k: v.to(dev).contiguous() for k, v in inp.items()}
+  if raw:
+    r = np.random.default_rng(seed + 99).standard_normal((B, 3072)) * 3.0
+    r[0, :64] = np.linspace(-30, 30, 64)            # softplus tails on both sides
+    inp['c_raw'] = torch.from_numpy(r.astype(np.float32))
+    inp['c'] = O.coefficients_from_raw(inp['c_raw'])
+    g['c_raw'], g['c'] = inp['c_raw'].to(dev), inp['c'].to(dev)
+  return inp, g
+
+
+def step(desc, g, c_key='c', gL=None, z_bar=None, g_bar=None, save_w=None):
+  """fwd_pre -> fwd_bwd_post -> bwd_pre through the raw ops; returns every output."""
+  from mulan_b200 import ops
+  B = g['a'].shape[0]
+  if gL is None:
+    gL = torch.full((B,), 1.0 / (B * 3072 * math.log(2.0)), device=g['a'].device)
+  save_w = ops.saves_w(desc) if save_w is None else save_w
+  pre = ops.fwd_pre(desc, g['x'], g['a'], g['b'], g[c_key], g['t'], g['eps_0'], g['eps'],
+                    save_w=save_w)
+  diff, n_bar = ops.fwd_bwd_post(desc, g['x'], g['a'], g['b'], g[c_key], g['t'], g['eps'],
+                                 g['net'], pre['w'], gL)
+  ab, bb, cb = ops.bwd_pre(desc, g['x'], g['a'], g['b'], g[c_key], g['t'], g['eps'], g['net'],
+                           z_bar, g_bar, gL)
+  out = dict(pre)
+  out.update(loss_diff=diff, n_bar=n_bar, a_bar=ab, b_bar=bb, c_bar=cb)
+  return out
+
+
+def rel(a, b):
+  a, b = a.double(), b.double()
+  return float(((a - b).abs() / b.abs().clamp_min(1e-30)).max())
+
+
+def rel_l2(a, b):
+  a, b = a.double(), b.double()
+  return float((a - b).norm() / b.norm().clamp_min(1e-300))
+
+
+@pytest.mark.parametrize('param', PARAMS)
+def test_c_raw_matches_activated_c(cuda_device, param):
+  """MULAN_FLAG_C_RAW: handing over the pre-activation r of dense_out_c gives the losses of
+  c = 1e-3 + softplus(r) (ldm/model_mulan_epsilon.py:537) and returns c_bar * sigmoid(r)."""
+  from mulan_b200 import ops
+  B = 6
+  inp, g = dev_inputs(B, 11, cuda_device, raw=True)
+  z_bar = (1e-4 * torch.randn(B, 3072, generator=torch.Generator().manual_seed(1))).to(cuda_device)
+  g_bar = (1e-3 * torch.randn(B, generator=torch.Generator().manual_seed(2))).to(cuda_device)
+  base = step(ops.Desc(param=param), g, 'c', z_bar=z_bar, g_bar=g_bar)
+  raw = step(ops.Desc(param=param, c_raw=True), g, 'c_raw', z_bar=z_bar, g_bar=g_bar)
+  for k in ('loss_recon', 'loss_klz_prior', 'loss_diff'):
+    assert rel(raw[k], base[k]) < 2e-6, k
+  assert rel_l2(raw['z_t'], base['z_t']) < 1e-6
+  assert rel_l2(raw['n_bar'], base['n_bar']) < 1e-5
+  assert rel_l2(raw['a_bar'], base['a_bar']) < 1e-5
+  assert rel_l2(raw['b_bar'], base['b_bar']) < 1e-5
+  want = base['c_bar'] * torch.sigmoid(g['c_raw'])
+  assert rel_l2(raw['c_bar'], want) < 1e-5
+  # and the in-kernel softplus against the oracle's (float64) element by element
+  c64 = O.coefficients_from_raw(inp['c_raw'].double())
+  pix = ops.Desc(param=param, gt_mode=1, c_raw=True)
+  g_pix = ops.fwd_pre(pix, g['x'], g['a'], g['b'], g['c_raw'], g['t'], g['eps_0'], g['eps'],
+                      save_w=False)['g_net']
+  cfg = O.OracleConfig()
+  want_g = O.eval_polynomial(inp['a'].double(), inp['b'].double(), c64,
+                             inp['t'].double().reshape(-1, 1), cfg)
+  assert (g_pix.double().cpu() - want_g).abs().max() < 5e-4     # cancellation-limited pixels
+  assert (g_pix.double().cpu() - want_g).abs().mean() < 5e-6
+
+
+def test_c_raw_through_the_model(cuda_device):
+  """model.VDM hands the built-in schedule head's pre-activation to the kernels; losses and
+  parameter gradients equal the unfused path (softplus and its backward in torch)."""
+  import sys
+  sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden'))
+  import golden_inputs as GI
+  from mulan_b200.model import VDM, VDMConfig, loss_fn
+  dev = cuda_device
+  B = 4
+  torch.manual_seed(0)
+  enc_w = (0.1 * torch.randn(256, 50)).to(dev)
+  w = torch.nn.Parameter(torch.tensor(0.7, device=dev))
+  model = VDM(VDMConfig(vdm_type='mulan_velocity'),
+              lambda f, det: f.reshape(f.shape[0], -1)[:, :256] @ enc_w,
+              lambda z, gt, cond, det: w * z + 0.01 * gt.reshape(-1, 1, 1, 1)).to(dev)
+  model.gamma.load_flax(GI.mlp_weights(5))
+  images = torch.randint(0, 256, (B, 32, 32, 3), device=dev,
+                         generator=torch.Generator(device=dev).manual_seed(3))
+  draws = model.make_draws(B, dev, torch.Generator(device=dev).manual_seed(4))
+  res = {}
+  for fused in (True, False):
+    model.fused_softplus = fused
+    model.zero_grad()
+    w.grad = None
+    bpd, _ = loss_fn(model, {'images': images}, draws=draws)
+    bpd.backward()
+    res[fused] = (bpd.item(), model.gamma.dense_out_c.bias.grad.clone(),
+                  model.gamma.dense_out_b.bias.grad.clone(), w.grad.clone())
+  assert abs(res[True][0] - res[False][0]) < 1e-5 * abs(res[False][0])
+  for i in (1, 2, 3):
+    assert rel_l2(res[True][i], res[False][i]) < 2e-5, i
+
+
+@pytest.mark.parametrize('param', PARAMS)
+def test_noise_rows_broadcast_is_bitwise_the_tiled_call(cuda_device, param):
+  """noise_rows = N: eps_0 / eps are [N, D] and row b reads row b % N -- the same bits as
+  materialising the tiled [B, D] arrays (dense-VLB evaluation, notebook_utils.py:178-185)."""
+  from mulan_b200 import ops
+  B, N = 12, 4
+  _, g = dev_inputs(B, 21, cuda_device)
+  gt = dict(g)
+  gt['eps_0'] = g['eps_0'][:N].repeat(B // N, 1).contiguous()
+  gt['eps'] = g['eps'][:N].repeat(B // N, 1).contiguous()
+  gt['net'] = g['net']
+  tiled = step(ops.Desc(param=param), gt)
+  gb = dict(g)
+  gb['eps_0'], gb['eps'] = g['eps_0'][:N].contiguous(), g['eps'][:N].contiguous()
+  bc = step(ops.Desc(param=param, noise_rows=N), gb)
+  for k, v in tiled.items():
+    if v is not None:
+      assert torch.equal(v, bc[k]), k
+
+
+@pytest.mark.parametrize('param', PARAMS)
+def test_pdl_launch_is_bitwise_the_plain_launch(cuda_device, param):
+  from mulan_b200 import ops
+  _, g = dev_inputs(9, 31, cuda_device)
+  plain = step(ops.Desc(param=param), g)
+  for _ in range(3):
+    pdl = step(ops.Desc(param=param, pdl=True), g)
+    for k, v in plain.items():
+      if v is not None:
+        assert torch.equal(v, pdl[k]), k
+
+
+@pytest.mark.parametrize('rows', [1, 5, 128, 129, 1000])
+@pytest.mark.parametrize('param', [O.MODE_EPS, O.MODE_VEL])
+def test_post_bpd_equals_separate_post_and_reduce(cuda_device, rows, param):
+  """mulan_post_bpd == mulan_fwd_bwd_post (or mulan_fwd_post) + mulan_bpd_reduce, bit for bit,
+  in all three forms of the reduction (fused, parallel with workspace, single CTA); the
+  workspace is left zero and is reusable; scalars match the oracle's loss_fn."""
+  from mulan_b200 import ops
+  dev = cuda_device
+  inp, g = dev_inputs(rows, 41 + rows, dev)
+  desc = ops.Desc(param=param)
+  gL = torch.full((rows,), 1.0 / (rows * 3072 * math.log(2.0)), device=dev)
+  kl_z = torch.rand(rows, generator=torch.Generator().manual_seed(5)).to(dev)
+  pre = ops.fwd_pre(desc, g['x'], g['a'], g['b'], g['c'], g['t'], g['eps_0'], g['eps'],
+                    save_w=ops.saves_w(desc))
+  diff, n_bar = ops.fwd_bwd_post(desc, g['x'], g['a'], g['b'], g['c'], g['t'], g['eps'],
+                                 g['net'], pre['w'], gL)
+  ws = ops.reduce_workspace(rows, dev)
+  sc_par, tot_par = ops.bpd_reduce(desc, pre['loss_recon'], pre['loss_klz_prior'], kl_z, diff,
+                                   pre['var_sums'], want_klz_total=True, ws=ws)
+  sc_one, tot_one = ops.bpd_reduce(desc, pre['loss_recon'], pre['loss_klz_prior'], kl_z, diff,
+                                   pre['var_sums'], want_klz_total=True, ws=None)
+  assert torch.equal(sc_par, sc_one) and torch.equal(tot_par, tot_one)
+  assert torch.count_nonzero(ws).item() == 0
+  for with_grad in (True, False, True):          # reuse the same workspace
+    f = ops.post_bpd(desc, g['x'], g['a'], g['b'], g['c'], g['t'], g['eps'], g['net'], pre['w'],
+                     gL if with_grad else None, pre['loss_recon'], pre['loss_klz_prior'], kl_z,
+                     pre['var_sums'], want_klz_total=True, ws=ws)
+    assert torch.equal(f['loss_diff'], diff)
+    assert torch.equal(f['scalars'], sc_par)
+    assert torch.equal(f['loss_klz_total'], tot_par)
+    if with_grad:
+      assert torch.equal(f['n_bar'], n_bar)
+    assert torch.count_nonzero(ws).item() == 0
+  # against the oracle's loss_fn (ldm/experiment_vdm.py:62-74)
+  out = O.elbo_terms(inp['x'], inp['a'], inp['b'], inp['c'], inp['t'], inp['eps_0'], inp['eps'],
+                     lambda z, gg: inp['net'], param, O.OracleConfig(), kl_z=kl_z.cpu())
+  bpd, sc = O.loss_fn_bpd(out)
+  got = sc_par.cpu()
+  for i, k in enumerate(('bpd', 'bpd_latent', 'bpd_recon', 'bpd_diff')):
+    assert abs(got[i].item() - sc[k].item()) < 1e-5 * abs(sc[k].item()), k
+  assert abs(got[4].item() - sc['var0'].item()) < 1e-6 * sc['var0'].item()
+  assert abs(got[5].item() - sc['var'].item()) < 1e-6
+
+
+def test_fwd_pre_kernel_shapes_agree(cuda_device, monkeypatch):
+  """MULAN_FWD_PRE_V: CTA size / residency / register double-buffering change how the loads are
+  scheduled, never the arithmetic -- per-pixel outputs are bit-identical, per-row sums agree to
+  float32 summation order."""
+  from mulan_b200 import ops
+  _, g = dev_inputs(37, 51, cuda_device)
+  desc = ops.Desc()
+  args = (g['x'], g['a'], g['b'], g['c'], g['t'], g['eps_0'], g['eps'])
+  monkeypatch.delenv('MULAN_FWD_PRE_V', raising=False)
+  base = ops.fwd_pre(desc, *args)
+  for v in range(9):
+    monkeypatch.setenv('MULAN_FWD_PRE_V', str(v))
+    for save_w in (True, False):
+      got = ops.fwd_pre(desc, *args, save_w=save_w)
+      assert torch.equal(got['z_t'], base['z_t']), v
+      if save_w:
+        assert torch.equal(got['w'], base['w']), v
+      for k in ('loss_recon', 'loss_klz_prior', 'g_net', 'var_sums'):
+        assert rel(got[k], base[k]) < 2e-6, (v, k)
+  monkeypatch.delenv('MULAN_FWD_PRE_V', raising=False)
+
+
+def test_concurrent_host_threads_bitwise_serial(cuda_device):
+  """The single-process contract of jax.pmap (ldm/experiment.py:89-91): XLA calls the custom-call
+  targets from one executor thread per device.  8 host threads, each with its own stream (and
+  its own device when several are visible), drive the legacy XLA targets concurrently; every
+  result equals the serial one bit for bit."""
+  from mulan_b200 import _lib, ops
+  lib = _lib.load()
+  n_dev = torch.cuda.device_count()
+  n_threads, iters, B = 8, 6, 96
+  jobs = []
+  for i in range(n_threads):
+    dev = torch.device(f'cuda:{i % n_dev}')
+    _, g = dev_inputs(B, 100 + i, dev)
+    jobs.append((dev, g))
+
+  def run(dev, g, stream):
+    """fwd_pre -> fwd_bwd_post -> bwd_pre -> bpd_reduce through the mulan_xla_* targets."""
+    with torch.cuda.device(dev):
+      f = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+      z, gn, w, rec, klz, vs = f(B, 3072), f(B), f(B, 3072), f(B), f(B), f(B, 2)
+      diff, nb, ab, bb, cb, sc, tot = f(B), f(B, 3072), f(B, 3072), f(B, 3072), f(B, 3072), f(6), f(B)
+      gL = torch.full((B,), 1.0 / (B * 3072 * math.log(2.0)), device=dev)
+      op = _lib.MulanXlaOpaque(desc=_lib.make_desc(rows=B), absent_mask=0, reserved=0)
+      opb = _lib.MulanXlaOpaque(desc=_lib.make_desc(rows=B), absent_mask=(1 << 7) | (1 << 8),
+                                reserved=0)
+      opr = _lib.MulanXlaOpaque(desc=_lib.make_desc(rows=B), absent_mask=1 << 2, reserved=0)
+
+      def call(name, bufs, o):
+        arr = (C.c_void_p * len(bufs))(*[b.data_ptr() for b in bufs])
+        getattr(lib, name)(C.c_void_p(stream.cuda_stream), arr, bytes(o), C.sizeof(o), None)
+      call('mulan_xla_fwd_pre', [g['x'], g['a'], g['b'], g['c'], g['t'], g['eps_0'], g['eps'],
+                                 z, gn, w, rec, klz, vs], op)
+      call('mulan_xla_fwd_bwd_post', [g['x'], g['a'], g['b'], g['c'], g['t'], g['eps'], g['net'],
+                                      w, gL, diff, nb], op)
+      call('mulan_xla_bwd_pre', [g['x'], g['a'], g['b'], g['c'], g['t'], g['eps'], g['net'],
+                                 g['eps'], g['t'], gL, ab, bb, cb], opb)
+      call('mulan_xla_bpd_reduce', [rec, klz, rec, diff, vs, sc, tot], opr)
+      stream.synchronize()
+      return [t.clone() for t in (z, gn, w, rec, klz, vs, diff, nb, ab, bb, cb, sc)]
+
+  streams = [torch.cuda.Stream(device=dev) for dev, _ in jobs]
+  serial = [run(dev, g, s) for (dev, g), s in zip(jobs, streams)]
+  results, errors = [None] * n_threads, []
+  start = threading.Barrier(n_threads)
+
+  def worker(i):
+    try:
+      dev, g = jobs[i]
+      torch.cuda.set_device(dev)
+      start.wait()
+      for _ in range(iters):
+        results[i] = run(dev, g, streams[i])
+    except Exception as exc:      # surfaced below
+      errors.append((i, repr(exc)))
+  threads = [threading.Thread(target=worker, args=(i,)) for i in range(n_threads)]
+  for t in threads:
+    t.start()
+  for t in threads:
+    t.join()
+  assert not errors, errors
+  for i in range(n_threads):
+    for a_, b_ in zip(results[i], serial[i]):
+      assert torch.equal(a_, b_), i
+  assert lib.mulan_last_error() is not None

@@ -35,26 +35,26 @@ def test_library_exports_every_declared_target(lib):
   for s in syms:
     assert hasattr(h, s), s
   assert set(syms) == set(lib.XLA_SIGNATURES)
-  assert C.sizeof(lib.MulanXlaOpaque) == 48 and lib.MulanXlaOpaque.absent_mask.offset == 40
+  assert C.sizeof(lib.MulanXlaOpaque) == 56 and lib.MulanXlaOpaque.absent_mask.offset == 48
   assert C.sizeof(lib.MulanXlaAuxOpaque) == 16
 
 
 def test_python_side_opaque_packing_matches_the_struct(lib):
-  """jax_binding/mulan_jax_legacy.py packs the opaque with struct.pack('<6i2d2I', ...)."""
+  """jax_binding/mulan_jax_legacy.py packs the opaque with struct.pack('<6i2dIi2I', ...)."""
   import struct
   src = open(os.path.join(ROOT, 'jax_binding', 'mulan_jax_legacy.py')).read()
-  assert "struct.pack('<6i2d2I'" in src
+  assert "struct.pack('<6i2dIi2I'" in src
   op = lib.MulanXlaOpaque(desc=lib.make_desc(rows=7, dim=3072, vocab=256, param=2, gt_mode=1,
                                              n_timesteps=0, gamma_min=-13.3, gamma_max=5.0),
                           absent_mask=0x240, reserved=0)
-  assert bytes(op) == struct.pack('<6i2d2I', 7, 3072, 256, 2, 1, 0, -13.3, 5.0, 0x240, 0)
+  assert bytes(op) == struct.pack('<6i2dIi2I', 7, 3072, 256, 2, 1, 0, -13.3, 5.0, 0, 0, 0x240, 0)
 
 
 def test_opaque_is_validated_without_gpu(lib, capfd):
   h = lib.load()
   bufs = (C.c_void_p * 13)()
   h.mulan_xla_fwd_pre(None, bufs, b'\0' * 7, 7, None)
-  assert b'opaque must be a mulan_xla_opaque (48 bytes)' in h.mulan_last_error()
+  assert b'opaque must be a mulan_xla_opaque (56 bytes)' in h.mulan_last_error()
   assert 'mulan_xla_fwd_pre' in capfd.readouterr().err
   # a well-formed opaque with a bad descriptor: the entry point's own message comes through
   op = lib.MulanXlaOpaque(desc=lib.make_desc(rows=2, dim=3070))

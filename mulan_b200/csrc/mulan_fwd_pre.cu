@@ -164,6 +164,47 @@ static bool is_shipped(const FwdPreParams& p) {
          eq(p.rc.off, Shipped::off);
 }
 
+// The general per-sub-pixel statements: the fixed-end fast path when S is in range, the IEEE
+// slow path otherwise, the per-pixel prior when sigmoid(gamma_1) is not uniform.
+template <bool FAST>
+__device__ __forceinline__ void pre_pixel_general(const FwdPreParams& p, const PreConsts& kc,
+                                                  const Poly& po, int xi, float xf, float f,
+                                                  float e0, float& gt, float& wt,
+                                                  float (&acc)[5]) {
+  const VocabInfo& vi = p.vi;
+  if (scale_in_range(po.S)) {                             // fixed ends are exact constants
+    const float rSd = kc.delta * rcp_nr(po.S);
+    gt = fmaf(po.P, rSd, kc.gmin);                        // gamma_t
+    wt = (po.q * po.q) * rSd;                             // d gamma / dt
+    const float z0 = f + kc.s0 * e0;                      // z_0_rescaled (two roundings)
+    acc[0] += FAST ? recon_logprob_fast(xf, f, z0, kc.rc)
+                   : recon_logprob_generic(xi, z0, kc.inv0, p.W, vi);
+    if (kc.v1_uniform) {
+      acc[1] += kc.om1 * (f * f) + kc.v1c - kc.lv1 - 1.0f;   // reference op order
+    } else {
+      const float2 pg = prior_general(po.S, kc.gmin, kc.delta, f);
+      acc[1] += pg.x;
+      acc[4] += pg.y - kc.v1c;
+    }
+  } else {
+    const SlowPix sp = slow_pixel(po, kc.gmin, kc.delta, xi, f, e0, vi);
+    gt = sp.gt; wt = sp.wt;
+    acc[0] += sp.lp; acc[1] += sp.kl;
+    acc[3] += sp.v0 - kc.v0c; acc[4] += sp.v1 - kc.v1c;
+  }
+}
+
+// One float4 column (4 sub-pixels) of one row: everything between the loads and the stores.
+// acc: logprob, klz summand, g_t, and (only off the fixed-end path) var0 / var1 corrections.
+//
+// The four sub-pixels are independent dependency chains of ~100 instructions each with six
+// MUFU results in series (rcp -> ex2, ex2 -> lg2 -> ex2 -> rcp -> rsqrt, rsqrt).  Written as a
+// per-sub-pixel `if (S in range) ... else slow_pixel()` they compile to four SERIAL blocks
+// separated by branches (round 1: issue slots 70 % busy at 47 % occupancy -- each warp waits on
+// its own MUFU latencies).  Here the range test is made once for the whole column, so the common
+// case is ONE straight-line block in which the compiler interleaves the four chains; a column
+// with any out-of-range S (or a non-uniform sigmoid(gamma_1)) takes the general code.  Every
+// sub-pixel runs the same statements in the same per-accumulator order either way: bit-identical.
 template <int GT, bool SAVEW, bool FAST, bool CRAW = false>
 __device__ __forceinline__ void pre_column(const FwdPreParams& p, const PreConsts& kc,
                                            const RowT& rt, const float4 A,
@@ -172,50 +213,46 @@ __device__ __forceinline__ void pre_column(const FwdPreParams& p, const PreConst
                                            float (&acc)[5]) {
   // MULAN_FLAG_C_RAW: c = 1e-3 + softplus(pre-activation), ldm/model_mulan_epsilon.py:537
   const float4 C = CRAW ? c_from_raw4(Cin) : Cin;
-  const float s0 = kc.s0, inv0 = kc.inv0, v0c = kc.v0c;
-  const float v1c = kc.v1c, om1 = kc.om1, lv1 = kc.lv1;
-  const bool v1_uniform = kc.v1_uniform;
   const VocabInfo& vi = p.vi;
   const ReconFast& rc = kc.rc;
-  const float gmin = kc.gmin, delta = kc.delta;
+  Poly po[4];
+  float xf[4], f[4], gt[4], wt[4];
+  int xi[4];
+  bool all_fast = FAST && kc.v1_uniform;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    xi[j] = getx(X, j);
+    xf[j] = (float)xi[j];
+    f[j] = FAST ? fmaf(xf[j], rc.two_iv, rc.off)          // encode(x), exact for 2^k vocab
+                : vi.xval(xi[j]);
+    po[j] = poly_eval(get(A, j), get(Bv, j), get(C, j), rt);
+    all_fast = all_fast && scale_in_range(po[j].S);
+  }
+  if (all_fast) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float rSd = kc.delta * rcp_nr(po[j].S);
+      gt[j] = fmaf(po[j].P, rSd, kc.gmin);                // gamma_t
+      wt[j] = (po[j].q * po[j].q) * rSd;                  // d gamma / dt
+      const float z0 = f[j] + kc.s0 * get(E0, j);         // z_0_rescaled (two roundings)
+      acc[0] += recon_logprob_fast(xf[j], f[j], z0, rc);
+      acc[1] += kc.om1 * (f[j] * f[j]) + kc.v1c - kc.lv1 - 1.0f;   // reference op order
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      pre_pixel_general<FAST>(p, kc, po[j], xi[j], xf[j], f[j], get(E0, j), gt[j], wt[j], acc);
+  }
   float4 Z, Wv, G;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const float a = get(A, j), b = get(Bv, j), c = get(C, j);
-    const float e0 = get(E0, j), e = get(E, j);
-    const int xi = getx(X, j);
-    const float xf = (float)xi;
-    const float f = FAST ? fmaf(xf, rc.two_iv, rc.off)    // encode(x), exact for 2^k vocab
-                         : vi.xval(xi);
-    const Poly po = poly_eval(a, b, c, rt);
-    float gt, wt;
-    if (scale_in_range(po.S)) {                           // fixed ends are exact constants
-      const float rSd = delta * rcp_nr(po.S);
-      gt = fmaf(po.P, rSd, gmin);                         // gamma_t
-      wt = (po.q * po.q) * rSd;                           // d gamma / dt
-      const float z0 = f + s0 * e0;                       // z_0_rescaled (two roundings)
-      acc[0] += FAST ? recon_logprob_fast(xf, f, z0, rc)
-                     : recon_logprob_generic(xi, z0, inv0, p.W, vi);
-      if (v1_uniform) {
-        acc[1] += om1 * (f * f) + v1c - lv1 - 1.0f;       // reference op order
-      } else {
-        const float2 pg = prior_general(po.S, gmin, delta, f);
-        acc[1] += pg.x;
-        acc[4] += pg.y - v1c;
-      }
-    } else {
-      const SlowPix sp = slow_pixel(po, gmin, delta, xi, f, e0, vi);
-      gt = sp.gt; wt = sp.wt;
-      acc[0] += sp.lp; acc[1] += sp.kl;
-      acc[3] += sp.v0 - v0c; acc[4] += sp.v1 - v1c;
-    }
-    const float vt = sigmoid_fast(gt);
+    const float vt = sigmoid_fast(gt[j]);
     const float om = 1.0f - vt;
     const float alpha = sqrt_fast0(om), sigma = sqrt_fast(vt);
-    put(Z, j, alpha * f + sigma * e);                     // z_t (two products, one add)
-    if (SAVEW) put(Wv, j, wt);
-    if (GT == MULAN_GT_PIXEL) put(G, j, gt);
-    acc[2] += gt;
+    put(Z, j, alpha * f[j] + sigma * get(E, j));          // z_t (two products, one add)
+    if (SAVEW) put(Wv, j, wt[j]);
+    if (GT == MULAN_GT_PIXEL) put(G, j, gt[j]);
+    acc[2] += gt[j];
   }
   st4(p.z_t, g4, Z);
   if (SAVEW) st4(p.w_save, g4, Wv);
@@ -241,15 +278,19 @@ __device__ __forceinline__ void pre_row_end(const FwdPreParams& p, int row, floa
 // ---------------------------------------------------------------------------------------
 // Direct-load kernel: one CTA (NT threads) per row, operands loaded straight into registers
 // (LDG.128).  Serves any dim (multiple of 4), any vocab / window, any 4-byte aligned x.
+// KIND: 0 generic window, 1 closed-form 3-bin term with the launch constants in the parameter
+// bank, 2 the same with the shipped configuration's constants as immediates.
 //
-// DBUF: register double-buffering -- the six loads of column k+1 are issued BEFORE the ~460
-// arithmetic instructions of column k, so every warp keeps 84 B per lane in flight while it
-// computes.  Memory-level parallelism then no longer depends on how many warps happen to sit in
-// their load phase (the plain loop: 4 CTAs/SM, 47 % occupancy, DRAM at 75 % of peak with the
-// issue slots 70 % busy -- co-limited by latency, profiles/r1_ncu_summary.md), at the price of
-// ~21 more live registers.  KIND: 0 generic window, 1 closed-form 3-bin term with the launch
-// constants in the parameter bank, 2 the same with the shipped configuration's constants as
-// immediates.
+// Shape (NT threads, MINB resident CTAs per SM), measured on B200 at 16384 rows
+// (profiles/r2_fwd_pre_variants.md): the kernel needs 64 registers, so 32 warps per SM are
+// resident whatever the CTA size; 128-thread CTAs (8 per SM) beat 256-thread ones (4 per SM) by
+// 5 % (epsilon form) / 9 % (plain velocity) -- the per-row prologue and the row-end barrier of a
+// CTA stall a quarter of the SM's warps instead of half.  Capping the registers for more CTAs
+// (48 registers: 5 x 256 or 10 x 128) spills and loses 10-15 %; prefetching the next column's
+// operands into registers (80 registers, 24 warps) loses 15-25 %; one warp per row with a
+// shared-memory table of encode(x) / the prior summand (no barrier, -10 instructions per
+// sub-pixel) and FRND / I2F-free arithmetic are no faster: at 6.2-6.4 TB/s of DRAM traffic,
+// 76 % issue utilisation and 52 % XU utilisation the kernel sits against all three limits.
 // ---------------------------------------------------------------------------------------
 struct PreCol {
   float4 A, B, C, E0, E;
@@ -263,7 +304,7 @@ __device__ __forceinline__ PreCol load_pre_col(const FwdPreParams& p, size_t g4,
   return c;
 }
 
-template <int GT, bool SAVEW, int KIND, bool CRAW, int NT, int MINB, bool DBUF>
+template <int GT, bool SAVEW, int KIND, bool CRAW, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB)
 fwd_pre_kernel(const FwdPreParams p) {
   constexpr bool FAST = KIND != 0, BAKED = KIND == 2;
@@ -273,33 +314,18 @@ fwd_pre_kernel(const FwdPreParams p) {
   const int row = blockIdx.x;
   const int tid = threadIdx.x;
   pdl_release_dependents();
+  const PreConsts kc = load_pre_consts<BAKED>(p);
   pdl_wait_for_primary();
   if (tid == 0) s_rt = make_row_t(__ldg(p.t + row));
-  const PreConsts kc = load_pre_consts<BAKED>(p);
   const size_t base4 = (size_t)row * p.dim4;
   // eps_0 / eps broadcast over the batch (dense-VLB evaluation: every image shares one key)
   const size_t nbase4 = (size_t)(p.noise_rows > 0 ? row % p.noise_rows : row) * p.dim4;
   float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-  if (DBUF) {
-    PreCol cur;
-    if (tid < p.dim4) cur = load_pre_col(p, base4 + tid, nbase4 + tid);
-    __syncthreads();
-    const RowT rt = s_rt;
-    for (int i4 = tid; i4 < p.dim4; i4 += NT) {
-      PreCol nxt;
-      const int n4 = i4 + NT;
-      if (n4 < p.dim4) nxt = load_pre_col(p, base4 + n4, nbase4 + n4);
-      pre_column<GT, SAVEW, FAST, CRAW>(p, kc, rt, cur.A, cur.B, cur.C, cur.E0, cur.E, cur.X,
-                                        base4 + i4, acc);
-      cur = nxt;
-    }
-  } else {
-    __syncthreads();
-    const RowT rt = s_rt;
-    for (int i4 = tid; i4 < p.dim4; i4 += NT) {
-      const PreCol c = load_pre_col(p, base4 + i4, nbase4 + i4);
-      pre_column<GT, SAVEW, FAST, CRAW>(p, kc, rt, c.A, c.B, c.C, c.E0, c.E, c.X, base4 + i4, acc);
-    }
+  __syncthreads();
+  const RowT rt = s_rt;
+  for (int i4 = tid; i4 < p.dim4; i4 += NT) {
+    const PreCol c = load_pre_col(p, base4 + i4, nbase4 + i4);
+    pre_column<GT, SAVEW, FAST, CRAW>(p, kc, rt, c.A, c.B, c.C, c.E0, c.E, c.X, base4 + i4, acc);
   }
   pre_row_end<GT, NW>(p, row, acc, red);
 }
@@ -393,18 +419,16 @@ fwd_pre_tma_kernel(const FwdPreParams p) {
 
 static bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; }
 
-// Shape of the default direct-load kernel (threads per CTA, minimum resident CTAs per SM,
-// register double-buffering), chosen by measurement on B200 (profiles/r2_fwd_pre_variants.md).
+// Shape of the default direct-load kernel (threads per CTA, minimum resident CTAs per SM),
+// chosen by measurement on B200 (profiles/r2_fwd_pre_variants.md).
 #ifndef MULAN_PRE_NT
-#define MULAN_PRE_NT 256
-#define MULAN_PRE_MINB 4
-#define MULAN_PRE_DBUF false
+#define MULAN_PRE_NT 128
+#define MULAN_PRE_MINB 8
 #endif
 
 // MULAN_FWD_PRE_V=<n> (read per launch; A/B measurements only) selects one of the alternative
-// shapes below for the shipped configuration's kernel; every shape is bit-identical in its
-// per-pixel outputs (same arithmetic, same per-thread accumulation order only when NT matches:
-// the per-row sums of a 128-thread shape differ from the 256-thread ones by float32 rounding).
+// shapes below for the shipped configuration's kernel.  Per-pixel outputs are bit-identical
+// across shapes (same arithmetic); per-row sums differ by float32 summation order.
 static int experimental_shape() {
   const char* e = getenv("MULAN_FWD_PRE_V");
   return (e == nullptr || e[0] == '\0') ? -1 : atoi(e);
@@ -413,26 +437,20 @@ static int experimental_shape() {
 template <int GT, bool SAVEW, int KIND, bool CRAW>
 static cudaError_t launch_shape(const FwdPreParams& p, cudaStream_t s) {
   if constexpr (GT == MULAN_GT_MEAN && KIND == 2 && !CRAW) {
-#define MULAN_SHAPE(NT, MINB, DBUF) \
-    return launch_kernel(fwd_pre_kernel<GT, SAVEW, KIND, CRAW, NT, MINB, DBUF>, p.rows, NT, s, \
+#define MULAN_SHAPE(NT, MINB) \
+    return launch_kernel(fwd_pre_kernel<GT, SAVEW, KIND, CRAW, NT, MINB>, p.rows, NT, s, \
                          p.pdl != 0, p)
     switch (experimental_shape()) {
-      case 0: MULAN_SHAPE(256, 4, false);
-      case 1: MULAN_SHAPE(256, 5, false);
-      case 2: MULAN_SHAPE(256, 3, true);
-      case 3: MULAN_SHAPE(256, 4, true);
-      case 4: MULAN_SHAPE(128, 6, true);
-      case 5: MULAN_SHAPE(128, 8, false);
-      case 6: MULAN_SHAPE(128, 5, true);
-      case 7: MULAN_SHAPE(384, 2, true);
-      case 8: MULAN_SHAPE(128, 10, false);
+      case 0: MULAN_SHAPE(256, 4);
+      case 1: MULAN_SHAPE(256, 5);
+      case 5: MULAN_SHAPE(128, 8);
+      case 12: MULAN_SHAPE(64, 16);
       default: break;
     }
 #undef MULAN_SHAPE
   }
-  return launch_kernel(
-      fwd_pre_kernel<GT, SAVEW, KIND, CRAW, MULAN_PRE_NT, MULAN_PRE_MINB, MULAN_PRE_DBUF>, p.rows,
-      MULAN_PRE_NT, s, p.pdl != 0, p);
+  return launch_kernel(fwd_pre_kernel<GT, SAVEW, KIND, CRAW, MULAN_PRE_NT, MULAN_PRE_MINB>,
+                       p.rows, MULAN_PRE_NT, s, p.pdl != 0, p);
 }
 
 template <int GT, bool SAVEW>

@@ -122,10 +122,20 @@ np.savez(sys.argv[1], **out)
     subprocess.run([sys.executable, '-c', code, path], check=True, env=env)
     outs.append(np.load(path))
     os.unlink(path)
-  for other in outs[1:]:
+  # outs: [generic constants, baked (default), TMA + baked, TMA + generic constants]
+  for i, other in enumerate(outs[1:], 1):
     assert set(outs[0].files) == set(other.files)
     for k in outs[0].files:
-      assert np.array_equal(outs[0][k], other[k]), k
+      per_row = k.split('_', 2)[2] in ('loss_recon', 'loss_klz_prior', 'var_sums') or \
+          (k.split('_', 2)[2] == 'g_net' and k.split('_')[1] == '0')
+      if per_row and i >= 2:
+        # the TMA pipeline runs 256-thread CTAs, the direct-load default 128-thread ones: the
+        # per-row sums differ by float32 summation order, the per-pixel outputs do not
+        np.testing.assert_allclose(outs[0][k], other[k], rtol=2e-6, atol=1e-6, err_msg=k)
+      else:
+        assert np.array_equal(outs[0][k], other[k]), k
+  for k in outs[2].files:                      # the two TMA builds agree bit for bit
+    assert np.array_equal(outs[2][k], outs[3][k]), k
 
 
 def test_vfe_eps_form_matches_literal_formula(cuda_device):

@@ -177,7 +177,8 @@ def test_post_bpd_equals_separate_post_and_reduce(cuda_device, rows, param):
   sc_one, tot_one = ops.bpd_reduce(desc, pre['loss_recon'], pre['loss_klz_prior'], kl_z, diff,
                                    pre['var_sums'], want_klz_total=True, ws=None)
   assert torch.equal(sc_par, sc_one) and torch.equal(tot_par, tot_one)
-  assert torch.count_nonzero(ws).item() == 0
+  n_counters = ((rows + 127) // 128 + 1 + 3) // 4 * 4      # the rest holds the group partials
+  assert torch.count_nonzero(ws[:n_counters]).item() == 0
   for with_grad in (True, False, True):          # reuse the same workspace
     f = ops.post_bpd(desc, g['x'], g['a'], g['b'], g['c'], g['t'], g['eps'], g['net'], pre['w'],
                      gL if with_grad else None, pre['loss_recon'], pre['loss_klz_prior'], kl_z,
@@ -187,7 +188,7 @@ def test_post_bpd_equals_separate_post_and_reduce(cuda_device, rows, param):
     assert torch.equal(f['loss_klz_total'], tot_par)
     if with_grad:
       assert torch.equal(f['n_bar'], n_bar)
-    assert torch.count_nonzero(ws).item() == 0
+    assert torch.count_nonzero(ws[:n_counters]).item() == 0
   # against the oracle's loss_fn (ldm/experiment_vdm.py:62-74)
   out = O.elbo_terms(inp['x'], inp['a'], inp['b'], inp['c'], inp['t'], inp['eps_0'], inp['eps'],
                      lambda z, gg: inp['net'], param, O.OracleConfig(), kl_z=kl_z.cpu())
@@ -200,16 +201,16 @@ def test_post_bpd_equals_separate_post_and_reduce(cuda_device, rows, param):
 
 
 def test_fwd_pre_kernel_shapes_agree(cuda_device, monkeypatch):
-  """MULAN_FWD_PRE_V: CTA size / residency / register double-buffering change how the loads are
-  scheduled, never the arithmetic -- per-pixel outputs are bit-identical, per-row sums agree to
-  float32 summation order."""
+  """MULAN_FWD_PRE_V: CTA size / residency change how the work is scheduled, never the
+  arithmetic -- per-pixel outputs are bit-identical, per-row sums agree to float32 summation
+  order."""
   from mulan_b200 import ops
   _, g = dev_inputs(37, 51, cuda_device)
   desc = ops.Desc()
   args = (g['x'], g['a'], g['b'], g['c'], g['t'], g['eps_0'], g['eps'])
   monkeypatch.delenv('MULAN_FWD_PRE_V', raising=False)
   base = ops.fwd_pre(desc, *args)
-  for v in range(9):
+  for v in (0, 1, 5, 12):
     monkeypatch.setenv('MULAN_FWD_PRE_V', str(v))
     for save_w in (True, False):
       got = ops.fwd_pre(desc, *args, save_w=save_w)

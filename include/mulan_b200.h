@@ -453,6 +453,47 @@ typedef struct mulan_adamw_desc {
 int mulan_adamw_ema(const mulan_adamw_desc* desc, float* params, const float* grads,
                     float* mu, float* nu, float* ema_params, void* stream);
 
+/*
+ * Gradient pmean FUSED with the update over NVLink peer memory -- SURVEY.md 8f row 1 as written.
+ * Replaces grads = jax.lax.pmean(grads, 'batch') (ldm/experiment.py:341) + state.apply_gradients
+ * (ldm/experiment.py:344 -> ldm/train_state.py:70-102) for one process per GPU on one node.
+ *
+ *   mulan_peer_alloc : cudaMalloc + zero + CUDA-IPC handle (MULAN_PEER_HANDLE_BYTES bytes) of a
+ *                      buffer the other ranks will map; mulan_peer_open maps a peer's handle
+ *                      (peer access over NVLink is enabled on first use); _close / _free undo them.
+ *   mulan_adamw_ema_peer(desc, peers, lo, hi, ...): for the parameter range [lo, hi) of the flat
+ *                      buffers, in ONE kernel per rank: flag barrier -> rank r sums the `world`
+ *                      gradient buckets over its 1/world shard by peer loads in rank order
+ *                      (deterministic) -> AdamW + EMA on that shard (mu, nu, ema local, touched
+ *                      for 1/world of the range) -> new parameters stored into every rank's
+ *                      buffer -> flag barrier; the kernel retires when every peer's shard has
+ *                      landed here.  desc->grad_scale = 1/world makes the sum the pmean;
+ *                      desc->n, n_decay describe the WHOLE flat buffer; clip_norm must be 0.
+ *                      Every rank must issue the same sequence of calls with the same (lo, hi)
+ *                      and a strictly increasing peers->epoch (>= 1).  world in {1, 2, 4, 8}.
+ *   flag block       : MULAN_PEER_FLAG_WORDS uint32 per rank, zero-initialised (mulan_peer_alloc
+ *                      zeroes); word MULAN_PEER_FLAG_ERR becomes non-zero if a barrier timed out
+ *                      (~4 s) instead of hanging the device.
+ */
+#define MULAN_PEER_HANDLE_BYTES 64
+#define MULAN_PEER_MAX 8
+#define MULAN_PEER_FLAG_WORDS 32
+#define MULAN_PEER_FLAG_ERR 17
+typedef struct mulan_peer_desc {
+  int32_t world, rank;
+  float* grads[MULAN_PEER_MAX];     /* this process's mapping of rank r's gradient bucket  */
+  float* params[MULAN_PEER_MAX];    /* ... of rank r's parameter buffer                     */
+  uint32_t* flags[MULAN_PEER_MAX];  /* ... of rank r's flag block                           */
+  uint32_t epoch;                   /* 1, 2, 3, ...: one per call, identical on every rank  */
+  uint32_t reserved;
+} mulan_peer_desc;
+int mulan_peer_alloc(size_t bytes, void** dev_ptr, void* handle_out);
+int mulan_peer_open(const void* handle, void** dev_ptr);
+int mulan_peer_close(void* dev_ptr);
+int mulan_peer_free(void* dev_ptr);
+int mulan_adamw_ema_peer(const mulan_adamw_desc* desc, const mulan_peer_desc* peers, int64_t lo,
+                         int64_t hi, float* mu, float* nu, float* ema_params, void* stream);
+
 /* out[0] (device float) = sum_i g[i]^2 over the flat bucket: optax.global_norm(grads)^2 for
  * clip_by_global_norm.  n % 4 == 0, g 16-byte aligned; scratch holds MULAN_SUMSQ_SCRATCH doubles.
  * Fixed-order two-launch reduction (float64 accumulation of float32 squares): run to run

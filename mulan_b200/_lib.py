@@ -50,6 +50,20 @@ class MulanAdamwDesc(C.Structure):
               ('grad_sumsq', C.c_void_p)]
 
 
+MULAN_PEER_HANDLE_BYTES = 64
+MULAN_PEER_MAX = 8
+MULAN_PEER_FLAG_WORDS = 32
+MULAN_PEER_FLAG_ERR = 17
+
+
+class MulanPeerDesc(C.Structure):
+  """struct mulan_peer_desc."""
+  _fields_ = [('world', C.c_int32), ('rank', C.c_int32),
+              ('grads', C.c_void_p * MULAN_PEER_MAX), ('params', C.c_void_p * MULAN_PEER_MAX),
+              ('flags', C.c_void_p * MULAN_PEER_MAX), ('epoch', C.c_uint32),
+              ('reserved', C.c_uint32)]
+
+
 class MulanError(RuntimeError):
   def __init__(self, status: int, msg: str):
     super().__init__(f'libmulan_b200 status {status}: {msg}')
@@ -100,6 +114,12 @@ SIGNATURES = {
     'mulan_rk45_norm': ([C.c_int64, C.c_int32, _P, C.c_double, C.c_double, C.c_double, _P, _P, _P,
                          C.c_int64, C.c_int32, _P, _P, _P], C.c_int),
     'mulan_adamw_ema': ([C.POINTER(MulanAdamwDesc)] + [_P] * 6, C.c_int),
+    'mulan_peer_alloc': ([C.c_size_t, C.POINTER(C.c_void_p), _P], C.c_int),
+    'mulan_peer_open': ([_P, C.POINTER(C.c_void_p)], C.c_int),
+    'mulan_peer_close': ([_P], C.c_int),
+    'mulan_peer_free': ([_P], C.c_int),
+    'mulan_adamw_ema_peer': ([C.POINTER(MulanAdamwDesc), C.POINTER(MulanPeerDesc), C.c_int64,
+                              C.c_int64, _P, _P, _P, _P], C.c_int),
     'mulan_rng_bits': ([C.c_uint32, C.c_uint32, C.c_int64, _P, _P], C.c_int),
     'mulan_rng_uniform': ([C.c_uint32, C.c_uint32, C.c_int64, C.c_float, C.c_float, _P, _P],
                           C.c_int),

@@ -15,7 +15,7 @@ CSRC = PKG_DIR / 'csrc'
 LIB_PATH = PKG_DIR / 'libmulan_b200.so'
 
 SOURCES = ['mulan_fwd_pre.cu', 'mulan_post.cu', 'mulan_bwd_pre.cu', 'mulan_aux.cu',
-           'mulan_optim.cu', 'mulan_sampler.cu', 'mulan_rk45.cu', 'mulan_rng.cu', 'mulan_abi.cu',
+           'mulan_optim.cu', 'mulan_peer.cu', 'mulan_sampler.cu', 'mulan_rk45.cu', 'mulan_rng.cu', 'mulan_abi.cu',
            'mulan_host.cu', 'mulan_xla_legacy.cu']
 
 NVCC_FLAGS = [

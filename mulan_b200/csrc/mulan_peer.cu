@@ -1,0 +1,259 @@
+// mulan_adamw_ema_peer: the gradient pmean FUSED with the optimizer update over NVLink peer
+// memory (SURVEY.md 8f row 1 as written: "fused AdamW(+EMA) update fused with the gradient
+// all-reduce bucket").  Reference statements: grads = jax.lax.pmean(grads, 'batch')
+// (ldm/experiment.py:341) followed by state.apply_gradients (ldm/experiment.py:344 ->
+// ldm/train_state.py:70-102) on every device.
+//
+// One process per GPU; every rank's gradient bucket, parameter buffer and a small flag block
+// live in cudaMalloc'ed memory that the other ranks of the node map through CUDA IPC
+// (mulan_peer_alloc / mulan_peer_open), so a kernel can load from and store to any peer over
+// NVLink 5 / NVSwitch.  ONE kernel per step (or per gradient bucket) on every rank:
+//
+//   A  flag barrier  "my gradients for this range are final" -> every peer; wait for all peers
+//   1  reduce-scatter by peer LOADS: rank r owns 1/world of the range and sums the `world`
+//      gradient buckets element-wise in rank order 0..world-1 (fixed order: deterministic)
+//   2  AdamW + EMA on the owned shard only -- mu, nu, ema are touched for 1/world of the
+//      parameters (36 B/param of optimizer traffic becomes 36/world + 4 B)
+//   3  all-gather by peer STORES: the new parameters of the shard go to every rank's buffer
+//   B  flag barrier  "my shard has landed everywhere"; the kernel retires only when every
+//      peer's shard has landed HERE, so stream order protects the next forward pass
+//
+// versus ncclAllReduce (reduce-scatter + all-gather of GRADIENTS over the same links) followed
+// by a full-size update on every rank: the same NVLink bytes, one launch, no intermediate
+// reduced-gradient buffer, 1/world of the optimizer's HBM traffic.
+//
+// Ordering.  A rank signals A from a kernel that is stream-ordered after its backward pass, so
+// when rank r has seen all A flags every bucket is final and no peer still needs the OLD
+// parameters; it signals B after a system-scope fence behind its last peer store, and nobody
+// re-zeroes or re-accumulates a gradient bucket before its own kernel (which waits for every B)
+// has retired.  Flags carry the call's epoch (strictly increasing), so no reset is needed.
+// A spin that exceeds ~4 s sets the error word instead of hanging the GPU.
+#include <stdio.h>
+
+#include "mulan_kernels.h"
+
+namespace mulan {
+namespace {
+
+constexpr int kMaxPeers = 8;
+constexpr int kFlagA = 0, kFlagB = kMaxPeers, kFlagCount = 2 * kMaxPeers, kFlagErr = kFlagCount + 1;
+
+struct PeerParams {
+  float* grads[kMaxPeers];
+  float* params[kMaxPeers];
+  unsigned* flags[kMaxPeers];
+  float *mu, *nu, *ema;
+  int world, rank;
+  unsigned epoch;
+  long long lo4, n4;       // this rank's shard: float4 columns [lo4, lo4 + n4)
+  long long decay4;
+  float lr, b1, b2, om_b1, om_b2, eps, wd, one_minus_ema, bc1, bc2, grad_scale;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_peer4(const float* p, long long i4) {
+  float4 v;
+  asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(reinterpret_cast<const float4*>(p) + i4) : "memory");
+  return v;
+}
+
+// Wait until every peer's flag in `slot` has reached this call's epoch (thread 0 of a CTA).
+__device__ __forceinline__ void wait_peers(const PeerParams& k, int slot) {
+  const unsigned* mine = k.flags[k.rank];
+  const long long t0 = clock64();
+  for (int r = 0; r < k.world; ++r) {
+    while ((int)(ld_acquire_sys(mine + slot + r) - k.epoch) < 0) {
+      if (clock64() - t0 > 8000000000LL) {       // ~4 s at 2 GHz: report, do not hang
+        k.flags[k.rank][kFlagErr] = 1u;
+        return;
+      }
+      __nanosleep(200);
+    }
+  }
+}
+
+__device__ __forceinline__ void adamw_elem(float& p, float g, float& mu, float& nu, float& ema,
+                                           const PeerParams& k, bool decay) {
+  g = g * k.grad_scale;                        // the 1/world of the pmean
+  mu = k.om_b1 * g + k.b1 * mu;
+  nu = k.om_b2 * (g * g) + k.b2 * nu;
+  const float mu_hat = __fdiv_rn(mu, k.bc1);
+  const float nu_hat = __fdiv_rn(nu, k.bc2);
+  float u = __fdiv_rn(mu_hat, sqrtf(nu_hat) + k.eps);
+  if (decay) u = u + k.wd * p;
+  p = p + (-k.lr) * u;
+  ema = ema + k.one_minus_ema * (p - ema);
+}
+
+template <int WORLD>
+__global__ void __launch_bounds__(kThreads)
+adamw_ema_peer_kernel(const PeerParams k) {
+  __shared__ int s_last;
+  const int tid = threadIdx.x;
+  // ---- A: my gradients are final (this kernel is stream-ordered after backward)
+  if (blockIdx.x == 0 && tid < WORLD) {
+    __threadfence_system();
+    st_release_sys(k.flags[tid] + kFlagA + k.rank, k.epoch);
+  }
+  if (tid == 0) wait_peers(k, kFlagA);
+  __syncthreads();
+  // ---- 1-3: one float4 column of the owned shard per thread
+  const long long j = (long long)blockIdx.x * kThreads + tid;
+  if (j < k.n4) {
+    const long long i = k.lo4 + j;
+    float4 G = ld_peer4(k.grads[0], i);
+#pragma unroll
+    for (int r = 1; r < WORLD; ++r) {
+      const float4 H = ld_peer4(k.grads[r], i);
+      G.x += H.x; G.y += H.y; G.z += H.z; G.w += H.w;     // rank order: deterministic
+    }
+    float4 P = reinterpret_cast<float4*>(k.params[k.rank])[i];
+    float4 M = reinterpret_cast<float4*>(k.mu)[i];
+    float4 V = reinterpret_cast<float4*>(k.nu)[i];
+    float4 E = reinterpret_cast<float4*>(k.ema)[i];
+    const bool decay = i < k.decay4;
+    adamw_elem(P.x, G.x, M.x, V.x, E.x, k, decay);
+    adamw_elem(P.y, G.y, M.y, V.y, E.y, k, decay);
+    adamw_elem(P.z, G.z, M.z, V.z, E.z, k, decay);
+    adamw_elem(P.w, G.w, M.w, V.w, E.w, k, decay);
+    reinterpret_cast<float4*>(k.mu)[i] = M;
+    reinterpret_cast<float4*>(k.nu)[i] = V;
+    reinterpret_cast<float4*>(k.ema)[i] = E;
+#pragma unroll
+    for (int r = 0; r < WORLD; ++r) reinterpret_cast<float4*>(k.params[r])[i] = P;
+  }
+  // ---- B: my shard has landed everywhere; retire only when every peer's has landed here
+  __threadfence_system();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned done = atomicAdd(k.flags[k.rank] + kFlagCount, 1u);
+    s_last = (done == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_last == 0) return;
+  if (tid < WORLD) {
+    __threadfence_system();
+    st_release_sys(k.flags[tid] + kFlagB + k.rank, k.epoch);
+  }
+  if (tid == 0) {
+    k.flags[k.rank][kFlagCount] = 0;
+    wait_peers(k, kFlagB);
+  }
+}
+
+}  // namespace
+}  // namespace mulan
+
+extern "C" {
+
+#define PEER_FAIL(code, ...)                                  \
+  do {                                                        \
+    char m_[256];                                             \
+    snprintf(m_, sizeof(m_), __VA_ARGS__);                    \
+    mulan::set_last_error(m_);                                \
+    return (int)(code);                                       \
+  } while (0)
+#define PEER_CU(call, fn)                                                              \
+  do {                                                                                 \
+    cudaError_t e_ = (call);                                                           \
+    if (e_ != cudaSuccess) PEER_FAIL(MULAN_ERR_CUDA, "%s: %s", fn, cudaGetErrorString(e_)); \
+  } while (0)
+
+int mulan_peer_alloc(size_t bytes, void** dev_ptr, void* handle_out) {
+  const char* fn = "mulan_peer_alloc";
+  if (dev_ptr == nullptr || handle_out == nullptr || bytes == 0)
+    PEER_FAIL(MULAN_ERR_INVALID_ARG, "%s: bad argument", fn);
+  static_assert(sizeof(cudaIpcMemHandle_t) == MULAN_PEER_HANDLE_BYTES, "handle size");
+  void* p = nullptr;
+  PEER_CU(cudaMalloc(&p, bytes), fn);
+  cudaError_t e = cudaMemset(p, 0, bytes);
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    PEER_FAIL(MULAN_ERR_CUDA, "%s: %s", fn, cudaGetErrorString(e));
+  }
+  memcpy(handle_out, &h, sizeof(h));
+  *dev_ptr = p;
+  return 0;
+}
+
+int mulan_peer_open(const void* handle, void** dev_ptr) {
+  const char* fn = "mulan_peer_open";
+  if (handle == nullptr || dev_ptr == nullptr) PEER_FAIL(MULAN_ERR_INVALID_ARG, "%s: NULL", fn);
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  PEER_CU(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess), fn);
+  return 0;
+}
+
+int mulan_peer_close(void* dev_ptr) {
+  if (dev_ptr != nullptr) PEER_CU(cudaIpcCloseMemHandle(dev_ptr), "mulan_peer_close");
+  return 0;
+}
+
+int mulan_peer_free(void* dev_ptr) {
+  if (dev_ptr != nullptr) PEER_CU(cudaFree(dev_ptr), "mulan_peer_free");
+  return 0;
+}
+
+int mulan_adamw_ema_peer(const mulan_adamw_desc* d, const mulan_peer_desc* peers, int64_t lo,
+                         int64_t hi, float* mu, float* nu, float* ema_params, void* stream) {
+  const char* fn = "mulan_adamw_ema_peer";
+  if (d == nullptr || peers == nullptr) PEER_FAIL(MULAN_ERR_INVALID_ARG, "%s: NULL desc", fn);
+  const int W = peers->world;
+  if (W < 1 || W > mulan::kMaxPeers || (W & (W - 1)) != 0 || peers->rank < 0 || peers->rank >= W)
+    PEER_FAIL(MULAN_ERR_INVALID_ARG, "%s: world=%d (1, 2, 4 or 8), rank=%d", fn, W, peers->rank);
+  if (lo < 0 || hi < lo || hi > d->n || lo % 4 != 0 || hi % 4 != 0 || d->n_decay % 4 != 0)
+    PEER_FAIL(MULAN_ERR_INVALID_ARG, "%s: need 0 <= lo <= hi <= n, multiples of 4", fn);
+  if (d->step < 1) PEER_FAIL(MULAN_ERR_INVALID_ARG, "%s: step must be >= 1", fn);
+  if (d->clip_norm > 0.0)
+    PEER_FAIL(MULAN_ERR_UNSUPPORTED, "%s: clip_by_global_norm needs the norm of the REDUCED "
+              "gradient before any update; use the all-reduce path", fn);
+  if (mu == nullptr || nu == nullptr || ema_params == nullptr)
+    PEER_FAIL(MULAN_ERR_INVALID_ARG, "%s: NULL state pointer", fn);
+  mulan::PeerParams k;
+  for (int r = 0; r < W; ++r) {
+    if (!peers->grads[r] || !peers->params[r] || !peers->flags[r])
+      PEER_FAIL(MULAN_ERR_INVALID_ARG, "%s: peer %d has a NULL mapping", fn, r);
+    k.grads[r] = peers->grads[r]; k.params[r] = peers->params[r]; k.flags[r] = peers->flags[r];
+  }
+  k.mu = mu; k.nu = nu; k.ema = ema_params;
+  k.world = W; k.rank = peers->rank; k.epoch = peers->epoch;
+  // the range is cut into `world` shards of whole float4 columns; the last takes the remainder
+  const long long cols = (hi - lo) / 4, per = (cols + W - 1) / W;
+  const long long first = per * k.rank < cols ? per * k.rank : cols;
+  const long long last = first + per < cols ? first + per : cols;
+  k.lo4 = lo / 4 + first; k.n4 = last - first;
+  k.decay4 = d->n_decay / 4;
+  k.lr = (float)d->lr; k.b1 = (float)d->b1; k.b2 = (float)d->b2; k.eps = (float)d->eps;
+  k.wd = (float)d->weight_decay;
+  k.om_b1 = (float)(1.0 - d->b1); k.om_b2 = (float)(1.0 - d->b2);
+  k.one_minus_ema = (float)(1.0 - d->ema_rate);
+  k.bc1 = 1.0f - powf((float)d->b1, (float)d->step);
+  k.bc2 = 1.0f - powf((float)d->b2, (float)d->step);
+  k.grad_scale = (float)d->grad_scale;
+  long long want = (k.n4 + mulan::kThreads - 1) / mulan::kThreads;
+  if (want < 1) want = 1;                       // an empty shard still takes part in the barriers
+  if (want > 0x7fffffffLL) PEER_FAIL(MULAN_ERR_INVALID_ARG, "%s: range too large", fn);
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (W) {
+    case 1: mulan::adamw_ema_peer_kernel<1><<<(int)want, mulan::kThreads, 0, s>>>(k); break;
+    case 2: mulan::adamw_ema_peer_kernel<2><<<(int)want, mulan::kThreads, 0, s>>>(k); break;
+    case 4: mulan::adamw_ema_peer_kernel<4><<<(int)want, mulan::kThreads, 0, s>>>(k); break;
+    default: mulan::adamw_ema_peer_kernel<8><<<(int)want, mulan::kThreads, 0, s>>>(k); break;
+  }
+  PEER_CU(cudaGetLastError(), fn);
+  return 0;
+}
+
+}  // extern "C"

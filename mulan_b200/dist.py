@@ -107,19 +107,31 @@ def train_step(model, optimizer, bucket: FlatGradBucket, batch: dict, step: int,
   return scalars
 
 
+def dense_images_per_launch(n_timesteps: int, max_rows: int = 16384) -> int:
+  """Images per launch for the dense-VLB driver: as many as fit `max_rows` rows.  Short launches
+  pay their ramp-up / drain and the partial last wave (2048 rows = 1.7 waves of resident CTAs:
+  36 M rows/s on one stream; 16384 rows: 52 M rows/s, profiles/r2_variants.md), and the U-Net
+  that sits between the two kernels in a real evaluation is batch-size agnostic."""
+  return max(1, max_rows // n_timesteps)
+
+
 @torch.no_grad()
 def eval_bpd_dense_sampling(model, images: torch.Tensor, n_timesteps: int = 128,
-                            images_per_launch: int = 16, seed: int = 0,
-                            base_draws: Optional[dict] = None):
+                            images_per_launch: Optional[int] = None, seed: int = 0,
+                            base_draws: Optional[dict] = None, broadcast_noise: bool = True):
   """eval_bpd_dense_sampling (ldm/notebook_utils.py:176-191), example-sharded.
 
   For every test image: tile it n_timesteps times (antithetic t gives a stratified
   n_timesteps-point estimate of the diffusion integral), evaluate loss_fn with is_train=False
   and THE SAME key for every image (:178,:185), collect bpd; return the mean.
   `images` is this process's view of the whole test set [N,32,32,3] uint8; each rank takes
-  images[rank::world], `images_per_launch` images (x n_timesteps rows) per kernel launch.
+  images[rank::world], `images_per_launch` images (x n_timesteps rows) per kernel launch
+  (default: dense_images_per_launch).
   base_draws: the four draws of ONE loss_fn call over n_timesteps rows (model.make_draws);
   default: drawn here from `seed` -- the reference uses PRNGKey(0) for every image.
+  broadcast_noise: hand eps_0 / eps to the kernels as [n_timesteps, D] (read by row %
+  n_timesteps) instead of tiling them over the images of a launch -- same bits, 8 B/sub-pixel
+  less HBM traffic in fwd_pre, 4 B less in the post kernel.
   Returns (mean_bpd over all ranks' images, this rank's per-image bpds).
   """
   from .model import sample_t
@@ -133,6 +145,8 @@ def eval_bpd_dense_sampling(model, images: torch.Tensor, n_timesteps: int = 128,
   t_img = (base['t'].to(torch.float32).reshape(n_timesteps) if 't' in base
            else sample_t(base['t0'], n_timesteps, cfg))   # one key for every image
   rescale = 1. / (np.prod(images.shape[1:]) * np.log(2.))
+  if images_per_launch is None:
+    images_per_launch = dense_images_per_launch(n_timesteps)
   bpds = []
   for s in range(0, mine.shape[0], images_per_launch):
     chunk = mine[s:s + images_per_launch]
@@ -142,8 +156,11 @@ def eval_bpd_dense_sampling(model, images: torch.Tensor, n_timesteps: int = 128,
     # latent noise: [10, n, L] for the gamma draw (tile axis 1), [n, L] for the gumbel /
     # gaussian / additive-noise variants (tile axis 0)
     G = G.repeat(1, m, 1) if G.dim() == 3 else G.repeat(m, 1)
-    draws = dict(t=t_img.repeat(m), G=G,
-                 eps_0=base['eps_0'].repeat(m, 1, 1, 1), eps=base['eps'].repeat(m, 1, 1, 1))
+    if broadcast_noise:
+      e0, e = base['eps_0'], base['eps']
+    else:
+      e0, e = base['eps_0'].repeat(m, 1, 1, 1), base['eps'].repeat(m, 1, 1, 1)
+    draws = dict(t=t_img.repeat(m), G=G, eps_0=e0, eps=e)
     out = model(tiled, labels=None, conditioning=None, step=0, deterministic=True, draws=draws)
     per_row = out.loss_recon + out.loss_klz + out.loss_diff
     # per image: mean over its rows of each term, summed (ldm/experiment_vdm.py:62-66)

@@ -176,6 +176,8 @@ class VDM(nn.Module):
     # derivative themselves (ldm/model_mulan_epsilon.py:537), saving the framework's
     # elementwise passes (8 B/sub-pixel forward, 12 B/sub-pixel backward)
     self.fused_softplus = True
+    # programmatic dependent launch between the kernels of one step (MULAN_FLAG_PDL)
+    self.pdl = True
 
   def apply_encoder(self, images_int):
     """ldm/model_mulan_epsilon.py:178-180."""
@@ -273,10 +275,18 @@ class VDM(nn.Module):
     else:
       a, b, c = self.gamma._compute_coefficients(embedding)
 
-    tape = ops.ElboTape(self.desc.replace(c_raw=True) if raw else self.desc)
+    # eps_0 / eps drawn for FEWER rows than the batch are broadcast by row % noise_rows (the
+    # dense-VLB driver evaluates several images per launch with ONE key's draws,
+    # ldm/notebook_utils.py:178-185) instead of being tiled in HBM
+    n_noise = draws['eps'].shape[0]
+    if n_noise != n_batch and (n_batch % n_noise != 0 or draws['eps_0'].shape[0] != n_noise):
+      raise ValueError(f'eps_0 / eps have {n_noise} rows for a batch of {n_batch}')
+    desc = self.desc.replace(c_raw=raw, pdl=self.pdl,
+                             noise_rows=n_noise if n_noise != n_batch else 0)
+    tape = ops.ElboTape(desc)
     z_t, g_net, loss_recon, klz_prior, var_sums, link = ops.mulan_pre(
-        tape, x_u8, a, b, c, t, draws['eps_0'].reshape(n_batch, D).contiguous(),
-        draws['eps'].reshape(n_batch, D).contiguous())
+        tape, x_u8, a, b, c, t, draws['eps_0'].reshape(n_noise, D).contiguous(),
+        draws['eps'].reshape(n_noise, D).contiguous())
     cond = embedding if cfg.z_conditioning else conditioning[:, None]
     g_in = g_net if cfg.unet_type == 'vdm' else g_net.reshape(n_batch, 32, 32, 3)
     net = self.score_model(z_t.reshape(n_batch, 32, 32, 3), g_in, cond, deterministic)

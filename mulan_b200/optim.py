@@ -10,6 +10,19 @@ each (decayed parameters first), so that
     loss scalars in its tail), and
   * the update is a single launch of mulan_adamw_ema (36 B per parameter) with the 1/world of
     the mean folded in.
+
+Three ways of running the exchange (`comm=`):
+  'allreduce'  one ncclAllReduce of the whole bucket after backward, then the full-size update
+               on every rank (round 1).
+  'overlap'    the bucket is cut into ranges; a post-accumulate-grad hook fires a range's
+               ncclAllReduce (async, NCCL's stream) as soon as its last gradient has been
+               written, so the exchange overlaps the rest of backward; then the full-size update.
+  'peer'       B200-native: parameters and gradients live in CUDA-IPC peer memory; as each range
+               completes, ONE kernel per rank (mulan_adamw_ema_peer, on a side stream) sums the
+               range's gradient shards over NVLink by peer loads, updates 1/world of it
+               (AdamW + EMA on the local shard of the optimizer state) and stores the new
+               parameters into every rank's buffer -- reduce-scatter, update and all-gather in
+               one launch, overlapped with backward, no NCCL call on the gradient path.
 """
 from __future__ import annotations
 
@@ -46,6 +59,104 @@ def decay_mask(name: str) -> bool:
   return not name.endswith('bias')
 
 
+def shard_range(lo: int, hi: int, world: int, rank: int) -> Tuple[int, int]:
+  """The part of the flat range [lo, hi) that `rank` reduces, updates and broadcasts in
+  mulan_adamw_ema_peer: whole float4 columns, ceil-divided, the last ranks take what is left
+  (mirrors the kernel launcher, csrc/mulan_peer.cu)."""
+  cols = (hi - lo) // 4
+  per = (cols + world - 1) // world
+  first = min(per * rank, cols)
+  last = min(first + per, cols)
+  return lo + 4 * first, lo + 4 * last
+
+
+def plan_buckets(layout: List[Tuple[str, int, int]], n: int, bucket_elems: int):
+  """Cut the flat buffer [0, n) into ranges of ~bucket_elems elements on parameter boundaries
+  (multiples of 4 by construction).  Returns (ranges [(lo, hi)], members: range index -> names)."""
+  ranges, members = [], []
+  lo, names = 0, []
+  for name, off, k in layout:
+    names.append(name)
+    end = off + (k + 3) // 4 * 4
+    if end - lo >= bucket_elems:
+      ranges.append((lo, end)); members.append(names)
+      lo, names = end, []
+  if lo < n or not ranges:
+    ranges.append((lo, n)); members.append(names)
+  return ranges, members
+
+
+class _DevArray:
+  """A raw device allocation exposed through __cuda_array_interface__ (zero-copy torch view)."""
+
+  def __init__(self, ptr: int, n: int, typestr: str):
+    self.__cuda_array_interface__ = {'shape': (n,), 'typestr': typestr, 'data': (ptr, False),
+                                     'version': 2}
+
+
+class PeerBuffers:
+  """Parameter buffer, gradient bucket and flag block of THIS rank in CUDA-IPC peer memory, and
+  this process's mappings of every other rank's (mulan_peer_alloc / mulan_peer_open)."""
+
+  def __init__(self, n_params: int, n_grads: int, device):
+    lib = _lib.load()
+    self.world, self.rank = dist.get_world_size(), dist.get_rank()
+    if self.world > _lib.MULAN_PEER_MAX or self.world & (self.world - 1):
+      raise ValueError(f'peer mode needs world in (1, 2, 4, 8), got {self.world}')
+    torch.cuda.set_device(device)
+    sizes = {'params': 4 * n_params, 'grads': 4 * n_grads, 'flags': 4 * _lib.MULAN_PEER_FLAG_WORDS}
+    self.own, handles = {}, {}
+    for k, nbytes in sizes.items():
+      ptr, h = C.c_void_p(), (C.c_char * _lib.MULAN_PEER_HANDLE_BYTES)()
+      _lib.check(lib.mulan_peer_alloc(nbytes, C.byref(ptr), h))
+      self.own[k], handles[k] = ptr.value, bytes(h)
+    everyone = [None] * self.world
+    dist.all_gather_object(everyone, handles)
+    self.maps = {k: [] for k in sizes}
+    self._opened = []
+    for r in range(self.world):
+      for k in sizes:
+        if r == self.rank:
+          self.maps[k].append(self.own[k])
+          continue
+        ptr = C.c_void_p()
+        _lib.check(lib.mulan_peer_open(everyone[r][k], C.byref(ptr)))
+        self.maps[k].append(ptr.value)
+        self._opened.append(ptr.value)
+    f32 = lambda key, n: torch.as_tensor(_DevArray(self.own[key], n, '<f4'), device=device)
+    self.params, self.grads = f32('params', n_params), f32('grads', n_grads)
+    self.flags = torch.as_tensor(_DevArray(self.own['flags'], _lib.MULAN_PEER_FLAG_WORDS, '<i4'),
+                                 device=device)
+    self.epoch = 0
+    dist.barrier()          # every rank has mapped every buffer before anyone launches
+
+  def desc(self) -> '_lib.MulanPeerDesc':
+    self.epoch += 1
+    d = _lib.MulanPeerDesc()
+    d.world, d.rank, d.epoch = self.world, self.rank, self.epoch
+    for r in range(self.world):
+      d.grads[r], d.params[r], d.flags[r] = (self.maps['grads'][r], self.maps['params'][r],
+                                             self.maps['flags'][r])
+    return d
+
+  def timed_out(self) -> bool:
+    return bool(self.flags[_lib.MULAN_PEER_FLAG_ERR].item())
+
+  def close(self):
+    lib = _lib.load()
+    torch.cuda.synchronize()
+    if dist.is_initialized():
+      dist.barrier()
+    for ptr in self._opened:
+      lib.mulan_peer_close(C.c_void_p(ptr))
+    self._opened = []
+    if dist.is_initialized():
+      dist.barrier()        # nobody frees while a peer still maps
+    for ptr in self.own.values():
+      lib.mulan_peer_free(C.c_void_p(ptr))
+    self.own = {}
+
+
 class FlatTrainState:
   """step, params, ema_params, opt_state of the reference's TrainState as flat buffers."""
 
@@ -53,7 +164,15 @@ class FlatTrainState:
                b1: float = 0.9, b2: float = 0.99, eps: float = 1e-8, weight_decay: float = 0.01,
                learning_rate: float = 2e-4, num_steps_lr_warmup: int = 100,
                ema_rate: float = 0.9999, gradient_clip_norm: Optional[float] = None,
-               lr_decay: bool = False, num_steps_train: int = 0):
+               lr_decay: bool = False, num_steps_train: int = 0, comm: str = 'allreduce',
+               bucket_mb: float = 32.0):
+    if comm not in ('allreduce', 'overlap', 'peer'):
+      raise ValueError("comm must be 'allreduce', 'overlap' or 'peer'")
+    multi = dist.is_initialized() and dist.get_world_size() > 1
+    self.comm = comm if multi else 'allreduce'
+    if self.comm == 'peer' and gradient_clip_norm:
+      raise ValueError("comm='peer' cannot clip by the global norm (the reduced gradient never "
+                       "exists in one place before the update); use 'overlap'")
     named = [(n, p) for n, p in named_params if p.requires_grad]
     if not named:
       raise ValueError('no trainable parameters')
@@ -75,8 +194,14 @@ class FlatTrainState:
     self.n = off
     self.extra = pad4(extra)
     f = lambda k: torch.zeros(k, dtype=torch.float32, device=dev)
-    self.params, self.mu, self.nu = f(self.n), f(self.n), f(self.n)
-    self.grads = f(self.n + self.extra)          # tail: loss scalars ride in the all-reduce
+    self.mu, self.nu = f(self.n), f(self.n)
+    self.peer = None
+    if self.comm == 'peer':
+      self.peer = PeerBuffers(self.n, self.n + self.extra, dev)
+      self.params, self.grads = self.peer.params, self.peer.grads
+    else:
+      self.params = f(self.n)
+      self.grads = f(self.n + self.extra)        # tail: loss scalars ride in the all-reduce
     self.tail = self.grads[self.n:]
     by_name = dict(named)
     with torch.no_grad():
@@ -96,6 +221,76 @@ class FlatTrainState:
     if self.clip_norm > 0.0:
       self._sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
       self._scratch = torch.empty(_lib.MULAN_SUMSQ_SCRATCH, dtype=torch.float64, device=dev)
+    # ---- ranges of the flat buffer exchanged as soon as their gradients are complete
+    self.ranges, self._members = [(0, self.n)], [[n for n, _, _ in self.layout]]
+    self._hooks = []
+    if self.comm in ('overlap', 'peer'):
+      self.ranges, self._members = plan_buckets(self.layout, self.n,
+                                                int(bucket_mb * (1 << 20) / 4))
+      self._range_of = {name: i for i, names in enumerate(self._members) for name in names}
+      self._side = torch.cuda.Stream(device=dev)
+      self._pending, self._fired, self._works = [], [], []
+      for name, p in named:
+        self._hooks.append(p.register_post_accumulate_grad_hook(
+            lambda _p, _name=name: self._grad_ready(_name)))
+      self._reset_ranges()
+
+  # ---- overlap of the exchange with backward -------------------------------------------------
+  def _reset_ranges(self):
+    self._pending = [len(m) for m in self._members]
+    self._fired = [False] * len(self.ranges)
+    self._works = []
+    self._step_desc = None
+
+  def _grad_ready(self, name: str):
+    i = self._range_of[name]
+    self._pending[i] -= 1
+    if self._pending[i] == 0 and not self._fired[i]:
+      self._fire(i)
+
+  def _adamw_desc(self, grad_scale: float):
+    if self._step_desc is None:                    # one (step, lr) for every range of a step
+      lr = lr_schedule(self.step, self.learning_rate, self.warmup, self.lr_decay,
+                       self.num_steps_train)
+      self.step += 1
+      self._lr = lr
+      self._step_desc = _lib.MulanAdamwDesc(
+          self.n, self.n_decay, self.step, 0, lr, self.hp['b1'], self.hp['b2'], self.hp['eps'],
+          self.hp['weight_decay'], self.ema_rate, grad_scale, 0.0, None)
+    return self._step_desc
+
+  def _fire(self, i: int):
+    """Range i's gradients are final on this rank: start its exchange."""
+    self._fired[i] = True
+    lo, hi = self.ranges[i]
+    if self.comm == 'overlap':
+      self._works.append(dist.all_reduce(self.grads[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
+      return
+    ptr = lambda t: C.c_void_p(t.data_ptr())
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream())
+    self._side.wait_event(ev)
+    d = self._adamw_desc(1.0 / self.peer.world)
+    pd = self.peer.desc()
+    _lib.check(_lib.load().mulan_adamw_ema_peer(
+        C.byref(d), C.byref(pd), lo, hi, ptr(self.mu), ptr(self.nu), ptr(self.ema),
+        C.c_void_p(self._side.cuda_stream)))
+
+  def finish_exchange(self):
+    """After backward: fire the ranges no hook completed (unused parameters), in index order --
+    the same on every rank -- and make the current stream wait for everything in flight."""
+    if self.comm == 'allreduce':
+      return
+    for i in range(len(self.ranges)):
+      if not self._fired[i]:
+        self._fire(i)
+    if self.comm == 'overlap':
+      for w in self._works:
+        w.wait()
+    else:
+      ev = torch.cuda.Event()
+      ev.record(self._side)
+      torch.cuda.current_stream().wait_event(ev)
 
   def grad_global_norm(self) -> torch.Tensor:
     """optax.global_norm of the (all-reduced, not yet averaged) gradient bucket: device scalar."""
@@ -109,16 +304,31 @@ class FlatTrainState:
 
   def zero_grad(self):
     self.grads.zero_()
+    if self.comm != 'allreduce':
+      self._reset_ranges()
 
   def all_reduce(self):
-    """pmean(grads) + pmean(scalars): ONE all-reduce (sum); the 1/world is applied by the
-    update kernel (gradients) / here (the few tail scalars)."""
-    if dist.is_initialized() and dist.get_world_size() > 1:
+    """pmean(grads) + pmean(scalars).  'allreduce': ONE all-reduce (sum) of bucket + tail; the
+    1/world is applied by the update kernel (gradients) / here (the few tail scalars).
+    'overlap' / 'peer': the gradient ranges are already in flight (or done); only the tail's
+    handful of scalars is reduced here."""
+    if not (dist.is_initialized() and dist.get_world_size() > 1):
+      return
+    if self.comm == 'allreduce':
       dist.all_reduce(self.grads, op=dist.ReduceOp.SUM)
-      self.tail.div_(dist.get_world_size())
+    else:
+      self.finish_exchange()
+      dist.all_reduce(self.tail, op=dist.ReduceOp.SUM)
+    self.tail.div_(dist.get_world_size())
 
   def apply_gradients(self, grad_scale: Optional[float] = None):
-    """TrainState.apply_gradients (ldm/train_state.py:70-102): one fused launch."""
+    """TrainState.apply_gradients (ldm/train_state.py:70-102): one fused launch.  In 'peer' mode
+    the update already ran range by range inside mulan_adamw_ema_peer."""
+    if self.comm == 'peer':
+      self.finish_exchange()
+      if self._step_desc is None:
+        raise RuntimeError('apply_gradients: no gradient range was exchanged this step')
+      return self._lr
     world = dist.get_world_size() if dist.is_initialized() else 1
     if grad_scale is None:
       grad_scale = 1.0 / world

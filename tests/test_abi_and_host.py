@@ -258,8 +258,10 @@ class _CpuStubVDM(torch.nn.Module):
     a = pix * self.head.weight[0, 0] + 0.3
     b = pix * self.head.weight[1, 1] - 0.2
     c = 1e-3 + torch.nn.functional.softplus(pix * self.head.weight[2, 2])
-    out = O.elbo_terms(images.reshape(B, -1), a, b, c, t, draws['eps_0'].reshape(B, -1),
-                       draws['eps'].reshape(B, -1), lambda z, g: self.w * z, O.MODE_EPS,
+    # the dense-VLB driver hands over ONE key's draws for several images (broadcast rows)
+    tile = lambda v: v if v.shape[0] == B else v.repeat(B // v.shape[0], 1, 1, 1)
+    out = O.elbo_terms(images.reshape(B, -1), a, b, c, t, tile(draws['eps_0']).reshape(B, -1),
+                       tile(draws['eps']).reshape(B, -1), lambda z, g: self.w * z, O.MODE_EPS,
                        O.OracleConfig())
     return VDMOutput(*out)
 

@@ -74,6 +74,20 @@ def parse_args():
                        'saving it in fwd_pre')
   ap.add_argument('--no-e2e', action='store_true')
   ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--no-configs', action='store_true',
+                  help='skip the `configs` block (velocity, v-from-eps, dense VLB, train step)')
+  ap.add_argument('--no-train-step', action='store_true',
+                  help='skip the train-step legs of the `configs` block')
+  ap.add_argument('--no-imagenet', action='store_true',
+                  help='skip the ImageNet-32 train-step leg at 8 GPUs')
+  ap.add_argument('--train-steps', type=int, default=3,
+                  help='timed steps of each train-step leg of the `configs` block')
+  ap.add_argument('--comm', choices=['all', 'allreduce', 'overlap', 'peer'], default='all',
+                  help='train_step: how the gradient exchange runs (mulan_b200/optim.py)')
+  ap.add_argument('--no-pdl', action='store_true',
+                  help='plain launches instead of programmatic dependent launch')
+  ap.add_argument('--no-sustained', action='store_true',
+                  help='skip the ~2 s sustained replay of the step graph')
   return ap.parse_args()
 
 
@@ -151,6 +165,18 @@ class ClockSampler:
     """Number of samples so far (to slice out the timed region)."""
     return len(self.samples) if self.how == 'nvml' else len(self.lines)
 
+  def window(self, lo, hi):
+    """Median SM clock / max power / throttle reasons of samples [lo, hi) (NVML mode only)."""
+    if self.how != 'nvml':
+      return None
+    bits = {'hw_slowdown': 0x8, 'hw_thermal_slowdown': 0x40, 'sw_thermal_slowdown': 0x20,
+            'sw_power_cap': 0x4}
+    sm = sorted(c for c, _, _ in self.samples[lo:hi])
+    reasons = sorted({n for _, r, _ in self.samples[lo:hi] for n, b in bits.items() if r & b})
+    pw = [p for _, _, p in self.samples[lo:hi]]
+    return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': self.smax,
+            'power_w_max': max(pw) if pw else None, 'samples': len(sm), 'reasons': reasons}
+
   def stop(self, lo=0, hi=None):
     names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
     sm, reasons, power = [], set(), []
@@ -213,103 +239,114 @@ def make_inputs(rows, device, seed):
 # ----------------------------------------------------------------------------------------
 # native arm
 # ----------------------------------------------------------------------------------------
-def run_native(args):
-  import torch
-  import torch.distributed as dist
-  from mulan_b200 import ops, host, _lib
+class Ctx:
+  """Process-wide state of the native arm: rank / device / torch.distributed."""
 
-  world = int(os.environ.get('WORLD_SIZE', '1'))
-  rank = int(os.environ.get('RANK', '0'))
-  local = int(os.environ.get('LOCAL_RANK', '0'))
-  if world > 1:
-    dist.init_process_group('nccl', device_id=torch.device(f'cuda:{local}'))
-  assert world == args.gpus, f'--gpus {args.gpus} but WORLD_SIZE={world}'
-  torch.cuda.set_device(local)
-  dev = torch.device(f'cuda:{local}')
-  _lib.load()   # loud failure if the CUDA library is missing
+  def __init__(self, args):
+    import torch
+    import torch.distributed as dist
+    from mulan_b200 import _lib
+    self.torch, self.dist = torch, dist
+    self.world = int(os.environ.get('WORLD_SIZE', '1'))
+    self.rank = int(os.environ.get('RANK', '0'))
+    self.local = int(os.environ.get('LOCAL_RANK', '0'))
+    bind_to_gpu_numa(self.local)      # before any pinned allocation (first touch decides)
+    if self.world > 1:
+      dist.init_process_group('nccl', device_id=torch.device(f'cuda:{self.local}'))
+    assert self.world == args.gpus, f'--gpus {args.gpus} but WORLD_SIZE={self.world}'
+    torch.cuda.set_device(self.local)
+    self.dev = torch.device(f'cuda:{self.local}')
+    _lib.load()   # loud failure if the CUDA library is missing
+    try:
+      self.uuid = torch.cuda.get_device_properties(self.local).uuid
+    except Exception:
+      self.uuid = None
+    self.peak, self.peak_src = load_peak()
 
-  rows, K, W = args.rows, args.steps, args.warmup
-  param = PARAMS[args.param]
-  desc = ops.Desc(param=param)
-  inp = make_inputs(rows, dev, seed=1234 + rank)
-  train = args.workload == 'train'
-  lrows = rows if train else min(args.launch_rows, rows)   # rows per launch
-  # velocity_from_epsilon evaluates the (algebraically identical) epsilon form: same kernels,
-  # same bytes as 'eps' (mulan_kernel_param; MULAN_VFE_LITERAL=1 restores the literal formula)
+  def barrier(self):
+    if self.world > 1:
+      self.dist.barrier()
+    self.torch.cuda.synchronize()
+
+  def max_over_ranks(self, value):
+    t = self.torch.tensor([value], device=self.dev, dtype=self.torch.float64)
+    if self.world > 1:
+      self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+    return t.item()
+
+  def close(self):
+    if self.world > 1:
+      self.dist.destroy_process_group()
+
+
+def bind_to_gpu_numa(local_rank):
+  """Run this rank on the CPUs of its GPU's NUMA node, so that page-locked host buffers
+  (first-touch placement) sit next to the PCIe root the GPU hangs off.  A no-op on single-node
+  hosts (the B200 boxes of this pool expose ONE NUMA node) and when sysfs has no answer."""
+  info = {'numa_node': None, 'cpus': None, 'bound': False}
+  try:
+    import torch
+    bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+    dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+    dev_id = torch.cuda.get_device_properties(local_rank).pci_device_id
+    path = f'/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev_id:02x}.0'
+    node = int(open(path + '/numa_node').read().strip())
+    info['numa_node'] = node
+    nodes = [d for d in os.listdir('/sys/devices/system/node') if d.startswith('node')]
+    if node >= 0 and len(nodes) > 1:
+      cpus = set()
+      for part in open(f'/sys/devices/system/node/node{node}/cpulist').read().strip().split(','):
+        lo, _, hi = part.partition('-')
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+      cpus &= os.sched_getaffinity(0)
+      if cpus:
+        os.sched_setaffinity(0, cpus)
+        info.update(cpus=len(cpus), bound=True)
+  except Exception as exc:      # best effort: the measurement proceeds unbound
+    info['error'] = repr(exc)[:80]
+  bind_to_gpu_numa.info = info
+  return info
+
+
+bind_to_gpu_numa.info = {}
+
+
+def measure_elbo(ctx, args, inp, param_name, K, W, extras):
+  """ELBO loss + gradients (fwd_pre -> post value-and-grad with the loss-scalar reduction in its
+  epilogue -> bwd_pre) over `rows` examples per GPU for one parameterisation: whole-step
+  throughput (CUDA-graph replay, max over ranks) and per-kernel roofline fractions."""
+  torch, dist = ctx.torch, ctx.dist
+  from mulan_b200 import ops, _lib
+  dev, world, rank = ctx.dev, ctx.world, ctx.rank
+  rows = args.rows
+  param = PARAMS[param_name]
   eps_form = _lib.kernel_param(param) == PARAMS['eps']
-  save_w = eps_form and not args.no_save_w   # fwd_pre +4 B, post -8 B per sub-pixel
-  assert rows % lrows == 0
-  chunks = []
-  for s0 in range(0, rows, lrows):
-    ci = {k: v[s0:s0 + lrows] for k, v in inp.items()}
-    chunks.append((ops.ElboWorkspace(desc, lrows, dev, save_w=save_w),
-                   ci, torch.full((lrows,), 1.0 / (lrows * D * math.log(2.0)), device=dev)))
-  ws = chunks[0][0]
-
-  # Several launches per step (dense VLB: 2048 rows each = 3.46 waves of 592 resident CTAs) are
-  # independent, so they go round-robin over a few streams: the ragged last wave of one launch
-  # overlaps the first wave of the next.  Fork/join by events, capturable in the CUDA graph.
-  n_side = min(len(chunks), args.streams) - 1
-  side = [torch.cuda.Stream() for _ in range(max(n_side, 0))]
-
-  def fan_out(per_chunk):
-    cur = torch.cuda.current_stream()
-    if not side:
-      for ch in chunks:
-        per_chunk(*ch)
-      return
-    fork = torch.cuda.Event()
-    fork.record(cur)
-    lanes = [cur] + side
-    for s in side:
-      s.wait_event(fork)
-    for j, ch in enumerate(chunks):
-      with torch.cuda.stream(lanes[j % len(lanes)]):
-        per_chunk(*ch)
-    for s in side:
-      join = torch.cuda.Event()
-      join.record(s)
-      cur.wait_event(join)
-
-  def each(fn):
-    return lambda: fan_out(fn)
-  per_chunk = {   # name -> launch on one chunk (all write into the preallocated workspaces)
-      'fwd_pre': lambda w_, i, g: w_.fwd_pre(i['x'], i['a'], i['b'], i['c'], i['t'],
-                                             i['eps0'], i['eps']),
-  }
-  if train and not args.separate_post:
-    # value-and-grad: the loss cotangent of a mean is known up front (jax.value_and_grad)
-    per_chunk['post_vg'] = lambda w_, i, g: w_.fwd_bwd_post(i['x'], i['a'], i['b'], i['c'],
-                                                            i['t'], i['eps'], i['net'], g)
+  save_w = eps_form and not args.no_save_w       # fwd_pre +4 B, post -8 B per sub-pixel
+  desc = ops.Desc(param=param, pdl=not args.no_pdl)
+  ws = ops.ElboWorkspace(desc, rows, dev, save_w=save_w)
+  gL = torch.full((rows,), 1.0 / (rows * D * math.log(2.0)), device=dev)
+  i = inp
+  kernels = {'fwd_pre': lambda: ws.fwd_pre(i['x'], i['a'], i['b'], i['c'], i['t'], i['eps0'],
+                                            i['eps'])}
+  if args.separate_post:
+    kernels['fwd_post'] = lambda: ws.fwd_post(i['x'], i['a'], i['b'], i['c'], i['t'], i['eps'],
+                                              i['net'])
+    kernels['bpd_reduce'] = lambda: ws.bpd_reduce(None)
+    kernels['bwd_post'] = lambda: ws.bwd_post(i['x'], i['a'], i['b'], i['c'], i['t'], i['eps'],
+                                              i['net'], gL)
   else:
-    per_chunk['fwd_post'] = lambda w_, i, g: w_.fwd_post(i['x'], i['a'], i['b'], i['c'], i['t'],
-                                                         i['eps'], i['net'])
-  per_chunk['bpd_reduce'] = lambda w_, i, g: w_.bpd_reduce(None)
-  if train:
-    if args.separate_post:
-      per_chunk['bwd_post'] = lambda w_, i, g: w_.bwd_post(i['x'], i['a'], i['b'], i['c'],
-                                                           i['t'], i['eps'], i['net'], g)
-    per_chunk['bwd_pre'] = lambda w_, i, g: w_.bwd_pre(i['x'], i['a'], i['b'], i['c'], i['t'],
-                                                       i['eps'], i['net'], i['z_bar'],
-                                                       i['g_bar'], g)
-  names = list(per_chunk)
-  kernels = {n: each(fn) for n, fn in per_chunk.items()}   # one kernel over every chunk
-  launches_per_step = len(names) * len(chunks)
-
-  def whole_chunk(w_, i, g):
-    for n in names:
-      per_chunk[n](w_, i, g)
+    # value-and-grad: the loss cotangent of a mean is known up front (jax.value_and_grad); the
+    # six loss_fn scalars come out of the same launch
+    kernels['post_vg'] = lambda: ws.post_bpd(i['x'], i['a'], i['b'], i['c'], i['t'], i['eps'],
+                                             i['net'], gL)
+  kernels['bwd_pre'] = lambda: ws.bwd_pre(i['x'], i['a'], i['b'], i['c'], i['t'], i['eps'],
+                                          i['net'], i['z_bar'], i['g_bar'], gL)
+  names = list(kernels)
 
   def step():
-    fan_out(whole_chunk)                  # chunk-major: a chunk's kernels stay in stream order
+    for n in names:
+      kernels[n]()
 
-  def barrier():
-    if world > 1:
-      dist.barrier()
-    torch.cuda.synchronize()
-
-  # ---- warm-up (eager), then capture ONE step in a CUDA graph: the timed loop replays it,
-  #      so host launch latency / Python jitter cannot starve the GPU -------------------
   stream = torch.cuda.Stream()
   with torch.cuda.stream(stream):
     for _ in range(max(W, 3)):
@@ -321,20 +358,16 @@ def run_native(args):
     with torch.cuda.graph(graph, stream=stream):
       step()
     graph.replay()
-  barrier()
+  ctx.barrier()
 
-  try:
-    uuid = torch.cuda.get_device_properties(local).uuid
-  except Exception:
-    uuid = None
-  sampler = ClockSampler(local, uuid)
-  if rank == 0:
+  sampler = ClockSampler(ctx.local, ctx.uuid) if (rank == 0 and extras) else None
+  if sampler:
     sampler.start()
     time.sleep(0.05)
   t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   with torch.cuda.stream(stream):
-    barrier()
-    mark0 = sampler.mark()
+    ctx.barrier()
+    mark0 = sampler.mark() if sampler else 0
     t_start.record(stream)
     works, reduced = [], torch.empty((K, 6), dtype=torch.float32, device=dev)
     for k in range(K):
@@ -348,18 +381,12 @@ def run_native(args):
     for wk in works:
       wk.wait()                      # the timed region ends only when every pmean has landed
     t_end.record(stream)
-    barrier()
-    mark1 = sampler.mark()
-  elapsed_ms = t_start.elapsed_time(t_end)
-  tmax = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
-  if world > 1:
-    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-  elapsed_ms = tmax.item()
-  timed_launches = launches_per_step * K
+    ctx.barrier()
+  elapsed_ms = ctx.max_over_ranks(t_start.elapsed_time(t_end))
   bpd = (reduced[-1][0] if world > 1 else ws.scalars[0]).item()
 
-  # ---- per-kernel durations, live, CUDA events on the launching stream: each kernel K times
-  #      back to back (its inputs alone exceed L2, so every launch streams from HBM) --------
+  # per-kernel durations, live, CUDA events on the launching stream: each kernel K times back
+  # to back (its inputs alone exceed L2, so every launch streams from HBM)
   kern_ms = {}
   with torch.cuda.stream(stream):
     for n in names:
@@ -372,139 +399,351 @@ def run_native(args):
       e1.record(stream)
       torch.cuda.synchronize()
       kern_ms[n] = e0.elapsed_time(e1) / K
-  clocks = sampler.stop(mark0, None) if rank == 0 else None
 
-  # ---- e2e: host buffers through the C ABI (mulan_elbo_host), copies inside the timing ----
-  e2e = None
-  if not args.no_e2e and train:
-    pin = lambda v: v.cpu().pin_memory()
-    h = {k: pin(inp[k]) for k in ('x', 'a', 'b', 'c', 't', 'eps0', 'eps', 'net')}
-    out = host.HostOutputs(rows, D, want_grad=True, pinned=True)
-    call = lambda: host.elbo_host(h['x'], h['a'], h['b'], h['c'], h['t'], h['eps0'], h['eps'],
-                                  h['net'], param=param, want_grad=True, out=out)
-    ke = max(2, min(K, 5))
-    call(); call()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(ke):
-      r = call()           # synchronises before returning
-    t1 = time.perf_counter()
-    te = torch.tensor([t1 - t0], device=dev, dtype=torch.float64)
-    if world > 1:
-      dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    h2d = rows * D * (1 + 6 * 4) + rows * 4
-    d2h = rows * D * 4 * 4 + (3 * rows + 6) * 4
-    e2e = {'value': world * rows * ke / te.item(), 'unit': 'samples/s', 'steps': ke,
-           'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-           'api': 'mulan_elbo_host (C ABI, pinned host buffers)',
-           'bpd': float(r['scalars'][0])}
-    # the same call with eps_0 / eps drawn on the device from their threefry keys (what
-    # VDM.__call__ itself does with its rng): 8 of the 25 H2D bytes per sub-pixel stay home
-    callk = lambda: host.elbo_host(h['x'], h['a'], h['b'], h['c'], h['t'], None, None, h['net'],
-                                   param=param, want_grad=True, out=out,
-                                   jax_keys=((1234, rank), (5678, rank)))
-    callk(); callk()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(ke):
-      rk = callk()
-    t1 = time.perf_counter()
-    tk = torch.tensor([t1 - t0], device=dev, dtype=torch.float64)
-    if world > 1:
-      dist.all_reduce(tk, op=dist.ReduceOp.MAX)
-    e2e['device_draws'] = {
-        'value': world * rows * ke / tk.item(), 'unit': 'samples/s',
-        'h2d_bytes_per_step': rows * D * (1 + 4 * 4) + rows * 4 + 16,
-        'd2h_bytes_per_step': d2h, 'api': 'mulan_elbo_host_keyed (eps_0, eps from JAX keys)',
-        'bpd': float(rk['scalars'][0])}
-    _lib.load().mulan_host_workspace_release()
+  # sustained: the same graph replayed for ~2 s (clocks and power under a long load)
+  sustained = None
+  if extras and not args.no_sustained:
+    n_rep = max(int(2000.0 / (elapsed_ms / K)), K)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+      ctx.barrier()
+      m0 = sampler.mark() if sampler else 0
+      e0.record(stream)
+      for _ in range(n_rep):
+        graph.replay()
+      e1.record(stream)
+      ctx.barrier()
+      m1 = sampler.mark() if sampler else 0
+    ms = ctx.max_over_ranks(e0.elapsed_time(e1))
+    sustained = {'replays': n_rep, 'seconds': ms * 1e-3,
+                 'value': world * rows * n_rep / (ms * 1e-3), 'unit': 'samples/s',
+                 'ms_per_step': ms / n_rep}
+    if sampler:
+      sustained['clocks'] = sampler.window(m0, m1)
+  clocks = sampler.stop(mark0, None) if sampler else None
 
-  # ---- latency of configs[1]'s literal size (one batch of 128 rows, CUDA graph) ----
-  lat = None
-  if rank == 0 and train:
+  nsub = rows * D
+  ab = dict(ALGO_BYTES['eps' if eps_form else param_name])
+  if eps_form and not save_w:
+    ab.update(fwd_pre=25, fwd_post=20, post_vg=24, bwd_post=24)   # w recomputed from a, b, c
+  ab = {k: v for k, v in ab.items() if k in names}
+  kinfo = {}
+  for n in names:
+    if n not in ab:
+      kinfo[n] = {'ms': kern_ms[n]}
+      continue
+    gbs = ab[n] * nsub / (kern_ms[n] * 1e-3) / 1e9
+    kinfo[n] = {'ms': kern_ms[n], 'algo_bytes_per_subpixel': ab[n], 'gbs': gbs,
+                'frac_of_measured': gbs / ctx.peak, 'frac_of_8TBs': gbs / 8000.0}
+  total_algo = sum(ab.values()) * nsub
+  ms_step = elapsed_ms / K
+  dom = max(ab, key=lambda n: kern_ms[n])
+  return {
+      'param': param_name, 'loss_form': 'eps' if eps_form else 'velocity', 'saved_w': save_w,
+      'value': world * rows * K / (elapsed_ms * 1e-3), 'unit': 'samples/s',
+      'ms_per_step': ms_step, 'steps': K, 'rows_per_gpu': rows, 'bpd': bpd,
+      'launches_per_step': len(names), 'kernels': kinfo, 'dominant': dom,
+      'step_hbm': {'algo_bytes_per_step': total_algo,
+                   'gbs': total_algo / (ms_step * 1e-3) / 1e9,
+                   'frac_of_measured': total_algo / (ms_step * 1e-3) / 1e9 / ctx.peak,
+                   'sum_kernel_ms': sum(kern_ms.values())},
+      'clocks': clocks, 'sustained': sustained, 'algo_bytes': ab,
+  }
+
+
+def measure_latency(ctx, args, inp):
+  """The literal per-GPU batch of configs[1] (128 rows): GPU time per step from a CUDA graph that
+  holds 20 consecutive steps (a one-step graph replayed back to back measures the host's
+  graph-launch rate, ~18 us, not the device)."""
+  torch = ctx.torch
+  from mulan_b200 import ops
+  dev = ctx.dev
+  out = {}
+  for label, pdl in (('pdl', True), ('plain', False)):
     sm = {k: (v[:GROUP].contiguous()) for k, v in inp.items()}
     gLs = torch.full((GROUP,), 1.0 / (GROUP * D * math.log(2.0)), device=dev)
-    wss = ops.ElboWorkspace(desc, GROUP, dev)
+    wss = ops.ElboWorkspace(ops.Desc(pdl=pdl), GROUP, dev)
+
     def small_step():
       wss.fwd_pre(sm['x'], sm['a'], sm['b'], sm['c'], sm['t'], sm['eps0'], sm['eps'])
-      wss.fwd_bwd_post(sm['x'], sm['a'], sm['b'], sm['c'], sm['t'], sm['eps'], sm['net'], gLs)
-      wss.bpd_reduce(None)
+      wss.post_bpd(sm['x'], sm['a'], sm['b'], sm['c'], sm['t'], sm['eps'], sm['net'], gLs)
       wss.bwd_pre(sm['x'], sm['a'], sm['b'], sm['c'], sm['t'], sm['eps'], sm['net'], sm['z_bar'],
                   sm['g_bar'], gLs)
+    stream = torch.cuda.Stream()
+    per_graph = 20
     with torch.cuda.stream(stream):
       for _ in range(3):
         small_step()
       torch.cuda.synchronize()
       g2 = torch.cuda.CUDAGraph()
       with torch.cuda.graph(g2, stream=stream):
-        small_step()
-      for _ in range(5):
+        for _ in range(per_graph):
+          small_step()
+      for _ in range(3):
         g2.replay()
       e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
       e0.record(stream)
-      for _ in range(200):
+      for _ in range(20):
         g2.replay()
       e1.record(stream)
       torch.cuda.synchronize()
-      us = e0.elapsed_time(e1) * 1000 / 200
-      lat = {'rows': GROUP, 'us_per_step': us, 'samples_per_s': GROUP / (us * 1e-6),
-             'how': 'CUDA graph of the 4 launches, 200 replays, L2-resident'}
+    out[label] = e0.elapsed_time(e1) * 1000 / (20 * per_graph)
+  us = out['pdl']
+  return {'rows': GROUP, 'us_per_step': us, 'us_per_step_plain_launches': out['plain'],
+          'samples_per_s': GROUP / (us * 1e-6), 'launches_per_step': 3,
+          'how': 'CUDA graph of 20 consecutive steps (3 launches each, programmatic dependent '
+                 'launch), 20 replays, L2-resident'}
+
+
+def measure_e2e(ctx, args, inp, K):
+  """The same loss + gradients through the host-buffer C-ABI call (mulan_elbo_host): H2D of every
+  operand and D2H of every result inside the timed region, from / to page-locked buffers; next to
+  it a COPY-ONLY leg moving exactly the same bytes with no kernel, i.e. what the platform's PCIe
+  path allows (e2e is judged as a fraction of it)."""
+  torch, dist = ctx.torch, ctx.dist
+  from mulan_b200 import host, _lib
+  rows, dev, world = args.rows, ctx.dev, ctx.world
+  param = PARAMS[args.param]
+  pin = lambda v: v.cpu().pin_memory()
+  h = {k: pin(inp[k]) for k in ('x', 'a', 'b', 'c', 't', 'eps0', 'eps', 'net')}
+  out = host.HostOutputs(rows, D, want_grad=True, pinned=True)
+  call = lambda: host.elbo_host(h['x'], h['a'], h['b'], h['c'], h['t'], h['eps0'], h['eps'],
+                                h['net'], param=param, want_grad=True, out=out)
+  ke = max(2, min(K, 5))
+
+  def timed(fn):
+    fn(); fn()
+    ctx.barrier()
+    t0 = time.perf_counter()
+    for _ in range(ke):
+      r = fn()           # synchronises before returning
+    return ctx.max_over_ranks(time.perf_counter() - t0), r
+  te, r = timed(call)
+  h2d = rows * D * (1 + 6 * 4) + rows * 4
+  d2h = rows * D * 4 * 4 + (3 * rows + 6) * 4
+  e2e = {'value': world * rows * ke / te, 'unit': 'samples/s', 'steps': ke,
+         'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+         'h2d_gbs_per_gpu': h2d * ke / te / 1e9, 'd2h_gbs_per_gpu': d2h * ke / te / 1e9,
+         'api': 'mulan_elbo_host (C ABI, pinned host buffers)', 'bpd': float(r['scalars'][0]),
+         'numa': bind_to_gpu_numa.info}
+  # the same call with eps_0 / eps drawn on the device from their threefry keys (what
+  # VDM.__call__ itself does with its rng): 8 of the 25 H2D bytes per sub-pixel stay home
+  callk = lambda: host.elbo_host(h['x'], h['a'], h['b'], h['c'], h['t'], None, None, h['net'],
+                                 param=param, want_grad=True, out=out,
+                                 jax_keys=((1234, ctx.rank), (5678, ctx.rank)))
+  tk, rk = timed(callk)
+  e2e['device_draws'] = {
+      'value': world * rows * ke / tk, 'unit': 'samples/s',
+      'h2d_bytes_per_step': rows * D * (1 + 4 * 4) + rows * 4 + 16,
+      'd2h_bytes_per_step': d2h, 'api': 'mulan_elbo_host_keyed (eps_0, eps from JAX keys)',
+      'bpd': float(rk['scalars'][0])}
+  _lib.load().mulan_host_workspace_release()
+  # ---- copy-only: the same pinned buffers, the same bytes, both directions at once, no kernel
+  d_in = {k: torch.empty_like(inp[k]) for k in h}
+  d_out = [torch.empty((rows, D), dtype=torch.float32, device=dev) for _ in range(4)]
+  h_out = [torch.from_numpy(v) for v in (out.a_bar, out.b_bar, out.c_bar, out.n_bar)]
+  s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+
+  def copy_only():
+    with torch.cuda.stream(s_in):
+      for k in h:
+        d_in[k].copy_(h[k], non_blocking=True)
+    with torch.cuda.stream(s_out):
+      for src, dst in zip(d_out, h_out):
+        dst.copy_(src, non_blocking=True)
+    s_in.synchronize(); s_out.synchronize()
+
+  def h2d_only():
+    with torch.cuda.stream(s_in):
+      for k in h:
+        d_in[k].copy_(h[k], non_blocking=True)
+    s_in.synchronize()
+  tc, _ = timed(copy_only)
+  th, _ = timed(h2d_only)
+  copy_value = world * rows * ke / tc
+  e2e['copy_only'] = {
+      'value': copy_value, 'unit': 'samples/s',
+      'h2d_gbs_per_gpu': h2d * ke / tc / 1e9, 'd2h_gbs_per_gpu': d2h * ke / tc / 1e9,
+      'h2d_alone_gbs_per_gpu': h2d * ke / th / 1e9,
+      'how': 'cudaMemcpyAsync of the same pinned buffers in both directions on two streams, no '
+             'kernels: the PCIe / host-memory ceiling of this box for these bytes'}
+  e2e['frac_of_copy_only'] = e2e['value'] / copy_value
+  return e2e
+
+
+def measure_dense(ctx, args, inp, K, W):
+  """BASELINE.json configs[4]: dense-VLB forward (recon + prior + diffusion terms; the velocity
+  model the CIFAR-10 config ships), images sharded over the ranks -- every rank evaluates
+  rows / 128 images x 128 timesteps per step, one (sum, count) all-reduce per step.  Launch
+  shapes: the reference-shaped 16 images x 128 timesteps = 2048 rows per launch on ONE stream,
+  the same over 8 streams, and the driver's own sizing (dist.dense_images_per_launch: all 128
+  images of the step in one launch) with eps_0 / eps broadcast instead of tiled."""
+  torch, dist = ctx.torch, ctx.dist
+  from mulan_b200 import ops, _lib
+  from mulan_b200.dist import dense_images_per_launch
+  dev, world = ctx.dev, ctx.world
+  rows = args.rows
+  param_name = 'vel'
+  param = PARAMS[param_name]
+  eps_form = _lib.kernel_param(param) == PARAMS['eps']
+  out = {}
+  T = GROUP
+  noise0, noise = inp['eps0'][:T].contiguous(), inp['eps'][:T].contiguous()
+
+  def build(lrows, n_streams, broadcast):
+    desc = ops.Desc(param=param, pdl=not args.no_pdl, noise_rows=T if broadcast else 0)
+    chunks = []
+    for s0 in range(0, rows, lrows):
+      ci = {k: v[s0:s0 + lrows] for k, v in inp.items()}
+      chunks.append((ops.ElboWorkspace(desc, lrows, dev, save_w=eps_form), ci))
+    side = [torch.cuda.Stream() for _ in range(min(len(chunks), n_streams) - 1)]
+
+    def one(w_, i):
+      e0, e = (noise0, noise) if broadcast else (i['eps0'], i['eps'])
+      w_.fwd_pre(i['x'], i['a'], i['b'], i['c'], i['t'], e0, e)
+      w_.post_bpd(i['x'], i['a'], i['b'], i['c'], i['t'], e, i['net'], None)
+
+    def step():
+      cur = torch.cuda.current_stream()
+      if not side:
+        for ch in chunks:
+          one(*ch)
+        return
+      fork = torch.cuda.Event()
+      fork.record(cur)
+      lanes = [cur] + side
+      for s in side:
+        s.wait_event(fork)
+      for j, ch in enumerate(chunks):
+        with torch.cuda.stream(lanes[j % len(lanes)]):
+          one(*ch)
+      for s in side:
+        join = torch.cuda.Event()
+        join.record(s)
+        cur.wait_event(join)
+    return step, chunks
+
+  acc = torch.zeros(2, dtype=torch.float64, device=dev)
+  shapes = [('ref_2048_rows_1_stream', min(args.launch_rows, rows), 1, False),
+            ('ref_2048_rows_8_streams', min(args.launch_rows, rows), 8, False),
+            ('driver_sized_1_stream', min(dense_images_per_launch(T) * T, rows), 1, True)]
+  for label, lrows, n_streams, broadcast in shapes:
+    step, chunks = build(lrows, n_streams, broadcast)
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+      for _ in range(max(W, 3)):
+        step()
+      torch.cuda.synchronize()
+      graph = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(graph, stream=stream):
+        step()
+      graph.replay()
+      ctx.barrier()
+      e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      e0.record(stream)
+      for _ in range(K):
+        graph.replay()
+        if world > 1:      # the one exchange: (sum of per-image bpd, image count)
+          acc[0] = chunks[0][0].scalars[0].double()
+          acc[1] = rows / T
+          dist.all_reduce(acc, op=dist.ReduceOp.SUM)
+      e1.record(stream)
+      ctx.barrier()
+    ms = ctx.max_over_ranks(e0.elapsed_time(e1)) / K
+    fwd_pre_b = (25 + (4 if eps_form else 0)) - (8.0 * (1 - T / lrows) if broadcast else 0.0)
+    post_b = (12 if eps_form else 21) - (4.0 * (1 - T / lrows) if broadcast else 0.0)
+    algo = (fwd_pre_b + post_b) * rows * D
+    out[label] = {'rows_per_launch': lrows, 'streams': n_streams, 'broadcast_noise': broadcast,
+                  'value': world * rows / (ms * 1e-3), 'unit': 'rows/s', 'ms_per_step': ms,
+                  'images_per_s': world * rows / T / (ms * 1e-3),
+                  'algo_bytes_per_subpixel': fwd_pre_b + post_b,
+                  'gbs': algo / (ms * 1e-3) / 1e9,
+                  'frac_of_measured': algo / (ms * 1e-3) / 1e9 / ctx.peak}
+    del graph, chunks
+  best = max(out, key=lambda k: out[k]['value'])
+  return {'workload': 'eval_bpd dense VLB forward (mulan_velocity: recon + prior + diffusion), '
+                      f'{rows // T} images x {T} timesteps per rank per step, images sharded over '
+                      f'{world} rank(s), denoiser output supplied',
+          'value': out[best]['value'], 'unit': 'rows/s', 'best_shape': best, 'shapes': out}
+
+
+def run_native(args):
+  ctx = Ctx(args)
+  torch = ctx.torch
+  rows, K, W = args.rows, args.steps, args.warmup
+  inp = make_inputs(rows, ctx.dev, seed=1234 + ctx.rank)
+  if args.workload == 'dense_vlb':
+    dense = measure_dense(ctx, args, inp, K, W)
+    if ctx.rank == 0:
+      emit({'metric': 'mulan_dense_vlb_rows_per_s', 'value': dense['value'], 'unit': 'rows/s',
+            'n_gpus': ctx.world, 'steps': K, 'warmup': max(W, 3), 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': dense['workload']}, 'dense_vlb': dense})
+    ctx.close()
+    return
+
+  main = measure_elbo(ctx, args, inp, args.param, K, W, extras=True)
+  e2e = measure_e2e(ctx, args, inp, K) if not args.no_e2e else None
+  lat = measure_latency(ctx, args, inp) if ctx.rank == 0 else None
+
+  configs = None
+  if not args.no_configs:
+    configs = {}
+    kc = max(10, min(K, 30))
+    for label, pn in (('cfg3_mulan_velocity', 'vel'),
+                      ('cfg4_mulan_velocity_from_epsilon', 'vel_from_eps')):
+      if pn == args.param:
+        continue
+      r = measure_elbo(ctx, args, inp, pn, kc, W, extras=False)
+      configs[label] = {k: r[k] for k in ('value', 'unit', 'ms_per_step', 'steps', 'rows_per_gpu',
+                                          'loss_form', 'saved_w', 'kernels', 'step_hbm', 'bpd')}
+    configs['cfg5_dense_vlb'] = measure_dense(ctx, args, inp, kc, W)
+  del inp
+  torch.cuda.empty_cache()
+  if configs is not None and not args.no_train_step:
+    configs['train_step'] = measure_train_steps(ctx, args)
 
   # ---- cpu baseline (oracle port on host cores; rank 0, N=1 only) ----
   cpu = None
-  if rank == 0 and world == 1 and not args.no_cpu_baseline:
-    cpu = cpu_reference(args, steps=0, warmup=1, min_seconds=10.0)
+  if ctx.rank == 0 and ctx.world == 1 and not args.no_cpu_baseline:
+    cpu = cpu_reference(args, steps=0, warmup=1, min_seconds=8.0)
+    cpu['single_thread'] = cpu_reference(args, steps=0, warmup=1, min_seconds=4.0, threads=1)
+    cpu['config1_b8'] = cpu_reference(args, steps=0, warmup=1, min_seconds=3.0, rows=8)
 
-  if rank != 0:
-    if world > 1:
-      dist.destroy_process_group()
+  if ctx.rank != 0:
+    ctx.close()
     return
-
+  world = ctx.world
+  dom = main['dominant']
+  kinfo = main['kernels']
+  ab = main['algo_bytes']
   nsub = rows * D
-  dom = max((n for n in names if n != 'bpd_reduce'), key=lambda n: kern_ms[n])
-  ab = dict(ALGO_BYTES['eps' if eps_form else args.param])
-  if eps_form and not save_w:
-    ab.update(fwd_pre=25, fwd_post=20, post_vg=24, bwd_post=24)   # w recomputed from a, b, c
-  ab = {k: v for k, v in ab.items() if k in names}
-  peaks, peak_src = load_peak()
-  kinfo = {}
-  for n in names:
-    if n == 'bpd_reduce':
-      kinfo[n] = {'ms': kern_ms[n]}
-      continue
-    gbs = ab[n] * nsub / (kern_ms[n] * 1e-3) / 1e9
-    kinfo[n] = {'ms': kern_ms[n], 'algo_bytes_per_subpixel': ab[n], 'gbs': gbs,
-                'frac_of_measured': gbs / peaks, 'frac_of_8TBs': gbs / 8000.0}
-  total_algo = sum(ab.values()) * nsub
-  traffic = load_traffic(dom, rows) if train else None
-  ms_step = elapsed_ms / K
+  traffic = load_traffic(dom, rows)
   line = {
-      'metric': 'mulan_elbo_train_samples_per_s' if train else 'mulan_dense_vlb_rows_per_s',
-      'value': world * rows * K / (elapsed_ms * 1e-3),
+      'metric': 'mulan_elbo_train_samples_per_s',
+      'value': main['value'],
       'unit': 'samples/s', 'n_gpus': world, 'steps': K, 'warmup': max(W, 3),
-      'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak',
+      'ms_per_step': main['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
       'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
       'config': {'workload': workload_name(args), 'rows_per_gpu': rows, 'dim': D,
-                 'param': args.param, 'loss_form': 'eps' if eps_form else 'velocity',
-                 'saved_w': save_w, 'l2': 'inputs larger than L2 (%.2f GB of HBM traffic per '
-                 'step)' % (total_algo / 1e9), 'parallelism': f'dp{world} (rows sharded)',
-                 'timed_loop': 'CUDA-graph replay of one step (%d launches)' % launches_per_step,
-                 'rows_per_launch': lrows, 'streams': 1 + len(side)},
+                 'param': args.param, 'loss_form': main['loss_form'],
+                 'saved_w': main['saved_w'], 'l2': 'inputs larger than L2 (%.2f GB of HBM traffic '
+                 'per step)' % (main['step_hbm']['algo_bytes_per_step'] / 1e9),
+                 'parallelism': f'dp{world} (rows sharded)',
+                 'timed_loop': 'CUDA-graph replay of one step (%d launches, programmatic '
+                               'dependent launch)' % main['launches_per_step']},
       'roofline': {'bound': 'hbm', 'kernel': dom, 'achieved': kinfo[dom]['gbs'],
-                   'peak': peaks, 'peak_source': peak_src, 'unit': 'GB/s',
-                   'frac': kinfo[dom]['gbs'] / peaks, 'traffic': traffic,
+                   'peak': ctx.peak, 'peak_source': ctx.peak_src, 'unit': 'GB/s',
+                   'frac': kinfo[dom]['gbs'] / ctx.peak, 'traffic': traffic,
                    'algo_bytes_per_launch': ab[dom] * nsub,
                    'how': 'CUDA events around %d back-to-back launches on the launch stream' % K},
-      'step_hbm': {'algo_bytes_per_step': total_algo,
-                   'gbs': total_algo / (ms_step * 1e-3) / 1e9,
-                   'frac_of_measured': total_algo / (ms_step * 1e-3) / 1e9 / peaks,
-                   'sum_kernel_ms': sum(kern_ms.values())},
-      'kernels': kinfo, 'gpu_launches': timed_launches, 'clocks': clocks, 'e2e': e2e,
-      'latency_b128': lat, 'cpu_baseline': cpu, 'bpd': bpd,
+      'step_hbm': main['step_hbm'],
+      'kernels': kinfo, 'gpu_launches': main['launches_per_step'] * K, 'clocks': main['clocks'],
+      'sustained': main['sustained'], 'e2e': e2e,
+      'latency_b128': lat, 'cpu_baseline': cpu, 'bpd': main['bpd'], 'configs': configs,
   }
   emit(line)
-  if world > 1:
-    dist.destroy_process_group()
+  ctx.close()
 
 
 def load_peak():
@@ -534,12 +773,12 @@ def load_traffic(kernel, rows):
 # ----------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port of the reference on the host cores
 # ----------------------------------------------------------------------------------------
-def cpu_reference(args, steps, warmup, min_seconds=0.0):
+def cpu_reference(args, steps, warmup, min_seconds=0.0, threads=None, rows=None):
   import torch
   from oracle import mulan_oracle as O   # CPU baseline leg: allowed to execute oracle/
-  cores = os.cpu_count() or 1
+  cores = threads or len(os.sched_getaffinity(0)) or os.cpu_count() or 1
   torch.set_num_threads(cores)
-  B = args.ref_rows
+  B = rows or args.ref_rows
   mode = PARAMS[args.param]
   inp = O.synth_inputs(B, seed=0)
   cfg = O.OracleConfig()
@@ -566,7 +805,8 @@ def cpu_reference(args, steps, warmup, min_seconds=0.0):
   dt = time.perf_counter() - t0
   return {'value': B * steps / dt, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
           'ms_per_step': dt / steps * 1e3,
-          'sample': f'{steps} steps of {B} rows (one per-GPU batch of the workload), oracle '
+          'rows': B,
+          'sample': f'{steps} steps of {B} rows ({"one per-GPU batch of the workload" if B == GROUP else "BASELINE.json configs[0]" if B == 8 else "sample"}), oracle '
                     f'float32 loss+grad with torch CPU, {cores} threads'}
 
 
@@ -605,171 +845,136 @@ def emit(line: dict):
     sys.stdout.flush()
 
 
-def run_train_step(args):
-  """Whole train step around the kernels (BASELINE.json configs[1..3]): stand-in encoder and
-  U-Net on cuDNN/cuBLAS float32 (mulan_b200/standin.py -- the reference keeps them on the
-  framework path), the ELBO kernels, ONE all-reduce of the flat gradient bucket (+ scalars),
-  ONE fused AdamW+EMA launch.  Reports samples/s and the ELBO kernels' share of the step."""
-  import torch
-  import torch.distributed as dist
-  from mulan_b200 import _lib, ops
+def train_step_leg(ctx, args, net_config, param_name, B, modes, K, W):
+  """Whole train step around the kernels (Experiment.train_step, ldm/experiment.py:335-356):
+  STAND-IN encoder and U-Net on cuDNN/cuBLAS float32 (mulan_b200/standin.py -- the reference
+  keeps them on the framework path; same layer structure and parameter count), the ELBO kernels,
+  the gradient exchange and the fused AdamW+EMA update, for each way of running the exchange
+  (mulan_b200/optim.py: 'allreduce' after backward, 'overlap' = bucketed NCCL during backward,
+  'peer' = mulan_adamw_ema_peer over NVLink peer memory during backward)."""
+  torch, dist = ctx.torch, ctx.dist
   from mulan_b200.model import VDM, VDMConfig
   from mulan_b200.optim import FlatTrainState, train_step
   from mulan_b200.standin import ScoreUNet, UnetEncoder
-
-  world = int(os.environ.get('WORLD_SIZE', '1'))
-  rank = int(os.environ.get('RANK', '0'))
-  local = int(os.environ.get('LOCAL_RANK', '0'))
-  if world > 1:
-    dist.init_process_group('nccl', device_id=torch.device(f'cuda:{local}'))
-  assert world == args.gpus, f'--gpus {args.gpus} but WORLD_SIZE={world}'
-  torch.cuda.set_device(local)
-  dev = torch.device(f'cuda:{local}')
-  _lib.load()
+  dev, world, rank = ctx.dev, ctx.world, ctx.rank
   torch.backends.cuda.matmul.allow_tf32 = args.tf32      # reference: matmul precision float32
   torch.backends.cudnn.allow_tf32 = args.tf32
   torch.backends.cudnn.benchmark = True
-  torch.manual_seed(1234)                                 # same init on every rank
-  n_embd = 128 if args.net_config == 'cifar10' else 256
-  B = args.global_batch // world if args.global_batch else args.batch
-  cfg = VDMConfig(vdm_type='mulan_epsilon' if args.param == 'eps' else 'mulan_velocity',
-                  velocity_from_epsilon=(args.param == 'vel_from_eps'))
-  model = VDM(cfg, UnetEncoder(n_embd, 4), ScoreUNet(n_embd, 32)).to(dev)
-  model.train()
-  state = FlatTrainState(model.named_parameters())
-  gen = torch.Generator(device=dev).manual_seed(100 + rank)
+  n_embd = 128 if net_config == 'cifar10' else 256
+  cfg = VDMConfig(vdm_type='mulan_epsilon' if param_name == 'eps' else 'mulan_velocity',
+                  velocity_from_epsilon=(param_name == 'vel_from_eps'))
   host_images = torch.randint(0, 256, (B, 32, 32, 3), dtype=torch.uint8).pin_memory()
-  K, W = args.steps, max(args.warmup, 3)
+  res = {'workload': f'{net_config} {cfg.vdm_type}'
+                     f'{"(velocity_from_epsilon)" if cfg.velocity_from_epsilon else ""} train '
+                     f'step, per-GPU batch {B}, global {B * world}; STAND-IN encoder / U-Net on '
+                     f'cuDNN/cuBLAS float32, ELBO kernels + gradient exchange + fused AdamW+EMA in '
+                     f'libmulan_b200', 'sm_n_embd': n_embd, 'per_gpu_batch': B, 'modes': {}}
+  for mode in modes:
+    torch.manual_seed(1234)                                 # same init on every rank
+    model = VDM(cfg, UnetEncoder(n_embd, 4), ScoreUNet(n_embd, 32)).to(dev)
+    model.train()
+    state = FlatTrainState(model.named_parameters(), comm=mode)
+    gen = torch.Generator(device=dev).manual_seed(100 + rank)
 
-  def barrier():
-    if world > 1:
-      dist.barrier()
-    torch.cuda.synchronize()
-
-  def one_step():
-    images = host_images.to(dev, non_blocking=True)       # H2D of the step's inputs
-    return train_step(model, state, {'images': images}, generator=gen)
-
-  for _ in range(W):
-    sc = one_step()
-  barrier()
-  try:
-    uuid = torch.cuda.get_device_properties(local).uuid
-  except Exception:
-    uuid = None
-  sampler = ClockSampler(local, uuid)
-  if rank == 0:
-    sampler.start()
-  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-  barrier()
-  mark0 = sampler.mark()
-  t0 = time.perf_counter()
-  e0.record()
-  for _ in range(K):
-    sc = one_step()
-    bpd = float(sc['bpd'])                                # D2H read of the step's result
-  e1.record()
-  barrier()
-  wall = time.perf_counter() - t0
-  clocks = sampler.stop(mark0, None) if rank == 0 else None
-  tm = torch.tensor([e0.elapsed_time(e1), wall * 1e3], device=dev, dtype=torch.float64)
-  if world > 1:
-    dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-  ms, wall_ms = tm[0].item() / K, tm[1].item() / K
-
-  # ELBO kernels alone at this batch (CUDA graph of the 4 launches)
-  elbo_us = None
-  if rank == 0:
-    desc = model.desc
-    inp = make_inputs(B, dev, seed=7)
-    ws = ops.ElboWorkspace(desc, B, dev)
-    gL = torch.full((B,), 1.0 / (B * D * math.log(2.0)), device=dev)
-    def elbo():
-      ws.fwd_pre(inp['x'], inp['a'], inp['b'], inp['c'], inp['t'], inp['eps0'], inp['eps'])
-      ws.fwd_bwd_post(inp['x'], inp['a'], inp['b'], inp['c'], inp['t'], inp['eps'], inp['net'], gL)
-      ws.bpd_reduce(None)
-      ws.bwd_pre(inp['x'], inp['a'], inp['b'], inp['c'], inp['t'], inp['eps'], inp['net'],
-                 inp['z_bar'], inp['g_bar'], gL)
-    st = torch.cuda.Stream()
-    with torch.cuda.stream(st):
-      for _ in range(3):
-        elbo()
-      torch.cuda.synchronize()
-      g2 = torch.cuda.CUDAGraph()
-      with torch.cuda.graph(g2, stream=st):
-        elbo()
+    def one_step():
+      images = host_images.to(dev, non_blocking=True)       # H2D of the step's inputs
+      return train_step(model, state, {'images': images}, generator=gen)
+    for _ in range(W):
+      sc = one_step()
+    ctx.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(K):
+      sc = one_step()
+      bpd = float(sc['bpd'])                                # D2H read of the step's result
+    e1.record()
+    ctx.barrier()
+    wall = time.perf_counter() - t0
+    ms = ctx.max_over_ranks(e0.elapsed_time(e1)) / K
+    wall_ms = ctx.max_over_ranks(wall * 1e3) / K
+    m = {'ms_per_step': ms, 'value': world * B / (ms * 1e-3), 'unit': 'samples/s',
+         'e2e_value': world * B / (wall_ms * 1e-3), 'bpd': bpd, 'steps': K,
+         'exchange_ranges': len(state.ranges)}
+    # ---- the pieces alone (CUDA events, 5 repetitions each)
+    def alone(fn, reps=5):
+      fn()
+      ctx.barrier()
       a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-      a0.record(st)
-      for _ in range(100):
-        g2.replay()
-      a1.record(st)
-      torch.cuda.synchronize()
-      elbo_us = a0.elapsed_time(a1) * 10.0
-  # fused AdamW+EMA alone (36 B per parameter) and, for context, torch's fused AdamW + foreach EMA
-  optim = None
-  if rank == 0:
-    o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    state.apply_gradients()
-    torch.cuda.synchronize()
-    o0.record()
-    for _ in range(20):
-      state.apply_gradients()
-    o1.record()
-    torch.cuda.synchronize()
-    us = o0.elapsed_time(o1) * 1000 / 20
-    peaks, peak_src = load_peak()
-    gbs = 36.0 * state.n / (us * 1e-6) / 1e9
-    optim = {'kernel': 'mulan_adamw_ema', 'us': us, 'algo_bytes': 36 * state.n, 'gbs': gbs,
-             'frac_of_measured': gbs / peaks}
-    try:
-      tp = [torch.nn.Parameter(torch.randn(state.n // 8, device=dev)) for _ in range(8)]
-      for q in tp:
-        q.grad = torch.randn_like(q)
-      te = [q.detach().clone() for q in tp]
-      topt = torch.optim.AdamW(tp, lr=2e-4, betas=(0.9, 0.99), weight_decay=0.01, fused=True)
-      def torch_step():
-        topt.step()
-        torch._foreach_lerp_(te, [q.detach() for q in tp], 1e-4)
-      torch_step()
-      torch.cuda.synchronize()
-      o0.record()
-      for _ in range(20):
-        torch_step()
-      o1.record()
-      torch.cuda.synchronize()
-      optim['torch_fused_adamw_plus_foreach_ema_us'] = o0.elapsed_time(o1) * 1000 / 20
-      del tp, te, topt
-    except Exception as exc:      # context figure only
-      optim['torch_fused_adamw_plus_foreach_ema_us'] = f'unavailable: {exc}'
-  if rank != 0:
-    if world > 1:
-      dist.destroy_process_group()
-    return
-  nparam = state.n
-  line = {
-      'metric': 'mulan_train_step_samples_per_s', 'value': world * B / (ms * 1e-3),
-      'unit': 'samples/s', 'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms,
-      'higher_is_better': True, 'scaling': 'strong' if args.global_batch else 'weak',
-      'vs_baseline': None, 'dtype': 'tf32' if args.tf32 else 'f32', 'data': 'synthetic',
-      'config': {'workload': f'{args.net_config} {cfg.vdm_type}'
-                             f'{"(velocity_from_epsilon)" if cfg.velocity_from_epsilon else ""} '
-                             f'train step, per-GPU batch {B}, global {B * world}; STAND-IN '
-                             f'encoder/U-Net on cuDNN/cuBLAS (mulan_b200/standin.py), ELBO in '
-                             f'libmulan_b200, flat-bucket all-reduce, fused AdamW+EMA',
-                 'sm_n_embd': n_embd, 'sm_n_layer': 32, 'parameters': nparam,
-                 'grad_allreduce_bytes': 4 * (nparam + state.extra), 'parallelism': f'dp{world}'},
-      'elbo_kernels': {'us_per_step': elbo_us, 'share_of_step': elbo_us / (ms * 1e3),
-                       'how': 'CUDA graph of fwd_pre, post value-and-grad, bpd_reduce, bwd_pre '
-                              'at this batch'},
-      'optimizer': optim,
-      'e2e': {'value': world * B / (wall_ms * 1e-3), 'unit': 'samples/s',
-              'h2d_bytes_per_step': B * D, 'd2h_bytes_per_step': 4,
-              'api': 'optim.train_step(model, state, batch) with host uint8 images'},
-      'gpu_launches': 7 * K, 'clocks': clocks, 'bpd': bpd,   # aux fwd/bwd, fwd_pre, post_vg, scale_rows, bwd_pre, adamw_ema
-  }
-  emit(line)
-  if world > 1:
-    dist.destroy_process_group()
+      a0.record()
+      for _ in range(reps):
+        fn()
+      a1.record()
+      ctx.barrier()
+      return ctx.max_over_ranks(a0.elapsed_time(a1)) / reps
+    nbytes = 4 * state.n
+    if mode == 'allreduce':
+      if world > 1:
+        t_ar = alone(lambda: dist.all_reduce(state.grads, op=dist.ReduceOp.SUM))
+        m['nccl_allreduce_ms'] = t_ar
+        m['nccl_allreduce_busbw_gbs'] = 2 * (world - 1) / world * nbytes / (t_ar * 1e-3) / 1e9
+      t_up = alone(lambda: state.apply_gradients())
+      m['adamw_ema_ms'] = t_up
+      m['adamw_ema_frac_of_measured'] = 36.0 * state.n / (t_up * 1e-3) / 1e9 / ctx.peak
+    elif mode == 'peer':
+      def fused():
+        state._reset_ranges()
+        for i in range(len(state.ranges)):
+          state._fire(i)
+        state.finish_exchange()
+      t_f = alone(fused)
+      m['fused_exchange_update_ms'] = t_f
+      # NVLink bytes per rank: (world-1)/world of the bucket read from peers + as much stored
+      m['nvlink_gbs_per_direction'] = (world - 1) / world * nbytes / (t_f * 1e-3) / 1e9
+      m['timed_out'] = state.peer.timed_out()
+    res['modes'][mode] = m
+    res['parameters'] = state.n
+    res['grad_bucket_bytes'] = nbytes
+    if state.peer is not None:
+      state.peer.close()
+    for h_ in state._hooks:
+      h_.remove()
+    del model, state
+    torch.cuda.empty_cache()
+  best = min(res['modes'], key=lambda k: res['modes'][k]['ms_per_step'])
+  res.update(value=res['modes'][best]['value'], unit='samples/s', best_mode=best,
+             ms_per_step=res['modes'][best]['ms_per_step'])
+  return res
+
+
+def measure_train_steps(ctx, args):
+  """The train-step legs of the bench line: configs[1]/[2] (CIFAR-10 networks, the velocity model
+  the config ships, per-GPU batch 128: global 1024 at 8 GPUs, 285 MB gradient bucket) at every N,
+  and configs[3] (ImageNet-32 networks, v-from-eps, 256 per GPU = global 2048, 682 MB) at N = 8."""
+  modes = ['allreduce'] if ctx.world == 1 else ['allreduce', 'overlap', 'peer']
+  K = max(2, min(args.train_steps, 10))
+  out = {'cfg2_cfg3_cifar10_velocity': train_step_leg(ctx, args, 'cifar10', 'vel', 128, modes,
+                                                      K, 2)}
+  if ctx.world == 8 and not args.no_imagenet:
+    out['cfg4_imagenet32_vfe'] = train_step_leg(ctx, args, 'imagenet32', 'vel_from_eps', 256,
+                                                modes, 2, 1)
+  return out
+
+
+def run_train_step(args):
+  """--workload train_step: one train-step leg on its own (see train_step_leg)."""
+  ctx = Ctx(args)
+  B = args.global_batch // ctx.world if args.global_batch else args.batch
+  modes = [args.comm] if args.comm != 'all' else (
+      ['allreduce'] if ctx.world == 1 else ['allreduce', 'overlap', 'peer'])
+  K, W = args.steps, max(args.warmup, 2)
+  leg = train_step_leg(ctx, args, args.net_config, args.param, B, modes, K, W)
+  if ctx.rank == 0:
+    emit({'metric': 'mulan_train_step_samples_per_s', 'value': leg['value'], 'unit': 'samples/s',
+          'n_gpus': ctx.world, 'steps': K, 'warmup': W, 'ms_per_step': leg['ms_per_step'],
+          'higher_is_better': True, 'scaling': 'strong' if args.global_batch else 'weak',
+          'vs_baseline': None, 'dtype': 'tf32' if args.tf32 else 'f32', 'data': 'synthetic',
+          'config': {'workload': leg['workload'], 'parallelism': f'dp{ctx.world}'},
+          'train_step': leg,
+          'e2e': {'value': leg['modes'][leg['best_mode']]['e2e_value'], 'unit': 'samples/s',
+                  'h2d_bytes_per_step': B * D, 'd2h_bytes_per_step': 4,
+                  'api': 'optim.train_step(model, state, batch) with host uint8 images'}})
+  ctx.close()
 
 
 def main():

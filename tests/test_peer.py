@@ -205,7 +205,16 @@ def _gpu_worker(rank, world, port, q):
                                           ptr(st.ema), cur))
     torch.cuda.synchronize()
     assert not st.peer.timed_out()
-    assert torch.equal(st.params, ref[0])
+    # the optimizer state is SHARDED: rank r's emulation is right on r's shards only (elsewhere
+    # its mu / nu are stale), so the expected parameters are assembled from the owners
+    refs = [torch.empty_like(ref[0]) for _ in range(world)]
+    dist.all_gather(refs, ref[0])
+    expect = torch.empty_like(ref[0])
+    for lo, hi in st.ranges:
+      for r in range(world):
+        a, b = shard_range(lo, hi, world, r)
+        expect[a:b] = refs[r][a:b]
+    assert torch.equal(st.params, expect)
     for lo, hi in st.ranges:
       a, b = shard_range(lo, hi, world, rank)
       for got, want in ((st.mu, ref[1]), (st.nu, ref[2]), (st.ema, ref[3])):

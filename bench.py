@@ -382,6 +382,7 @@ def measure_elbo(ctx, args, inp, param_name, K, W, extras):
       wk.wait()                      # the timed region ends only when every pmean has landed
     t_end.record(stream)
     ctx.barrier()
+    mark1 = sampler.mark() if sampler else 0
   elapsed_ms = ctx.max_over_ranks(t_start.elapsed_time(t_end))
   bpd = (reduced[-1][0] if world > 1 else ws.scalars[0]).item()
 
@@ -420,7 +421,7 @@ def measure_elbo(ctx, args, inp, param_name, K, W, extras):
                  'ms_per_step': ms / n_rep}
     if sampler:
       sustained['clocks'] = sampler.window(m0, m1)
-  clocks = sampler.stop(mark0, None) if sampler else None
+  clocks = sampler.stop(mark0, max(mark1, mark0 + 1)) if sampler else None
 
   nsub = rows * D
   ab = dict(ALGO_BYTES['eps' if eps_form else param_name])
@@ -459,7 +460,7 @@ def measure_latency(ctx, args, inp):
   from mulan_b200 import ops
   dev = ctx.dev
   out = {}
-  for label, pdl in (('pdl', True), ('plain', False)):
+  for label, pdl in (('plain', False), ('pdl', True)):
     sm = {k: (v[:GROUP].contiguous()) for k, v in inp.items()}
     gLs = torch.full((GROUP,), 1.0 / (GROUP * D * math.log(2.0)), device=dev)
     wss = ops.ElboWorkspace(ops.Desc(pdl=pdl), GROUP, dev)
@@ -488,11 +489,12 @@ def measure_latency(ctx, args, inp):
       e1.record(stream)
       torch.cuda.synchronize()
     out[label] = e0.elapsed_time(e1) * 1000 / (20 * per_graph)
-  us = out['pdl']
-  return {'rows': GROUP, 'us_per_step': us, 'us_per_step_plain_launches': out['plain'],
+  us = out['plain']
+  return {'rows': GROUP, 'us_per_step': us, 'us_per_step_with_pdl': out['pdl'],
           'samples_per_s': GROUP / (us * 1e-6), 'launches_per_step': 3,
-          'how': 'CUDA graph of 20 consecutive steps (3 launches each, programmatic dependent '
-                 'launch), 20 replays, L2-resident'}
+          'how': 'CUDA graph of 20 consecutive steps (3 plain launches each: fwd_pre, post '
+                 'value-and-grad + loss scalars, bwd_pre; 768 threads per row), 20 replays, '
+                 'L2-resident'}
 
 
 def measure_e2e(ctx, args, inp, K):
@@ -598,10 +600,17 @@ def measure_dense(ctx, args, inp, K, W):
       chunks.append((ops.ElboWorkspace(desc, lrows, dev, save_w=eps_form), ci))
     side = [torch.cuda.Stream() for _ in range(min(len(chunks), n_streams) - 1)]
 
-    def one(w_, i):
+    def k_pre(w_, i):
       e0, e = (noise0, noise) if broadcast else (i['eps0'], i['eps'])
       w_.fwd_pre(i['x'], i['a'], i['b'], i['c'], i['t'], e0, e)
+
+    def k_post(w_, i):
+      e = noise if broadcast else i['eps']
       w_.post_bpd(i['x'], i['a'], i['b'], i['c'], i['t'], e, i['net'], None)
+
+    def one(w_, i):
+      k_pre(w_, i)
+      k_post(w_, i)
 
     def step():
       cur = torch.cuda.current_stream()
@@ -621,14 +630,16 @@ def measure_dense(ctx, args, inp, K, W):
         join = torch.cuda.Event()
         join.record(s)
         cur.wait_event(join)
-    return step, chunks
+    return step, chunks, (k_pre, k_post)
 
   acc = torch.zeros(2, dtype=torch.float64, device=dev)
+  drv = min(dense_images_per_launch(T) * T, rows)
   shapes = [('ref_2048_rows_1_stream', min(args.launch_rows, rows), 1, False),
             ('ref_2048_rows_8_streams', min(args.launch_rows, rows), 8, False),
-            ('driver_sized_1_stream', min(dense_images_per_launch(T) * T, rows), 1, True)]
+            ('driver_sized_tiled_noise_1_stream', drv, 1, False),
+            ('driver_sized_1_stream', drv, 1, True)]
   for label, lrows, n_streams, broadcast in shapes:
-    step, chunks = build(lrows, n_streams, broadcast)
+    step, chunks, kfn = build(lrows, n_streams, broadcast)
     stream = torch.cuda.Stream()
     with torch.cuda.stream(stream):
       for _ in range(max(W, 3)):
@@ -659,6 +670,23 @@ def measure_dense(ctx, args, inp, K, W):
                   'algo_bytes_per_subpixel': fwd_pre_b + post_b,
                   'gbs': algo / (ms * 1e-3) / 1e9,
                   'frac_of_measured': algo / (ms * 1e-3) / 1e9 / ctx.peak}
+    if n_streams == 1:
+      # each kernel alone, launch after launch on the one stream (CUDA events)
+      for kname, fn, nb in (('fwd_pre', kfn[0], fwd_pre_b), ('fwd_post', kfn[1], post_b)):
+        with torch.cuda.stream(stream):
+          for ch in chunks:
+            fn(*ch)
+          torch.cuda.synchronize()
+          a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+          a0.record(stream)
+          for _ in range(K):
+            for ch in chunks:
+              fn(*ch)
+          a1.record(stream)
+          torch.cuda.synchronize()
+        kms = a0.elapsed_time(a1) / K
+        out[label][kname] = {'ms': kms, 'algo_bytes_per_subpixel': nb,
+                             'frac_of_measured': nb * rows * D / (kms * 1e-3) / 1e9 / ctx.peak}
     del graph, chunks
   best = max(out, key=lambda k: out[k]['value'])
   return {'workload': 'eval_bpd dense VLB forward (mulan_velocity: recon + prior + diffusion), '

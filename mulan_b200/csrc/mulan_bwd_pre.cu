@@ -25,31 +25,26 @@ namespace mulan {
 // CRAW (MULAN_FLAG_C_RAW): p.c is the pre-activation r of dense_out_c; c = 1e-3 + softplus(r) is
 // formed here and c_bar is returned as the cotangent of r (c_bar * sigmoid(r)), so the
 // framework's softplus backward (12 B/sub-pixel) disappears (ldm/model_mulan_epsilon.py:537).
-template <int PARAM, int GT, bool DISC, bool POW2, bool CRAW>
-__global__ void __launch_bounds__(kThreads, 5)   // <= 51 registers: 5 CTAs (40 warps) per SM
+// NT / MINB: 256 threads, <= 51 registers, 5 CTAs (40 warps) per SM (throughput), or 768 threads
+// = one float4 column per thread for launches of at most one row per SM (latency).  Every thread
+// forms the row constants itself (broadcast loads): no staging barrier before the operand loads.
+template <int PARAM, int GT, bool DISC, bool POW2, bool CRAW, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
 bwd_pre_kernel(const BwdPreParams p) {
-  __shared__ RowT s_rt;
-  __shared__ RowD s_rd;
-  __shared__ float s_gLh, s_gbar;
   const int row = blockIdx.x, tid = threadIdx.x;
   const bool has_gL = p.gL != nullptr;
   const bool has_zb = p.z_bar != nullptr;
   const bool has_gb = p.g_bar != nullptr;
   pdl_release_dependents();
   pdl_wait_for_primary();
-  if (tid == 0) {
-    s_rt = make_row_t(__ldg(p.t + row));
-    if (DISC) s_rd = make_row_d(__ldg(p.t + row), __ldg(p.t + row) - p.inv_T);   // s = t - 1/T
-    s_gLh = has_gL ? 0.5f * __ldg(p.gL + row) : 0.f;
-    // jnp.mean backward: cotangent / D broadcast to every sub-pixel
-    s_gbar = (GT == MULAN_GT_MEAN && has_gb)
-                 ? __fdiv_rn(__ldg(p.g_bar + row), (float)(p.dim4 * 4)) : 0.f;
-  }
-  __syncthreads();
-  const RowT rt = s_rt;
+  const float t_row = __ldg(p.t + row);
+  const RowT rt = make_row_t(t_row);
   RowD rd;
-  if (DISC) rd = s_rd;
-  const float gLh = s_gLh, gbar_row = s_gbar;
+  if (DISC) rd = make_row_d(t_row, t_row - p.inv_T);                 // s = t - 1/T
+  const float gLh = has_gL ? 0.5f * __ldg(p.gL + row) : 0.f;
+  // jnp.mean backward: cotangent / D broadcast to every sub-pixel
+  const float gbar_row = (GT == MULAN_GT_MEAN && has_gb)
+                             ? __fdiv_rn(__ldg(p.g_bar + row), (float)(p.dim4 * 4)) : 0.f;
   const VocabInfo vi = p.vi;
   const float two_iv = vi.inv_vocab + vi.inv_vocab, off = vi.inv_vocab - 1.0f;
   // t-dependent coefficients of P_a, P_b, P_c with the factors 2 folded in (exact scalings)
@@ -60,7 +55,7 @@ bwd_pre_kernel(const BwdPreParams p) {
   const size_t nbase4 = (size_t)(p.noise_rows > 0 ? row % p.noise_rows : row) * p.dim4;
   const bool need_x = has_zb || (has_gL && PARAM != MULAN_PARAM_EPS);
 
-  for (int i4 = tid; i4 < p.dim4; i4 += kThreads) {
+  for (int i4 = tid; i4 < p.dim4; i4 += NT) {
     const size_t g4 = base4 + i4;
     const float4 A = ld4(p.a, g4), Bv = ld4(p.b, g4), C = ld4(p.c, g4);
     float4 E = make_float4(0.f, 0.f, 0.f, 0.f), N = E, ZB = E, GB = E;
@@ -159,29 +154,40 @@ bwd_pre_kernel(const BwdPreParams p) {
   }
 }
 
-template <int PARAM, bool POW2, bool CRAW>
+template <int PARAM, bool POW2, bool CRAW, int NT, int MINB>
 static cudaError_t launch_gt(const BwdPreParams& p, cudaStream_t s) {
   const bool pdl = p.pdl != 0;
   if (PARAM == MULAN_PARAM_EPS && p.T > 0) {
     if (p.gt_mode == MULAN_GT_MEAN)
-      return launch_kernel(bwd_pre_kernel<MULAN_PARAM_EPS, MULAN_GT_MEAN, true, POW2, CRAW>,
-                           p.rows, kThreads, s, pdl, p);
-    return launch_kernel(bwd_pre_kernel<MULAN_PARAM_EPS, MULAN_GT_PIXEL, true, POW2, CRAW>,
-                         p.rows, kThreads, s, pdl, p);
+      return launch_kernel(
+          bwd_pre_kernel<MULAN_PARAM_EPS, MULAN_GT_MEAN, true, POW2, CRAW, NT, MINB>, p.rows, NT,
+          s, pdl, p);
+    return launch_kernel(
+        bwd_pre_kernel<MULAN_PARAM_EPS, MULAN_GT_PIXEL, true, POW2, CRAW, NT, MINB>, p.rows, NT, s,
+        pdl, p);
   }
   if (p.gt_mode == MULAN_GT_MEAN)
-    return launch_kernel(bwd_pre_kernel<PARAM, MULAN_GT_MEAN, false, POW2, CRAW>, p.rows,
-                         kThreads, s, pdl, p);
-  return launch_kernel(bwd_pre_kernel<PARAM, MULAN_GT_PIXEL, false, POW2, CRAW>, p.rows, kThreads,
-                       s, pdl, p);
+    return launch_kernel(bwd_pre_kernel<PARAM, MULAN_GT_MEAN, false, POW2, CRAW, NT, MINB>, p.rows,
+                         NT, s, pdl, p);
+  return launch_kernel(bwd_pre_kernel<PARAM, MULAN_GT_PIXEL, false, POW2, CRAW, NT, MINB>, p.rows,
+                       NT, s, pdl, p);
+}
+
+template <int PARAM, bool POW2, bool CRAW>
+static cudaError_t launch_nt(const BwdPreParams& p, cudaStream_t s) {
+  // at most one CTA per SM: one float4 column per thread (see latency_rows()); the shipped
+  // configs' power-of-two vocabulary only (the generic vocab keeps the throughput shape)
+  if (POW2 && p.rows <= latency_rows() && p.dim4 <= kLatencyThreads)
+    return launch_gt<PARAM, POW2, CRAW, POW2 ? kLatencyThreads : kThreads, POW2 ? 1 : 5>(p, s);
+  return launch_gt<PARAM, POW2, CRAW, kThreads, 5>(p, s);
 }
 
 template <int PARAM>
 static cudaError_t launch_param(const BwdPreParams& p, cudaStream_t s) {
   const bool pow2 = p.vi.pow2 != 0;
   // the pre-activation form is built for power-of-two vocabularies (both shipped configs)
-  if (p.c_raw) return pow2 ? launch_gt<PARAM, true, true>(p, s) : cudaErrorNotSupported;
-  return pow2 ? launch_gt<PARAM, true, false>(p, s) : launch_gt<PARAM, false, false>(p, s);
+  if (p.c_raw) return pow2 ? launch_nt<PARAM, true, true>(p, s) : cudaErrorNotSupported;
+  return pow2 ? launch_nt<PARAM, true, false>(p, s) : launch_nt<PARAM, false, false>(p, s);
 }
 
 // w = expm1(gamma(t) - gamma(t - 1/T)): the discrete-time weight of the epsilon loss

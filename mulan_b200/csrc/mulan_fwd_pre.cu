@@ -309,20 +309,19 @@ __global__ void __launch_bounds__(NT, MINB)
 fwd_pre_kernel(const FwdPreParams p) {
   constexpr bool FAST = KIND != 0, BAKED = KIND == 2;
   constexpr int NW = NT / 32;
-  __shared__ RowT s_rt;
   __shared__ float red[NW][5];
   const int row = blockIdx.x;
   const int tid = threadIdx.x;
   pdl_release_dependents();
   const PreConsts kc = load_pre_consts<BAKED>(p);
   pdl_wait_for_primary();
-  if (tid == 0) s_rt = make_row_t(__ldg(p.t + row));
+  // every thread forms the row's t powers itself (one broadcast load, eight multiplies): no
+  // shared-memory staging, no barrier between the CTA's start and its first operand loads
+  const RowT rt = make_row_t(__ldg(p.t + row));
   const size_t base4 = (size_t)row * p.dim4;
   // eps_0 / eps broadcast over the batch (dense-VLB evaluation: every image shares one key)
   const size_t nbase4 = (size_t)(p.noise_rows > 0 ? row % p.noise_rows : row) * p.dim4;
   float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-  __syncthreads();
-  const RowT rt = s_rt;
   for (int i4 = tid; i4 < p.dim4; i4 += NT) {
     const PreCol c = load_pre_col(p, base4 + i4, nbase4 + i4);
     pre_column<GT, SAVEW, FAST, CRAW>(p, kc, rt, c.A, c.B, c.C, c.E0, c.E, c.X, base4 + i4, acc);
@@ -449,6 +448,14 @@ static cudaError_t launch_shape(const FwdPreParams& p, cudaStream_t s) {
     }
 #undef MULAN_SHAPE
   }
+  // Launches that put at most one row on an SM are latency bound: one float4 column per thread
+  // (768 threads for D = 3072) instead of six; up to four rows per SM: three columns per thread.
+  if (KIND != 0 && p.rows <= latency_rows() && p.dim4 <= kLatencyThreads)
+    return launch_kernel(fwd_pre_kernel<GT, SAVEW, KIND, CRAW, kLatencyThreads, 1>, p.rows,
+                         kLatencyThreads, s, p.pdl != 0, p);
+  if (KIND != 0 && p.rows <= 4 * latency_rows())
+    return launch_kernel(fwd_pre_kernel<GT, SAVEW, KIND, CRAW, 256, 4>, p.rows, 256, s,
+                         p.pdl != 0, p);
   return launch_kernel(fwd_pre_kernel<GT, SAVEW, KIND, CRAW, MULAN_PRE_NT, MULAN_PRE_MINB>,
                        p.rows, MULAN_PRE_NT, s, p.pdl != 0, p);
 }

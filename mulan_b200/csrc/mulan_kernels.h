@@ -214,6 +214,19 @@ inline int resident_ctas(const void* kernel, int threads = kThreads) {
   return sms * per_sm;
 }
 
+// Small launches (the literal per-GPU batch of 128 rows, ldm/configs/cifar10-conditioned.py:88)
+// are latency bound: with one CTA per row and at most one row per SM, a row is spread over
+// kLatencyThreads threads (one float4 column each for D = 3072) instead of the throughput
+// shapes' 3-6 columns per thread.  Per-pixel outputs do not depend on the shape; per-row sums
+// differ by float32 summation order (a launch's shape is a function of its row count only).
+constexpr int kLatencyThreads = 768;
+inline int latency_rows() {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms;
+}
+
 // Which loss formula the post / bwd_pre kernels run for desc->param.
 //
 // velocity_from_epsilon (ldm/model_mulan_velocity.py:246-249, 256-260) is the epsilon loss in

@@ -74,32 +74,29 @@ __device__ __forceinline__ PostPix post_pixel(float a, float b, float c, int xi,
 // REDUCE (mulan_post_bpd): the CTA that makes the last row of a 128-row group final folds the
 // group's loss terms, the CTA that completes the last group writes the six loss_fn scalars
 // (mulan_reduce.cuh) -- VDMOutput + bpd without a separate single-CTA launch.
-template <int PARAM, bool HAVEW, int MODE, bool CRAW, bool REDUCE>
-__global__ void __launch_bounds__(kThreads)
+// NT: threads per row -- 256 (throughput) or 768 (one float4 column per thread: the latency shape
+// for launches of at most one CTA per SM).  Every thread forms the row constants itself (a
+// broadcast load of t / gL): no shared-memory staging, no barrier before the first operand load.
+template <int PARAM, bool HAVEW, int MODE, bool CRAW, bool REDUCE, int NT>
+__global__ void __launch_bounds__(NT)
 post_kernel(const PostParams p) {
   constexpr bool BWD = MODE != 0;
   constexpr bool FWD = MODE != 1;
-  __shared__ RowT s_rt;
-  __shared__ float s_g;
-  __shared__ float red[kWarps][1];
+  constexpr int NW = NT / 32;
+  __shared__ float red[NW][1];
   const int row = blockIdx.x, tid = threadIdx.x;
   constexpr bool kNeedPoly = !(PARAM == MULAN_PARAM_EPS && HAVEW);
   constexpr bool kNeedX = PARAM != MULAN_PARAM_EPS;
   pdl_release_dependents();
   pdl_wait_for_primary();
-  if (tid == 0) {
-    if (kNeedPoly) s_rt = make_row_t(__ldg(p.t + row));
-    if (BWD) s_g = __ldg(p.gL + row) * p.scale;
-  }
-  __syncthreads();
   RowT rt;
-  if (kNeedPoly) rt = s_rt;
-  const float gs = BWD ? s_g : 0.f;
+  if (kNeedPoly) rt = make_row_t(__ldg(p.t + row));
+  const float gs = BWD ? __ldg(p.gL + row) * p.scale : 0.f;
   const VocabInfo vi = p.vi;
   const size_t base4 = (size_t)row * p.dim4;
   const size_t nbase4 = (size_t)(p.noise_rows > 0 ? row % p.noise_rows : row) * p.dim4;
   float acc[1] = {0.f};
-  for (int i4 = tid; i4 < p.dim4; i4 += kThreads) {
+  for (int i4 = tid; i4 < p.dim4; i4 += NT) {
     const size_t g4 = base4 + i4;
     float4 A, Bv, C, Wv;
     uchar4 X;
@@ -124,24 +121,32 @@ post_kernel(const PostParams p) {
     if (BWD) st4(p.n_bar, g4, NB);
   }
   if (FWD) {
-    block_sum<1>(acc, red);
+    block_sum<1, NW>(acc, red);
     if (tid == 0) p.loss_diff[row] = p.scale * acc[0];
     if (REDUCE) {
-      __shared__ float red5[kWarps][5];
+      __shared__ float red5[NW][5];
       __shared__ int s_flag;
-      red_rows_done(p.red, row / kRedGroup, 1, red5, &s_flag);
+      red_rows_done<NW>(p.red, row / kRedGroup, 1, red5, &s_flag);
     }
   }
 }
 
-template <int PARAM, bool HAVEW, int MODE, bool CRAW>
-static cudaError_t launch_post_r(const PostParams& p, cudaStream_t s) {
+template <int PARAM, bool HAVEW, int MODE, bool CRAW, int NT>
+static cudaError_t launch_post_nt(const PostParams& p, cudaStream_t s) {
   const bool pdl = p.pdl != 0;
   if constexpr (MODE != 1) {
     if (p.red.ws != nullptr)
-      return launch_kernel(post_kernel<PARAM, HAVEW, MODE, CRAW, true>, p.rows, kThreads, s, pdl, p);
+      return launch_kernel(post_kernel<PARAM, HAVEW, MODE, CRAW, true, NT>, p.rows, NT, s, pdl, p);
   }
-  return launch_kernel(post_kernel<PARAM, HAVEW, MODE, CRAW, false>, p.rows, kThreads, s, pdl, p);
+  return launch_kernel(post_kernel<PARAM, HAVEW, MODE, CRAW, false, NT>, p.rows, NT, s, pdl, p);
+}
+
+template <int PARAM, bool HAVEW, int MODE, bool CRAW>
+static cudaError_t launch_post_r(const PostParams& p, cudaStream_t s) {
+  // at most one CTA per SM: one float4 column per thread (see latency_rows())
+  if (p.rows <= latency_rows() && p.dim4 <= kLatencyThreads)
+    return launch_post_nt<PARAM, HAVEW, MODE, CRAW, kLatencyThreads>(p, s);
+  return launch_post_nt<PARAM, HAVEW, MODE, CRAW, kThreads>(p, s);
 }
 
 template <int MODE>

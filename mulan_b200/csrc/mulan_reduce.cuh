@@ -27,6 +27,7 @@ __host__ __device__ inline int red_partials_offset(int groups) { return (groups 
 
 // Sum of one group's rows; valid in thread 0 (all 256 threads call).  Also writes
 // loss_klz_total = kl_z + loss_klz_prior (ldm/model_mulan_epsilon.py:359) for the group's rows.
+template <int NW = kWarps>
 __device__ __forceinline__ void red_group_sum(const BpdReduceParams& p, int g, float (&acc)[5],
                                               float (*red)[5]) {
   const int i = threadIdx.x, row = g * kRedGroup + i;
@@ -44,7 +45,7 @@ __device__ __forceinline__ void red_group_sum(const BpdReduceParams& p, int g, f
     acc[4] = __ldcg(p.var_sums + 2 * row + 1);
   }
   __syncthreads();          // `red` may still be read by thread 0 from a previous call
-  block_sum<5>(acc, red);
+  block_sum<5, NW>(acc, red);      // warps beyond the fourth add zeros: same bits for any NW
 }
 
 __device__ __forceinline__ void red_write_scalars(const BpdReduceParams& p, const float (&acc)[5]) {
@@ -62,8 +63,10 @@ __device__ __forceinline__ void red_write_scalars(const BpdReduceParams& p, cons
   p.scalars[5] = __fdiv_rn(acc[4], nd);
 }
 
-// Called by every thread of a CTA that has just made `done_rows` more rows of group g final
-// (their loss_diff is written and fenced by thread 0 before the call).  Whole-CTA uniform.
+// Called by every thread of a CTA (NW warps, >= 8) that has just made `done_rows` more rows of
+// group g final (their loss_diff is written and fenced by thread 0 before the call).
+// Whole-CTA uniform.
+template <int NW = kWarps>
 __device__ __forceinline__ void red_rows_done(const BpdReduceParams& p, int g, int done_rows,
                                               float (*red)[5], int* s_flag) {
   const int G = red_groups(p.rows);
@@ -78,7 +81,16 @@ __device__ __forceinline__ void red_rows_done(const BpdReduceParams& p, int g, i
   if (*s_flag == 0) return;
   __threadfence();
   float acc[5];
-  red_group_sum(p, g, acc, red);
+  red_group_sum<NW>(p, g, acc, red);
+  if (G == 1) {
+    // one group: its sum IS the final sum (0 + x and a tree of zeros leave x unchanged), so the
+    // second round trip through the partials is skipped -- the small-batch (<= 128 rows) case
+    if (threadIdx.x == 0) {
+      red_write_scalars(p, acc);
+      p.ws[1] = 0;
+    }
+    return;
+  }
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int k = 0; k < 5; ++k) __stcg(partials + 8 * g + k, acc[k]);
@@ -92,12 +104,14 @@ __device__ __forceinline__ void red_rows_done(const BpdReduceParams& p, int g, i
   __threadfence();
 #pragma unroll
   for (int k = 0; k < 5; ++k) acc[k] = 0.f;
-  for (int gg = threadIdx.x; gg < G; gg += kThreads) {
+  if (threadIdx.x < kThreads) {       // the canonical order is defined on 256 accumulators
+    for (int gg = threadIdx.x; gg < G; gg += kThreads) {
 #pragma unroll
-    for (int k = 0; k < 5; ++k) acc[k] += __ldcg(partials + 8 * gg + k);
+      for (int k = 0; k < 5; ++k) acc[k] += __ldcg(partials + 8 * gg + k);
+    }
   }
   __syncthreads();
-  block_sum<5>(acc, red);
+  block_sum<5, NW>(acc, red);
   if (threadIdx.x == 0) {
     red_write_scalars(p, acc);
     p.ws[0] = 0;

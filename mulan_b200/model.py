@@ -281,7 +281,9 @@ class VDM(nn.Module):
     n_noise = draws['eps'].shape[0]
     if n_noise != n_batch and (n_batch % n_noise != 0 or draws['eps_0'].shape[0] != n_noise):
       raise ValueError(f'eps_0 / eps have {n_noise} rows for a batch of {n_batch}')
-    desc = self.desc.replace(c_raw=raw, pdl=self.pdl,
+    # (programmatic dependent launch pays from ~2000 rows on; below, the early-resident CTAs of
+    # the next kernel cost more than the launch gap they hide -- profiles/r2_latency.md)
+    desc = self.desc.replace(c_raw=raw, pdl=self.pdl and n_batch >= 2048,
                              noise_rows=n_noise if n_noise != n_batch else 0)
     tape = ops.ElboTape(desc)
     z_t, g_net, loss_recon, klz_prior, var_sums, link = ops.mulan_pre(

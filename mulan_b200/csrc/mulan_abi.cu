@@ -94,6 +94,7 @@ int recon_window(const mulan_desc* d) {
 }  // namespace
 
 namespace mulan {
+thread_local int tl_shape_rows = 0;
 void set_last_error(const char* msg) { snprintf(g_err, sizeof(g_err), "%s", msg); }
 
 int kernel_param(int param) {

@@ -177,7 +177,7 @@ template <int PARAM, bool POW2, bool CRAW>
 static cudaError_t launch_nt(const BwdPreParams& p, cudaStream_t s) {
   // at most one CTA per SM: one float4 column per thread (see latency_rows()); the shipped
   // configs' power-of-two vocabulary only (the generic vocab keeps the throughput shape)
-  if (POW2 && p.rows <= latency_rows() && p.dim4 <= kLatencyThreads)
+  if (POW2 && shape_rows(p.rows) <= latency_rows() && p.dim4 <= kLatencyThreads)
     return launch_gt<PARAM, POW2, CRAW, POW2 ? kLatencyThreads : kThreads, POW2 ? 1 : 5>(p, s);
   return launch_gt<PARAM, POW2, CRAW, kThreads, 5>(p, s);
 }

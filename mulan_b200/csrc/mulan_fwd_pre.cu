@@ -450,10 +450,10 @@ static cudaError_t launch_shape(const FwdPreParams& p, cudaStream_t s) {
   }
   // Launches that put at most one row on an SM are latency bound: one float4 column per thread
   // (768 threads for D = 3072) instead of six; up to four rows per SM: three columns per thread.
-  if (KIND != 0 && p.rows <= latency_rows() && p.dim4 <= kLatencyThreads)
+  if (KIND != 0 && shape_rows(p.rows) <= latency_rows() && p.dim4 <= kLatencyThreads)
     return launch_kernel(fwd_pre_kernel<GT, SAVEW, KIND, CRAW, kLatencyThreads, 1>, p.rows,
                          kLatencyThreads, s, p.pdl != 0, p);
-  if (KIND != 0 && p.rows <= 4 * latency_rows())
+  if (KIND != 0 && shape_rows(p.rows) <= 4 * latency_rows())
     return launch_kernel(fwd_pre_kernel<GT, SAVEW, KIND, CRAW, 256, 4>, p.rows, 256, s,
                          p.pdl != 0, p);
   return launch_kernel(fwd_pre_kernel<GT, SAVEW, KIND, CRAW, MULAN_PRE_NT, MULAN_PRE_MINB>,

@@ -137,6 +137,11 @@ static int elbo_host_impl(const mulan_desc* d, const uint8_t* x, const float* a,
   const size_t B = (size_t)d->rows, D = (size_t)d->dim, N = B * D;
   HostWs& ws = g_ws;
   if (int r = ensure_ws(ws, B, d->dim)) return r;
+  // every chunk launches with the shape of the WHOLE batch: chunking changes no bit
+  struct ShapeScope {
+    explicit ShapeScope(int rows) { mulan::tl_shape_rows = rows; }
+    ~ShapeScope() { mulan::tl_shape_rows = 0; }
+  } shape_scope((int)B);
 #undef CU
 #define CU(call)                                                        \
   do {                                                                  \

@@ -220,6 +220,11 @@ inline int resident_ctas(const void* kernel, int threads = kThreads) {
 // shapes' 3-6 columns per thread.  Per-pixel outputs do not depend on the shape; per-row sums
 // differ by float32 summation order (a launch's shape is a function of its row count only).
 constexpr int kLatencyThreads = 768;
+// The row count that decides the launch shape: the launch's own, unless the host-buffer pipeline
+// (mulan_elbo_host) is cutting ONE batch into row chunks -- then the whole batch's, so that a
+// chunked batch and a single launch of it produce the same bits (defined in mulan_abi.cu).
+extern thread_local int tl_shape_rows;
+inline int shape_rows(int rows) { return tl_shape_rows > 0 ? tl_shape_rows : rows; }
 inline int latency_rows() {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);

@@ -144,7 +144,7 @@ static cudaError_t launch_post_nt(const PostParams& p, cudaStream_t s) {
 template <int PARAM, bool HAVEW, int MODE, bool CRAW>
 static cudaError_t launch_post_r(const PostParams& p, cudaStream_t s) {
   // at most one CTA per SM: one float4 column per thread (see latency_rows())
-  if (p.rows <= latency_rows() && p.dim4 <= kLatencyThreads)
+  if (shape_rows(p.rows) <= latency_rows() && p.dim4 <= kLatencyThreads)
     return launch_post_nt<PARAM, HAVEW, MODE, CRAW, kLatencyThreads>(p, s);
   return launch_post_nt<PARAM, HAVEW, MODE, CRAW, kThreads>(p, s);
 }

@@ -403,8 +403,20 @@ def test_full_size_properties(cuda_device):
   sub = {k: v[sl].contiguous() for k, v in g.items()}
   rs = ops.fwd_pre(desc, sub['x'], sub['a'], sub['b'], sub['c'], sub['t'], sub['eps_0'],
                    sub['eps'])
-  for k in ('z_t', 'g_net', 'w', 'loss_recon', 'loss_klz_prior'):
+  # per-pixel outputs are independent of the launch; per-row sums depend on the launch's SHAPE
+  # (threads per row is a function of the row count: 768 up to one row per SM, 256 up to four,
+  # 128 beyond) only through the float32 summation order
+  for k in ('z_t', 'w'):
     assert torch.equal(r1[k][sl], rs[k]), k
+  for k in ('g_net', 'loss_recon', 'loss_klz_prior'):
+    assert _rel(rs[k], r1[k][sl]) < 2e-6, k
+  # same shape (two launches of more than 4 rows per SM): bitwise row independence
+  big = slice(300, 1100)
+  sub2 = {k: v[big].contiguous() for k, v in g.items()}
+  rb = ops.fwd_pre(desc, sub2['x'], sub2['a'], sub2['b'], sub2['c'], sub2['t'], sub2['eps_0'],
+                   sub2['eps'])
+  for k in ('z_t', 'g_net', 'w', 'loss_recon', 'loss_klz_prior'):
+    assert torch.equal(r1[k][big], rb[k]), k
   assert (r1['w'] >= 0).all()
   assert (r1['loss_recon'] >= 0).all() and (r1['loss_klz_prior'] >= 0).all()
   d_eps = ops.fwd_post(ops.Desc(param=0), g['x'], g['a'], g['b'], g['c'], g['t'], g['eps'],

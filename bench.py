@@ -652,12 +652,13 @@ def measure_dense(ctx, args, inp, K, W):
       ctx.barrier()
       e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
       e0.record(stream)
+      acc.zero_()
       for _ in range(K):
         graph.replay()
-        if world > 1:      # the one exchange: (sum of per-image bpd, image count)
-          acc[0] = chunks[0][0].scalars[0].double()
-          acc[1] = rows / T
-          dist.all_reduce(acc, op=dist.ReduceOp.SUM)
+        acc[0] += chunks[0][0].scalars[0].double()     # running (sum of bpd, image count)
+        acc[1] += rows / T
+      if world > 1:        # the ONE exchange of the evaluation: a final (sum, count) all-reduce
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM)     # (ldm/notebook_utils.py:191: np.mean(bpds))
       e1.record(stream)
       ctx.barrier()
     ms = ctx.max_over_ranks(e0.elapsed_time(e1)) / K

@@ -85,28 +85,41 @@ _bwd_pre_p = _primitive('mulan_xla_bwd_pre',
                         lambda x, a, *rest, opaque: (_f32(*a.shape),) * 3)
 
 
+# ONE mulan_bwd_pre launch per backward pass (as mulan_jax.py / the tested PyTorch binding): the
+# loss cotangent gL and the denoiser output `net` travel back to mulan_pre's vjp as the
+# cotangents of two zero carrier outputs (link [B], link_net [B, D]) that only mulan_post
+# consumes; a, b, c enter mulan_post under stop_gradient.
+MULAN_FLAG_C_RAW = 1
+
+
 # ---- mulan_pre: everything before the denoiser (model_mulan_epsilon.py:300-328, 339-343) ----
-@partial(jax.custom_vjp, nondiff_argnums=(0, 1))
-def mulan_pre(cfg, param, x, a, b, c, t, eps0, eps):
-  return _pre_fwd(cfg, param, x, a, b, c, t, eps0, eps)[0]
+@partial(jax.custom_vjp, nondiff_argnums=(0, 1, 2))
+def mulan_pre(cfg, param, c_raw, x, a, b, c, t, eps0, eps):
+  return _pre_fwd(cfg, param, c_raw, x, a, b, c, t, eps0, eps)[0]
 
 
-def _pre_fwd(cfg, param, x, a, b, c, t, eps0, eps):
+def _flags(c_raw):
+  return MULAN_FLAG_C_RAW if c_raw else 0
+
+
+def _pre_fwd(cfg, param, c_raw, x, a, b, c, t, eps0, eps):
   B, D = a.shape
   z_t, g_net, w, rec, klz, var_sums = _fwd_pre_p.bind(
-      x, a, b, c, t, eps0, eps, opaque=_opaque(cfg, param, B, D),
+      x, a, b, c, t, eps0, eps, opaque=_opaque(cfg, param, B, D, flags=_flags(c_raw)),
       pixel_gt=cfg.unet_type != 'vdm')
-  return (z_t, g_net, rec, klz, var_sums, w), (x, a, b, c, t, eps)
+  link, link_net = jnp.zeros((B,), jnp.float32), jnp.zeros((B, D), jnp.float32)
+  return (z_t, g_net, rec, klz, var_sums, w, link, link_net), (x, a, b, c, t, eps)
 
 
-def _pre_bwd(cfg, param, res, cts):
+def _pre_bwd(cfg, param, c_raw, res, cts):
   x, a, b, c, t, eps = res
-  z_bar, g_bar = cts[0], cts[1]          # recon / prior KL: fixed ends, zero (a,b,c) gradient
+  # recon / prior KL: fixed ends, zero (a,b,c) gradient; gL and net arrive through the carriers
+  z_bar, g_bar, gL, net = cts[0], cts[1], cts[6], cts[7]
   B, D = a.shape
-  # buffers: x a b c t eps net z_bar g_bar gL ; net (6) and gL (9) are absent here
+  # buffers: x a b c t eps net z_bar g_bar gL : nothing absent, ONE launch for every path
   a_bar, b_bar, c_bar = _bwd_pre_p.bind(
-      x, a, b, c, t, eps, eps, z_bar, g_bar, t,
-      opaque=_opaque(cfg, param, B, D, absent_mask=(1 << 6) | (1 << 9)))
+      x, a, b, c, t, eps, net, z_bar, g_bar, gL,
+      opaque=_opaque(cfg, param, B, D, flags=_flags(c_raw)))
   return (None, a_bar, b_bar, c_bar, None, None, None)
 
 
@@ -115,25 +128,30 @@ mulan_pre.defvjp(_pre_fwd, _pre_bwd)
 
 # ---- mulan_post: the diffusion loss after the denoiser (model_mulan_epsilon.py:345-355,
 #      model_mulan_velocity.py:243-260) ----
-@partial(jax.custom_vjp, nondiff_argnums=(0, 1))
-def mulan_post(cfg, param, x, a, b, c, t, eps, w, net):
+@partial(jax.custom_vjp, nondiff_argnums=(0, 1, 2))
+def _post(cfg, param, c_raw, x, a, b, c, t, eps, w, net, link, link_net):
   B, D = a.shape
-  return _fwd_post_p.bind(x, a, b, c, t, eps, net, w, opaque=_opaque(cfg, param, B, D))[0]
+  return _fwd_post_p.bind(x, a, b, c, t, eps, net, w,
+                          opaque=_opaque(cfg, param, B, D, flags=_flags(c_raw)))[0]
 
 
-def _post_fwd(cfg, param, x, a, b, c, t, eps, w, net):
-  return mulan_post(cfg, param, x, a, b, c, t, eps, w, net), (x, a, b, c, t, eps, w, net)
+def _post_fwd(cfg, param, c_raw, x, a, b, c, t, eps, w, net, link, link_net):
+  return (_post(cfg, param, c_raw, x, a, b, c, t, eps, w, net, link, link_net),
+          (x, a, b, c, t, eps, w, net))
 
 
-def _post_bwd(cfg, param, res, gL):
+def _post_bwd(cfg, param, c_raw, res, gL):
   x, a, b, c, t, eps, w, net = res
   B, D = a.shape
-  n_bar, = _bwd_post_p.bind(x, a, b, c, t, eps, net, w, gL, opaque=_opaque(cfg, param, B, D))
-  # the (a,b,c) path through loss_diff: z_bar (7) and g_bar (8) absent
-  a_bar, b_bar, c_bar = _bwd_pre_p.bind(
-      x, a, b, c, t, eps, net, eps, t, gL,
-      opaque=_opaque(cfg, param, B, D, absent_mask=(1 << 7) | (1 << 8)))
-  return (None, a_bar, b_bar, c_bar, None, None, None, n_bar)
+  n_bar, = _bwd_post_p.bind(x, a, b, c, t, eps, net, w, gL,
+                            opaque=_opaque(cfg, param, B, D, flags=_flags(c_raw)))
+  # x a b c t eps w | net | link <- gL | link_net <- net (carried to mulan_pre's vjp)
+  return (None, None, None, None, None, None, None, n_bar, gL, net)
 
 
-mulan_post.defvjp(_post_fwd, _post_bwd)
+_post.defvjp(_post_fwd, _post_bwd)
+
+
+def mulan_post(cfg, param, c_raw, x, a, b, c, t, eps, w, net, link, link_net):
+  sg = jax.lax.stop_gradient
+  return _post(cfg, param, c_raw, x, sg(a), sg(b), sg(c), t, eps, sg(w), net, link, link_net)

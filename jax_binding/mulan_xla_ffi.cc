@@ -26,11 +26,16 @@ static ffi::Error Check(int status) {
                     mulan_last_error());
 }
 
+// `flags`: mulan_flags of the C ABI (MULAN_FLAG_C_RAW: the `c` operand is the pre-activation of
+// dense_out_c, ldm/model_mulan_epsilon.py:537; MULAN_FLAG_PDL).  noise_rows stays 0 here: XLA
+// hands over full [B, D] draws.
 static mulan_desc MakeDesc(int64_t rows, int64_t dim, int32_t vocab, int32_t param,
-                           int32_t gt_mode, int32_t n_timesteps, double gmin, double gmax) {
+                           int32_t gt_mode, int32_t n_timesteps, double gmin, double gmax,
+                           int32_t flags = 0) {
   mulan_desc d;
   d.rows = (int32_t)rows; d.dim = (int32_t)dim; d.vocab = vocab; d.param = param;
   d.gt_mode = gt_mode; d.n_timesteps = n_timesteps; d.gamma_min = gmin; d.gamma_max = gmax;
+  d.flags = (uint32_t)flags; d.noise_rows = 0;
   return d;
 }
 
@@ -43,10 +48,11 @@ static ffi::Error FwdPreImpl(cudaStream_t stream, ffi::Buffer<ffi::U8> x, ffi::B
                              ffi::ResultBuffer<ffi::F32> loss_recon,
                              ffi::ResultBuffer<ffi::F32> loss_klz,
                              ffi::ResultBuffer<ffi::F32> var_sums, int32_t vocab, int32_t param,
-                             int32_t gt_mode, int32_t n_timesteps, double gamma_min,
-                             double gamma_max) {
+                             int32_t gt_mode, int32_t n_timesteps, int32_t flags,
+                             double gamma_min, double gamma_max) {
   auto dims = a.dimensions();
-  mulan_desc d = MakeDesc(dims[0], dims[1], vocab, param, gt_mode, n_timesteps, gamma_min, gamma_max);
+  mulan_desc d = MakeDesc(dims[0], dims[1], vocab, param, gt_mode, n_timesteps, gamma_min, gamma_max,
+                          flags);
   return Check(mulan_fwd_pre(&d, x.typed_data(), a.typed_data(), b.typed_data(), c.typed_data(),
                              t.typed_data(), eps0.typed_data(), eps.typed_data(),
                              z_t->typed_data(), g_net->typed_data(), w->typed_data(),
@@ -63,7 +69,8 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(
         .Ret<ffi::Buffer<ffi::F32>>().Ret<ffi::Buffer<ffi::F32>>().Ret<ffi::Buffer<ffi::F32>>()
         .Ret<ffi::Buffer<ffi::F32>>().Ret<ffi::Buffer<ffi::F32>>().Ret<ffi::Buffer<ffi::F32>>()
         .Attr<int32_t>("vocab").Attr<int32_t>("param").Attr<int32_t>("gt_mode")
-        .Attr<int32_t>("n_timesteps").Attr<double>("gamma_min").Attr<double>("gamma_max"));
+        .Attr<int32_t>("n_timesteps").Attr<int32_t>("flags").Attr<double>("gamma_min")
+        .Attr<double>("gamma_max"));
 
 // ---- fwd_post / bwd_post: ldm/model_mulan_epsilon.py:338-355, velocity.py:246-260 ------------
 static ffi::Error FwdPostImpl(cudaStream_t stream, ffi::Buffer<ffi::U8> x, ffi::Buffer<ffi::F32> a,
@@ -71,12 +78,13 @@ static ffi::Error FwdPostImpl(cudaStream_t stream, ffi::Buffer<ffi::U8> x, ffi::
                               ffi::Buffer<ffi::F32> t, ffi::Buffer<ffi::F32> eps,
                               ffi::Buffer<ffi::F32> net, ffi::Buffer<ffi::F32> w,
                               ffi::ResultBuffer<ffi::F32> loss_diff, int32_t vocab, int32_t param,
-                              int32_t gt_mode, int32_t n_timesteps, double gamma_min,
-                              double gamma_max) {
+                              int32_t gt_mode, int32_t n_timesteps, int32_t flags,
+                              double gamma_min, double gamma_max) {
   auto dims = a.dimensions();
   // n_timesteps > 0: the loss is .5 * T * sum(w ...) with the discrete weight fwd_pre saved
   // (ldm/model_mulan_epsilon.py:348-355)
-  mulan_desc d = MakeDesc(dims[0], dims[1], vocab, param, gt_mode, n_timesteps, gamma_min, gamma_max);
+  mulan_desc d = MakeDesc(dims[0], dims[1], vocab, param, gt_mode, n_timesteps, gamma_min, gamma_max,
+                          flags);
   return Check(mulan_fwd_post(&d, x.typed_data(), a.typed_data(), b.typed_data(), c.typed_data(),
                               t.typed_data(), eps.typed_data(), net.typed_data(),
                               mulan_kernel_param(param) == MULAN_PARAM_EPS ? w.typed_data() : nullptr,
@@ -91,7 +99,8 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(
         .Arg<ffi::Buffer<ffi::F32>>().Arg<ffi::Buffer<ffi::F32>>()
         .Ret<ffi::Buffer<ffi::F32>>()
         .Attr<int32_t>("vocab").Attr<int32_t>("param").Attr<int32_t>("gt_mode")
-        .Attr<int32_t>("n_timesteps").Attr<double>("gamma_min").Attr<double>("gamma_max"));
+        .Attr<int32_t>("n_timesteps").Attr<int32_t>("flags").Attr<double>("gamma_min")
+        .Attr<double>("gamma_max"));
 
 static ffi::Error BwdPostImpl(cudaStream_t stream, ffi::Buffer<ffi::U8> x, ffi::Buffer<ffi::F32> a,
                               ffi::Buffer<ffi::F32> b, ffi::Buffer<ffi::F32> c,
@@ -99,9 +108,10 @@ static ffi::Error BwdPostImpl(cudaStream_t stream, ffi::Buffer<ffi::U8> x, ffi::
                               ffi::Buffer<ffi::F32> net, ffi::Buffer<ffi::F32> w,
                               ffi::Buffer<ffi::F32> gL, ffi::ResultBuffer<ffi::F32> n_bar,
                               int32_t vocab, int32_t param, int32_t gt_mode, int32_t n_timesteps,
-                              double gamma_min, double gamma_max) {
+                              int32_t flags, double gamma_min, double gamma_max) {
   auto dims = a.dimensions();
-  mulan_desc d = MakeDesc(dims[0], dims[1], vocab, param, gt_mode, n_timesteps, gamma_min, gamma_max);
+  mulan_desc d = MakeDesc(dims[0], dims[1], vocab, param, gt_mode, n_timesteps, gamma_min, gamma_max,
+                          flags);
   return Check(mulan_bwd_post(&d, x.typed_data(), a.typed_data(), b.typed_data(), c.typed_data(),
                               t.typed_data(), eps.typed_data(), net.typed_data(),
                               mulan_kernel_param(param) == MULAN_PARAM_EPS ? w.typed_data() : nullptr,
@@ -116,7 +126,8 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(
         .Arg<ffi::Buffer<ffi::F32>>().Arg<ffi::Buffer<ffi::F32>>().Arg<ffi::Buffer<ffi::F32>>()
         .Ret<ffi::Buffer<ffi::F32>>()
         .Attr<int32_t>("vocab").Attr<int32_t>("param").Attr<int32_t>("gt_mode")
-        .Attr<int32_t>("n_timesteps").Attr<double>("gamma_min").Attr<double>("gamma_max"));
+        .Attr<int32_t>("n_timesteps").Attr<int32_t>("flags").Attr<double>("gamma_min")
+        .Attr<double>("gamma_max"));
 
 // ---- bwd_pre: cotangents of (a, b, c) ----------------------------------------------------------
 static ffi::Error BwdPreImpl(cudaStream_t stream, ffi::Buffer<ffi::U8> x, ffi::Buffer<ffi::F32> a,
@@ -126,11 +137,13 @@ static ffi::Error BwdPreImpl(cudaStream_t stream, ffi::Buffer<ffi::U8> x, ffi::B
                              ffi::Buffer<ffi::F32> g_bar, ffi::Buffer<ffi::F32> gL,
                              ffi::ResultBuffer<ffi::F32> a_bar, ffi::ResultBuffer<ffi::F32> b_bar,
                              ffi::ResultBuffer<ffi::F32> c_bar, int32_t vocab, int32_t param,
-                             int32_t gt_mode, int32_t n_timesteps, double gamma_min,
-                             double gamma_max) {
+                             int32_t gt_mode, int32_t n_timesteps, int32_t flags,
+                             double gamma_min, double gamma_max) {
   auto dims = a.dimensions();
-  // n_timesteps > 0 selects the discrete-time branch of the backward (expm1 weight)
-  mulan_desc d = MakeDesc(dims[0], dims[1], vocab, param, gt_mode, n_timesteps, gamma_min, gamma_max);
+  // n_timesteps > 0 selects the discrete-time branch of the backward (expm1 weight); with
+  // MULAN_FLAG_C_RAW c_bar is the cotangent of the pre-activation
+  mulan_desc d = MakeDesc(dims[0], dims[1], vocab, param, gt_mode, n_timesteps, gamma_min, gamma_max,
+                          flags);
   return Check(mulan_bwd_pre(&d, x.typed_data(), a.typed_data(), b.typed_data(), c.typed_data(),
                              t.typed_data(), eps.typed_data(), net.typed_data(),
                              z_bar.typed_data(), g_bar.typed_data(), gL.typed_data(),
@@ -146,4 +159,5 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(
         .Arg<ffi::Buffer<ffi::F32>>()
         .Ret<ffi::Buffer<ffi::F32>>().Ret<ffi::Buffer<ffi::F32>>().Ret<ffi::Buffer<ffi::F32>>()
         .Attr<int32_t>("vocab").Attr<int32_t>("param").Attr<int32_t>("gt_mode")
-        .Attr<int32_t>("n_timesteps").Attr<double>("gamma_min").Attr<double>("gamma_max"));
+        .Attr<int32_t>("n_timesteps").Attr<int32_t>("flags").Attr<double>("gamma_min")
+        .Attr<double>("gamma_max"));

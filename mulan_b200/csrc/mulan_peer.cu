@@ -94,7 +94,10 @@ __device__ __forceinline__ void adamw_elem(float& p, float g, float& mu, float& 
   ema = ema + k.one_minus_ema * (p - ema);
 }
 
-template <int WORLD>
+// COLS float4 columns per thread (COLS * (WORLD - 1) peer loads in flight per thread before the
+// first dependent use): with two ranks a single remote load per thread leaves NVLink latency
+// exposed (measured 176 GB/s per direction), so small worlds take more columns.
+template <int WORLD, int COLS>
 __global__ void __launch_bounds__(kThreads)
 adamw_ema_peer_kernel(const PeerParams k) {
   __shared__ int s_last;
@@ -106,25 +109,41 @@ adamw_ema_peer_kernel(const PeerParams k) {
   }
   if (tid == 0) wait_peers(k, kFlagA);
   __syncthreads();
-  // ---- 1-3: one float4 column of the owned shard per thread
-  const long long j = (long long)blockIdx.x * kThreads + tid;
-  if (j < k.n4) {
-    const long long i = k.lo4 + j;
-    float4 G = ld_peer4(k.grads[0], i);
+  // ---- 1-3: COLS float4 columns of the owned shard per thread (CTA-strided: coalesced)
+  const long long j0 = (long long)blockIdx.x * (kThreads * COLS) + tid;
+  float4 G[COLS];
 #pragma unroll
-    for (int r = 1; r < WORLD; ++r) {
-      const float4 H = ld_peer4(k.grads[r], i);
-      G.x += H.x; G.y += H.y; G.z += H.z; G.w += H.w;     // rank order: deterministic
+  for (int c = 0; c < COLS; ++c) {
+    const long long j = j0 + (long long)c * kThreads;
+    if (j < k.n4) G[c] = ld_peer4(k.grads[0], k.lo4 + j);
+  }
+#pragma unroll
+  for (int r = 1; r < WORLD; ++r) {
+    float4 H[COLS];
+#pragma unroll
+    for (int c = 0; c < COLS; ++c) {
+      const long long j = j0 + (long long)c * kThreads;
+      if (j < k.n4) H[c] = ld_peer4(k.grads[r], k.lo4 + j);
     }
+#pragma unroll
+    for (int c = 0; c < COLS; ++c) {                      // rank order: deterministic
+      G[c].x += H[c].x; G[c].y += H[c].y; G[c].z += H[c].z; G[c].w += H[c].w;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < COLS; ++c) {
+    const long long j = j0 + (long long)c * kThreads;
+    if (j >= k.n4) continue;
+    const long long i = k.lo4 + j;
     float4 P = reinterpret_cast<float4*>(k.params[k.rank])[i];
     float4 M = reinterpret_cast<float4*>(k.mu)[i];
     float4 V = reinterpret_cast<float4*>(k.nu)[i];
     float4 E = reinterpret_cast<float4*>(k.ema)[i];
     const bool decay = i < k.decay4;
-    adamw_elem(P.x, G.x, M.x, V.x, E.x, k, decay);
-    adamw_elem(P.y, G.y, M.y, V.y, E.y, k, decay);
-    adamw_elem(P.z, G.z, M.z, V.z, E.z, k, decay);
-    adamw_elem(P.w, G.w, M.w, V.w, E.w, k, decay);
+    adamw_elem(P.x, G[c].x, M.x, V.x, E.x, k, decay);
+    adamw_elem(P.y, G[c].y, M.y, V.y, E.y, k, decay);
+    adamw_elem(P.z, G[c].z, M.z, V.z, E.z, k, decay);
+    adamw_elem(P.w, G[c].w, M.w, V.w, E.w, k, decay);
     reinterpret_cast<float4*>(k.mu)[i] = M;
     reinterpret_cast<float4*>(k.nu)[i] = V;
     reinterpret_cast<float4*>(k.ema)[i] = E;
@@ -242,15 +261,17 @@ int mulan_adamw_ema_peer(const mulan_adamw_desc* d, const mulan_peer_desc* peers
   k.bc1 = 1.0f - powf((float)d->b1, (float)d->step);
   k.bc2 = 1.0f - powf((float)d->b2, (float)d->step);
   k.grad_scale = (float)d->grad_scale;
-  long long want = (k.n4 + mulan::kThreads - 1) / mulan::kThreads;
+  const int per_thread = W <= 2 ? 4 : (W == 4 ? 2 : 1);
+  long long want = (k.n4 + (long long)mulan::kThreads * per_thread - 1) /
+                   ((long long)mulan::kThreads * per_thread);
   if (want < 1) want = 1;                       // an empty shard still takes part in the barriers
   if (want > 0x7fffffffLL) PEER_FAIL(MULAN_ERR_INVALID_ARG, "%s: range too large", fn);
   cudaStream_t s = (cudaStream_t)stream;
   switch (W) {
-    case 1: mulan::adamw_ema_peer_kernel<1><<<(int)want, mulan::kThreads, 0, s>>>(k); break;
-    case 2: mulan::adamw_ema_peer_kernel<2><<<(int)want, mulan::kThreads, 0, s>>>(k); break;
-    case 4: mulan::adamw_ema_peer_kernel<4><<<(int)want, mulan::kThreads, 0, s>>>(k); break;
-    default: mulan::adamw_ema_peer_kernel<8><<<(int)want, mulan::kThreads, 0, s>>>(k); break;
+    case 1: mulan::adamw_ema_peer_kernel<1, 4><<<(int)want, mulan::kThreads, 0, s>>>(k); break;
+    case 2: mulan::adamw_ema_peer_kernel<2, 4><<<(int)want, mulan::kThreads, 0, s>>>(k); break;
+    case 4: mulan::adamw_ema_peer_kernel<4, 2><<<(int)want, mulan::kThreads, 0, s>>>(k); break;
+    default: mulan::adamw_ema_peer_kernel<8, 1><<<(int)want, mulan::kThreads, 0, s>>>(k); break;
   }
   PEER_CU(cudaGetLastError(), fn);
   return 0;

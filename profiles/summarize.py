@@ -20,6 +20,11 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+try:
+  COMMIT = subprocess.run(['git', '-C', HERE, 'rev-parse', '--short', 'HEAD'], capture_output=True,
+                          text=True).stdout.strip()
+except OSError:
+  COMMIT = None
 KEYS = [
     ('gpu__time_duration.sum', 'duration'),
     ('dram__bytes_read.sum', 'dram read'),
@@ -42,8 +47,19 @@ KEYS = [
     ('l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum', 'L1 global load sectors'),
     ('l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum', 'L1 global load requests'),
 ]
-ALGO = {'fwd_pre': 29, 'post_kernel<0, 1, 0>': 12, 'post_kernel<0, 1, 1>': 16,
-        'post_kernel<0, 1, 2>': 16, 'bwd_pre': 37}
+ALGO = {'fwd_pre': 29, 'fwd_post': 12, 'bwd_post': 16, 'post_vg': 16, 'bwd_pre': 37}
+
+
+def kernel_key(name):
+  """fwd_pre | bwd_pre | fwd_post | bwd_post | post_vg from a demangled kernel name
+  (post_kernel<PARAM, HAVEW, MODE, CRAW, REDUCE, NT>: MODE 0 value, 1 gradient, 2 both)."""
+  if 'fwd_pre' in name:
+    return 'fwd_pre'
+  if 'bwd_pre' in name:
+    return 'bwd_pre'
+  m = re.search(r'post_kernel<\s*\(?[^,]*,\s*\(?[^,]*,\s*\(?(?:int\))?(\d)', name)
+  mode = int(m.group(1)) if m else 2
+  return ('fwd_post', 'bwd_post', 'post_vg')[mode]
 
 
 def ncu_csv(rep, page, extra=()):
@@ -79,16 +95,16 @@ def main():
         md.append(f'| {label} (`{k}`) | {r[col[k]]} {units[col[k]]} |')
     rd = to_bytes(*vals['dram__bytes_read.sum'])
     wr = to_bytes(*vals['dram__bytes_write.sum'])
-    algo = next((v for k, v in ALGO.items() if k in name), None)
+    algo = ALGO.get(kernel_key(name))
     inst = float(vals['smsp__inst_executed.sum'][0])
     md.append(f'| dram traffic per launch | {(rd + wr) / 1e9:.4f} GB |')
     if algo:
       md.append(f'| algorithmic bytes per launch | {algo * nsub / 1e9:.4f} GB ({algo} B/sub-pixel) |')
       md.append(f'| traffic / algorithmic | {(rd + wr) / (algo * nsub):.3f} |')
     md.append(f'| thread instructions per sub-pixel | {inst * 32 / nsub:.1f} |')
-    key = 'fwd_pre' if 'fwd_pre' in name else 'bwd_pre' if 'bwd_pre' in name else (
-        'fwd_post' if ', 0>(' in name else 'bwd_post' if ', 1>(' in name else 'post_vg')
-    traffic[key] = {'rows': rows, 'dram_bytes_per_launch': rd + wr, 'kernel': short}
+    key = kernel_key(name)
+    traffic[key] = {'rows': rows, 'dram_bytes_per_launch': rd + wr, 'kernel': short,
+                    'capture': os.path.basename(rep), 'commit': COMMIT}
     # instruction mix from the source page
     src = ncu_csv(rep, 'source', ['--kernel-name', 'regex:' + re.escape(short.split('<')[0].split('::')[-1])])
     try:

@@ -12,11 +12,11 @@ python bench.py > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err
 cut -c1-300 gpurun_out/bench_$tag.json
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
     --log-file gpurun_out/launches_$tag.csv \
-    python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/ncu_launch_$tag.log 2>&1
+    python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --no-configs --no-sustained > gpurun_out/ncu_launch_$tag.log 2>&1
 # second eager warm-up step: one instance each of fwd_pre, post (value-and-grad), bwd_pre
 ncu --set full --clock-control none --import-source on \
     -k regex:'fwd_pre_kernel|post_kernel|bwd_pre_kernel' -s 3 -c 3 -o gpurun_out/prof_$tag -f \
-    python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/ncu_full_$tag.log 2>&1
+    python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --no-configs --no-sustained > gpurun_out/ncu_full_$tag.log 2>&1
 ls -la gpurun_out/prof_$tag.ncu-rep gpurun_out/launches_$tag.csv
 # kernel sweep and the "next" rows' per-kernel rooflines
 bash tools/sweep.sh

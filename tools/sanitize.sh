@@ -21,7 +21,25 @@ for mode in (0, 1, 2):
     gb = torch.zeros((B,) if gt == 0 else (B, 3072), device=dev)
     ops.bwd_pre(d, g['x'], g['a'], g['b'], g['c'], g['t'], g['eps'], g['net'], torch.zeros_like(g['a']), gb, gL)
     ops.bpd_reduce(d, r['loss_recon'], r['loss_klz_prior'], None, diff, r['var_sums'])
+    ops.bpd_reduce(d, r['loss_recon'], r['loss_klz_prior'], None, diff, r['var_sums'], ws=None)
+    ops.post_bpd(d, g['x'], g['a'], g['b'], g['c'], g['t'], g['eps'], g['net'], r['w'], gL,
+                 r['loss_recon'], r['loss_klz_prior'], None, r['var_sums'])
     ops.scale_rows(nb, gL * 2, gL)
+# ABI v2: pre-activation c, broadcast noise rows, programmatic dependent launch; the three launch
+# shapes (768 threads per row up to one row per SM, 256 up to four, 128 beyond) and a multi-group
+# fused reduction
+for rows_ in (6, 300, 1300):
+  big = O.synth_inputs(rows_, 5)
+  gb_ = {k: v.to(dev).contiguous() for k, v in big.items()}
+  gLb = torch.full((rows_,), 1e-6, device=dev)
+  for mode in (0, 1):
+    d2 = ops.Desc(param=mode, c_raw=True, pdl=True, noise_rows=3)
+    e0, e1 = gb_['eps_0'][:3].contiguous(), gb_['eps'][:3].contiguous()
+    r = ops.fwd_pre(d2, gb_['x'], gb_['a'], gb_['b'], gb_['c'], gb_['t'], e0, e1, save_w=(mode == 0))
+    ops.post_bpd(d2, gb_['x'], gb_['a'], gb_['b'], gb_['c'], gb_['t'], e1, gb_['net'], r['w'], gLb,
+                 r['loss_recon'], r['loss_klz_prior'], None, r['var_sums'])
+    ops.bwd_pre(d2, gb_['x'], gb_['a'], gb_['b'], gb_['c'], gb_['t'], e1, gb_['net'],
+                torch.zeros_like(gb_['a']), torch.zeros(rows_, device=dev), gLb)
 dT = ops.Desc(n_timesteps=10)
 tT = O.sample_t(0.3, B, O.OracleConfig(sm_n_timesteps=10)).to(dev)
 r = ops.fwd_pre(dT, g['x'], g['a'], g['b'], g['c'], tT, g['eps_0'], g['eps'])

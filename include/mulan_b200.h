@@ -168,6 +168,26 @@ int mulan_fwd_pre_consts(const mulan_desc* desc, const mulan_end_consts* consts,
 int mulan_host_end_consts(const mulan_desc* desc, mulan_end_consts* out);
 int mulan_fwd_pre_variant_consts(const mulan_desc* desc, const mulan_end_consts* consts);
 
+/*
+ * mulan_fwd_pre_keyed -- mulan_fwd_pre with eps_0 and eps DRAWN INSIDE THE KERNEL from the raw
+ * 2 x uint32 threefry keys that make_rng('sample') hands to jax.random.normal(rng, f.shape)
+ * (ldm/model_mulan_epsilon.py:315, :327; "next" row 2 of the scope table as written).  The draws
+ * equal mulan_rng_normal(key, rows * dim) reshaped to [rows, dim], bit for bit, and every output
+ * equals mulan_fwd_pre's on those arrays.  eps_out [B,D] (eps is read again by the post /
+ * bwd_pre entry points) and eps0_out [B,D] are optional (NULL: not written).
+ * rows must be even (JAX pairs element e with e + N/2, so a CTA serves the row pair
+ * (r, r + rows/2)); continuous time; the shipped configurations' closed-form reconstruction term.
+ * 17 (+4 eps_out, +4 w_save) B/sub-pixel of HBM traffic instead of 25, but ~300 instead of ~105
+ * instructions per sub-pixel: issue bound.  It replaces TWO stand-alone draws (8 B written, 8 B
+ * read back) plus mulan_fwd_pre at about the same total time (profiles/r2_variants.md); against
+ * draws that already sit in HBM, mulan_fwd_pre is faster.
+ */
+int mulan_fwd_pre_keyed(const mulan_desc* desc, const uint32_t* key_eps0, const uint32_t* key_eps,
+                        const uint8_t* x, const float* a, const float* b, const float* c,
+                        const float* t, float* z_t, float* g_net, float* w_save, float* eps0_out,
+                        float* eps_out, float* loss_recon, float* loss_klz_prior, float* var_sums,
+                        void* stream);
+
 /* Host-only query: which mulan_fwd_pre kernel this descriptor selects on this host --
  * 0 generic (windowed log-softmax over the vocab bins), 1 closed-form 3-bin reconstruction term
  * with the launch constants in the parameter bank, 2 the same with the constants of the shipped

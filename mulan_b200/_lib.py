@@ -83,6 +83,7 @@ SIGNATURES = {
     'mulan_kernel_param': ([C.c_int32], C.c_int),
     'mulan_fwd_pre': ([_D] + [_P] * 14, C.c_int),
     'mulan_fwd_pre_variant': ([_D], C.c_int),
+    'mulan_fwd_pre_keyed': ([_D] + [_P] * 16, C.c_int),
     'mulan_fwd_pre_consts': ([_D, _P] + [_P] * 14, C.c_int),
     'mulan_host_end_consts': ([_D, _P], C.c_int),
     'mulan_fwd_pre_variant_consts': ([_D, _P], C.c_int),

@@ -219,6 +219,48 @@ int mulan_fwd_pre_consts(const mulan_desc* d, const mulan_end_consts* kc, const 
   return e == cudaSuccess ? 0 : cuda_fail(fn, e);
 }
 
+int mulan_fwd_pre_keyed(const mulan_desc* d, const uint32_t* key_eps0, const uint32_t* key_eps,
+                        const uint8_t* x, const float* a, const float* b, const float* c,
+                        const float* t, float* z_t, float* g_net, float* w_save, float* eps0_out,
+                        float* eps_out, float* loss_recon, float* loss_klz_prior, float* var_sums,
+                        void* stream) {
+  const char* fn = "mulan_fwd_pre_keyed";
+  if (int r = check_desc(d, fn)) return r;
+  if (d->n_timesteps > 0)
+    return fail(MULAN_ERR_UNSUPPORTED, "%s: use mulan_fwd_pre for sm_n_timesteps > 0", fn);
+  if (d->rows % 2 != 0)
+    return fail(MULAN_ERR_UNSUPPORTED, "%s: rows=%d must be even (JAX pairs element e with e + "
+                "N/2: a CTA draws for the row pair (r, r + rows/2))", fn, d->rows);
+  if (d->noise_rows != 0)
+    return fail(MULAN_ERR_UNSUPPORTED, "%s: noise_rows does not apply to in-kernel draws", fn);
+  if ((int64_t)d->rows * d->dim >= 0xFFFFFFFFLL)
+    return fail(MULAN_ERR_INVALID_ARG, "%s: rows * dim must be below 2^32 - 1", fn);
+  if (d->rows == 0) return 0;
+  REQ_PTR(key_eps0, fn); REQ_PTR(key_eps, fn);
+  REQ_X(x, fn);
+  REQ_VEC(a, fn); REQ_VEC(b, fn); REQ_VEC(c, fn); REQ_PTR(t, fn); REQ_VEC(z_t, fn);
+  REQ_PTR(g_net, fn); OPT_VEC(w_save, fn); OPT_VEC(eps0_out, fn); OPT_VEC(eps_out, fn);
+  if (d->gt_mode == MULAN_GT_PIXEL) REQ_VEC(g_net, fn);
+  REQ_PTR(loss_recon, fn); REQ_PTR(loss_klz_prior, fn); REQ_PTR(var_sums, fn);
+  mulan::FwdPreKeyedParams q;
+  memset(&q, 0, sizeof(q));
+  mulan::FwdPreParams& p = q.p;
+  p.x = x; p.a = a; p.b = b; p.c = c; p.t = t;
+  p.z_t = z_t; p.g_net = g_net; p.w_save = w_save;
+  p.loss_recon = loss_recon; p.loss_klz = loss_klz_prior; p.var_sums = var_sums;
+  p.rows = d->rows; p.dim4 = d->dim / 4; p.gt_mode = d->gt_mode;
+  p.c_raw = flag(d, MULAN_FLAG_C_RAW); p.pdl = flag(d, MULAN_FLAG_PDL);
+  fill_pre_consts(d, nullptr, &p);
+  if (!(p.W == 1 && p.vi.pow2 && p.k.v1_uniform))
+    return fail(MULAN_ERR_UNSUPPORTED, "%s: only the closed-form reconstruction term (power-of-"
+                "two vocab, 3-bin window at gamma_min) with a uniform prior end", fn);
+  q.k_eps0[0] = key_eps0[0]; q.k_eps0[1] = key_eps0[1];
+  q.k_eps[0] = key_eps[0]; q.k_eps[1] = key_eps[1];
+  q.eps0_out = eps0_out; q.eps_out = eps_out;
+  cudaError_t e = mulan::launch_fwd_pre_keyed(q, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(fn, e);
+}
+
 int mulan_fwd_pre_variant(const mulan_desc* d) {
   const char* fn = "mulan_fwd_pre_variant";
   if (int r = check_desc(d, fn)) return r;

@@ -33,6 +33,7 @@
 #include <string.h>
 
 #include "mulan_kernels.h"
+#include "mulan_rng.cuh"
 
 namespace mulan {
 
@@ -330,6 +331,81 @@ fwd_pre_kernel(const FwdPreParams p) {
 }
 
 // ---------------------------------------------------------------------------------------
+// In-kernel draws (SURVEY.md 8f "next" row 2 as written): eps_0 and eps are GENERATED here from
+// the raw threefry keys that make_rng('sample') hands to jax.random.normal(rng, f.shape)
+// (ldm/model_mulan_epsilon.py:315, :327) instead of being read from HBM.
+//
+// JAX's counter layout pairs element e with element e + N/2 (one threefry2x32 block yields both
+// words), so a CTA owns the ROW PAIR (r, r + B/2): for every float4 column it runs four blocks
+// per draw and gets the four normals of row r and the four of row r + B/2 -- no round wasted,
+// bit-identical to mulan_rng_normal(key, B*D) reshaped to [B, D].  eps_out (needed again by the
+// post / bwd_pre kernels) and eps0_out are optional.
+// Cost: ~95 thread-instructions per normal-pair-share on top of the ~105 of the ELBO arithmetic
+// -- the kernel is issue bound at ~2.7x the read version's time; whether that pays depends on
+// what produced the arrays it replaces (profiles/r2_variants.md: against stand-alone draws that
+// write 8 B and are read back, it is on par; against draws that already exist, it loses).
+// ---------------------------------------------------------------------------------------
+template <int GT, bool SAVEW, bool BAKED, bool CRAW>
+__global__ void __launch_bounds__(128, 4)
+fwd_pre_keyed_kernel(const FwdPreKeyedParams q) {
+  constexpr int NT = 128, NW = NT / 32;
+  const FwdPreParams& p = q.p;
+  __shared__ float red[NW][5];
+  const int half_rows = p.rows / 2;
+  const int tid = threadIdx.x;
+  pdl_release_dependents();
+  const PreConsts kc = load_pre_consts<BAKED>(p);
+  pdl_wait_for_primary();
+  const int row_lo = blockIdx.x, row_hi = blockIdx.x + half_rows;
+  const RowT rt_lo = make_row_t(__ldg(p.t + row_lo)), rt_hi = make_row_t(__ldg(p.t + row_hi));
+  const size_t b_lo = (size_t)row_lo * p.dim4, b_hi = (size_t)row_hi * p.dim4;
+  const uint32_t half = (uint32_t)half_rows * (uint32_t)(p.dim4 * 4);      // N / 2
+  float acc_lo[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, acc_hi[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int i4 = tid; i4 < p.dim4; i4 += NT) {
+    float4 E0lo, E0hi, Elo, Ehi;
+    const uint32_t e = (uint32_t)row_lo * (uint32_t)(p.dim4 * 4) + 4u * (uint32_t)i4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t x0 = e + j, x1 = e + j + half;
+      threefry2x32(q.k_eps0[0], q.k_eps0[1], x0, x1);
+      put(E0lo, j, bits_to_normal(x0)); put(E0hi, j, bits_to_normal(x1));
+      x0 = e + j; x1 = e + j + half;
+      threefry2x32(q.k_eps[0], q.k_eps[1], x0, x1);
+      put(Elo, j, bits_to_normal(x0)); put(Ehi, j, bits_to_normal(x1));
+    }
+    if (q.eps_out != nullptr) { st4(q.eps_out, b_lo + i4, Elo); st4(q.eps_out, b_hi + i4, Ehi); }
+    if (q.eps0_out != nullptr) { st4(q.eps0_out, b_lo + i4, E0lo); st4(q.eps0_out, b_hi + i4, E0hi); }
+    {
+      const size_t g4 = b_lo + i4;
+      pre_column<GT, SAVEW, true, CRAW>(p, kc, rt_lo, ld4(p.a, g4), ld4(p.b, g4), ld4(p.c, g4),
+                                        E0lo, Elo, ldx4(p.x, g4), g4, acc_lo);
+    }
+    {
+      const size_t g4 = b_hi + i4;
+      pre_column<GT, SAVEW, true, CRAW>(p, kc, rt_hi, ld4(p.a, g4), ld4(p.b, g4), ld4(p.c, g4),
+                                        E0hi, Ehi, ldx4(p.x, g4), g4, acc_hi);
+    }
+  }
+  pre_row_end<GT, NW>(p, row_lo, acc_lo, red);
+  __syncthreads();
+  pre_row_end<GT, NW>(p, row_hi, acc_hi, red);
+}
+
+template <int GT, bool SAVEW>
+static cudaError_t launch_keyed_w(const FwdPreKeyedParams& q, cudaStream_t s) {
+  const FwdPreParams& p = q.p;
+  const bool baked = is_shipped(p);
+  const int grid = p.rows / 2;
+  const bool pdl = p.pdl != 0;
+#define MULAN_KEYED(BAKED, CRAW) \
+  return launch_kernel(fwd_pre_keyed_kernel<GT, SAVEW, BAKED, CRAW>, grid, 128, s, pdl, q)
+  if (p.c_raw) { if (baked) MULAN_KEYED(true, true); MULAN_KEYED(false, true); }
+  if (baked) MULAN_KEYED(true, false);
+  MULAN_KEYED(false, false);
+#undef MULAN_KEYED
+}
+
+// ---------------------------------------------------------------------------------------
 // TMA-pipelined kernel (the shipped configs: dim % 1024 == 0, 16-byte aligned operands).
 // Persistent CTAs walk rows blockIdx.x, += gridDim.x; a row is consumed in slabs of 256 float4
 // columns.  Thread 0 moves each slab global -> shared with six cp.async.bulk copies (4 KB per
@@ -508,6 +584,20 @@ int fwd_pre_variant(const FwdPreParams& p) {
   const bool fast = p.W == 1 && p.vi.pow2;
   if (!fast) return 0;
   return is_shipped(p) ? 2 : 1;
+}
+
+// rows even, closed-form reconstruction term with a uniform prior (the shipped configurations)
+cudaError_t launch_fwd_pre_keyed(const FwdPreKeyedParams& q, cudaStream_t s) {
+  const FwdPreParams& p = q.p;
+  if (p.rows == 0) return cudaSuccess;
+  const bool fast = p.W == 1 && p.vi.pow2;
+  if (!fast || (p.rows & 1) || p.noise_rows != 0) return cudaErrorNotSupported;
+  const bool savew = p.w_save != nullptr;
+  if (p.gt_mode == MULAN_GT_MEAN)
+    return savew ? launch_keyed_w<MULAN_GT_MEAN, true>(q, s)
+                 : launch_keyed_w<MULAN_GT_MEAN, false>(q, s);
+  return savew ? launch_keyed_w<MULAN_GT_PIXEL, true>(q, s)
+               : launch_keyed_w<MULAN_GT_PIXEL, false>(q, s);
 }
 
 cudaError_t launch_fwd_pre(const FwdPreParams& p, cudaStream_t s) {

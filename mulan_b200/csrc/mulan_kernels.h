@@ -108,6 +108,14 @@ struct BpdReduceParams {
   int rows, dim;
 };
 
+// mulan_fwd_pre_keyed: eps_0 / eps drawn inside the kernel from their threefry keys
+struct FwdPreKeyedParams {
+  FwdPreParams p;              // p.eps0 / p.eps unused
+  uint32_t k_eps0[2], k_eps[2];
+  float *eps0_out, *eps_out;   // optional [B, D] copies of the draws (eps feeds the post kernels)
+};
+cudaError_t launch_fwd_pre_keyed(const FwdPreKeyedParams& q, cudaStream_t s);
+
 struct PostParams {
   const uint8_t* x;
   const float *a, *b, *c, *t, *eps, *net, *w_save, *gL;

@@ -127,6 +127,33 @@ def fwd_pre(desc: Desc, x, a, b, c, t, eps0, eps, save_w: bool = True, end_const
   return dict(z_t=z_t, g_net=g_net, w=w, loss_recon=rec, loss_klz_prior=klz, var_sums=vs)
 
 
+def fwd_pre_keyed(desc: Desc, key_eps0, key_eps, x, a, b, c, t, save_w: bool = True,
+                  want_eps: bool = True, want_eps0: bool = False):
+  """mulan_fwd_pre_keyed: eps_0 / eps drawn inside the kernel from their (k0, k1) threefry keys.
+  Returns fwd_pre's dict + eps (and eps_0) when asked for."""
+  B, D = a.shape
+  _req(x, torch.uint8, (B, D), 'x')
+  for n, v in (('a', a), ('b', b), ('c', c)):
+    _req(v, torch.float32, (B, D), n)
+  _req(t, torch.float32, (B,), 't')
+  dev = a.device
+  f = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+  z_t = f(B, D)
+  g_net = f(B) if desc.gt_mode == MULAN_GT_MEAN else f(B, D)
+  w = f(B, D) if save_w else None
+  eps = f(B, D) if want_eps else None
+  eps0 = f(B, D) if want_eps0 else None
+  rec, klz, vs = f(B), f(B), f(B, 2)
+  k0 = (C.c_uint32 * 2)(int(key_eps0[0]), int(key_eps0[1]))
+  k1 = (C.c_uint32 * 2)(int(key_eps[0]), int(key_eps[1]))
+  d = desc.c(B)
+  _lib.check(_lib.load().mulan_fwd_pre_keyed(
+      C.byref(d), k0, k1, _p(x), _p(a), _p(b), _p(c), _p(t), _p(z_t), _p(g_net), _p(w), _p(eps0),
+      _p(eps), _p(rec), _p(klz), _p(vs), _stream()))
+  return dict(z_t=z_t, g_net=g_net, w=w, loss_recon=rec, loss_klz_prior=klz, var_sums=vs, eps=eps,
+              eps_0=eps0)
+
+
 def fwd_post(desc: Desc, x, a, b, c, t, eps, net, w=None):
   """mulan_fwd_post -> loss_diff[B]."""
   B, D = net.shape

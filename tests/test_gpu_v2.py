@@ -286,3 +286,43 @@ def test_concurrent_host_threads_bitwise_serial(cuda_device):
     for a_, b_ in zip(results[i], serial[i]):
       assert torch.equal(a_, b_), i
   assert lib.mulan_last_error() is not None
+
+
+@pytest.mark.parametrize('rows', [2, 10, 300])
+@pytest.mark.parametrize('gt,c_raw', [(0, False), (1, False), (0, True)])
+def test_fwd_pre_keyed_equals_device_draws_plus_fwd_pre(cuda_device, rows, gt, c_raw):
+  """mulan_fwd_pre_keyed draws eps_0 / eps INSIDE the kernel from their threefry keys
+  (jax.random.normal(make_rng('sample'), f.shape), ldm/model_mulan_epsilon.py:315, :327): the
+  draws are bit for bit mulan_rng_normal's, the per-pixel outputs bit for bit mulan_fwd_pre's on
+  those arrays, the per-row sums equal to float32 summation order (different CTA shape)."""
+  from mulan_b200 import ops
+  inp, g = dev_inputs(rows, 77 + rows, cuda_device, raw=True)
+  k0, k1 = (123, 456), (789, 1011)
+  D = 3072
+  eps0 = ops.rng_normal(k0, (rows, D), device=cuda_device)
+  eps = ops.rng_normal(k1, (rows, D), device=cuda_device)
+  desc = ops.Desc(gt_mode=gt, c_raw=c_raw)
+  c = g['c_raw'] if c_raw else g['c']
+  base = ops.fwd_pre(desc, g['x'], g['a'], g['b'], c, g['t'], eps0, eps)
+  got = ops.fwd_pre_keyed(desc, k0, k1, g['x'], g['a'], g['b'], c, g['t'], want_eps0=True)
+  assert torch.equal(got['eps'], eps) and torch.equal(got['eps_0'], eps0)
+  assert torch.equal(got['z_t'], base['z_t']) and torch.equal(got['w'], base['w'])
+  if gt == 1:
+    assert torch.equal(got['g_net'], base['g_net'])
+  else:
+    assert rel(got['g_net'], base['g_net']) < 2e-6
+  for k in ('loss_recon', 'loss_klz_prior', 'var_sums'):
+    assert rel(got[k], base[k]) < 2e-6, k
+  # without the optional copies
+  lean = ops.fwd_pre_keyed(desc, k0, k1, g['x'], g['a'], g['b'], c, g['t'], save_w=False,
+                           want_eps=False)
+  assert lean['eps'] is None and lean['w'] is None
+  assert torch.equal(lean['z_t'], base['z_t'])
+  assert torch.equal(lean['loss_recon'], got['loss_recon'])
+
+
+def test_fwd_pre_keyed_rejects_what_it_cannot_pair(cuda_device):
+  from mulan_b200 import _lib, ops
+  _, g = dev_inputs(3, 5, cuda_device)
+  with pytest.raises(_lib.MulanError, match='even'):
+    ops.fwd_pre_keyed(ops.Desc(), (1, 2), (3, 4), g['x'], g['a'], g['b'], g['c'], g['t'])

@@ -108,6 +108,36 @@ def main():
   emit(what='torch_softplus_bwd', ms=timeit(lambda: cb * torch.sigmoid(c_raw)))
   del wr, c_raw, cb
 
+  # ---- in-kernel draws (f2): mulan_fwd_pre_keyed vs two stand-alone draws + mulan_fwd_pre
+  import ctypes as C
+  from mulan_b200 import _lib
+  lib = _lib.load()
+  wk = ops.ElboWorkspace(ops.Desc(), rows, dev)
+  eps_out = torch.empty((rows, D), device=dev)
+  k0, k1 = (C.c_uint32 * 2)(1, 2), (C.c_uint32 * 2)(3, 4)
+  pp = lambda t_: C.c_void_p(t_.data_ptr()) if t_ is not None else None
+  def keyed(w_save, eps_o):
+    _lib.check(lib.mulan_fwd_pre_keyed(
+        C.byref(wk._d), k0, k1, pp(inp['x']), pp(inp['a']), pp(inp['b']), pp(inp['c']), pp(inp['t']),
+        pp(wk.z_t), pp(wk.g_net), pp(wk.w if w_save else None), None, pp(eps_o),
+        pp(wk.loss_recon), pp(wk.loss_klz_prior), pp(wk.var_sums),
+        C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+  e0b, e1b = torch.empty((rows, D), device=dev), torch.empty((rows, D), device=dev)
+  def separate():
+    ops.rng_normal((1, 2), (rows, D), device=dev, out=e0b)
+    ops.rng_normal((3, 4), (rows, D), device=dev, out=e1b)
+    wk.fwd_pre(inp['x'], inp['a'], inp['b'], inp['c'], inp['t'], e0b, e1b)
+  emit(what='fwd_pre_keyed_w_and_eps_out', ms=timeit(lambda: keyed(True, eps_out)))
+  emit(what='fwd_pre_keyed_no_copies', ms=timeit(lambda: keyed(False, None)))
+  emit(what='two_rng_normal_plus_fwd_pre', ms=timeit(separate))
+  emit(what='fwd_pre_reading_existing_draws',
+       ms=timeit(lambda: wk.fwd_pre(inp['x'], inp['a'], inp['b'], inp['c'], inp['t'], e0b, e1b)))
+  g_ = torch.Generator(device=dev).manual_seed(0)
+  emit(what='two_torch_philox_randn_plus_fwd_pre', ms=timeit(lambda: (
+      e0b.normal_(generator=g_), e1b.normal_(generator=g_),
+      wk.fwd_pre(inp['x'], inp['a'], inp['b'], inp['c'], inp['t'], e0b, e1b))))
+  del wk, eps_out, e0b, e1b
+
   # ---- full steps at `rows` (graph): separate reduce vs fused, plain vs PDL
   def make_step(desc, fused, rws):
     def step():

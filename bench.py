@@ -652,13 +652,12 @@ def measure_dense(ctx, args, inp, K, W):
       ctx.barrier()
       e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
       e0.record(stream)
-      acc.zero_()
       for _ in range(K):
         graph.replay()
-        acc[0] += chunks[0][0].scalars[0].double()     # running (sum of bpd, image count)
-        acc[1] += rows / T
       if world > 1:        # the ONE exchange of the evaluation: a final (sum, count) all-reduce
-        dist.all_reduce(acc, op=dist.ReduceOp.SUM)     # (ldm/notebook_utils.py:191: np.mean(bpds))
+        acc[0] = chunks[0][0].scalars[0].double() * K  # (ldm/notebook_utils.py:191: np.mean(bpds))
+        acc[1] = K * rows / T
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM)
       e1.record(stream)
       ctx.barrier()
     ms = ctx.max_over_ranks(e0.elapsed_time(e1)) / K

@@ -952,6 +952,13 @@ def train_step_leg(ctx, args, net_config, param_name, B, modes, K, W):
         state.finish_exchange()
       t_f = alone(fused)
       m['fused_exchange_update_ms'] = t_f
+
+      def fused_whole():            # the whole bucket in ONE call (as the all-reduce leg does)
+        state._reset_ranges()
+        state.peer_update_range(0, state.n)
+      t_w = alone(fused_whole)
+      m['fused_exchange_update_single_call_ms'] = t_w
+      m['nvlink_gbs_per_direction_single_call'] = (world - 1) / world * nbytes / (t_w * 1e-3) / 1e9
       # NVLink bytes per rank: (world-1)/world of the bucket read from peers + as much stored
       m['nvlink_gbs_per_direction'] = (world - 1) / world * nbytes / (t_f * 1e-3) / 1e9
       m['timed_out'] = state.peer.timed_out()

@@ -266,15 +266,22 @@ class FlatTrainState:
     if self.comm == 'overlap':
       self._works.append(dist.all_reduce(self.grads[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
       return
-    ptr = lambda t: C.c_void_p(t.data_ptr())
     ev = torch.cuda.Event()
     ev.record(torch.cuda.current_stream())
     self._side.wait_event(ev)
+    self.peer_update_range(lo, hi, self._side)
+
+  def peer_update_range(self, lo: int, hi: int, stream=None):
+    """ONE mulan_adamw_ema_peer call over the flat range [lo, hi) (every rank must make the same
+    call): reduce-scatter by peer loads, AdamW+EMA on this rank's shard, all-gather by peer
+    stores.  The first call of a step fixes the step count and learning rate."""
+    ptr = lambda t: C.c_void_p(t.data_ptr())
+    stream = stream or torch.cuda.current_stream()
     d = self._adamw_desc(1.0 / self.peer.world)
     pd = self.peer.desc()
     _lib.check(_lib.load().mulan_adamw_ema_peer(
         C.byref(d), C.byref(pd), lo, hi, ptr(self.mu), ptr(self.nu), ptr(self.ema),
-        C.c_void_p(self._side.cuda_stream)))
+        C.c_void_p(stream.cuda_stream)))
 
   def finish_exchange(self):
     """After backward: fire the ranges no hook completed (unused parameters), in index order --
@@ -348,7 +355,22 @@ class FlatTrainState:
         C.c_void_p(torch.cuda.current_stream().cuda_stream)))
     return lr
 
+  def gather_sharded_state(self):
+    """'peer' mode keeps mu / nu / ema up to date only on the shards this rank owns.  Before a
+    checkpoint or an evaluation with ema_params (ldm/experiment.py:292-303) every rank collects
+    the other shards from their owners (one broadcast per range, shard and tensor: a rare path)."""
+    if self.comm != 'peer':
+      return
+    world = dist.get_world_size()
+    for lo, hi in self.ranges:
+      for r in range(world):
+        a, b = shard_range(lo, hi, world, r)
+        if b > a:
+          for t in (self.mu, self.nu, self.ema):
+            dist.broadcast(t[a:b], src=r)
+
   def ema_state_dict(self) -> Dict[str, torch.Tensor]:
+    self.gather_sharded_state()
     return {n: self.ema[o:o + k] for n, o, k in self.layout}
 
 

@@ -158,7 +158,10 @@ def _gpu_worker(rank, world, port, q):
         st.apply_gradients()
         torch.cuda.synchronize()
         snaps.append(float(st.tail[0]))
+      st.gather_sharded_state()     # 'peer': mu / nu / ema shards from their owners
+      torch.cuda.synchronize()
       results[comm] = [t.clone() for t in (st.params, st.ema)] + [snaps, st.step, len(st.ranges)]
+      results[comm + '_moments'] = [st.mu.clone(), st.nu.clone()]
       if comm == 'peer':
         assert not st.peer.timed_out()
       results[comm + '_ranges'] = list(st.ranges)
@@ -168,6 +171,9 @@ def _gpu_worker(rank, world, port, q):
       for a_, b_ in zip(results[comm][:2], results['allreduce'][:2]):
         err = ((a_ - b_).abs().max() / b_.abs().max()).item()
         assert err < 2e-6, (comm, err)
+      for a_, b_ in zip(results[comm + '_moments'], results['allreduce_moments']):
+        err = ((a_ - b_).abs().max() / b_.abs().max()).item()
+        assert err < 1e-5, (comm, 'moments', err)       # every shard, after the gather
       assert results[comm][3] == results['allreduce'][3] == 3
       assert np.allclose(results[comm][2], results['allreduce'][2], rtol=1e-6)
     # parameters identical on every rank after the fused all-gather

@@ -84,6 +84,9 @@ def parse_args():
                   help='timed steps of each train-step leg of the `configs` block')
   ap.add_argument('--comm', choices=['all', 'allreduce', 'overlap', 'peer'], default='all',
                   help='train_step: how the gradient exchange runs (mulan_b200/optim.py)')
+  ap.add_argument('--nccl-scalars', action='store_true',
+                  help='N > 1: pmean of the six loss scalars as one NCCL all-reduce per step '
+                       '(round 1) instead of the peer-memory board written by the post kernel')
   ap.add_argument('--no-pdl', action='store_true',
                   help='plain launches instead of programmatic dependent launch')
   ap.add_argument('--no-sustained', action='store_true',
@@ -326,6 +329,12 @@ def measure_elbo(ctx, args, inp, param_name, K, W, extras):
   ws = ops.ElboWorkspace(desc, rows, dev, save_w=save_w)
   gL = torch.full((rows,), 1.0 / (rows * D * math.log(2.0)), device=dev)
   i = inp
+  # N > 1: the pmean of the six loss scalars (ldm/experiment.py:347-348) is an all-gather by peer
+  # stores in the post kernel's epilogue (mulan_post_bpd_peer) -- no collective call per step
+  board = None
+  if world > 1 and not args.nccl_scalars and not args.separate_post:
+    from mulan_b200.peer import ScalarBoard
+    board = ScalarBoard(dev)
   kernels = {'fwd_pre': lambda: ws.fwd_pre(i['x'], i['a'], i['b'], i['c'], i['t'], i['eps0'],
                                             i['eps'])}
   if args.separate_post:
@@ -338,7 +347,7 @@ def measure_elbo(ctx, args, inp, param_name, K, W, extras):
     # value-and-grad: the loss cotangent of a mean is known up front (jax.value_and_grad); the
     # six loss_fn scalars come out of the same launch
     kernels['post_vg'] = lambda: ws.post_bpd(i['x'], i['a'], i['b'], i['c'], i['t'], i['eps'],
-                                             i['net'], gL)
+                                             i['net'], gL, board=board)
   kernels['bwd_pre'] = lambda: ws.bwd_pre(i['x'], i['a'], i['b'], i['c'], i['t'], i['eps'],
                                           i['net'], i['z_bar'], i['g_bar'], gL)
   names = list(kernels)
@@ -351,7 +360,7 @@ def measure_elbo(ctx, args, inp, param_name, K, W, extras):
   with torch.cuda.stream(stream):
     for _ in range(max(W, 3)):
       step()
-      if world > 1:
+      if world > 1 and board is None:
         dist.all_reduce(ws.scalars, op=dist.ReduceOp.AVG)
     torch.cuda.synchronize()
     graph = torch.cuda.CUDAGraph()
@@ -372,19 +381,26 @@ def measure_elbo(ctx, args, inp, param_name, K, W, extras):
     works, reduced = [], torch.empty((K, 6), dtype=torch.float32, device=dev)
     for k in range(K):
       graph.replay()
-      if world > 1:
-        # the one exchange that follows the path: pmean of the six loss scalars
-        # (ldm/experiment.py:347-348).  Nothing downstream waits for it, so it runs on NCCL's
-        # own stream from a snapshot of the scalars and overlaps the next step.
+      if world > 1 and board is None:
+        # round 1's exchange: one NCCL all-reduce of the six scalars per step, on NCCL's own
+        # stream from a snapshot of the scalars
         reduced[k].copy_(ws.scalars)
         works.append(dist.all_reduce(reduced[k], op=dist.ReduceOp.AVG, async_op=True))
     for wk in works:
       wk.wait()                      # the timed region ends only when every pmean has landed
+    if board is not None:
+      # every step's scalars were stored into every rank's board by the post kernel; the read
+      # waits until the LAST step's rows of all ranks have landed here and averages them
+      pmean, pstep = board.read()
     t_end.record(stream)
     ctx.barrier()
     mark1 = sampler.mark() if sampler else 0
   elapsed_ms = ctx.max_over_ranks(t_start.elapsed_time(t_end))
-  bpd = (reduced[-1][0] if world > 1 else ws.scalars[0]).item()
+  if board is not None:
+    bpd = pmean[0].item()
+    assert int(pstep.item()) > 0, 'scalar board: a peer row was missing (timed out / lapped)'
+  else:
+    bpd = (reduced[-1][0] if world > 1 else ws.scalars[0]).item()
 
   # per-kernel durations, live, CUDA events on the launching stream: each kernel K times back
   # to back (its inputs alone exceed L2, so every launch streams from HBM)
@@ -439,6 +455,9 @@ def measure_elbo(ctx, args, inp, param_name, K, W, extras):
   total_algo = sum(ab.values()) * nsub
   ms_step = elapsed_ms / K
   dom = max(ab, key=lambda n: kern_ms[n])
+  if board is not None:
+    del graph
+    board.close()
   return {
       'param': param_name, 'loss_form': 'eps' if eps_form else 'velocity', 'saved_w': save_w,
       'value': world * rows * K / (elapsed_ms * 1e-3), 'unit': 'samples/s',
@@ -449,6 +468,10 @@ def measure_elbo(ctx, args, inp, param_name, K, W, extras):
                    'frac_of_measured': total_algo / (ms_step * 1e-3) / 1e9 / ctx.peak,
                    'sum_kernel_ms': sum(kern_ms.values())},
       'clocks': clocks, 'sustained': sustained, 'algo_bytes': ab,
+      'scalar_pmean': ('none (1 GPU)' if world == 1 else
+                       'peer-memory board written by the post kernel (mulan_post_bpd_peer), read '
+                       'once after the timed steps' if board is not None else
+                       'one 24-byte NCCL all-reduce per step'),
   }
 
 
@@ -759,7 +782,8 @@ def run_native(args):
                  'per step)' % (main['step_hbm']['algo_bytes_per_step'] / 1e9),
                  'parallelism': f'dp{world} (rows sharded)',
                  'timed_loop': 'CUDA-graph replay of one step (%d launches, programmatic '
-                               'dependent launch)' % main['launches_per_step']},
+                               'dependent launch)' % main['launches_per_step'],
+                 'scalar_pmean': main['scalar_pmean']},
       'roofline': {'bound': 'hbm', 'kernel': dom, 'achieved': kinfo[dom]['gbs'],
                    'peak': ctx.peak, 'peak_source': ctx.peak_src, 'unit': 'GB/s',
                    'frac': kinfo[dom]['gbs'] / ctx.peak, 'traffic': traffic,

@@ -514,6 +514,35 @@ int mulan_peer_free(void* dev_ptr);
 int mulan_adamw_ema_peer(const mulan_adamw_desc* desc, const mulan_peer_desc* peers, int64_t lo,
                          int64_t hi, float* mu, float* nu, float* ema_params, void* stream);
 
+/*
+ * pmean of the six loss scalars WITHOUT a collective call (ldm/experiment.py:347-348, 365-366:
+ * jax.lax.pmean of each metric right after the ELBO): mulan_post_bpd_peer is mulan_post_bpd whose
+ * finalising thread also stores this rank's scalars, tagged with a step counter, into slot
+ * [step % 64][rank] of EVERY rank's board over NVLink peer memory (boards allocated with
+ * mulan_peer_alloc(mulan_scalar_board_bytes()), mapped with mulan_peer_open) -- an all-gather by
+ * peer stores in the kernel's epilogue: no NCCL launch per step, nothing for the next kernel to
+ * wait for.  The step counter lives in the rank's own board, so CUDA-graph replays advance it.
+ * mulan_scalar_board_read(board, mean_out[6], epoch_out, stream): the mean over the ranks of the
+ * latest step this rank has published -- waits (bounded, ~4 s) for every rank's row of that
+ * slot, sums in rank order (the same bits on every rank), divides by world; epoch_out = the step
+ * (0 and NaNs if a peer had already lapped the ring or the wait timed out).  Called when the host
+ * wants the metrics (the reference logs every 1000 steps), not once per step.
+ */
+typedef struct mulan_scalar_board {
+  int32_t world, rank;
+  float* boards[MULAN_PEER_MAX];   /* this process's mapping of rank r's board */
+} mulan_scalar_board;
+size_t mulan_scalar_board_bytes(void);
+int mulan_post_bpd_peer(const mulan_desc* desc,
+                        const uint8_t* x, const float* a, const float* b, const float* c,
+                        const float* t, const float* eps, const float* net, const float* w_save,
+                        const float* gL, const float* loss_recon, const float* loss_klz_prior,
+                        const float* kl_z, const float* var_sums,
+                        float* loss_diff, float* n_bar, float* scalars, float* loss_klz_total,
+                        void* reduce_ws, const mulan_scalar_board* board, void* stream);
+int mulan_scalar_board_read(const mulan_scalar_board* board, float* mean_out, uint32_t* epoch_out,
+                            void* stream);
+
 /* out[0] (device float) = sum_i g[i]^2 over the flat bucket: optax.global_norm(grads)^2 for
  * clip_by_global_norm.  n % 4 == 0, g 16-byte aligned; scratch holds MULAN_SUMSQ_SCRATCH doubles.
  * Fixed-order two-launch reduction (float64 accumulation of float32 squares): run to run

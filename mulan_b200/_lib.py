@@ -64,6 +64,11 @@ class MulanPeerDesc(C.Structure):
               ('reserved', C.c_uint32)]
 
 
+class MulanScalarBoard(C.Structure):
+  """struct mulan_scalar_board."""
+  _fields_ = [('world', C.c_int32), ('rank', C.c_int32), ('boards', C.c_void_p * MULAN_PEER_MAX)]
+
+
 class MulanError(RuntimeError):
   def __init__(self, status: int, msg: str):
     super().__init__(f'libmulan_b200 status {status}: {msg}')
@@ -103,6 +108,9 @@ SIGNATURES = {
     'mulan_bpd_reduce': ([_D] + [_P] * 9, C.c_int),
     'mulan_reduce_ws_bytes': ([C.c_int32], C.c_size_t),
     'mulan_post_bpd': ([_D] + [_P] * 19, C.c_int),
+    'mulan_post_bpd_peer': ([_D] + [_P] * 20, C.c_int),
+    'mulan_scalar_board_bytes': ([], C.c_size_t),
+    'mulan_scalar_board_read': ([_P, _P, _P, _P], C.c_int),
     'mulan_elbo_host': ([_D] + [_P] * 8 + [DENOISER_FN, _P, C.c_int32] + [_P] * 6, C.c_int),
     'mulan_elbo_host_keyed': ([_D] + [_P] * 8 + [DENOISER_FN, _P, C.c_int32] + [_P] * 6, C.c_int),
     'mulan_sample_gamma': ([_D, C.c_int32] + [_P] * 6, C.c_int),

@@ -507,6 +507,21 @@ static int fill_reduce(const char* fn, const mulan_desc* d, const float* loss_re
   r->loss_diff = loss_diff; r->var_sums = var_sums; r->scalars = scalars;
   r->loss_klz_total = loss_klz_total; r->ws = static_cast<unsigned*>(reduce_ws);
   r->rows = d->rows; r->dim = d->dim;
+  memset(&r->board, 0, sizeof(r->board));
+  return 0;
+}
+
+static int fill_board(const char* fn, const mulan_scalar_board* b, mulan::ScalarBoard* out) {
+  memset(out, 0, sizeof(*out));
+  if (b == nullptr) return 0;
+  if (b->world < 1 || b->world > 8 || b->rank < 0 || b->rank >= b->world)
+    return fail(MULAN_ERR_INVALID_ARG, "%s: scalar board world=%d rank=%d", fn, b->world, b->rank);
+  for (int r = 0; r < b->world; ++r) {
+    if (b->boards[r] == nullptr || !aligned(b->boards[r], 16))
+      return fail(MULAN_ERR_INVALID_ARG, "%s: scalar board of rank %d is NULL / misaligned", fn, r);
+    out->boards[r] = b->boards[r];
+  }
+  out->world = b->world; out->rank = b->rank;
   return 0;
 }
 
@@ -531,6 +546,31 @@ int mulan_post_bpd(const mulan_desc* d, const uint8_t* x, const float* a, const 
                    const float* loss_klz_prior, const float* kl_z, const float* var_sums,
                    float* loss_diff, float* n_bar, float* scalars, float* loss_klz_total,
                    void* reduce_ws, void* stream) {
+  return mulan_post_bpd_peer(d, x, a, b, c, t, eps, net, w_save, gL, loss_recon, loss_klz_prior,
+                             kl_z, var_sums, loss_diff, n_bar, scalars, loss_klz_total, reduce_ws,
+                             nullptr, stream);
+}
+
+size_t mulan_scalar_board_bytes(void) {
+  return sizeof(float) * (size_t)(mulan::kBoardSlots * 8 * mulan::kBoardRow) + 16;
+}
+
+int mulan_scalar_board_read(const mulan_scalar_board* board, float* mean_out, uint32_t* epoch_out,
+                            void* stream) {
+  const char* fn = "mulan_scalar_board_read";
+  REQ_PTR(board, fn); REQ_PTR(mean_out, fn);
+  mulan::ScalarBoard b;
+  if (int r = fill_board(fn, board, &b)) return r;
+  cudaError_t e = mulan::launch_board_read(b, mean_out, epoch_out, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(fn, e);
+}
+
+int mulan_post_bpd_peer(const mulan_desc* d, const uint8_t* x, const float* a, const float* b,
+                        const float* c, const float* t, const float* eps, const float* net,
+                        const float* w_save, const float* gL, const float* loss_recon,
+                        const float* loss_klz_prior, const float* kl_z, const float* var_sums,
+                        float* loss_diff, float* n_bar, float* scalars, float* loss_klz_total,
+                        void* reduce_ws, const mulan_scalar_board* board, void* stream) {
   const char* fn = "mulan_post_bpd";
   if (int r = check_desc(d, fn)) return r;
   if (d->rows == 0) return fail(MULAN_ERR_INVALID_ARG, "%s: rows=0 has no mean", fn);
@@ -542,6 +582,7 @@ int mulan_post_bpd(const mulan_desc* d, const uint8_t* x, const float* a, const 
   p.gL = gL; p.loss_diff = loss_diff; p.n_bar = gL != nullptr ? n_bar : nullptr;
   if (int r = fill_reduce(fn, d, loss_recon, loss_klz_prior, kl_z, loss_diff, var_sums, scalars,
                           loss_klz_total, reduce_ws, &p.red)) return r;
+  if (int r = fill_board(fn, board, &p.red.board)) return r;
   cudaError_t e = gL != nullptr ? mulan::launch_fwd_bwd_post(p, (cudaStream_t)stream)
                                 : mulan::launch_fwd_post(p, (cudaStream_t)stream);
   return e == cudaSuccess ? 0 : cuda_fail(fn, e);

@@ -352,6 +352,47 @@ bpd_reduce_single_kernel(const BpdReduceParams p) {
   if (threadIdx.x == 0) red_write_scalars(p, acc);
 }
 
+// mulan_scalar_board_read: the mean over the ranks of the latest step THIS rank has published.
+// Waits (bounded) until every rank's row of that slot carries the step's tag, then sums in rank
+// order (identical on every rank) and divides by the world size.
+__global__ void __launch_bounds__(32)
+board_read_kernel(const ScalarBoard b, float* __restrict__ mean_out,
+                  unsigned* __restrict__ epoch_out) {
+  const int lane = threadIdx.x;
+  const float* mine = b.boards[b.rank];
+  const unsigned step = *reinterpret_cast<const unsigned*>(mine + kBoardSlots * 8 * kBoardRow);
+  const int slot = (int)(step % (unsigned)kBoardSlots);
+  bool ok = true;
+  if (lane < b.world) {
+    const unsigned* tag =
+        reinterpret_cast<const unsigned*>(mine + ((size_t)slot * 8 + lane) * kBoardRow + 7);
+    const long long t0 = clock64();
+    for (;;) {
+      unsigned v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(tag) : "memory");
+      // a peer may already be LATER in the ring (same slot, step + k * slots): its row for this
+      // step is gone; report the step as incomplete rather than mixing steps
+      if (v == step) break;
+      if ((int)(v - step) > 0 || clock64() - t0 > 8000000000LL) { ok = false; break; }
+      __nanosleep(200);
+    }
+  }
+  ok = __all_sync(0xffffffffu, ok);
+  if (lane < 6) {
+    float s = 0.f;
+    for (int r = 0; r < b.world; ++r)
+      s += __ldcv(mine + ((size_t)slot * 8 + r) * kBoardRow + lane);
+    mean_out[lane] = ok ? __fdiv_rn(s, (float)b.world) : __int_as_float(0x7fc00000);
+  }
+  if (lane == 0 && epoch_out != nullptr) *epoch_out = ok ? step : 0u;
+}
+
+cudaError_t launch_board_read(const ScalarBoard& b, float* mean_out, unsigned* epoch_out,
+                              cudaStream_t s) {
+  board_read_kernel<<<1, 32, 0, s>>>(b, mean_out, epoch_out);
+  return cudaGetLastError();
+}
+
 size_t reduce_ws_bytes(int rows) {
   const int G = red_groups(rows < 1 ? 1 : rows);
   return sizeof(unsigned) * (size_t)(red_partials_offset(G) + 8 * G);

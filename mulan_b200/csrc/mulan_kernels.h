@@ -101,12 +101,24 @@ struct FwdPreParams {
 
 // VDMOutput assembly + loss_fn scalars (ldm/model_mulan_epsilon.py:357-363,
 // ldm/experiment_vdm.py:62-74), stand-alone or fused into the post kernel's epilogue.
+// pmean of the six scalars without a collective (mulan_scalar_board, include/mulan_b200.h): the
+// thread that writes a rank's scalars also stores them, tagged with a step counter, into slot
+// [step % slots][rank] of EVERY rank's board over NVLink peer memory.
+constexpr int kBoardSlots = 64, kBoardRow = 8;   // 6 scalars, 1 pad, 1 tag per (slot, rank)
+struct ScalarBoard {
+  float* boards[8];   // this process's mapping of rank r's board; boards[rank] is its own
+  int world, rank;    // world == 0: no board
+};
+
 struct BpdReduceParams {
   const float *loss_recon, *loss_klz_prior, *kl_z, *loss_diff, *var_sums;
   float *scalars, *loss_klz_total;
   unsigned* ws;       // mulan_reduce_ws_bytes(rows) bytes, zero before first use (self-resetting)
   int rows, dim;
+  ScalarBoard board;
 };
+cudaError_t launch_board_read(const ScalarBoard& b, float* mean_out, unsigned* epoch_out,
+                              cudaStream_t s);
 
 // mulan_fwd_pre_keyed: eps_0 / eps drawn inside the kernel from their threefry keys
 struct FwdPreKeyedParams {

@@ -48,6 +48,31 @@ __device__ __forceinline__ void red_group_sum(const BpdReduceParams& p, int g, f
   block_sum<5, NW>(acc, red);      // warps beyond the fourth add zeros: same bits for any NW
 }
 
+// The pmean of the six scalars (ldm/experiment.py:347-348) as an all-gather by peer stores: the
+// ONE thread that has just written this rank's scalars bumps the rank's step counter (the word
+// behind the slots of its own board, so CUDA-graph replays advance it) and stores the row
+// {6 scalars, pad, tag = step} into slot [step % kBoardSlots][rank] of every rank's board.
+// Data first, system fence, then the tag with release semantics: a reader that sees the tag sees
+// the scalars.  No collective call, no extra launch; mulan_scalar_board_read averages on demand.
+__device__ __forceinline__ void board_publish(const ScalarBoard& b, const float* scalars) {
+  unsigned* counter = reinterpret_cast<unsigned*>(b.boards[b.rank] + kBoardSlots * 8 * kBoardRow);
+  const unsigned step = *counter + 1u;
+  *counter = step;
+  const int slot = (int)(step % (unsigned)kBoardSlots);
+  const float4 lo = make_float4(scalars[0], scalars[1], scalars[2], scalars[3]);
+  for (int r = 0; r < b.world; ++r) {
+    float* row = b.boards[r] + ((size_t)slot * 8 + b.rank) * kBoardRow;
+    *reinterpret_cast<float4*>(row) = lo;
+    row[4] = scalars[4];
+    row[5] = scalars[5];
+  }
+  __threadfence_system();
+  for (int r = 0; r < b.world; ++r) {
+    unsigned* tag = reinterpret_cast<unsigned*>(b.boards[r] + ((size_t)slot * 8 + b.rank) * kBoardRow + 7);
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(tag), "r"(step) : "memory");
+  }
+}
+
 __device__ __forceinline__ void red_write_scalars(const BpdReduceParams& p, const float (&acc)[5]) {
   const float n = (float)p.rows;
   const float rescale = (float)(1.0 / ((double)p.dim * 0.6931471805599453));
@@ -61,6 +86,7 @@ __device__ __forceinline__ void red_write_scalars(const BpdReduceParams& p, cons
   const float nd = (float)((double)p.rows * (double)p.dim);
   p.scalars[4] = __fdiv_rn(acc[3], nd);
   p.scalars[5] = __fdiv_rn(acc[4], nd);
+  if (p.board.world > 0) board_publish(p.board, p.scalars);
 }
 
 // Called by every thread of a CTA (NW warps, >= 8) that has just made `done_rows` more rows of

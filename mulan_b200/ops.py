@@ -441,13 +441,15 @@ class ElboWorkspace:
         _p(self.loss_diff), _p(self.var_sums), _p(self.scalars), _p(self.loss_klz),
         _p(self.reduce_ws if parallel else None), _stream()))
 
-  def post_bpd(self, x, a, b, c, t, eps, net, gL=None, kl_z=None):
-    """post kernel (value-and-grad when gL is given) + the six scalars, one launch."""
-    _lib.check(self._lib.mulan_post_bpd(
+  def post_bpd(self, x, a, b, c, t, eps, net, gL=None, kl_z=None, board=None):
+    """post kernel (value-and-grad when gL is given) + the six scalars, one launch.  board
+    (peer.ScalarBoard): also publish the scalars to every rank over NVLink peer memory."""
+    _lib.check(self._lib.mulan_post_bpd_peer(
         C.byref(self._d), _p(x), _p(a), _p(b), _p(c), _p(t), _p(eps), _p(net), _p(self.w), _p(gL),
         _p(self.loss_recon), _p(self.loss_klz_prior), _p(kl_z), _p(self.var_sums),
         _p(self.loss_diff), _p(self.n_bar if gL is not None else None), _p(self.scalars),
-        _p(self.loss_klz), _p(self.reduce_ws), _stream()))
+        _p(self.loss_klz), _p(self.reduce_ws), board.byref() if board is not None else None,
+        _stream()))
 
   def bwd_post(self, x, a, b, c, t, eps, net, gL):
     _lib.check(self._lib.mulan_bwd_post(

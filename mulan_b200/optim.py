@@ -33,6 +33,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
+from .peer import PeerAllocations, device_view
 
 
 def lr_schedule(step: int, learning_rate: float = 2e-4, num_steps_lr_warmup: int = 100,
@@ -86,49 +87,21 @@ def plan_buckets(layout: List[Tuple[str, int, int]], n: int, bucket_elems: int):
   return ranges, members
 
 
-class _DevArray:
-  """A raw device allocation exposed through __cuda_array_interface__ (zero-copy torch view)."""
-
-  def __init__(self, ptr: int, n: int, typestr: str):
-    self.__cuda_array_interface__ = {'shape': (n,), 'typestr': typestr, 'data': (ptr, False),
-                                     'version': 2}
-
-
 class PeerBuffers:
   """Parameter buffer, gradient bucket and flag block of THIS rank in CUDA-IPC peer memory, and
-  this process's mappings of every other rank's (mulan_peer_alloc / mulan_peer_open)."""
+  this process's mappings of every other rank's (mulan_b200/peer.py)."""
 
   def __init__(self, n_params: int, n_grads: int, device):
-    lib = _lib.load()
-    self.world, self.rank = dist.get_world_size(), dist.get_rank()
-    if self.world > _lib.MULAN_PEER_MAX or self.world & (self.world - 1):
-      raise ValueError(f'peer mode needs world in (1, 2, 4, 8), got {self.world}')
-    torch.cuda.set_device(device)
-    sizes = {'params': 4 * n_params, 'grads': 4 * n_grads, 'flags': 4 * _lib.MULAN_PEER_FLAG_WORDS}
-    self.own, handles = {}, {}
-    for k, nbytes in sizes.items():
-      ptr, h = C.c_void_p(), (C.c_char * _lib.MULAN_PEER_HANDLE_BYTES)()
-      _lib.check(lib.mulan_peer_alloc(nbytes, C.byref(ptr), h))
-      self.own[k], handles[k] = ptr.value, bytes(h)
-    everyone = [None] * self.world
-    dist.all_gather_object(everyone, handles)
-    self.maps = {k: [] for k in sizes}
-    self._opened = []
-    for r in range(self.world):
-      for k in sizes:
-        if r == self.rank:
-          self.maps[k].append(self.own[k])
-          continue
-        ptr = C.c_void_p()
-        _lib.check(lib.mulan_peer_open(everyone[r][k], C.byref(ptr)))
-        self.maps[k].append(ptr.value)
-        self._opened.append(ptr.value)
-    f32 = lambda key, n: torch.as_tensor(_DevArray(self.own[key], n, '<f4'), device=device)
-    self.params, self.grads = f32('params', n_params), f32('grads', n_grads)
-    self.flags = torch.as_tensor(_DevArray(self.own['flags'], _lib.MULAN_PEER_FLAG_WORDS, '<i4'),
-                                 device=device)
+    world = dist.get_world_size()
+    if world & (world - 1):
+      raise ValueError(f'peer mode needs world in (1, 2, 4, 8), got {world}')
+    self.mem = PeerAllocations({'params': 4 * n_params, 'grads': 4 * n_grads,
+                                'flags': 4 * _lib.MULAN_PEER_FLAG_WORDS}, device)
+    self.world, self.rank, self.maps = self.mem.world, self.mem.rank, self.mem.maps
+    self.params = device_view(self.mem.own['params'], n_params, '<f4', device)
+    self.grads = device_view(self.mem.own['grads'], n_grads, '<f4', device)
+    self.flags = device_view(self.mem.own['flags'], _lib.MULAN_PEER_FLAG_WORDS, '<i4', device)
     self.epoch = 0
-    dist.barrier()          # every rank has mapped every buffer before anyone launches
 
   def desc(self) -> '_lib.MulanPeerDesc':
     self.epoch += 1
@@ -143,18 +116,7 @@ class PeerBuffers:
     return bool(self.flags[_lib.MULAN_PEER_FLAG_ERR].item())
 
   def close(self):
-    lib = _lib.load()
-    torch.cuda.synchronize()
-    if dist.is_initialized():
-      dist.barrier()
-    for ptr in self._opened:
-      lib.mulan_peer_close(C.c_void_p(ptr))
-    self._opened = []
-    if dist.is_initialized():
-      dist.barrier()        # nobody frees while a peer still maps
-    for ptr in self.own.values():
-      lib.mulan_peer_free(C.c_void_p(ptr))
-    self.own = {}
+    self.mem.close()
 
 
 class FlatTrainState:

@@ -227,6 +227,34 @@ def _gpu_worker(rank, world, port, q):
         assert torch.equal(got[a:b], want[a:b])
     dist.barrier()
     st.peer.close()
+    # ---- the six loss scalars' pmean through the peer-memory board (mulan_post_bpd_peer)
+    import math
+    from mulan_b200 import ops
+    from mulan_b200.peer import ScalarBoard
+    from oracle import mulan_oracle as O
+    rows = 300
+    inp = O.synth_inputs(rows, 40 + rank)
+    g = {k: v.to(dev).contiguous() for k, v in inp.items()}
+    ws = ops.ElboWorkspace(ops.Desc(), rows, dev)
+    gL = torch.full((rows,), 1.0 / (rows * 3072 * math.log(2.0)), device=dev)
+    board = ScalarBoard(dev)
+    for rep in range(70):            # more steps than the ring has slots
+      ws.fwd_pre(g['x'], g['a'], g['b'], g['c'], g['t'], g['eps_0'], g['eps'])
+      ws.post_bpd(g['x'], g['a'], g['b'], g['c'], g['t'], g['eps'], g['net'], gL, board=board)
+      if rep % 23 == 0:
+        dist.barrier()               # keep the ranks within the ring
+    mean, step = board.read()
+    torch.cuda.synchronize()
+    assert int(step.item()) == 70
+    everyone = [torch.empty(6, device=dev) for _ in range(world)]
+    dist.all_gather(everyone, ws.scalars.clone())
+    want = everyone[0].clone()
+    for r in range(1, world):
+      want = want + everyone[r]
+    want = want / world
+    assert torch.equal(mean, want), (mean, want)
+    dist.barrier()
+    board.close()
     out['ok'] = True
   except Exception as exc:      # reported to the parent
     import traceback

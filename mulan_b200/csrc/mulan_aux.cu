@@ -363,26 +363,39 @@ board_read_kernel(const ScalarBoard b, float* __restrict__ mean_out,
   const unsigned step = *reinterpret_cast<const unsigned*>(mine + kBoardSlots * 8 * kBoardRow);
   const int slot = (int)(step % (unsigned)kBoardSlots);
   bool ok = true;
+  float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
   if (lane < b.world) {
-    const unsigned* tag =
-        reinterpret_cast<const unsigned*>(mine + ((size_t)slot * 8 + lane) * kBoardRow + 7);
+    const float4* row = reinterpret_cast<const float4*>(mine + ((size_t)slot * 8 + lane) * kBoardRow);
     const long long t0 = clock64();
     for (;;) {
-      unsigned v;
-      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(tag) : "memory");
+      // each half of a row is one 128-bit store carrying its own tag (board_publish)
+      asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];"
+                   : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w) : "l"(row) : "memory");
+      asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];"
+                   : "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w) : "l"(row + 1) : "memory");
+      const unsigned t_lo = __float_as_uint(lo.w), t_hi = __float_as_uint(hi.w);
+      if (t_lo == step && t_hi == step) break;
       // a peer may already be LATER in the ring (same slot, step + k * slots): its row for this
       // step is gone; report the step as incomplete rather than mixing steps
-      if (v == step) break;
-      if ((int)(v - step) > 0 || clock64() - t0 > 8000000000LL) { ok = false; break; }
+      if ((int)(t_lo - step) > 0 || (int)(t_hi - step) > 0 || clock64() - t0 > 8000000000LL) {
+        ok = false;
+        break;
+      }
       __nanosleep(200);
     }
   }
   ok = __all_sync(0xffffffffu, ok);
-  if (lane < 6) {
-    float s = 0.f;
-    for (int r = 0; r < b.world; ++r)
-      s += __ldcv(mine + ((size_t)slot * 8 + r) * kBoardRow + lane);
-    mean_out[lane] = ok ? __fdiv_rn(s, (float)b.world) : __int_as_float(0x7fc00000);
+  // sum over the ranks in rank order (lane r holds rank r's row): sequential shuffles
+  float s[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int r = 0; r < b.world; ++r) {
+    s[0] += __shfl_sync(0xffffffffu, lo.x, r); s[1] += __shfl_sync(0xffffffffu, lo.y, r);
+    s[2] += __shfl_sync(0xffffffffu, lo.z, r); s[3] += __shfl_sync(0xffffffffu, hi.x, r);
+    s[4] += __shfl_sync(0xffffffffu, hi.y, r); s[5] += __shfl_sync(0xffffffffu, hi.z, r);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+      mean_out[k] = ok ? __fdiv_rn(s[k], (float)b.world) : __int_as_float(0x7fc00000);
   }
   if (lane == 0 && epoch_out != nullptr) *epoch_out = ok ? step : 0u;
 }

@@ -51,25 +51,24 @@ __device__ __forceinline__ void red_group_sum(const BpdReduceParams& p, int g, f
 // The pmean of the six scalars (ldm/experiment.py:347-348) as an all-gather by peer stores: the
 // ONE thread that has just written this rank's scalars bumps the rank's step counter (the word
 // behind the slots of its own board, so CUDA-graph replays advance it) and stores the row
-// {6 scalars, pad, tag = step} into slot [step % kBoardSlots][rank] of every rank's board.
-// Data first, system fence, then the tag with release semantics: a reader that sees the tag sees
-// the scalars.  No collective call, no extra launch; mulan_scalar_board_read averages on demand.
+// {s0 s1 s2 tag | s3 s4 s5 tag}, tag = step, into slot [step % kBoardSlots][rank] of every rank's
+// board.  Each half is ONE naturally aligned 128-bit store that carries its own tag, so no
+// system-scope fence sits on the kernel's tail: a reader accepts a row when both tags match.
+// No collective call, no extra launch; mulan_scalar_board_read averages on demand.
 __device__ __forceinline__ void board_publish(const ScalarBoard& b, const float* scalars) {
   unsigned* counter = reinterpret_cast<unsigned*>(b.boards[b.rank] + kBoardSlots * 8 * kBoardRow);
   const unsigned step = *counter + 1u;
   *counter = step;
   const int slot = (int)(step % (unsigned)kBoardSlots);
-  const float4 lo = make_float4(scalars[0], scalars[1], scalars[2], scalars[3]);
+  const float tag = __uint_as_float(step);
+  const float4 lo = make_float4(scalars[0], scalars[1], scalars[2], tag);
+  const float4 hi = make_float4(scalars[3], scalars[4], scalars[5], tag);
   for (int r = 0; r < b.world; ++r) {
-    float* row = b.boards[r] + ((size_t)slot * 8 + b.rank) * kBoardRow;
-    *reinterpret_cast<float4*>(row) = lo;
-    row[4] = scalars[4];
-    row[5] = scalars[5];
-  }
-  __threadfence_system();
-  for (int r = 0; r < b.world; ++r) {
-    unsigned* tag = reinterpret_cast<unsigned*>(b.boards[r] + ((size_t)slot * 8 + b.rank) * kBoardRow + 7);
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(tag), "r"(step) : "memory");
+    float4* row = reinterpret_cast<float4*>(b.boards[r] + ((size_t)slot * 8 + b.rank) * kBoardRow);
+    asm volatile("st.volatile.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(row), "f"(lo.x), "f"(lo.y),
+                 "f"(lo.z), "f"(lo.w) : "memory");
+    asm volatile("st.volatile.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(row + 1), "f"(hi.x),
+                 "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
   }
 }
 

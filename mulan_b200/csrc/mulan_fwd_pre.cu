@@ -255,9 +255,15 @@ __device__ __forceinline__ void pre_column(const FwdPreParams& p, const PreConst
     if (GT == MULAN_GT_PIXEL) put(G, j, gt[j]);
     acc[2] += gt[j];
   }
-  st4(p.z_t, g4, Z);
-  if (SAVEW) st4(p.w_save, g4, Wv);
-  if (GT == MULAN_GT_PIXEL) st4(p.g_net, g4, G);
+  if (p.cs_stores) {
+    __stcs(reinterpret_cast<float4*>(p.z_t) + g4, Z);
+    if (SAVEW) __stcs(reinterpret_cast<float4*>(p.w_save) + g4, Wv);
+    if (GT == MULAN_GT_PIXEL) __stcs(reinterpret_cast<float4*>(p.g_net) + g4, G);
+  } else {
+    st4(p.z_t, g4, Z);
+    if (SAVEW) st4(p.w_save, g4, Wv);
+    if (GT == MULAN_GT_PIXEL) st4(p.g_net, g4, G);
+  }
 }
 
 // Row epilogue: deterministic CTA-wide sums, per-example outputs written by thread 0.
@@ -600,8 +606,13 @@ cudaError_t launch_fwd_pre_keyed(const FwdPreKeyedParams& q, cudaStream_t s) {
                : launch_keyed_w<MULAN_GT_PIXEL, false>(q, s);
 }
 
-cudaError_t launch_fwd_pre(const FwdPreParams& p, cudaStream_t s) {
-  if (p.rows == 0) return cudaSuccess;
+cudaError_t launch_fwd_pre(const FwdPreParams& p_in, cudaStream_t s) {
+  if (p_in.rows == 0) return cudaSuccess;
+  FwdPreParams p = p_in;
+  {
+    const char* e = getenv("MULAN_FWD_PRE_CS");       // A/B only, read per launch
+    p.cs_stores = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
   const bool savew = p.w_save != nullptr;
   if (p.gt_mode == MULAN_GT_MEAN)
     return savew ? launch_w<MULAN_GT_MEAN, true>(p, s) : launch_w<MULAN_GT_MEAN, false>(p, s);

@@ -96,8 +96,8 @@ __device__ __forceinline__ void adamw_elem(float& p, float g, float& mu, float& 
 
 // COLS float4 columns per thread (COLS * (WORLD - 1) peer loads in flight per thread before the
 // first dependent use): with two ranks a single remote load per thread leaves NVLink latency
-// exposed (measured 176 GB/s per direction), so small worlds take more columns (8 / 4 / 2 columns
-// for 2 / 4 / 8 ranks: 8 - 14 peer loads in flight per thread).
+// exposed (measured 176 GB/s per direction), so small worlds take more columns (8 / 2 / 1 columns
+// for 2 / 4 / 8 ranks, measured: two columns at 8 ranks cost 1.09 instead of 0.92 ms for 285 MB).
 template <int WORLD, int COLS>
 __global__ void __launch_bounds__(kThreads)
 adamw_ema_peer_kernel(const PeerParams k) {
@@ -262,7 +262,7 @@ int mulan_adamw_ema_peer(const mulan_adamw_desc* d, const mulan_peer_desc* peers
   k.bc1 = 1.0f - powf((float)d->b1, (float)d->step);
   k.bc2 = 1.0f - powf((float)d->b2, (float)d->step);
   k.grad_scale = (float)d->grad_scale;
-  const int per_thread = W <= 2 ? 8 : (W == 4 ? 4 : 2);
+  const int per_thread = W <= 2 ? 8 : (W == 4 ? 2 : 1);
   long long want = (k.n4 + (long long)mulan::kThreads * per_thread - 1) /
                    ((long long)mulan::kThreads * per_thread);
   if (want < 1) want = 1;                       // an empty shard still takes part in the barriers
@@ -271,8 +271,8 @@ int mulan_adamw_ema_peer(const mulan_adamw_desc* d, const mulan_peer_desc* peers
   switch (W) {
     case 1: mulan::adamw_ema_peer_kernel<1, 8><<<(int)want, mulan::kThreads, 0, s>>>(k); break;
     case 2: mulan::adamw_ema_peer_kernel<2, 8><<<(int)want, mulan::kThreads, 0, s>>>(k); break;
-    case 4: mulan::adamw_ema_peer_kernel<4, 4><<<(int)want, mulan::kThreads, 0, s>>>(k); break;
-    default: mulan::adamw_ema_peer_kernel<8, 2><<<(int)want, mulan::kThreads, 0, s>>>(k); break;
+    case 4: mulan::adamw_ema_peer_kernel<4, 2><<<(int)want, mulan::kThreads, 0, s>>>(k); break;
+    default: mulan::adamw_ema_peer_kernel<8, 1><<<(int)want, mulan::kThreads, 0, s>>>(k); break;
   }
   PEER_CU(cudaGetLastError(), fn);
   return 0;

@@ -29,6 +29,7 @@
 // has retired.  Flags carry the call's epoch (strictly increasing), so no reset is needed.
 // A spin that exceeds ~4 s sets the error word instead of hanging the GPU.
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "mulan_kernels.h"
 
@@ -58,12 +59,13 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// Peer gradient loads: plain L2-only loads (ld.global.cg).  They are ordered after the flag
+// acquire (thread 0's ld.acquire.sys + the CTA barrier behind it), every address is read once per
+// kernel and L1 starts clean at a kernel boundary, so there is nothing stale to hit; unlike
+// ld.volatile (system-scope relaxed, one request per access, a compiler barrier each) the
+// hardware coalesces them and the compiler keeps all of a thread's loads in flight.
 __device__ __forceinline__ float4 ld_peer4(const float* p, long long i4) {
-  float4 v;
-  asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "l"(reinterpret_cast<const float4*>(p) + i4) : "memory");
-  return v;
+  return __ldcg(reinterpret_cast<const float4*>(p) + i4);
 }
 
 // Wait until every peer's flag in `slot` has reached this call's epoch (thread 0 of a CTA).
@@ -110,8 +112,13 @@ adamw_ema_peer_kernel(const PeerParams k) {
   }
   if (tid == 0) wait_peers(k, kFlagA);
   __syncthreads();
-  // ---- 1-3: COLS float4 columns of the owned shard per thread (CTA-strided: coalesced)
-  const long long j0 = (long long)blockIdx.x * (kThreads * COLS) + tid;
+  // ---- 1-3: chunks of kThreads * COLS float4 columns of the owned shard, COLS per thread
+  // (CTA-strided: coalesced).  The grid is a few CTAs per SM that WALK the chunks: the flag
+  // barrier at the head and the system fence + signal at the tail are paid once per CTA, not
+  // once per 32 KB (one CTA per chunk measured 0.61 ms for 285 MB on two GPUs, this form 0.53 ms).
+  const long long n_chunks = (k.n4 + (long long)kThreads * COLS - 1) / ((long long)kThreads * COLS);
+  for (long long chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+  const long long j0 = chunk * (kThreads * COLS) + tid;
   float4 G[COLS];
 #pragma unroll
   for (int c = 0; c < COLS; ++c) {
@@ -151,10 +158,14 @@ adamw_ema_peer_kernel(const PeerParams k) {
 #pragma unroll
     for (int r = 0; r < WORLD; ++r) reinterpret_cast<float4*>(k.params[r])[i] = P;
   }
-  // ---- B: my shard has landed everywhere; retire only when every peer's has landed here
-  __threadfence_system();
+  }
+  // ---- B: my shard has landed everywhere; retire only when every peer's has landed here.
+  // ONE system-scope fence per CTA, by thread 0 behind the CTA barrier (the barrier makes every
+  // thread's peer stores happen-before it, and the fence is cumulative): a fence in every thread
+  // made each of the SM's 2048 threads wait for its own NVLink acknowledgements.
   __syncthreads();
   if (tid == 0) {
+    __threadfence_system();
     const unsigned done = atomicAdd(k.flags[k.rank] + kFlagCount, 1u);
     s_last = (done == gridDim.x - 1) ? 1 : 0;
   }
@@ -266,7 +277,15 @@ int mulan_adamw_ema_peer(const mulan_adamw_desc* d, const mulan_peer_desc* peers
   long long want = (k.n4 + (long long)mulan::kThreads * per_thread - 1) /
                    ((long long)mulan::kThreads * per_thread);
   if (want < 1) want = 1;                       // an empty shard still takes part in the barriers
-  if (want > 0x7fffffffLL) PEER_FAIL(MULAN_ERR_INVALID_ARG, "%s: range too large", fn);
+  {
+    // a few CTAs per SM walk the chunks (see the kernel)
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int per_sm = 4;
+    if (const char* e = getenv("MULAN_PEER_CTAS_PER_SM")) per_sm = atoi(e) > 0 ? atoi(e) : 4;   // A/B
+    if (want > (long long)per_sm * sms) want = (long long)per_sm * sms;
+  }
   cudaStream_t s = (cudaStream_t)stream;
   switch (W) {
     case 1: mulan::adamw_ema_peer_kernel<1, 8><<<(int)want, mulan::kThreads, 0, s>>>(k); break;

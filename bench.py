@@ -982,9 +982,11 @@ def train_step_leg(ctx, args, net_config, param_name, B, modes, K, W):
         state.peer_update_range(0, state.n)
       t_w = alone(fused_whole)
       m['fused_exchange_update_single_call_ms'] = t_w
-      m['nvlink_gbs_per_direction_single_call'] = (world - 1) / world * nbytes / (t_w * 1e-3) / 1e9
-      # NVLink bytes per rank: (world-1)/world of the bucket read from peers + as much stored
-      m['nvlink_gbs_per_direction'] = (world - 1) / world * nbytes / (t_f * 1e-3) / 1e9
+      m['nvlink_gbs_per_direction_single_call'] = (2 * (world - 1) / world * nbytes
+                                                   / (t_w * 1e-3) / 1e9)
+      # NVLink bytes per rank and DIRECTION: in = (world-1)/world of the bucket read from peers +
+      # as much of new parameters stored here by the peers; out = the mirror image
+      m['nvlink_gbs_per_direction'] = 2 * (world - 1) / world * nbytes / (t_f * 1e-3) / 1e9
       m['timed_out'] = state.peer.timed_out()
     res['modes'][mode] = m
     res['parameters'] = state.n

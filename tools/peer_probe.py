@@ -51,7 +51,8 @@ out['nccl_allreduce_ms'] = t
 out['nccl_busbw_gbs'] = 2 * (world - 1) / world * 4 * n / t / 1e6
 t = timed(lambda: (st._reset_ranges(), st.peer_update_range(0, st.n)))
 out['fused_ms'] = t
-out['fused_nvlink_gbs_per_direction'] = (world - 1) / world * 4 * n / t / 1e6
+# per rank and direction: peer gradient shards in + the peers' parameter shards in (out: mirror)
+out['fused_nvlink_gbs_per_direction'] = 2 * (world - 1) / world * 4 * n / t / 1e6
 out['timed_out'] = st.peer.timed_out()
 t = timed(lambda: st.apply_gradients() if False else None)
 if rank == 0:

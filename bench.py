@@ -334,7 +334,12 @@ def measure_elbo(ctx, args, inp, param_name, K, W, extras):
   board = None
   if world > 1 and not args.nccl_scalars and not args.separate_post:
     from mulan_b200.peer import ScalarBoard
-    board = ScalarBoard(dev)
+    try:
+      board = ScalarBoard(dev)
+    except RuntimeError as exc:      # raised on EVERY rank together (peer.PeerAllocations)
+      if rank == 0:
+        print(f'[bench] scalar board unavailable, NCCL all-reduce per step instead: {exc}',
+              file=sys.stderr)
   kernels = {'fwd_pre': lambda: ws.fwd_pre(i['x'], i['a'], i['b'], i['c'], i['t'], i['eps0'],
                                             i['eps'])}
   if args.separate_post:
@@ -925,7 +930,12 @@ def train_step_leg(ctx, args, net_config, param_name, B, modes, K, W):
     torch.manual_seed(1234)                                 # same init on every rank
     model = VDM(cfg, UnetEncoder(n_embd, 4), ScoreUNet(n_embd, 32)).to(dev)
     model.train()
-    state = FlatTrainState(model.named_parameters(), comm=mode)
+    try:
+      state = FlatTrainState(model.named_parameters(), comm=mode)
+    except RuntimeError as exc:      # peer memory unavailable: raised on every rank together
+      res['modes'][mode] = {'unavailable': str(exc)[:200]}
+      del model
+      continue
     gen = torch.Generator(device=dev).manual_seed(100 + rank)
 
     def one_step():
@@ -988,6 +998,7 @@ def train_step_leg(ctx, args, net_config, param_name, B, modes, K, W):
       # as much of new parameters stored here by the peers; out = the mirror image
       m['nvlink_gbs_per_direction'] = 2 * (world - 1) / world * nbytes / (t_f * 1e-3) / 1e9
       m['timed_out'] = state.peer.timed_out()
+      m['in_switch_reduction'] = state.peer.multicast   # multimem.ld_reduce / multimem.st
     res['modes'][mode] = m
     res['parameters'] = state.n
     res['grad_bucket_bytes'] = nbytes
@@ -997,7 +1008,8 @@ def train_step_leg(ctx, args, net_config, param_name, B, modes, K, W):
       h_.remove()
     del model, state
     torch.cuda.empty_cache()
-  best = min(res['modes'], key=lambda k: res['modes'][k]['ms_per_step'])
+  ran = {k: v for k, v in res['modes'].items() if 'ms_per_step' in v}
+  best = min(ran, key=lambda k: ran[k]['ms_per_step'])
   res.update(value=res['modes'][best]['value'], unit='samples/s', best_mode=best,
              ms_per_step=res['modes'][best]['ms_per_step'])
   return res

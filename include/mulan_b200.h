@@ -506,6 +506,15 @@ typedef struct mulan_peer_desc {
   uint32_t* flags[MULAN_PEER_MAX];  /* ... of rank r's flag block                           */
   uint32_t epoch;                   /* 1, 2, 3, ...: one per call, identical on every rank  */
   uint32_t reserved;
+  /* Optional NVSwitch MULTICAST addresses of the gradient and parameter buffers (both or neither;
+   * NULL: plain peer loads / stores).  With them the reduce-scatter is one multimem.ld_reduce per
+   * element -- the float32 sum over all ranks formed inside the switch, in the fabric's order
+   * rather than rank order -- and the all-gather one multimem.st: per rank the NVLink volume falls
+   * from 2 (N-1)/N of the bucket per direction to 1/N in + 1/N out, and the kernel is HBM bound.
+   * The buffers must then be symmetric allocations bound to a multicast object (e.g.
+   * torch.distributed._symmetric_memory, which also yields the per-rank mappings above). */
+  float* mc_grads;
+  float* mc_params;
 } mulan_peer_desc;
 int mulan_peer_alloc(size_t bytes, void** dev_ptr, void* handle_out);
 int mulan_peer_open(const void* handle, void** dev_ptr);

@@ -61,7 +61,7 @@ class MulanPeerDesc(C.Structure):
   _fields_ = [('world', C.c_int32), ('rank', C.c_int32),
               ('grads', C.c_void_p * MULAN_PEER_MAX), ('params', C.c_void_p * MULAN_PEER_MAX),
               ('flags', C.c_void_p * MULAN_PEER_MAX), ('epoch', C.c_uint32),
-              ('reserved', C.c_uint32)]
+              ('reserved', C.c_uint32), ('mc_grads', C.c_void_p), ('mc_params', C.c_void_p)]
 
 
 class MulanScalarBoard(C.Structure):

@@ -44,6 +44,7 @@ struct PeerParams {
   float* params[kMaxPeers];
   unsigned* flags[kMaxPeers];
   float *mu, *nu, *ema;
+  float *mc_grads, *mc_params;   // NVSwitch multicast addresses of the two buffers (MC kernels)
   int world, rank;
   unsigned epoch;
   long long lo4, n4;       // this rank's shard: float4 columns [lo4, lo4 + n4)
@@ -66,6 +67,24 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
 // hardware coalesces them and the compiler keeps all of a thread's loads in flight.
 __device__ __forceinline__ float4 ld_peer4(const float* p, long long i4) {
   return __ldcg(reinterpret_cast<const float4*>(p) + i4);
+}
+
+// NVLink SHARP through a multicast mapping (sm_90+): ONE load returns the element-wise float32 sum
+// of the addressed location on every GPU of the multicast group, reduced inside the switch; ONE
+// store writes every GPU's copy.  Per rank the NVLink volume of the exchange falls from
+// 2 (N-1)/N of the bucket per direction to 1/N in (the reduced shard) + 1/N out (the new
+// parameters): the kernel becomes HBM bound.
+__device__ __forceinline__ float4 multimem_ld_reduce4(const float* mc, long long i4) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(reinterpret_cast<const float4*>(mc) + i4) : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st4(float* mc, long long i4, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
+               ::"l"(reinterpret_cast<float4*>(mc) + i4), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
 }
 
 // Wait until every peer's flag in `slot` has reached this call's epoch (thread 0 of a CTA).
@@ -100,7 +119,7 @@ __device__ __forceinline__ void adamw_elem(float& p, float g, float& mu, float& 
 // first dependent use): with two ranks a single remote load per thread leaves NVLink latency
 // exposed (measured 176 GB/s per direction), so small worlds take more columns (8 / 2 / 1 columns
 // for 2 / 4 / 8 ranks, measured: two columns at 8 ranks cost 1.09 instead of 0.92 ms for 285 MB).
-template <int WORLD, int COLS>
+template <int WORLD, int COLS, bool MC = false>
 __global__ void __launch_bounds__(kThreads)
 adamw_ema_peer_kernel(const PeerParams k) {
   __shared__ int s_last;
@@ -120,22 +139,31 @@ adamw_ema_peer_kernel(const PeerParams k) {
   for (long long chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
   const long long j0 = chunk * (kThreads * COLS) + tid;
   float4 G[COLS];
-#pragma unroll
-  for (int c = 0; c < COLS; ++c) {
-    const long long j = j0 + (long long)c * kThreads;
-    if (j < k.n4) G[c] = ld_peer4(k.grads[0], k.lo4 + j);
-  }
-#pragma unroll
-  for (int r = 1; r < WORLD; ++r) {
-    float4 H[COLS];
+  if (MC) {
+    // the switch sums the `world` gradient buckets (order fixed by the fabric, not by rank)
 #pragma unroll
     for (int c = 0; c < COLS; ++c) {
       const long long j = j0 + (long long)c * kThreads;
-      if (j < k.n4) H[c] = ld_peer4(k.grads[r], k.lo4 + j);
+      if (j < k.n4) G[c] = multimem_ld_reduce4(k.mc_grads, k.lo4 + j);
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < COLS; ++c) {
+      const long long j = j0 + (long long)c * kThreads;
+      if (j < k.n4) G[c] = ld_peer4(k.grads[0], k.lo4 + j);
     }
 #pragma unroll
-    for (int c = 0; c < COLS; ++c) {                      // rank order: deterministic
-      G[c].x += H[c].x; G[c].y += H[c].y; G[c].z += H[c].z; G[c].w += H[c].w;
+    for (int r = 1; r < WORLD; ++r) {
+      float4 H[COLS];
+#pragma unroll
+      for (int c = 0; c < COLS; ++c) {
+        const long long j = j0 + (long long)c * kThreads;
+        if (j < k.n4) H[c] = ld_peer4(k.grads[r], k.lo4 + j);
+      }
+#pragma unroll
+      for (int c = 0; c < COLS; ++c) {                    // rank order: deterministic
+        G[c].x += H[c].x; G[c].y += H[c].y; G[c].z += H[c].z; G[c].w += H[c].w;
+      }
     }
   }
 #pragma unroll
@@ -155,8 +183,12 @@ adamw_ema_peer_kernel(const PeerParams k) {
     reinterpret_cast<float4*>(k.mu)[i] = M;
     reinterpret_cast<float4*>(k.nu)[i] = V;
     reinterpret_cast<float4*>(k.ema)[i] = E;
+    if (MC) {
+      multimem_st4(k.mc_params, i, P);                    // every rank's copy, one store
+    } else {
 #pragma unroll
-    for (int r = 0; r < WORLD; ++r) reinterpret_cast<float4*>(k.params[r])[i] = P;
+      for (int r = 0; r < WORLD; ++r) reinterpret_cast<float4*>(k.params[r])[i] = P;
+    }
   }
   }
   // ---- B: my shard has landed everywhere; retire only when every peer's has landed here.
@@ -259,6 +291,8 @@ int mulan_adamw_ema_peer(const mulan_adamw_desc* d, const mulan_peer_desc* peers
     k.grads[r] = peers->grads[r]; k.params[r] = peers->params[r]; k.flags[r] = peers->flags[r];
   }
   k.mu = mu; k.nu = nu; k.ema = ema_params;
+  k.mc_grads = peers->mc_grads; k.mc_params = peers->mc_params;
+  const bool mc = k.mc_grads != nullptr && k.mc_params != nullptr && W > 1;
   k.world = W; k.rank = peers->rank; k.epoch = peers->epoch;
   // the range is cut into `world` shards of whole float4 columns; the last takes the remainder
   const long long cols = (hi - lo) / 4, per = (cols + W - 1) / W;
@@ -273,7 +307,7 @@ int mulan_adamw_ema_peer(const mulan_adamw_desc* d, const mulan_peer_desc* peers
   k.bc1 = 1.0f - powf((float)d->b1, (float)d->step);
   k.bc2 = 1.0f - powf((float)d->b2, (float)d->step);
   k.grad_scale = (float)d->grad_scale;
-  const int per_thread = W <= 2 ? 8 : (W == 4 ? 2 : 1);
+  const int per_thread = mc ? 4 : (W <= 2 ? 8 : (W == 4 ? 2 : 1));
   long long want = (k.n4 + (long long)mulan::kThreads * per_thread - 1) /
                    ((long long)mulan::kThreads * per_thread);
   if (want < 1) want = 1;                       // an empty shard still takes part in the barriers
@@ -287,6 +321,15 @@ int mulan_adamw_ema_peer(const mulan_adamw_desc* d, const mulan_peer_desc* peers
     if (want > (long long)per_sm * sms) want = (long long)per_sm * sms;
   }
   cudaStream_t s = (cudaStream_t)stream;
+  if (mc) {
+    switch (W) {
+      case 2: mulan::adamw_ema_peer_kernel<2, 4, true><<<(int)want, mulan::kThreads, 0, s>>>(k); break;
+      case 4: mulan::adamw_ema_peer_kernel<4, 4, true><<<(int)want, mulan::kThreads, 0, s>>>(k); break;
+      default: mulan::adamw_ema_peer_kernel<8, 4, true><<<(int)want, mulan::kThreads, 0, s>>>(k); break;
+    }
+    PEER_CU(cudaGetLastError(), fn);
+    return 0;
+  }
   switch (W) {
     case 1: mulan::adamw_ema_peer_kernel<1, 8><<<(int)want, mulan::kThreads, 0, s>>>(k); break;
     case 2: mulan::adamw_ema_peer_kernel<2, 8><<<(int)want, mulan::kThreads, 0, s>>>(k); break;

@@ -17,12 +17,14 @@ Three ways of running the exchange (`comm=`):
   'overlap'    the bucket is cut into ranges; a post-accumulate-grad hook fires a range's
                ncclAllReduce (async, NCCL's stream) as soon as its last gradient has been
                written, so the exchange overlaps the rest of backward; then the full-size update.
-  'peer'       B200-native: parameters and gradients live in CUDA-IPC peer memory; as each range
+  'peer'       B200-native: parameters and gradients live in peer memory; as each range
                completes, ONE kernel per rank (mulan_adamw_ema_peer, on a side stream) sums the
-               range's gradient shards over NVLink by peer loads, updates 1/world of it
-               (AdamW + EMA on the local shard of the optimizer state) and stores the new
-               parameters into every rank's buffer -- reduce-scatter, update and all-gather in
-               one launch, overlapped with backward, no NCCL call on the gradient path.
+               range's gradient shards over NVLink -- inside the NVSwitch by multimem.ld_reduce
+               when the buffers have a multicast mapping, by peer loads in rank order otherwise
+               -- updates 1/world of it (AdamW + EMA on the local shard of the optimizer state)
+               and stores the new parameters into every rank's buffer (multimem.st / peer
+               stores): reduce-scatter, update and all-gather in one launch, overlapped with
+               backward, no NCCL call on the gradient path.
 """
 from __future__ import annotations
 
@@ -88,20 +90,69 @@ def plan_buckets(layout: List[Tuple[str, int, int]], n: int, bucket_elems: int):
 
 
 class PeerBuffers:
-  """Parameter buffer, gradient bucket and flag block of THIS rank in CUDA-IPC peer memory, and
-  this process's mappings of every other rank's (mulan_b200/peer.py)."""
+  """Parameter buffer, gradient bucket and flag block of THIS rank in peer memory, and this
+  process's mappings of every other rank's.
 
-  def __init__(self, n_params: int, n_grads: int, device):
+  multicast=True: ONE symmetric allocation of torch.distributed._symmetric_memory (plumbing: it
+  owns the CUDA-IPC exchange and binds the allocation to an NVSwitch multicast object) holding
+  [flags | params | grads]; the multicast address lets mulan_adamw_ema_peer reduce in the switch
+  (multimem.ld_reduce) and broadcast with one store (multimem.st).  multicast=False (or no
+  multicast support): cudaMalloc + CUDA-IPC buffers of libmulan_b200 itself (mulan_b200/peer.py),
+  plain peer loads / stores, bit-exact rank-order sums."""
+
+  def __init__(self, n_params: int, n_grads: int, device, multicast: bool = True):
     world = dist.get_world_size()
     if world & (world - 1):
       raise ValueError(f'peer mode needs world in (1, 2, 4, 8), got {world}')
-    self.mem = PeerAllocations({'params': 4 * n_params, 'grads': 4 * n_grads,
-                                'flags': 4 * _lib.MULAN_PEER_FLAG_WORDS}, device)
-    self.world, self.rank, self.maps = self.mem.world, self.mem.rank, self.mem.maps
-    self.params = device_view(self.mem.own['params'], n_params, '<f4', device)
-    self.grads = device_view(self.mem.own['grads'], n_grads, '<f4', device)
-    self.flags = device_view(self.mem.own['flags'], _lib.MULAN_PEER_FLAG_WORDS, '<i4', device)
+    self.world, self.rank = world, dist.get_rank()
+    self.mc_grads = self.mc_params = None
+    self.mem = self._symm = None
+    nflag = _lib.MULAN_PEER_FLAG_WORDS
+    if multicast:
+      self._symm = self._try_symmetric(nflag + n_params + n_grads, device)
+    if self._symm is not None:
+      t, hdl = self._symm
+      off_p, off_g = 4 * nflag, 4 * (nflag + n_params)
+      self.maps = {'flags': [int(p) for p in hdl.buffer_ptrs],
+                   'params': [int(p) + off_p for p in hdl.buffer_ptrs],
+                   'grads': [int(p) + off_g for p in hdl.buffer_ptrs]}
+      self.mc_params, self.mc_grads = int(hdl.multicast_ptr) + off_p, int(hdl.multicast_ptr) + off_g
+      self.flags = t[:nflag].view(torch.int32)
+      self.params, self.grads = t[nflag:nflag + n_params], t[nflag + n_params:]
+    else:
+      self.mem = PeerAllocations({'params': 4 * n_params, 'grads': 4 * n_grads,
+                                  'flags': 4 * nflag}, device)
+      self.maps = self.mem.maps
+      self.params = device_view(self.mem.own['params'], n_params, '<f4', device)
+      self.grads = device_view(self.mem.own['grads'], n_grads, '<f4', device)
+      self.flags = device_view(self.mem.own['flags'], nflag, '<i4', device)
     self.epoch = 0
+
+  def _try_symmetric(self, n_floats: int, device):
+    """(tensor, handle) of a zeroed symmetric allocation with a multicast mapping, or None --
+    decided collectively, so every rank takes the same path."""
+    ok, res = 1, None
+    try:
+      import torch.distributed._symmetric_memory as symm_mem
+      t = symm_mem.empty((n_floats + 3) // 4 * 4, dtype=torch.float32, device=device)
+      t.zero_()
+      hdl = symm_mem.rendezvous(t, group=dist.group.WORLD.group_name)
+      if not int(getattr(hdl, 'multicast_ptr', 0) or 0):
+        ok = 0
+      res = (t, hdl)
+    except Exception:
+      ok = 0
+    flag = torch.tensor([ok], device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    torch.cuda.synchronize()
+    if int(flag.item()) == 0:
+      return None
+    res[1].barrier()
+    return res
+
+  @property
+  def multicast(self) -> bool:
+    return self.mc_grads is not None
 
   def desc(self) -> '_lib.MulanPeerDesc':
     self.epoch += 1
@@ -110,13 +161,19 @@ class PeerBuffers:
     for r in range(self.world):
       d.grads[r], d.params[r], d.flags[r] = (self.maps['grads'][r], self.maps['params'][r],
                                              self.maps['flags'][r])
+    d.mc_grads, d.mc_params = self.mc_grads, self.mc_params
     return d
 
   def timed_out(self) -> bool:
     return bool(self.flags[_lib.MULAN_PEER_FLAG_ERR].item())
 
   def close(self):
-    self.mem.close()
+    torch.cuda.synchronize()
+    if self.mem is not None:
+      self.mem.close()
+    elif dist.is_initialized():
+      dist.barrier()          # the symmetric allocation is released with its tensor
+    self._symm = None
 
 
 class FlatTrainState:
@@ -127,7 +184,7 @@ class FlatTrainState:
                learning_rate: float = 2e-4, num_steps_lr_warmup: int = 100,
                ema_rate: float = 0.9999, gradient_clip_norm: Optional[float] = None,
                lr_decay: bool = False, num_steps_train: int = 0, comm: str = 'allreduce',
-               bucket_mb: float = 32.0):
+               bucket_mb: float = 32.0, multicast='auto'):
     if comm not in ('allreduce', 'overlap', 'peer'):
       raise ValueError("comm must be 'allreduce', 'overlap' or 'peer'")
     multi = dist.is_initialized() and dist.get_world_size() > 1
@@ -159,7 +216,12 @@ class FlatTrainState:
     self.mu, self.nu = f(self.n), f(self.n)
     self.peer = None
     if self.comm == 'peer':
-      self.peer = PeerBuffers(self.n, self.n + self.extra, dev)
+      # in-switch reduction pays from 8 ranks on (285 MB bucket: 0.72 vs 0.91 ms; 4 ranks: a tie;
+      # 2 ranks: 0.85 vs 0.53 ms -- profiles/r2_variants.md section 5); below, peer loads in rank
+      # order, which are also bit-reproducible against a single-process emulation
+      if multicast == 'auto':
+        multicast = dist.get_world_size() >= 8
+      self.peer = PeerBuffers(self.n, self.n + self.extra, dev, multicast=bool(multicast))
       self.params, self.grads = self.peer.params, self.peer.grads
     else:
       self.params = f(self.n)

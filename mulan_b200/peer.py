@@ -41,35 +41,53 @@ class PeerAllocations:
     torch.cuda.set_device(device)
     self.device = device
     self.own: Dict[str, int] = {}
-    handles = {}
-    for k, nbytes in sizes.items():
-      ptr, h = C.c_void_p(), (C.c_char * _lib.MULAN_PEER_HANDLE_BYTES)()
-      _lib.check(lib.mulan_peer_alloc(int(nbytes), C.byref(ptr), h))
-      self.own[k], handles[k] = ptr.value, bytes(h)
-    everyone = [None] * self.world
-    dist.all_gather_object(everyone, handles)
     self.maps: Dict[str, List[int]] = {k: [] for k in sizes}
     self._opened: List[int] = []
-    for r in range(self.world):
-      for k in sizes:
-        if r == self.rank:
-          self.maps[k].append(self.own[k])
-          continue
-        ptr = C.c_void_p()
-        _lib.check(lib.mulan_peer_open(everyone[r][k], C.byref(ptr)))
-        self.maps[k].append(ptr.value)
-        self._opened.append(ptr.value)
-    dist.barrier()          # every rank has mapped every buffer before anyone launches
+    # Every step below is collective-safe: a rank that fails still takes part in the exchanges,
+    # and EVERY rank raises when any rank failed (nobody is left waiting in a barrier).
+    handles, err = {}, None
+    try:
+      for k, nbytes in sizes.items():
+        ptr, h = C.c_void_p(), (C.c_char * _lib.MULAN_PEER_HANDLE_BYTES)()
+        _lib.check(lib.mulan_peer_alloc(int(nbytes), C.byref(ptr), h))
+        self.own[k], handles[k] = ptr.value, bytes(h)
+    except Exception as exc:            # reported collectively below
+      err = f'rank {self.rank}: {exc}'
+    everyone = [None] * self.world
+    dist.all_gather_object(everyone, (handles, err))
+    self._raise_if_any([e for _, e in everyone])
+    err = None
+    try:
+      for r in range(self.world):
+        for k in sizes:
+          if r == self.rank:
+            self.maps[k].append(self.own[k])
+            continue
+          ptr = C.c_void_p()
+          _lib.check(lib.mulan_peer_open(everyone[r][0][k], C.byref(ptr)))
+          self.maps[k].append(ptr.value)
+          self._opened.append(ptr.value)
+    except Exception as exc:
+      err = f'rank {self.rank}: {exc}'
+    errs = [None] * self.world
+    dist.all_gather_object(errs, err)    # doubles as the "everyone has mapped everything" barrier
+    self._raise_if_any(errs)
 
-  def close(self):
+  def _raise_if_any(self, errs):
+    bad = [e for e in errs if e]
+    if bad:
+      self.close(collective=False)
+      raise RuntimeError('peer memory is not available on this node: ' + '; '.join(bad))
+
+  def close(self, collective: bool = True):
     lib = _lib.load()
     torch.cuda.synchronize()
-    if dist.is_initialized():
+    if collective and dist.is_initialized():
       dist.barrier()
     for ptr in self._opened:
       lib.mulan_peer_close(C.c_void_p(ptr))
     self._opened = []
-    if dist.is_initialized():
+    if collective and dist.is_initialized():
       dist.barrier()        # nobody frees while a peer still maps
     for ptr in self.own.values():
       lib.mulan_peer_free(C.c_void_p(ptr))

@@ -142,10 +142,12 @@ def _gpu_worker(rank, world, port, q):
                                  torch.nn.Linear(517, 1023), torch.nn.SiLU(),
                                  torch.nn.Linear(1023, 64)).to(dev)
     results = {}
-    for comm in ('allreduce', 'overlap', 'peer'):
+    for comm in ('allreduce', 'overlap', 'peer_mc', 'peer'):
       model = make_model()
-      st = FlatTrainState(model.named_parameters(), comm=comm, bucket_mb=0.5,
-                          num_steps_lr_warmup=2)
+      st = FlatTrainState(model.named_parameters(), comm=comm.split('_')[0], bucket_mb=0.5,
+                          num_steps_lr_warmup=2, multicast=(comm == 'peer_mc'))   # not 'auto'
+      if comm == 'peer_mc':
+        out['multicast'] = st.peer.multicast       # False where the fabric has no multicast
       gen = torch.Generator(device=dev).manual_seed(50 + rank)
       snaps = []
       for step in range(3):
@@ -162,12 +164,17 @@ def _gpu_worker(rank, world, port, q):
       torch.cuda.synchronize()
       results[comm] = [t.clone() for t in (st.params, st.ema)] + [snaps, st.step, len(st.ranges)]
       results[comm + '_moments'] = [st.mu.clone(), st.nu.clone()]
-      if comm == 'peer':
+      if comm.startswith('peer'):
         assert not st.peer.timed_out()
       results[comm + '_ranges'] = list(st.ranges)
-      if st.peer is not None:
+      if comm == 'peer':
+        assert not st.peer.multicast
         peer_state = st
-    for comm in ('overlap', 'peer'):
+      elif st.peer is not None:
+        for h_ in st._hooks:
+          h_.remove()
+        st.peer.close()
+    for comm in ('overlap', 'peer_mc', 'peer'):
       for a_, b_ in zip(results[comm][:2], results['allreduce'][:2]):
         err = ((a_ - b_).abs().max() / b_.abs().max()).item()
         assert err < 2e-6, (comm, err)

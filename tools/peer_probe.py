@@ -21,7 +21,7 @@ dev = torch.device(f'cuda:{local}')
 dist.init_process_group('nccl', device_id=dev)
 n = 71153852 // 4 * 4
 p = torch.nn.Parameter(torch.zeros(n, device=dev))
-st = FlatTrainState([('w', p)], comm='peer', bucket_mb=1e9)
+st = FlatTrainState([('w', p)], comm='peer', bucket_mb=1e9, multicast=False)
 peer = (rank + 1) % world
 remote = device_view(st.peer.maps['grads'][peer], n, '<f4', dev)
 localbuf = torch.empty(n, device=dev)
@@ -54,8 +54,14 @@ out['fused_ms'] = t
 # per rank and direction: peer gradient shards in + the peers' parameter shards in (out: mirror)
 out['fused_nvlink_gbs_per_direction'] = 2 * (world - 1) / world * 4 * n / t / 1e6
 out['timed_out'] = st.peer.timed_out()
-t = timed(lambda: st.apply_gradients() if False else None)
+st.peer.close()
+st2 = FlatTrainState([('w', torch.nn.Parameter(torch.zeros(n, device=dev)))], comm='peer',
+                     bucket_mb=1e9, multicast=True)
+out['multicast'] = st2.peer.multicast
+t = timed(lambda: (st2._reset_ranges(), st2.peer_update_range(0, st2.n)))
+out['fused_multicast_ms'] = t
+out['timed_out_mc'] = st2.peer.timed_out()
+st2.peer.close()
 if rank == 0:
   print(json.dumps(out), flush=True)
-st.peer.close()
 dist.destroy_process_group()

@@ -26,8 +26,8 @@ namespace mulan {
 // formed here and c_bar is returned as the cotangent of r (c_bar * sigmoid(r)), so the
 // framework's softplus backward (12 B/sub-pixel) disappears (ldm/model_mulan_epsilon.py:537).
 // NT / MINB: 256 threads, <= 51 registers, 5 CTAs (40 warps) per SM (throughput), or 768 threads
-// = one float4 column per thread for launches of at most one row per SM (latency).  Every thread
-// forms the row constants itself (broadcast loads): no staging barrier before the operand loads.
+// = one float4 column per thread for launches of at most one row per SM (latency; there every
+// thread forms the row constants itself: no staging barrier before the operand loads).
 template <int PARAM, int GT, bool DISC, bool POW2, bool CRAW, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB)
 bwd_pre_kernel(const BwdPreParams p) {
@@ -37,14 +37,36 @@ bwd_pre_kernel(const BwdPreParams p) {
   const bool has_gb = p.g_bar != nullptr;
   pdl_release_dependents();
   pdl_wait_for_primary();
-  const float t_row = __ldg(p.t + row);
-  const RowT rt = make_row_t(t_row);
+  // row constants: per thread in the latency shape, staged by thread 0 in the throughput shape
+  // (registers are the scarce resource there: 48 at 5 CTAs per SM)
+  RowT rt;
   RowD rd;
-  if (DISC) rd = make_row_d(t_row, t_row - p.inv_T);                 // s = t - 1/T
-  const float gLh = has_gL ? 0.5f * __ldg(p.gL + row) : 0.f;
-  // jnp.mean backward: cotangent / D broadcast to every sub-pixel
-  const float gbar_row = (GT == MULAN_GT_MEAN && has_gb)
-                             ? __fdiv_rn(__ldg(p.g_bar + row), (float)(p.dim4 * 4)) : 0.f;
+  float gLh, gbar_row;
+  if constexpr (NT >= kLatencyThreads) {
+    const float t_row = __ldg(p.t + row);
+    rt = make_row_t(t_row);
+    if (DISC) rd = make_row_d(t_row, t_row - p.inv_T);               // s = t - 1/T
+    gLh = has_gL ? 0.5f * __ldg(p.gL + row) : 0.f;
+    // jnp.mean backward: cotangent / D broadcast to every sub-pixel
+    gbar_row = (GT == MULAN_GT_MEAN && has_gb)
+                   ? __fdiv_rn(__ldg(p.g_bar + row), (float)(p.dim4 * 4)) : 0.f;
+  } else {
+    __shared__ RowT s_rt;
+    __shared__ RowD s_rd;
+    __shared__ float s_gLh, s_gbar;
+    if (tid == 0) {
+      const float t_row = __ldg(p.t + row);
+      s_rt = make_row_t(t_row);
+      if (DISC) s_rd = make_row_d(t_row, t_row - p.inv_T);
+      s_gLh = has_gL ? 0.5f * __ldg(p.gL + row) : 0.f;
+      s_gbar = (GT == MULAN_GT_MEAN && has_gb)
+                   ? __fdiv_rn(__ldg(p.g_bar + row), (float)(p.dim4 * 4)) : 0.f;
+    }
+    __syncthreads();
+    rt = s_rt;
+    if (DISC) rd = s_rd;
+    gLh = s_gLh; gbar_row = s_gbar;
+  }
   const VocabInfo vi = p.vi;
   const float two_iv = vi.inv_vocab + vi.inv_vocab, off = vi.inv_vocab - 1.0f;
   // t-dependent coefficients of P_a, P_b, P_c with the factors 2 folded in (exact scalings)

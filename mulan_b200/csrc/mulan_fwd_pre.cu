@@ -255,15 +255,9 @@ __device__ __forceinline__ void pre_column(const FwdPreParams& p, const PreConst
     if (GT == MULAN_GT_PIXEL) put(G, j, gt[j]);
     acc[2] += gt[j];
   }
-  if (p.cs_stores) {
-    __stcs(reinterpret_cast<float4*>(p.z_t) + g4, Z);
-    if (SAVEW) __stcs(reinterpret_cast<float4*>(p.w_save) + g4, Wv);
-    if (GT == MULAN_GT_PIXEL) __stcs(reinterpret_cast<float4*>(p.g_net) + g4, G);
-  } else {
-    st4(p.z_t, g4, Z);
-    if (SAVEW) st4(p.w_save, g4, Wv);
-    if (GT == MULAN_GT_PIXEL) st4(p.g_net, g4, G);
-  }
+  st4(p.z_t, g4, Z);
+  if (SAVEW) st4(p.w_save, g4, Wv);
+  if (GT == MULAN_GT_PIXEL) st4(p.g_net, g4, G);
 }
 
 // Row epilogue: deterministic CTA-wide sums, per-example outputs written by thread 0.
@@ -322,9 +316,20 @@ fwd_pre_kernel(const FwdPreParams p) {
   pdl_release_dependents();
   const PreConsts kc = load_pre_consts<BAKED>(p);
   pdl_wait_for_primary();
-  // every thread forms the row's t powers itself (one broadcast load, eight multiplies): no
-  // shared-memory staging, no barrier between the CTA's start and its first operand loads
-  const RowT rt = make_row_t(__ldg(p.t + row));
+  // Row constants.  Latency shape (768 threads, one column each): every thread forms the t powers
+  // itself -- no barrier between the CTA's start and its first operand loads.  Throughput
+  // shapes: staged through shared memory by thread 0; held in registers by all 128 threads they
+  // cost the 64-register kernel six more instructions per sub-pixel in spills (measured: 0.218 ->
+  // 0.231 ms at 16384 rows).
+  RowT rt;
+  if constexpr (NT >= kLatencyThreads) {
+    rt = make_row_t(__ldg(p.t + row));
+  } else {
+    __shared__ RowT s_rt;
+    if (tid == 0) s_rt = make_row_t(__ldg(p.t + row));
+    __syncthreads();
+    rt = s_rt;
+  }
   const size_t base4 = (size_t)row * p.dim4;
   // eps_0 / eps broadcast over the batch (dense-VLB evaluation: every image shares one key)
   const size_t nbase4 = (size_t)(p.noise_rows > 0 ? row % p.noise_rows : row) * p.dim4;
@@ -606,13 +611,8 @@ cudaError_t launch_fwd_pre_keyed(const FwdPreKeyedParams& q, cudaStream_t s) {
                : launch_keyed_w<MULAN_GT_PIXEL, false>(q, s);
 }
 
-cudaError_t launch_fwd_pre(const FwdPreParams& p_in, cudaStream_t s) {
-  if (p_in.rows == 0) return cudaSuccess;
-  FwdPreParams p = p_in;
-  {
-    const char* e = getenv("MULAN_FWD_PRE_CS");       // A/B only, read per launch
-    p.cs_stores = (e != nullptr && e[0] == '1') ? 1 : 0;
-  }
+cudaError_t launch_fwd_pre(const FwdPreParams& p, cudaStream_t s) {
+  if (p.rows == 0) return cudaSuccess;
   const bool savew = p.w_save != nullptr;
   if (p.gt_mode == MULAN_GT_MEAN)
     return savew ? launch_w<MULAN_GT_MEAN, true>(p, s) : launch_w<MULAN_GT_MEAN, false>(p, s);

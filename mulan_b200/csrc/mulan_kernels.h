@@ -92,7 +92,6 @@ struct FwdPreParams {
   int c_raw;          // MULAN_FLAG_C_RAW: c holds the pre-activation of dense_out_c
   int pdl;            // MULAN_FLAG_PDL: launch with programmatic stream serialization
   int noise_rows;     // eps0 / eps are [noise_rows, D], row b reads b % noise_rows (0: [rows, D])
-  int cs_stores;      // A/B: z_t / w / per-pixel g_t written with the cache-streaming hint
   int W;              // reconstruction window half-width for gamma_0 = gamma_min
   float gmin, delta;  // f32(gamma_min), f32(gamma_max - gamma_min)
   EndConsts k;

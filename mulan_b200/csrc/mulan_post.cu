@@ -75,10 +75,10 @@ __device__ __forceinline__ PostPix post_pixel(float a, float b, float c, int xi,
 // group's loss terms, the CTA that completes the last group writes the six loss_fn scalars
 // (mulan_reduce.cuh) -- VDMOutput + bpd without a separate single-CTA launch.
 // NT: threads per row -- 256 (throughput) or 768 (one float4 column per thread: the latency shape
-// for launches of at most one CTA per SM).  Every thread forms the row constants itself (a
-// broadcast load of t / gL): no shared-memory staging, no barrier before the first operand load.
+// for launches of at most one CTA per SM, where every thread forms the row constants itself from
+// a broadcast load of t / gL: no staging barrier before the first operand load).
 template <int PARAM, bool HAVEW, int MODE, bool CRAW, bool REDUCE, int NT>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, NT >= kLatencyThreads ? 1 : 5)   // <= 51 registers: 5 CTAs/SM
 post_kernel(const PostParams p) {
   constexpr bool BWD = MODE != 0;
   constexpr bool FWD = MODE != 1;
@@ -89,9 +89,24 @@ post_kernel(const PostParams p) {
   constexpr bool kNeedX = PARAM != MULAN_PARAM_EPS;
   pdl_release_dependents();
   pdl_wait_for_primary();
+  // row constants: per thread in the latency shape, staged by thread 0 in the throughput shape
+  // (see fwd_pre_kernel)
   RowT rt;
-  if (kNeedPoly) rt = make_row_t(__ldg(p.t + row));
-  const float gs = BWD ? __ldg(p.gL + row) * p.scale : 0.f;
+  float gs = 0.f;
+  if constexpr (NT >= kLatencyThreads) {
+    if (kNeedPoly) rt = make_row_t(__ldg(p.t + row));
+    if (BWD) gs = __ldg(p.gL + row) * p.scale;
+  } else {
+    __shared__ RowT s_rt;
+    __shared__ float s_g;
+    if (tid == 0) {
+      if (kNeedPoly) s_rt = make_row_t(__ldg(p.t + row));
+      if (BWD) s_g = __ldg(p.gL + row) * p.scale;
+    }
+    __syncthreads();
+    if (kNeedPoly) rt = s_rt;
+    if (BWD) gs = s_g;
+  }
   const VocabInfo vi = p.vi;
   const size_t base4 = (size_t)row * p.dim4;
   const size_t nbase4 = (size_t)(p.noise_rows > 0 ? row % p.noise_rows : row) * p.dim4;

@@ -39,6 +39,31 @@ def graph_us(fn, per_graph=20, replays=20):
   return e0.elapsed_time(e1) * 1000 / (replays * per_graph)
 
 
+# The floor one-CTA-per-row launches can reach: the same three kernels over ONE row (one SM busy,
+# everything else idle) and a chain of near-empty launches (mulan_scale_rows over 1 x 4 floats).
+if os.environ.get('LATENCY_FLOOR', '1') == '1':
+  one = {k: v[:1].contiguous() for k, v in inp.items()}
+  tiny = torch.zeros(1, 4, device=dev)
+  tiny_s = torch.ones(1, device=dev)
+  null = lambda: ops.scale_rows(tiny, tiny_s, tiny_s)
+  print(json.dumps(dict(floor='null_launch_chain', per_launch_us=graph_us(null, per_graph=60))),
+        flush=True)
+  for rows in (1, 8, 32, 64, 96, 128, 148):
+    sm = {k: v[:rows].contiguous() for k, v in inp.items()}
+    gL = torch.full((rows,), 1.0 / (rows * D * math.log(2.0)), device=dev)
+    for pdl in (False, True):
+      ws = ops.ElboWorkspace(ops.Desc(pdl=pdl), rows, dev)
+      a = (sm['x'], sm['a'], sm['b'], sm['c'], sm['t'], sm['eps'], sm['net'])
+
+      def step():
+        ws.fwd_pre(sm['x'], sm['a'], sm['b'], sm['c'], sm['t'], sm['eps0'], sm['eps'])
+        ws.post_bpd(*a, gL)
+        ws.bwd_pre(*a, sm['z_bar'], sm['g_bar'], gL)
+      print(json.dumps(dict(floor='elbo_step', rows=rows, pdl=pdl, step_us=graph_us(step))),
+            flush=True)
+  if os.environ.get('LATENCY_FLOOR_ONLY') == '1':
+    sys.exit(0)
+
 for rows in (128, 256, 512, 1024, 2048, 4096):
   sm = {k: v[:rows].contiguous() for k, v in inp.items()}
   gL = torch.full((rows,), 1.0 / (rows * D * math.log(2.0)), device=dev)

@@ -61,6 +61,32 @@ for tt_ in (torch.full((Bs,), 0.5, device=dev),
   for mode in (0, 1):
     ops.sample_step(ops.Desc(param=mode), g['a'][:1], g['b'][:1], g['c'][:1], tt_, tt_ - 0.001,
                     zb_, nb_, eb_)
+# in-kernel draws (row-pair CTAs) and the loss-scalar board (one rank: the peer stores land in
+# this process's own board; mulan_adamw_ema_peer needs >= 2 processes and is covered by
+# tests/test_peer.py)
+big6 = O.synth_inputs(6, 7); g6 = {k: v.to(dev).contiguous() for k, v in big6.items()}
+for mode in (0, 1):
+  rk = ops.fwd_pre_keyed(ops.Desc(param=mode), (1, 2), (3, 4), g6['x'], g6['a'], g6['b'], g6['c'],
+                         g6['t'], save_w=(mode == 0), want_eps=True, want_eps0=True)
+import os, torch.distributed as dist
+os.environ.setdefault('MASTER_ADDR', '127.0.0.1'); os.environ.setdefault('MASTER_PORT', '29791')
+dist.init_process_group('gloo', rank=0, world_size=1)
+from mulan_b200.peer import ScalarBoard
+try:
+  board = ScalarBoard(dev)
+  for rows_ in (6, 300):
+    bb = O.synth_inputs(rows_, 9); gb_ = {k: v.to(dev).contiguous() for k, v in bb.items()}
+    wsb = ops.ElboWorkspace(ops.Desc(), rows_, dev)
+    wsb.fwd_pre(gb_['x'], gb_['a'], gb_['b'], gb_['c'], gb_['t'], gb_['eps_0'], gb_['eps'])
+    wsb.post_bpd(gb_['x'], gb_['a'], gb_['b'], gb_['c'], gb_['t'], gb_['eps'], gb_['net'],
+                 torch.full((rows_,), 1e-6, device=dev), board=board)
+    m_, e_ = board.read()
+  torch.cuda.synchronize()
+  print('board ok', m_.tolist(), int(e_))
+  board.close()
+except Exception as exc:     # CUDA IPC may be unavailable under the sanitizer
+  print('board skipped:', exc)
+dist.destroy_process_group()
 # JAX-compatible draws
 for shp in ((7,), (4096,), (3, 1001)):
   ops.rng_bits((1, 2), shp, device=dev); ops.rng_uniform((3, 4), shp, device=dev)
@@ -114,11 +140,11 @@ PY
 mkdir -p gpurun_out
 for tool in memcheck racecheck synccheck; do
   MULAN_FWD_PRE_TMA=0 timeout 600 compute-sanitizer --tool $tool --kernel-regex kns=mulan --print-limit 5 python /tmp/san_drive.py > gpurun_out/sanitizer_$tool.txt 2>&1
-  echo "== $tool: $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|drive ok' gpurun_out/sanitizer_$tool.txt | tr '\n' ' ')"
+  echo "== $tool: $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|drive ok|board ok|board skipped' gpurun_out/sanitizer_$tool.txt | tr '\n' ' ')"
 done
 # initcheck must see torch's own initialising kernels (a kernel filter makes every torch-written
 # input look uninitialised) and needs the caching allocator off
 MULAN_FWD_PRE_TMA=0 PYTORCH_NO_CUDA_MEMORY_CACHING=1 timeout 900 compute-sanitizer --tool initcheck --print-limit 5 python /tmp/san_drive.py > gpurun_out/sanitizer_initcheck.txt 2>&1
-echo "== initcheck: $(grep -E 'ERROR SUMMARY|drive ok' gpurun_out/sanitizer_initcheck.txt | tr '\n' ' ')"
+echo "== initcheck: $(grep -E 'ERROR SUMMARY|drive ok|board ok|board skipped' gpurun_out/sanitizer_initcheck.txt | tr '\n' ' ')"
 # (the opt-in TMA fwd_pre under racecheck: see profiles/r1_sanitizer.md; rerun with
 #  MULAN_FWD_PRE_TMA=1 compute-sanitizer --tool racecheck --kernel-regex kns=mulan python /tmp/san_drive.py)

@@ -326,3 +326,67 @@ def test_fwd_pre_keyed_rejects_what_it_cannot_pair(cuda_device):
   _, g = dev_inputs(3, 5, cuda_device)
   with pytest.raises(_lib.MulanError, match='even'):
     ops.fwd_pre_keyed(ops.Desc(), (1, 2), (3, 4), g['x'], g['a'], g['b'], g['c'], g['t'])
+
+
+def _rows_l2(got, want):
+  """per-row relative L2 distance, float64 on the host"""
+  got, want = got.double().cpu(), want.double().cpu()
+  return ((got - want).flatten(1).norm(dim=1) / want.flatten(1).norm(dim=1).clamp_min(1e-30))
+
+
+def _oracle_terms_and_grads(inp, param, gL, zbar, gbar, dtype):
+  """Forward terms, z_t and the cotangents of (a, b, c, net) for
+  L = sum gL * loss_diff + <zbar, z_t> + <gbar, mean gamma_t>, evaluated in `dtype`."""
+  cfg = O.OracleConfig()
+  d = {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in inp.items()}
+  a, b, c, net = (d[k].clone().requires_grad_(True) for k in ('a', 'b', 'c', 'net'))
+  o, x = O.elbo_terms(d['x'], a, b, c, d['t'], d['eps_0'], d['eps'], lambda z, g: net, param, cfg,
+                      dtype=dtype, return_aux=True)
+  B = a.shape[0]
+  L = (gL.to(dtype) * o.loss_diff).sum() + (zbar.to(dtype) * x['z_t'].reshape(B, -1)).sum()
+  L = L + (gbar.to(dtype) * O.score_model_gt(x['g_t'], cfg).reshape(B)).sum()
+  grads = torch.autograd.grad(L, [a, b, c, net])
+  terms = dict(loss_recon=o.loss_recon.detach(), loss_diff=o.loss_diff.detach(),
+               loss_klz_prior=x['loss_klz_prior'].detach(),
+               g_net=x['g_t'].detach().reshape(B, -1).mean(dim=1))
+  return terms, x['z_t'].detach().reshape(B, -1), dict(zip(('a_bar', 'b_bar', 'c_bar', 'n_bar'), grads))
+
+
+@pytest.mark.parametrize('D', [4, 100, 768, 3076, 12288])
+@pytest.mark.parametrize('param', [O.MODE_EPS, O.MODE_VEL])
+def test_other_row_lengths(cuda_device, D, param):
+  """The descriptor's dim is not tied to 32x32x3: rows shorter than a CTA's stride, rows that
+  are not a multiple of it, and 64x64x3 rows, in every launch shape (3 / 64 / 200 / 700 rows),
+  against the oracle on the same inputs.  The bars are the usual ones (per-example terms 1e-5,
+  gradients 1e-4 per-row L2, against the float64 oracle); where the float32 ORACLE itself is
+  further than that from float64 -- short rows average less per-pixel rounding away than 3072
+  sub-pixels do, and single rows cancel badly in the velocity gradient -- four times the float32
+  oracle's own distance for that row (or its worst row's distance) is allowed instead, and the
+  whole tensor must still meet the bar."""
+  from mulan_b200 import ops
+  for B, seed in ((3, 5), (64, 8), (200, 6), (700, 7)):
+    if B * D > 1_000_000:       # keep the float64 autograd oracle in seconds
+      continue
+    inp = O.synth_inputs(B, seed, D=D)
+    rng = np.random.default_rng(seed)
+    gL = torch.from_numpy(rng.uniform(0.5, 1.5, B).astype(np.float32)) / (B * D * math.log(2))
+    zbar = torch.from_numpy(rng.standard_normal((B, D)).astype(np.float32)) * 1e-4
+    gbar = torch.from_numpy(rng.standard_normal((B,)).astype(np.float32)) * 1e-3
+    t32, z32, g32 = _oracle_terms_and_grads(inp, param, gL, zbar, gbar, torch.float32)
+    t64, z64, g64 = _oracle_terms_and_grads(inp, param, gL, zbar, gbar, torch.float64)
+    g = {k: v.to(cuda_device).contiguous() for k, v in inp.items()}
+    desc = ops.Desc(param=param, dim=D)
+    got = step(desc, g, gL=gL.to(cuda_device), z_bar=zbar.to(cuda_device),
+               g_bar=gbar.to(cuda_device))
+    for name in ('loss_recon', 'loss_klz_prior', 'loss_diff', 'g_net'):
+      e_got = (got[name].cpu().double() - t64[name]).abs()
+      e_ref = (t32[name].double() - t64[name]).abs().max()
+      assert bool((e_got <= 1e-5 * t64[name].abs() + 4 * e_ref + 1e-7).all()), \
+          (name, B, D, float(e_got.max()), float(e_ref))
+    checks = [('z_t', got['z_t'], z32, z64, 1e-5)]
+    checks += [(n, got[n], g32[n], g64[n], 1e-4) for n in ('a_bar', 'b_bar', 'c_bar', 'n_bar')]
+    for name, have, w32, w64, bar in checks:
+      e_got, e_ref = _rows_l2(have, w64), _rows_l2(w32, w64)
+      assert bool((e_got <= torch.clamp(4 * e_ref, min=max(bar, float(e_ref.max())))).all()), \
+          (name, B, D, float(e_got.max()), float(e_ref.max()))
+      assert rel_l2(have.cpu(), w64) < bar, (name, B, D)

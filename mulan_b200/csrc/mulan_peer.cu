@@ -119,7 +119,11 @@ __device__ __forceinline__ void adamw_elem(float& p, float g, float& mu, float& 
 // first dependent use): with two ranks a single remote load per thread leaves NVLink latency
 // exposed (measured 176 GB/s per direction), so small worlds take more columns (8 / 2 / 1 columns
 // for 2 / 4 / 8 ranks, measured: two columns at 8 ranks cost 1.09 instead of 0.92 ms for 285 MB).
-template <int WORLD, int COLS, bool MC = false>
+// PF (multicast form only): the switch-reduced gradients of a CTA's NEXT chunk are requested
+// before the current chunk is updated and stored, so the reduce-scatter stream (the switch pulls
+// every GPU's bucket: outbound-heavy) and the all-gather stream (multimem.st: inbound-heavy) of
+// the fabric stay busy at the same time instead of alternating.
+template <int WORLD, int COLS, bool MC = false, bool PF = false>
 __global__ void __launch_bounds__(kThreads)
 adamw_ema_peer_kernel(const PeerParams k) {
   __shared__ int s_last;
@@ -136,10 +140,29 @@ adamw_ema_peer_kernel(const PeerParams k) {
   // barrier at the head and the system fence + signal at the tail are paid once per CTA, not
   // once per 32 KB (one CTA per chunk measured 0.61 ms for 285 MB on two GPUs, this form 0.53 ms).
   const long long n_chunks = (k.n4 + (long long)kThreads * COLS - 1) / ((long long)kThreads * COLS);
+  float4 Gnext[COLS];
+  if (MC && PF && blockIdx.x < n_chunks) {
+#pragma unroll
+    for (int c = 0; c < COLS; ++c) {
+      const long long j = (long long)blockIdx.x * (kThreads * COLS) + tid + (long long)c * kThreads;
+      if (j < k.n4) Gnext[c] = multimem_ld_reduce4(k.mc_grads, k.lo4 + j);
+    }
+  }
   for (long long chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
   const long long j0 = chunk * (kThreads * COLS) + tid;
   float4 G[COLS];
-  if (MC) {
+  if (MC && PF) {
+#pragma unroll
+    for (int c = 0; c < COLS; ++c) G[c] = Gnext[c];
+    const long long nxt = chunk + gridDim.x;
+    if (nxt < n_chunks) {
+#pragma unroll
+      for (int c = 0; c < COLS; ++c) {
+        const long long j = nxt * (kThreads * COLS) + tid + (long long)c * kThreads;
+        if (j < k.n4) Gnext[c] = multimem_ld_reduce4(k.mc_grads, k.lo4 + j);
+      }
+    }
+  } else if (MC) {
     // the switch sums the `world` gradient buckets (order fixed by the fabric, not by rank)
 #pragma unroll
     for (int c = 0; c < COLS; ++c) {
@@ -322,10 +345,20 @@ int mulan_adamw_ema_peer(const mulan_adamw_desc* d, const mulan_peer_desc* peers
   }
   cudaStream_t s = (cudaStream_t)stream;
   if (mc) {
-    switch (W) {
-      case 2: mulan::adamw_ema_peer_kernel<2, 4, true><<<(int)want, mulan::kThreads, 0, s>>>(k); break;
-      case 4: mulan::adamw_ema_peer_kernel<4, 4, true><<<(int)want, mulan::kThreads, 0, s>>>(k); break;
-      default: mulan::adamw_ema_peer_kernel<8, 4, true><<<(int)want, mulan::kThreads, 0, s>>>(k); break;
+    bool pf = false;
+    if (const char* e = getenv("MULAN_PEER_MC_PREFETCH")) pf = atoi(e) != 0;                  // A/B
+    if (pf) {
+      switch (W) {
+        case 2: mulan::adamw_ema_peer_kernel<2, 4, true, true><<<(int)want, mulan::kThreads, 0, s>>>(k); break;
+        case 4: mulan::adamw_ema_peer_kernel<4, 4, true, true><<<(int)want, mulan::kThreads, 0, s>>>(k); break;
+        default: mulan::adamw_ema_peer_kernel<8, 4, true, true><<<(int)want, mulan::kThreads, 0, s>>>(k); break;
+      }
+    } else {
+      switch (W) {
+        case 2: mulan::adamw_ema_peer_kernel<2, 4, true><<<(int)want, mulan::kThreads, 0, s>>>(k); break;
+        case 4: mulan::adamw_ema_peer_kernel<4, 4, true><<<(int)want, mulan::kThreads, 0, s>>>(k); break;
+        default: mulan::adamw_ema_peer_kernel<8, 4, true><<<(int)want, mulan::kThreads, 0, s>>>(k); break;
+      }
     }
     PEER_CU(cudaGetLastError(), fn);
     return 0;

@@ -72,8 +72,8 @@ HOT = [  # what bench.py's default line and its configs block launch at 16384 / 
     'post_kernel<0, true, 2, false, true, 768>', 'post_kernel<1, false, 0, false, true, 256>',
     'bwd_pre_kernel<0, 0, false, true, false, 256, 5>', 'bwd_pre_kernel<1, 0, false, true, false, 256, 5>',
     'bwd_pre_kernel<0, 0, false, true, false, 768, 1>', 'adamw_ema_kernel<false>',
-    'adamw_ema_peer_kernel<2, 8, false>', 'adamw_ema_peer_kernel<4, 2, false>',
-    'adamw_ema_peer_kernel<8, 4, true>']
+    'adamw_ema_peer_kernel<2, 8, false, false>', 'adamw_ema_peer_kernel<4, 2, false, false>',
+    'adamw_ema_peer_kernel<8, 4, true, false>']
 want = sys.argv[1:] or None
 HDR = ('| kernel | regs | stack | smem B | SASS instr | LDG.128 | STG.128 | other LDG / STG | MUFU '
        '| BAR | SHFL | LDGMC | local LD/ST |\n|---|---|---|---|---|---|---|---|---|---|---|---|---|')

@@ -222,6 +222,16 @@ def test_shard_rows():
       assert got == list(range(n))
 
 
+def test_dense_launches_are_sized_in_whole_images():
+  """The dense-VLB driver sizes its launches itself (whole images, as many as fit 16384 rows;
+  ldm/notebook_utils.py:176-191 evaluates 16 x 128 rows per call)."""
+  from mulan_b200.dist import dense_images_per_launch
+  assert dense_images_per_launch(128) == 128
+  assert dense_images_per_launch(1000) == 16
+  assert dense_images_per_launch(128, max_rows=2048) == 16       # the reference's shape
+  assert dense_images_per_launch(100000) == 1                     # never less than one image
+
+
 def _free_port():
   s = socket.socket()
   s.bind(('127.0.0.1', 0))
